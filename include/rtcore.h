@@ -1,0 +1,247 @@
+/*
+ * rtcore.h — C ABI of the B200-native ray-tracing core.
+ *
+ * This is the drop-in boundary for what the reference samples
+ * (vulkan-raytracing-basic/main.cpp == vulkan-raytraced-triangle/main.cpp) hand to the
+ * Vulkan driver through the KHR entry-point table they load at main.cpp:25-33,135-145:
+ *
+ *   vkGetAccelerationStructureBuildSizesKHR   main.cpp:757,893   -> rt_blas_build_sizes / rt_tlas_build_sizes
+ *   vkCreateAccelerationStructureKHR +
+ *   vkCmdBuildAccelerationStructuresKHR (BLAS) main.cpp:775-820  -> rt_build_blas / rt_build_blas_batch
+ *   vkCmdBuildAccelerationStructuresKHR (TLAS) main.cpp:911-942  -> rt_build_tlas
+ *   UBO {cameraPos, yFov_degree}              main.cpp:1001-1017 -> rt_camera
+ *   SBT hit-record payloads / miss constant   main.cpp:1310-1317,1065 -> rt_set_hit_records / rt_set_miss_color
+ *   traceRayEXT arguments                     main.cpp:1047-1052 -> rt_set_ray_params
+ *   vkCmdTraceRaysKHR(W,H,1) + fence          main.cpp:1333,1349-1355,1411 -> rt_trace / rt_trace_rows
+ *   vkDestroyAccelerationStructureKHR         main.cpp:89-96     -> rt_free_blas / rt_free_tlas
+ *
+ * Plain C: pointers and sizes only, no C++/torch types. All calls are synchronous on return
+ * (the reference does vkQueueWaitIdle after every build, main.cpp:820,942) unless the name
+ * ends in _async. A context is bound to one CUDA device and is not thread-safe.
+ * No CPU fallback exists: every entry point fails with RT_ERROR_CUDA when no device is usable.
+ */
+#ifndef RTCORE_H_
+#define RTCORE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API __attribute__((visibility("default")))
+
+/* ---- status codes -------------------------------------------------------------------- */
+enum {
+    RT_SUCCESS            =  0,
+    RT_ERROR_INVALID_ARG  = -1,
+    RT_ERROR_CUDA         = -2,   /* a CUDA runtime call failed; see rt_last_error() */
+    RT_ERROR_OUT_OF_MEMORY= -3,
+    RT_ERROR_STACK_DEPTH  = -4,   /* BVH deeper than the traversal stack (never silently wrong) */
+    RT_ERROR_SBT_RANGE    = -5,   /* an instance/geometry addresses a hit record that was not set */
+    RT_ERROR_INTERNAL     = -6    /* device-side watchdog / invariant violation */
+};
+
+/* ---- geometry flags (rt_geometry.flags) ------------------------------------------------ */
+#define RT_GEOMETRY_OPAQUE          0x1u  /* VK_GEOMETRY_OPAQUE_BIT_KHR, main.cpp:741 */
+#define RT_GEOMETRY_DEVICE_POINTERS 0x100u /* vertices/indices/transform are CUDA device pointers */
+
+/* ---- build flags ---------------------------------------------------------------------- */
+#define RT_BUILD_PREFER_FAST_TRACE  0x4u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, main.cpp:751 */
+#define RT_BUILD_INSTANCES_ON_DEVICE 0x100u /* rt_build_tlas: the rt_instance array is device memory */
+
+/* ---- instance flags (rt_instance.flags, low 8 bits like VkGeometryInstanceFlagsKHR) ---- */
+#define RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE 0x1u /* main.cpp:852 */
+
+/* ---- rt_trace output flags -------------------------------------------------------------- */
+#define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
+#define RT_TRACE_STATS      0x2u  /* also accumulate traversal counters (slower kernel variant) */
+
+typedef struct rt_context rt_context;
+typedef struct rt_blas    rt_blas;
+typedef struct rt_tlas    rt_tlas;
+
+/* One triangle geometry of a BLAS: mirrors VkAccelerationStructureGeometryTrianglesDataKHR
+ * (R32G32B32_SFLOAT vertices, UINT32 indices, optional 3x4 row-major VkTransformMatrixKHR)
+ * plus the primitiveCount of its VkAccelerationStructureBuildRangeInfoKHR (main.cpp:726-746,795-804). */
+typedef struct rt_geometry {
+    const float*    vertices;            /* vertex_count x (vertex_stride_bytes/4) floats        */
+    uint32_t        vertex_count;        /* maxVertex + 1                                        */
+    uint32_t        vertex_stride_bytes; /* >= 12, multiple of 4                                 */
+    const uint32_t* indices;             /* 3*triangle_count indices, or NULL = non-indexed list  */
+    uint32_t        triangle_count;      /* primitiveCount                                       */
+    const float*    transform3x4;        /* row-major 3x4 applied at build time, or NULL         */
+    uint32_t        flags;               /* RT_GEOMETRY_*                                        */
+} rt_geometry;
+
+/* 64-byte TLAS instance record, same layout as VkAccelerationStructureInstanceKHR (main.cpp:848-858)
+ * with the BLAS handle in place of accelerationStructureReference. */
+typedef struct rt_instance {
+    float    transform[12];              /* object->world, row-major 3x4 */
+    uint32_t custom_index : 24;          /* instanceCustomIndex */
+    uint32_t mask         : 8;
+    uint32_t sbt_offset   : 24;          /* instanceShaderBindingTableRecordOffset */
+    uint32_t flags        : 8;
+    const rt_blas* blas;                 /* accelerationStructureReference */
+} rt_instance;
+
+/* UBO of the raygen shader (main.cpp:1003-1006,1015): {0,0,10, 60} in the sample. */
+typedef struct rt_camera {
+    float pos[3];
+    float yfov_deg;
+} rt_camera;
+
+/* traceRayEXT parameters (main.cpp:1047-1052). Defaults are the sample's. */
+typedef struct rt_ray_params {
+    float    tmin;              /* 0.0   */
+    float    tmax;              /* 100.0 */
+    uint32_t cull_mask;         /* 0xff  */
+    uint32_t sbt_record_offset; /* 0     */
+    uint32_t sbt_record_stride; /* 1     */
+    uint32_t bounce_seed;       /* seed of the deterministic diffuse bounce (ours; default 1) */
+} rt_ray_params;
+
+/* Per-ray result: the built-ins the closest-hit shader sees (main.cpp:1080-1086).
+ * A miss has all four ids == 0xFFFFFFFF and t == tmax. */
+typedef struct rt_hit {
+    uint32_t instance_id;     /* gl_InstanceID (slot in the rt_instance array) */
+    uint32_t geometry_index;  /* gl_GeometryIndexEXT */
+    uint32_t primitive_id;    /* gl_PrimitiveID (index within its geometry) */
+    uint32_t custom_index;    /* gl_InstanceCustomIndexEXT */
+    float    t;               /* along the un-normalised ray direction */
+    float    u, v;            /* hitAttributeEXT barycentrics: weights of vertex 1 and vertex 2 */
+} rt_hit;
+
+typedef struct rt_build_sizes {           /* VkAccelerationStructureBuildSizesInfoKHR */
+    uint64_t acceleration_structure_size;
+    uint64_t build_scratch_size;
+} rt_build_sizes;
+
+/* Device-side traversal counters (RT_TRACE_STATS); summed over all rays of the call. */
+typedef struct rt_trace_stats {
+    uint64_t rays_primary;
+    uint64_t rays_secondary;
+    uint64_t nodes_visited;       /* 64-byte BVH nodes fetched (TLAS + BLAS) */
+    uint64_t triangles_tested;
+    uint64_t instances_entered;
+    uint64_t primary_hits;
+    uint64_t secondary_hits;
+    uint64_t near_edge_hits;      /* hits with min barycentric < 2^-20: the "within epsilon of a shared edge" count */
+} rt_trace_stats;
+
+/* Phase timings of the most recent build on this context, CUDA-event milliseconds. */
+typedef struct rt_build_timing {
+    float total_ms;        /* first setup kernel .. last refit kernel (no H2D) */
+    float setup_ms;        /* triangle fetch + transform + bounds */
+    float morton_ms;
+    float sort_ms;
+    float hierarchy_ms;
+    float refit_ms;        /* leaf emit + atomic bottom-up refit */
+    float h2d_ms;          /* staging copies of host inputs (outside total_ms) */
+    uint64_t primitives;
+} rt_build_timing;
+
+/* ---- context ---------------------------------------------------------------------------- */
+RT_API int  rt_create(int device_ordinal, rt_context** out);
+RT_API void rt_destroy(rt_context* ctx);
+RT_API const char* rt_last_error(const rt_context* ctx);       /* never NULL */
+RT_API int  rt_device_info(const rt_context* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+/* Run subsequent work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's. */
+RT_API int  rt_set_stream(rt_context* ctx, void* cuda_stream);
+RT_API int  rt_sync(rt_context* ctx);
+
+/* ---- acceleration structures ------------------------------------------------------------ */
+RT_API int  rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, uint32_t n_geoms, rt_build_sizes* out);
+RT_API int  rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes* out);
+
+/* Builds one BLAS over n_geoms geometries. Inputs are copied/consumed before return: the caller
+ * may free them immediately (the reference does, main.cpp:823-830). */
+RT_API int  rt_build_blas(rt_context* ctx, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags, rt_blas** out);
+
+/* Builds n_blas independent BLASes in ONE set of kernel launches (segmented LBVH).
+ * geoms holds all geometries back to back; geom_counts[b] of them belong to BLAS b. */
+RT_API int  rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts,
+                                uint32_t n_blas, uint32_t build_flags, rt_blas** out_array);
+
+RT_API int  rt_build_tlas(rt_context* ctx, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags, rt_tlas** out);
+/* Re-fit an existing TLAS to new instance transforms (same count, same BLASes): the per-frame path. */
+RT_API int  rt_update_tlas(rt_context* ctx, rt_tlas* tlas, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags);
+
+RT_API void rt_free_blas(rt_context* ctx, rt_blas* blas);
+RT_API void rt_free_tlas(rt_context* ctx, rt_tlas* tlas);
+
+RT_API int  rt_last_build_timing(const rt_context* ctx, rt_build_timing* out);
+RT_API float rt_last_build_ms(const rt_context* ctx);
+
+/* Introspection used by the parity tests (build invariants) and by multi-GPU BLAS broadcast. */
+typedef struct rt_blas_info {
+    uint32_t triangle_count;
+    uint32_t node_count;        /* 64-byte internal nodes stored */
+    int32_t  root_ref;          /* >=0 internal node, <0 leaf, RT_REF_EMPTY for an empty BLAS */
+    uint32_t max_depth;
+    float    bounds_lo[3], bounds_hi[3];
+    uint64_t storage_bytes;     /* relocatable device blob: nodes then triangles */
+    void*    device_storage;    /* device pointer of that blob */
+} rt_blas_info;
+#define RT_REF_EMPTY 0x7FFFFFFD
+RT_API int  rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out);
+/* Copies nodes (node_count x 64 B) and triangles (triangle_count x 48 B) to host buffers; either may be NULL. */
+RT_API int  rt_blas_export(rt_context* ctx, const rt_blas* blas, void* nodes_out, void* tris_out);
+/* Debug/parity export of the sorted Morton keys+primitive ids of the most recent single-BLAS build. */
+RT_API int  rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* prim_out, uint32_t capacity, uint32_t* n_out);
+/* Wraps a device blob produced by another context/GPU's rt_blas_get_info().device_storage
+ * (after ncclBroadcast) as a BLAS on this context. The blob is copied. */
+RT_API int  rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device_blob, rt_blas** out);
+
+typedef struct rt_tlas_info {
+    uint32_t instance_count;
+    uint32_t node_count;
+    int32_t  root_ref;
+    uint32_t max_depth;
+    float    bounds_lo[3], bounds_hi[3];
+} rt_tlas_info;
+RT_API int  rt_tlas_get_info(rt_context* ctx, const rt_tlas* tlas, rt_tlas_info* out);
+
+/* ---- shader data ------------------------------------------------------------------------ */
+/* Payloads of the hit-group records: count x {r,g,b} (main.cpp:1310-1317). */
+RT_API int  rt_set_hit_records(rt_context* ctx, const float* rgb, uint32_t count);
+RT_API int  rt_set_miss_color(rt_context* ctx, const float rgb[3]);          /* default (0,0,0.2), main.cpp:1065 */
+RT_API int  rt_set_ray_params(rt_context* ctx, const rt_ray_params* params); /* NULL restores the defaults */
+
+/* ---- dispatch --------------------------------------------------------------------------- */
+/* vkCmdTraceRaysKHR(width, height, 1): raygen + traversal + closest-hit/miss + imageStore.
+ * rgba_out: width*height*4 bytes, logical R,G,B,A with A = 0 (imageStore(vec4(hitValue,0.0)), main.cpp:1054).
+ * bounces: 0 = the reference's pipeline (recursion depth 1); 1 = plus one deterministic diffuse bounce.
+ * primary_hits_out / secondary_hits_out: width*height rt_hit each, or NULL. */
+RT_API int  rt_trace(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam,
+                     uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
+                     uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
+
+/* Image-space partition for multi-GPU: traces only the row blocks b (of block_rows scanlines) with
+ * b % part_count == part_index, writing them PACKED (block after block, each block_rows*width pixels;
+ * the last block of the image may be short and is zero-padded) so that equal-sized rank buffers can
+ * be gathered. Output capacity: rt_rows_packed_pixels(). Ray generation still uses the full
+ * width x height launch size. */
+RT_API int  rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam,
+                          uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
+                          uint32_t block_rows, uint32_t part_index, uint32_t part_count,
+                          uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
+RT_API uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_rows, uint32_t part_count);
+/* Rank 0 after the gather: scatter part_count packed buffers (contiguous, each
+ * rt_rows_packed_pixels()*4 bytes, device memory) into the final width*height*4 framebuffer (device). */
+RT_API int  rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t width, uint32_t height,
+                           uint32_t block_rows, uint32_t part_count, uint8_t* rgba_out_device);
+
+RT_API int  rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out);
+/* CUDA-event milliseconds of the kernels of the most recent rt_trace*/rt_unpack call (no copies). */
+RT_API float rt_last_trace_ms(const rt_context* ctx);
+/* Number of kernels this library has launched on the context since creation. */
+RT_API uint64_t rt_kernel_launch_count(const rt_context* ctx);
+
+RT_API const char* rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTCORE_H_ */
