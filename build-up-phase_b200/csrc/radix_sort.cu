@@ -1,0 +1,233 @@
+// radix_sort.cu — "onesweep" LSD radix sort of (u64 Morton key, u32 primitive id) pairs for sm_100a.
+//
+// One up-front histogram kernel reads the keys once and produces the global digit histogram of
+// EVERY 8-bit pass; each pass is then a single kernel: a tile (3072 pairs) is ranked in
+// shared memory with warp-level match_any multi-split, its per-digit counts are published to a
+// (tile x 256) state array, and the exclusive prefix over preceding tiles is obtained by
+// decoupled look-back (status|value packed in one 32-bit word, so no fence is needed between
+// them). Tile ids are handed out by an atomic counter so a tile only ever waits on tiles that
+// have already started (forward progress without co-residency assumptions). Keys and values are
+// reordered through shared memory so global stores are coalesced runs. HBM traffic per pass is
+// one read + one write of each pair (24 B/pair), the bound this kernel is measured against.
+//
+// A spin watchdog turns a (theoretically impossible) look-back stall into an error flag instead
+// of a hung GPU.
+#include "rt_internal.h"
+
+namespace rt {
+
+namespace {
+
+constexpr int RADIX = 256;
+constexpr int SORT_THREADS = 256;            // == RADIX: thread d owns digit d in the scan / look-back
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int SORT_ITEMS = 12;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 3072 pairs
+constexpr int MAX_PASSES = 8;
+
+constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// hist[p][d] += number of keys whose p-th 8-bit digit is d
+__global__ void __launch_bounds__(512) k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int passes, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[MAX_PASSES * RADIX];
+    for (int j = threadIdx.x; j < passes * RADIX; j += blockDim.x) sh[j] = 0;
+    __syncthreads();
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        uint64_t k = keys[i];
+        for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * RADIX + (uint32_t)((k >> (8 * p)) & 255u)], 1u);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < passes * RADIX; j += blockDim.x)
+        if (sh[j]) atomicAdd(&hist[j], sh[j]);
+}
+
+// in-place exclusive scan of each pass's 256-bin histogram; one block of 256 threads per pass
+__global__ void __launch_bounds__(RADIX) k_sort_scan_hist(uint32_t* hist) {
+    __shared__ uint32_t wtot[SORT_WARPS];
+    const int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+    uint32_t* h = hist + blockIdx.x * RADIX;
+    uint32_t v = h[d], inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    uint32_t base = 0;
+    for (int w = 0; w < warp; ++w) base += wtot[w];
+    h[d] = base + inc - v;
+}
+
+__global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
+    const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
+    const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
+    uint32_t n, int shift, const uint32_t* __restrict__ digit_base,
+    uint32_t* tile_state, uint32_t* tile_counter, int* error_flag) {
+    __shared__ uint32_t s_cnt[SORT_WARPS * RADIX];   // per-warp digit counts -> per-warp exclusive offsets
+    __shared__ uint64_t s_keys[SORT_TILE];
+    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_loff[RADIX];               // start of digit d inside the tile-local order
+    __shared__ uint32_t s_goff[RADIX];               // global position of local slot p with digit d = s_goff[d] + p
+    __shared__ uint32_t s_wtot[SORT_WARPS];
+    __shared__ uint32_t s_tile;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(tile_counter, 1u);
+    for (int j = tid; j < SORT_WARPS * RADIX; j += SORT_THREADS) s_cnt[j] = 0;
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    const uint32_t base = tile * (uint32_t)SORT_TILE;
+    const uint32_t tile_n = min((uint32_t)SORT_TILE, n - base);
+    const uint32_t wbase = warp * (32 * SORT_ITEMS) + lane;     // tile-local index of item 0 of this lane
+
+    uint64_t key[SORT_ITEMS];
+    uint32_t rank[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        uint32_t li = wbase + i * 32;
+        key[i] = li < tile_n ? keys_in[base + li] : ~0ull;
+    }
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const bool valid = (wbase + i * 32) < tile_n;
+        const uint32_t d = valid ? (uint32_t)((key[i] >> shift) & 255u) : 0xFFFFFFFFu;
+        const uint32_t m = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(m) - 1;
+        uint32_t prev = 0;
+        if (valid && lane == leader) {
+            prev = s_cnt[warp * RADIX + d];
+            s_cnt[warp * RADIX + d] = prev + __popc(m);
+        }
+        prev = __shfl_sync(0xffffffffu, prev, leader);
+        rank[i] = prev + __popc(m & lt_mask);
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // thread d: exclusive scan over warps for digit d, tile count, publish, look back
+    {
+        const int d = tid;
+        uint32_t run = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) { uint32_t c = s_cnt[w * RADIX + d]; s_cnt[w * RADIX + d] = run; run += c; }
+        uint32_t* my_state = tile_state + (size_t)tile * RADIX + d;
+        if (tile == 0) st_volatile_u32(my_state, FLAG_PREFIX | run);
+        else st_volatile_u32(my_state, FLAG_AGG | run);
+
+        // exclusive scan of the tile counts over digits -> local offsets
+        uint32_t inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_wtot[warp] = inc;
+        __syncthreads();
+        uint32_t wb = 0;
+        for (int w = 0; w < warp; ++w) wb += s_wtot[w];
+        const uint32_t loff = wb + inc - run;
+
+        uint32_t excl = 0;
+        if (tile > 0) {
+            int t = (int)tile - 1;
+            uint32_t spins = 0;
+            for (;;) {
+                uint32_t s = ld_volatile_u32(tile_state + (size_t)t * RADIX + d);
+                uint32_t flag = s >> 30;
+                if (flag == 0) {
+                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1); break; }
+                    __nanosleep(32);
+                    continue;
+                }
+                excl += s & VALUE_MASK;
+                if (flag == 2 || t == 0) break;
+                --t;
+            }
+            st_volatile_u32(my_state, FLAG_PREFIX | ((excl + run) & VALUE_MASK));
+        }
+        s_loff[d] = loff;
+        s_goff[d] = digit_base[d] + excl - loff;
+    }
+    __syncthreads();
+
+    // scatter keys into tile-local sorted order
+    uint32_t lpos[SORT_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const bool valid = (wbase + i * 32) < tile_n;
+        if (valid) {
+            const uint32_t d = (uint32_t)((key[i] >> shift) & 255u);
+            lpos[i] = s_loff[d] + s_cnt[warp * RADIX + d] + rank[i];
+            s_keys[lpos[i]] = key[i];
+        } else lpos[i] = 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        uint32_t li = wbase + i * 32;
+        if (li < tile_n) s_vals[lpos[i]] = vals_in[base + li];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const uint32_t p = i * SORT_THREADS + tid;
+        if (p < tile_n) {
+            const uint64_t k = s_keys[p];
+            const uint32_t d = (uint32_t)((k >> shift) & 255u);
+            const uint32_t g = s_goff[d] + p;
+            keys_out[g] = k;
+            vals_out[g] = s_vals[p];
+        }
+    }
+}
+
+}  // namespace
+
+SortPlan sort_plan(uint32_t n, int key_bits) {
+    SortPlan p;
+    p.n = n;
+    p.passes = (key_bits + 7) / 8;
+    if (p.passes < 1) p.passes = 1;
+    if (p.passes > MAX_PASSES) p.passes = MAX_PASSES;
+    p.tiles = (n + SORT_TILE - 1) / SORT_TILE;
+    p.scratch_bytes = (size_t)MAX_PASSES * RADIX * 4 + 64 + (size_t)p.passes * p.tiles * RADIX * 4;
+    return p;
+}
+
+int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+               void* scratch, int* device_error_flag, cudaStream_t stream, bool* result_in_b) {
+    *result_in_b = false;
+    if (plan.n == 0) return 0;
+    uint32_t* hist = (uint32_t*)scratch;
+    uint32_t* counters = hist + MAX_PASSES * RADIX;
+    uint32_t* states = counters + 16;
+    if (cudaMemsetAsync(scratch, 0, plan.scratch_bytes, stream) != cudaSuccess) return -1;
+    int launches = 0;
+    int hist_blocks = (int)((plan.n + 512 * 16 - 1) / (512 * 16));
+    if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
+    if (hist_blocks < 1) hist_blocks = 1;
+    k_sort_hist<<<hist_blocks, 512, 0, stream>>>(keys_a, plan.n, plan.passes, hist);
+    k_sort_scan_hist<<<plan.passes, RADIX, 0, stream>>>(hist);
+    launches += 2;
+    uint64_t* kin = keys_a; uint64_t* kout = keys_b;
+    uint32_t* vin = vals_a; uint32_t* vout = vals_b;
+    for (int p = 0; p < plan.passes; ++p) {
+        k_onesweep_pass<<<plan.tiles, SORT_THREADS, 0, stream>>>(kin, kout, vin, vout, plan.n, 8 * p, hist + p * RADIX,
+                                                                 states + (size_t)p * plan.tiles * RADIX, counters + p,
+                                                                 device_error_flag);
+        ++launches;
+        uint64_t* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+    }
+    *result_in_b = (plan.passes & 1) != 0;
+    if (cudaGetLastError() != cudaSuccess) return -1;
+    return launches;
+}
+
+}  // namespace rt

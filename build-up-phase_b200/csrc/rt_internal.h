@@ -1,0 +1,160 @@
+// rt_internal.h — device data layout + internal host interfaces of librtcore (sm_100a).
+//
+// HBM layout (all little-endian, 16-byte aligned so every fetch is an LDG.128):
+//   BvhNode     64 B  = two 32-B halves {lo.xyz, hi.xyz, ref, height}, one per child. A half is
+//                       exactly one 32-B DRAM sector and is written by the ONE thread that climbs
+//                       through that child during the atomic bottom-up refit.
+//   TriRec      48 B  = v0.xyz v1.xyz v2.xyz geometryIndex primitiveIndex pad  (3 x LDG.128);
+//                       BLAS-space vertices with the per-geometry transform already baked in
+//                       (vkCmdBuildAccelerationStructuresKHR semantics, reference main.cpp:795-808).
+//   InstanceRec 96 B  = world->object 3x4, BLAS node/triangle base pointers, root ref, packed
+//                       customIndex|mask and sbtOffset|flags (VkAccelerationStructureInstanceKHR,
+//                       reference main.cpp:848-858), TLAS slot id, |BLAS bounds| for the slab pad.
+// Child refs: >= 0 internal node index (relative to the AS's node base); < 0 leaf = ~((first<<3)|(count-1))
+// into the AS's primitive array; large positive values are traversal sentinels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtcore.h"
+
+namespace rt {
+
+constexpr int32_t REF_DONE  = 0x7FFFFFFF;
+constexpr int32_t REF_POP_INSTANCE = 0x7FFFFFFE;
+constexpr int32_t REF_EMPTY = RT_REF_EMPTY;      // 0x7FFFFFFD
+constexpr int32_t REF_SENTINEL_MIN = 0x7FFFFFF0;
+constexpr int BLAS_LEAF_MAX = 4;
+constexpr int TLAS_LEAF_MAX = 1;
+constexpr uint32_t MORTON_BITS = 30;
+constexpr uint32_t MAX_PRIMS = 1u << 28;         // leaf ref packs (first << 3) into 31 bits
+
+struct __align__(32) BvhNodeHalf { float lo[3]; float hi[3]; int32_t ref; uint32_t height; };
+struct __align__(64) BvhNode { BvhNodeHalf c[2]; };
+static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
+
+struct __align__(16) TriRec { float v[9]; uint32_t geo, prim, pad; };
+static_assert(sizeof(TriRec) == 48, "TriRec must be 48 B");
+
+struct __align__(16) InstanceRec {
+    float w2o[12];              // 48
+    const BvhNode* nodes;       // 56
+    const TriRec*  tris;        // 64
+    int32_t  root;              // 68
+    uint32_t custom_mask;       // 72   custom_index:24 | mask:8
+    uint32_t sbt_flags;         // 76   sbt_offset:24 | flags:8
+    uint32_t instance_id;       // 80   slot in the caller's rt_instance array (gl_InstanceID)
+    float    absmax[3];         // 92   max(|blas.lo|, |blas.hi|) per axis
+    uint32_t active;            // 96
+};
+static_assert(sizeof(InstanceRec) == 96, "InstanceRec must be 96 B");
+
+// What accelerationStructureReference points at: one record per BLAS in device memory.
+struct __align__(16) BlasRecord {
+    const BvhNode* nodes;
+    const TriRec*  tris;
+    int32_t  root;
+    uint32_t height;
+    float    lo[3], hi[3];
+    uint32_t tri_count;
+    uint32_t n_geoms;
+    uint32_t first;             // first primitive of this BLAS inside a batched build
+    uint32_t pad[1];
+};
+static_assert(sizeof(BlasRecord) == 64, "BlasRecord must be 64 B");
+
+// One geometry of a (possibly batched) BLAS build, device-resident inputs.
+struct GeomDesc {
+    const float*    verts;
+    const uint32_t* idx;        // may be null
+    uint32_t stride_f;          // vertex stride in floats
+    uint32_t tri_first;         // global index of this geometry's first triangle
+    uint32_t tri_count;
+    uint32_t blas;              // which BLAS of the batch
+    uint32_t geo_index;         // gl_GeometryIndexEXT inside that BLAS
+    uint32_t has_xform;
+    float    xform[12];
+};
+
+// ---- radix sort (csrc/radix_sort.cu) ---------------------------------------------------------
+struct SortPlan {
+    uint32_t n = 0;
+    int passes = 0;             // 8-bit digits
+    uint32_t tiles = 0;
+    size_t scratch_bytes = 0;   // histogram + look-back state
+};
+SortPlan sort_plan(uint32_t n, int key_bits);
+// Sorts (keys, vals) by the low key_bits of the key, stable. Result ends in keys_a/vals_a or keys_b/vals_b;
+// *result_in_b tells which. Returns the number of kernels launched, or <0 on a launch error.
+int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
+               void* scratch, int* device_error_flag, cudaStream_t stream, bool* result_in_b);
+
+// ---- LBVH build (csrc/lbvh_build.cu) -----------------------------------------------------------
+struct BuildScratch {           // all device pointers, sized for n primitives
+    uint64_t* keys_a; uint64_t* keys_b;
+    uint32_t* vals_a; uint32_t* vals_b;
+    uint32_t* parent_leaf;      // n
+    uint32_t* parent_node;      // n
+    int32_t*  other_end;        // n
+    uint32_t* arrived;          // n
+    void*     sort_scratch;
+    int*      error_flag;       // 1 int
+};
+
+struct BlasBuildArgs {
+    const GeomDesc* geoms; uint32_t n_geoms;
+    const uint32_t* geom_tri_first;   // n_geoms+1 prefix array (device) for the binary search
+    uint32_t n_tris; uint32_t n_blas;
+    uint32_t seg_bits;                // ceil(log2(n_blas))
+    TriRec*   tris_unsorted;          // scratch, n_tris
+    TriRec*   tris_sorted;            // output
+    BvhNode*  nodes;                  // output, n_tris slots
+    BlasRecord* records;              // n_blas (device), nodes/tris/first/tri_count/n_geoms pre-filled by the host
+    int*      bounds_ordered;         // n_blas * 6 ints (ordered-int encoded floats), pre-initialised
+    BuildScratch s;
+    SortPlan  sort;
+};
+struct BuildEvents { cudaEvent_t e[6]; };  // setup | morton | sort | hierarchy | refit | end
+int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b);
+
+struct TlasBuildArgs {
+    const rt_instance* instances;     // device copy of the caller's 64-byte records (blas field = BlasRecord device address)
+    uint32_t n;
+    InstanceRec* inst_unsorted;       // scratch
+    InstanceRec* inst_sorted;         // output
+    float*       boxes_unsorted;      // scratch n*6
+    BvhNode*     nodes;               // output
+    int*         bounds_ordered;      // 6 ints
+    int32_t*     root_out;            // {root, height, max_sbt_plus_geo, max_sbt, max_geo, max_blas_height}  (6 ints, device)
+    float*       bounds_out;          // 6 floats (device)
+    BuildScratch s;
+    SortPlan     sort;
+};
+int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st);
+
+// ---- trace (csrc/trace.cu) -----------------------------------------------------------------------
+struct TraceParams {
+    const BvhNode* tlas_nodes;
+    const InstanceRec* instances;
+    int32_t tlas_root;
+    float tlas_absmax[3];
+    float cam_pos[3];
+    float aspect_x, aspect_y;
+    uint32_t width, height;
+    uint32_t block_rows, part_index, part_count;   // image-space partition (1 part = whole image)
+    uint32_t local_rows;                           // rows this launch covers (packed)
+    float tmin, tmax;
+    uint32_t cull_mask, sbt_offset, sbt_stride, bounce_seed;
+    uint32_t bounces;
+    const float* hit_records; uint32_t n_records;
+    float miss[3];
+    uint8_t* rgba;              // packed local_rows x width x 4
+    rt_hit* primary_hits;       // may be null
+    rt_hit* secondary_hits;     // may be null
+    unsigned long long* stats;  // 8 counters (rt_trace_stats order), may be null
+};
+int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st);
+int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,
+                       uint32_t part_count, uint8_t* out, cudaStream_t st);
+
+}  // namespace rt

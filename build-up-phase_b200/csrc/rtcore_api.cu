@@ -1,0 +1,692 @@
+// rtcore_api.cu — implementation of the C ABI in include/rtcore.h (host runtime of librtcore).
+//
+// Mirrors the reference's host-side sequence: createBLAS (main.cpp:674-831) -> rt_build_blas,
+// createTLAS (main.cpp:833-949) -> rt_build_tlas, createUniformBuffer/createShaderBindingTable
+// (main.cpp:1001-1017,1264-1320) -> rt_camera / rt_set_hit_records, render (main.cpp:1322-1423)
+// -> rt_trace. Builds are synchronous on return like the reference's vkQueueWaitIdle
+// (main.cpp:820,942); inputs are consumed before return (the reference frees them at :823-830).
+// There is no CPU path: without a CUDA device every call fails with RT_ERROR_CUDA.
+#include <float.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "rt_device.cuh"
+
+using namespace rt;
+
+struct rt_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaDeviceProp prop{};
+    std::string err;
+    // shader data
+    float* d_hit_records = nullptr; uint32_t n_records = 0;
+    float miss[3] = {0.0f, 0.0f, 0.2f};                           // main.cpp:1065
+    rt_ray_params rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u};          // main.cpp:1047-1052
+    // grow-only device buffers
+    void* scratch = nullptr; size_t scratch_cap = 0;
+    void* fb = nullptr; size_t fb_cap = 0;
+    void* hits1 = nullptr; size_t hits1_cap = 0;
+    void* hits2 = nullptr; size_t hits2_cap = 0;
+    unsigned long long* d_stats = nullptr;
+    int* d_error = nullptr;
+    cudaEvent_t ev[8]{};
+    rt_build_timing timing{};
+    float last_trace_ms = 0.0f;
+    rt_trace_stats last_stats{};
+    uint64_t launches = 0;
+    // debug view of the last BLAS build's sorted keys (lives in scratch until the next build)
+    const uint64_t* dbg_keys = nullptr; const uint32_t* dbg_vals = nullptr; uint32_t dbg_n = 0;
+};
+
+struct BlasStorage {
+    int refs = 0;
+    void* dev = nullptr;            // nodes[N] | tris[N] | records[n_blas]
+    size_t bytes = 0;
+    BvhNode* nodes = nullptr; TriRec* tris = nullptr; BlasRecord* records = nullptr;
+    uint32_t n_tris = 0, n_blas = 0;
+};
+struct rt_blas {
+    BlasStorage* st = nullptr;
+    uint32_t index = 0;
+    BlasRecord rec{};               // host copy
+};
+struct rt_tlas {
+    void* dev = nullptr; size_t bytes = 0;
+    InstanceRec* inst = nullptr; BvhNode* nodes = nullptr;
+    uint32_t n = 0;
+    int32_t root = REF_EMPTY; uint32_t height = 0;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int32_t max_sbt_plus_geo = 0, max_sbt = 0, max_geo = 0, max_blas_height = 0;
+};
+
+namespace {
+
+int fail(rt_context* ctx, int code, const char* fmt, ...) {
+    if (ctx) {
+        char buf[512];
+        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+        ctx->err = buf;
+    }
+    return code;
+}
+#define RT_CUDA(ctx, call)                                                                                     \
+    do {                                                                                                       \
+        cudaError_t e__ = (call);                                                                              \
+        if (e__ != cudaSuccess)                                                                                \
+            return fail(ctx, e__ == cudaErrorMemoryAllocation ? RT_ERROR_OUT_OF_MEMORY : RT_ERROR_CUDA,        \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);         \
+    } while (0)
+
+int ensure(rt_context* ctx, void** p, size_t* cap, size_t need) {
+    if (*cap >= need && *p) return RT_SUCCESS;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    size_t want = need + need / 8 + 256;
+    RT_CUDA(ctx, cudaMalloc(p, want));
+    *cap = want;
+    return RT_SUCCESS;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    uint8_t* base; size_t off = 0;
+    explicit Carver(void* b) : base((uint8_t*)b) {}
+    template <typename T> T* take(size_t count) { off = align_up(off, 256); T* p = (T*)(base + off); off += sizeof(T) * count; return p; }
+};
+
+size_t build_scratch_bytes(uint32_t n, const SortPlan& sp, bool tris, uint32_t n_geoms, uint32_t n_blas) {
+    size_t b = 0;
+    auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
+    add(8ull * n); add(8ull * n); add(4ull * n); add(4ull * n);          // keys a/b, vals a/b
+    add(4ull * n); add(4ull * n); add(4ull * n); add(4ull * n);          // parent_leaf, parent_node, other_end, arrived
+    add(sp.scratch_bytes);
+    if (tris) { add(48ull * n); add(sizeof(GeomDesc) * (size_t)n_geoms); add(4ull * (n_geoms + 1)); add(24ull * n_blas); }
+    else { add(96ull * n); add(24ull * n); add(64ull * n); add(64); add(64); }
+    return b + 4096;
+}
+
+void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
+    s.keys_a = c.take<uint64_t>(n); s.keys_b = c.take<uint64_t>(n);
+    s.vals_a = c.take<uint32_t>(n); s.vals_b = c.take<uint32_t>(n);
+    s.parent_leaf = c.take<uint32_t>(n); s.parent_node = c.take<uint32_t>(n);
+    s.other_end = c.take<int32_t>(n); s.arrived = c.take<uint32_t>(n);
+    s.sort_scratch = c.take<uint8_t>(sp.scratch_bytes);
+}
+
+uint32_t ceil_log2(uint32_t v) { uint32_t b = 0; while ((1ull << b) < v) ++b; return b; }
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_version(void) { return "rtcore-b200 0.1 (sm_100a)"; }
+
+int rt_create(int device_ordinal, rt_context** out) {
+    if (!out) return RT_ERROR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device_ordinal < 0 || device_ordinal >= count) return RT_ERROR_CUDA;
+    if (cudaSetDevice(device_ordinal) != cudaSuccess) return RT_ERROR_CUDA;
+    rt_context* ctx = new rt_context();
+    ctx->device = device_ordinal;
+    if (cudaGetDeviceProperties(&ctx->prop, device_ordinal) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    ctx->own_stream = true;
+    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    cudaMemset(ctx->d_error, 0, 64);
+    *out = ctx;
+    return RT_SUCCESS;
+}
+
+void rt_destroy(rt_context* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
+    cudaFree(ctx->d_stats); cudaFree(ctx->d_error);
+    for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable?)"; }
+
+int rt_device_info(const rt_context* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+    if (cc_major) *cc_major = ctx->prop.major;
+    if (cc_minor) *cc_minor = ctx->prop.minor;
+    if (total_mem) *total_mem = ctx->prop.totalGlobalMem;
+    return RT_SUCCESS;
+}
+
+int rt_set_stream(rt_context* ctx, void* cuda_stream) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return RT_SUCCESS;
+}
+
+int rt_sync(rt_context* ctx) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_SUCCESS;
+}
+
+int rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, uint32_t n_geoms, rt_build_sizes* out) {
+    if (!ctx || !out || (!max_triangle_counts && n_geoms)) return RT_ERROR_INVALID_ARG;
+    uint64_t n = 0;
+    for (uint32_t g = 0; g < n_geoms; ++g) n += max_triangle_counts[g];
+    if (n > MAX_PRIMS) return fail(ctx, RT_ERROR_INVALID_ARG, "too many triangles (%llu > %u)", (unsigned long long)n, MAX_PRIMS);
+    SortPlan sp = sort_plan((uint32_t)n, MORTON_BITS);
+    out->acceleration_structure_size = n * (sizeof(BvhNode) + sizeof(TriRec)) + sizeof(BlasRecord) + 512;
+    out->build_scratch_size = build_scratch_bytes((uint32_t)n, sp, true, n_geoms, 1);
+    return RT_SUCCESS;
+}
+
+int rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes* out) {
+    if (!ctx || !out) return RT_ERROR_INVALID_ARG;
+    SortPlan sp = sort_plan(max_instances, MORTON_BITS);
+    out->acceleration_structure_size = (uint64_t)max_instances * (sizeof(BvhNode) + sizeof(InstanceRec)) + 512;
+    out->build_scratch_size = build_scratch_bytes(max_instances, sp, false, 0, 0);
+    return RT_SUCCESS;
+}
+
+static void storage_release(BlasStorage* st) {
+    if (!st) return;
+    if (--st->refs <= 0) { cudaFree(st->dev); delete st; }
+}
+
+int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
+                        uint32_t /*build_flags*/, rt_blas** out_array) {
+    if (!ctx || !out_array || n_blas == 0 || !geom_counts) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    for (uint32_t b = 0; b < n_blas; ++b) out_array[b] = nullptr;
+    uint32_t n_geoms = 0;
+    for (uint32_t b = 0; b < n_blas; ++b) n_geoms += geom_counts[b];
+    if (n_geoms && !geoms) return RT_ERROR_INVALID_ARG;
+
+    // ---- host-side layout: geometry prefix, per-BLAS segments ----
+    std::vector<GeomDesc> descs(n_geoms);
+    std::vector<uint32_t> prefix(n_geoms + 1, 0);
+    std::vector<BlasRecord> recs(n_blas);
+    std::vector<int> bounds(6 * (size_t)n_blas);
+    uint64_t total = 0; size_t stage_bytes = 0;
+    {
+        uint32_t g = 0;
+        for (uint32_t b = 0; b < n_blas; ++b) {
+            memset(&recs[b], 0, sizeof(BlasRecord));
+            recs[b].first = (uint32_t)total; recs[b].n_geoms = geom_counts[b]; recs[b].root = REF_EMPTY;
+            for (int k = 0; k < 3; ++k) { recs[b].lo[k] = FLT_MAX; recs[b].hi[k] = -FLT_MAX; bounds[6 * b + k] = float_to_ordered(FLT_MAX); bounds[6 * b + 3 + k] = float_to_ordered(-FLT_MAX); }
+            uint64_t bt = 0;
+            for (uint32_t k = 0; k < geom_counts[b]; ++k, ++g) {
+                const rt_geometry& G = geoms[g];
+                if (G.triangle_count && (!G.vertices || G.vertex_stride_bytes < 12 || (G.vertex_stride_bytes & 3)))
+                    return fail(ctx, RT_ERROR_INVALID_ARG, "geometry %u: bad vertex buffer/stride", g);
+                if (!G.indices && G.triangle_count && (uint64_t)G.triangle_count * 3 > G.vertex_count)
+                    return fail(ctx, RT_ERROR_INVALID_ARG, "geometry %u: non-indexed list needs 3*triangle_count vertices", g);
+                prefix[g] = (uint32_t)total;
+                GeomDesc& D = descs[g];
+                memset(&D, 0, sizeof(D));
+                D.stride_f = G.vertex_stride_bytes / 4; D.tri_first = (uint32_t)total; D.tri_count = G.triangle_count;
+                D.blas = b; D.geo_index = k;
+                total += G.triangle_count; bt += G.triangle_count;
+                if (!(G.flags & RT_GEOMETRY_DEVICE_POINTERS)) {
+                    stage_bytes = align_up(stage_bytes, 16) + (size_t)G.vertex_count * G.vertex_stride_bytes;
+                    if (G.indices) stage_bytes = align_up(stage_bytes, 16) + 12ull * G.triangle_count;
+                    if (G.transform3x4) memcpy(D.xform, G.transform3x4, 48);
+                    D.has_xform = G.transform3x4 ? 1u : 0u;
+                }
+            }
+            recs[b].tri_count = (uint32_t)bt;
+        }
+        prefix[n_geoms] = (uint32_t)total;
+    }
+    if (total > MAX_PRIMS) return fail(ctx, RT_ERROR_INVALID_ARG, "too many triangles in one build (%llu > %u)", (unsigned long long)total, MAX_PRIMS);
+    const uint32_t N = (uint32_t)total;
+    const uint32_t seg_bits = ceil_log2(n_blas);
+    if (seg_bits + MORTON_BITS > 64) return RT_ERROR_INVALID_ARG;
+    const SortPlan sp = sort_plan(N, (int)(MORTON_BITS + seg_bits));
+
+    // ---- output storage: nodes | tris | records ----
+    BlasStorage* st = new BlasStorage();
+    st->n_tris = N; st->n_blas = n_blas;
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    st->bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
+    cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
+    if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", st->bytes, cudaGetErrorString(ce)); }
+    st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
+    for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->nodes + recs[b].first; recs[b].tris = st->tris + recs[b].first; }
+    st->refs = 1;   // held by this function until handles exist
+    struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{st};
+
+    // ---- scratch ----
+    const size_t need = build_scratch_bytes(N ? N : 1, sp, true, n_geoms, n_blas) + align_up(stage_bytes, 256) + 4096;
+    int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
+    if (rc != RT_SUCCESS) return rc;
+    Carver c(ctx->scratch);
+    BlasBuildArgs a{};
+    carve_common(c, N ? N : 1, sp, a.s);
+    a.s.error_flag = ctx->d_error;
+    a.tris_unsorted = c.take<TriRec>(N ? N : 1);
+    GeomDesc* d_descs = c.take<GeomDesc>(n_geoms ? n_geoms : 1);
+    uint32_t* d_prefix = c.take<uint32_t>(n_geoms + 1);
+    int* d_bounds = c.take<int>(6 * (size_t)n_blas);
+    uint8_t* d_stage = c.take<uint8_t>(stage_bytes + 16);
+
+    // ---- stage host inputs (H2D, timed separately) ----
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+    {
+        std::vector<uint8_t> pack;           // small arrays are packed into one copy; large ones go directly
+        const size_t DIRECT = 1u << 20;
+        size_t off = 0;
+        struct Direct { size_t off; const void* src; size_t bytes; };
+        std::vector<Direct> direct;
+        pack.resize(stage_bytes + 16);
+        uint32_t g = 0;
+        for (uint32_t b = 0; b < n_blas; ++b)
+            for (uint32_t k = 0; k < geom_counts[b]; ++k, ++g) {
+                const rt_geometry& G = geoms[g];
+                GeomDesc& D = descs[g];
+                if (G.flags & RT_GEOMETRY_DEVICE_POINTERS) {
+                    D.verts = G.vertices; D.idx = G.indices;
+                    if (G.transform3x4) {
+                        RT_CUDA(ctx, cudaMemcpyAsync(D.xform, G.transform3x4, 48, cudaMemcpyDeviceToHost, ctx->stream));
+                        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                        D.has_xform = 1u;
+                    }
+                    continue;
+                }
+                const size_t vb = (size_t)G.vertex_count * G.vertex_stride_bytes;
+                off = align_up(off, 16);
+                D.verts = (const float*)(d_stage + off);
+                if (vb >= DIRECT) direct.push_back({off, G.vertices, vb}); else if (vb) memcpy(pack.data() + off, G.vertices, vb);
+                off += vb;
+                if (G.indices) {
+                    const size_t ib = 12ull * G.triangle_count;
+                    off = align_up(off, 16);
+                    D.idx = (const uint32_t*)(d_stage + off);
+                    if (ib >= DIRECT) direct.push_back({off, G.indices, ib}); else if (ib) memcpy(pack.data() + off, G.indices, ib);
+                    off += ib;
+                }
+            }
+        if (direct.empty()) {
+            if (off) RT_CUDA(ctx, cudaMemcpyAsync(d_stage, pack.data(), off, cudaMemcpyHostToDevice, ctx->stream));
+        } else {
+            // copy packed small arrays piecewise around the direct ones
+            size_t cur = 0;
+            for (const Direct& dct : direct) {
+                if (dct.off > cur) RT_CUDA(ctx, cudaMemcpyAsync(d_stage + cur, pack.data() + cur, dct.off - cur, cudaMemcpyHostToDevice, ctx->stream));
+                RT_CUDA(ctx, cudaMemcpyAsync(d_stage + dct.off, dct.src, dct.bytes, cudaMemcpyHostToDevice, ctx->stream));
+                cur = dct.off + dct.bytes;
+            }
+            if (off > cur) RT_CUDA(ctx, cudaMemcpyAsync(d_stage + cur, pack.data() + cur, off - cur, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        if (n_geoms) RT_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(GeomDesc) * n_geoms, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), 4ull * (n_geoms + 1), cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(d_bounds, bounds.data(), 24ull * n_blas, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemcpyAsync(st->records, recs.data(), sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream));
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // pack/descs are host temporaries
+    }
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+
+    // ---- device build ----
+    a.geoms = d_descs; a.n_geoms = n_geoms; a.geom_tri_first = d_prefix; a.n_tris = N; a.n_blas = n_blas; a.seg_bits = seg_bits;
+    a.tris_sorted = st->tris; a.nodes = st->nodes; a.records = st->records; a.bounds_ordered = d_bounds; a.sort = sp;
+    BuildEvents be; for (int k = 0; k < 6; ++k) be.e[k] = ctx->ev[k];
+    bool in_b = false;
+    int launches = 0;
+    if (N > 0) {
+        launches = launch_blas_build(a, ctx->stream, &be, &in_b);
+        if (launches < 0) return fail(ctx, RT_ERROR_CUDA, "BLAS build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->launches += (uint64_t)launches;
+    }
+    int h_err = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(recs.data(), st->records, sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->timing.primitives = N;
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[6], ctx->ev[7]);
+    if (N > 0) {
+        cudaEventElapsedTime(&ctx->timing.setup_ms, be.e[0], be.e[1]);
+        cudaEventElapsedTime(&ctx->timing.morton_ms, be.e[1], be.e[2]);
+        cudaEventElapsedTime(&ctx->timing.sort_ms, be.e[2], be.e[3]);
+        cudaEventElapsedTime(&ctx->timing.hierarchy_ms, be.e[3], be.e[4]);
+        cudaEventElapsedTime(&ctx->timing.refit_ms, be.e[4], be.e[5]);
+        cudaEventElapsedTime(&ctx->timing.total_ms, be.e[0], be.e[5]);
+    }
+    ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N;
+
+    for (uint32_t b = 0; b < n_blas; ++b) {
+        rt_blas* h = new rt_blas();
+        h->st = st; h->index = b; h->rec = recs[b];
+        ++st->refs;
+        out_array[b] = h;
+    }
+    return RT_SUCCESS;   // guard drops the construction reference
+}
+
+int rt_build_blas(rt_context* ctx, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags, rt_blas** out) {
+    if (!out) return RT_ERROR_INVALID_ARG;
+    uint32_t counts[1] = {n_geoms};
+    return rt_build_blas_batch(ctx, geoms, counts, 1, build_flags, out);
+}
+
+void rt_free_blas(rt_context* ctx, rt_blas* blas) {
+    if (!blas) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    storage_release(blas->st);
+    delete blas;
+}
+
+int rt_last_build_timing(const rt_context* ctx, rt_build_timing* out) {
+    if (!ctx || !out) return RT_ERROR_INVALID_ARG;
+    *out = ctx->timing;
+    return RT_SUCCESS;
+}
+float rt_last_build_ms(const rt_context* ctx) { return ctx ? ctx->timing.total_ms : 0.0f; }
+
+int rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out) {
+    if (!ctx || !blas || !out) return RT_ERROR_INVALID_ARG;
+    out->triangle_count = blas->rec.tri_count;
+    out->node_count = blas->rec.tri_count;     // Karras slots [0, n); slot indices are BLAS-relative
+    out->root_ref = blas->rec.root;
+    out->max_depth = blas->rec.height;
+    for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = blas->rec.lo[k]; out->bounds_hi[k] = blas->rec.hi[k]; }
+    out->storage_bytes = blas->st->n_blas == 1 ? (uint64_t)blas->st->bytes : 0;
+    out->device_storage = blas->st->n_blas == 1 ? blas->st->dev : nullptr;
+    return RT_SUCCESS;
+}
+
+int rt_blas_export(rt_context* ctx, const rt_blas* blas, void* nodes_out, void* tris_out) {
+    if (!ctx || !blas) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t n = blas->rec.tri_count;
+    if (nodes_out && n) RT_CUDA(ctx, cudaMemcpy(nodes_out, blas->rec.nodes, sizeof(BvhNode) * n, cudaMemcpyDeviceToHost));
+    if (tris_out && n) RT_CUDA(ctx, cudaMemcpy(tris_out, blas->rec.tris, sizeof(TriRec) * n, cudaMemcpyDeviceToHost));
+    return RT_SUCCESS;
+}
+
+int rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* prim_out, uint32_t capacity, uint32_t* n_out) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    if (n_out) *n_out = ctx->dbg_n;
+    const uint32_t n = ctx->dbg_n < capacity ? ctx->dbg_n : capacity;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (n && keys_out) RT_CUDA(ctx, cudaMemcpy(keys_out, ctx->dbg_keys, 8ull * n, cudaMemcpyDeviceToHost));
+    if (n && prim_out) RT_CUDA(ctx, cudaMemcpy(prim_out, ctx->dbg_vals, 4ull * n, cudaMemcpyDeviceToHost));
+    return RT_SUCCESS;
+}
+
+int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device_blob, rt_blas** out) {
+    if (!ctx || !info || !device_blob || !out) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint32_t N = info->triangle_count;
+    BlasStorage* st = new BlasStorage();
+    st->n_tris = N; st->n_blas = 1;
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    st->bytes = nodes_b + tris_b + sizeof(BlasRecord) + 256;
+    if (info->storage_bytes != st->bytes) { delete st; return fail(ctx, RT_ERROR_INVALID_ARG, "blob size mismatch"); }
+    cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
+    if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc failed"); }
+    st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
+    st->refs = 1;
+    rt_blas* h = new rt_blas();
+    h->st = st; h->index = 0;
+    BlasRecord& R = h->rec;
+    memset(&R, 0, sizeof(R));
+    R.nodes = st->nodes; R.tris = st->tris; R.root = info->root_ref; R.height = info->max_depth; R.tri_count = N; R.n_geoms = 0; R.first = 0;
+    for (int k = 0; k < 3; ++k) { R.lo[k] = info->bounds_lo[k]; R.hi[k] = info->bounds_hi[k]; }
+    cudaError_t e1 = cudaMemcpyAsync(st->dev, device_blob, nodes_b + tris_b, cudaMemcpyDeviceToDevice, ctx->stream);
+    // n_geoms travels in the source record
+    BlasRecord src{};
+    cudaError_t e2 = cudaMemcpyAsync(&src, (const uint8_t*)device_blob + nodes_b + tris_b, sizeof(BlasRecord), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    R.n_geoms = src.n_geoms;
+    cudaError_t e4 = cudaMemcpy(st->records, &R, sizeof(BlasRecord), cudaMemcpyHostToDevice);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) { rt_free_blas(ctx, h); return fail(ctx, RT_ERROR_CUDA, "blob import copy failed"); }
+    *out = h;
+    return RT_SUCCESS;
+}
+
+// ---- TLAS -------------------------------------------------------------------------------------------
+static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* instances, uint32_t n, uint32_t build_flags) {
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const SortPlan sp = sort_plan(n, MORTON_BITS);
+    const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256);
+    const size_t bytes = inst_b + nodes_b + 256;
+    if (T->bytes < bytes) {
+        if (T->dev) cudaFree(T->dev);
+        T->dev = nullptr; T->bytes = 0;
+        RT_CUDA(ctx, cudaMalloc(&T->dev, bytes));
+        T->bytes = bytes;
+    }
+    T->inst = (InstanceRec*)T->dev; T->nodes = (BvhNode*)((uint8_t*)T->dev + inst_b);
+    T->n = n; T->root = REF_EMPTY; T->height = 0;
+    for (int k = 0; k < 3; ++k) { T->lo[k] = FLT_MAX; T->hi[k] = -FLT_MAX; }
+    T->max_sbt_plus_geo = T->max_sbt = T->max_geo = T->max_blas_height = 0;
+    if (n == 0) return RT_SUCCESS;
+
+    const size_t need = build_scratch_bytes(n, sp, false, 0, 0) + 64ull * n + 4096;
+    int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
+    if (rc != RT_SUCCESS) return rc;
+    Carver c(ctx->scratch);
+    TlasBuildArgs a{};
+    carve_common(c, n, sp, a.s);
+    a.s.error_flag = ctx->d_error;
+    a.inst_unsorted = c.take<InstanceRec>(n);
+    a.boxes_unsorted = c.take<float>(6 * (size_t)n);
+    rt_instance* d_inst = c.take<rt_instance>(n);
+    a.bounds_ordered = c.take<int>(8);
+    a.root_out = c.take<int32_t>(8);
+    a.bounds_out = c.take<float>(8);
+
+    if (build_flags & RT_BUILD_INSTANCES_ON_DEVICE) {
+        a.instances = instances;
+    } else {
+        std::vector<rt_instance> tmp(instances, instances + n);
+        for (uint32_t i = 0; i < n; ++i) {
+            const rt_blas* b = instances[i].blas;
+            uint64_t addr = b ? (uint64_t)(uintptr_t)(b->st->records + b->index) : 0ull;
+            memcpy(&tmp[i].blas, &addr, 8);
+        }
+        RT_CUDA(ctx, cudaMemcpyAsync(d_inst, tmp.data(), sizeof(rt_instance) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        a.instances = d_inst;
+    }
+    int hb[8]; for (int k = 0; k < 3; ++k) { hb[k] = float_to_ordered(FLT_MAX); hb[3 + k] = float_to_ordered(-FLT_MAX); }
+    int32_t hmeta[8] = {REF_EMPTY, 0, 0, 0, 0, 0, 0, 0};
+    float hbo[8] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, 0, 0};
+    RT_CUDA(ctx, cudaMemcpyAsync(a.bounds_ordered, hb, 24, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(a.root_out, hmeta, 32, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(a.bounds_out, hbo, 32, cudaMemcpyHostToDevice, ctx->stream));
+    RT_CUDA(ctx, cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream));
+    a.n = n; a.inst_sorted = T->inst; a.nodes = T->nodes; a.sort = sp;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int launches = launch_tlas_build(a, ctx->stream);
+    if (launches < 0) return fail(ctx, RT_ERROR_CUDA, "TLAS build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += (uint64_t)launches;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
+    int h_err = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(hmeta, a.root_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(hbo, a.bounds_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
+    T->root = hmeta[0]; T->height = (uint32_t)hmeta[1];
+    T->max_sbt_plus_geo = hmeta[2]; T->max_sbt = hmeta[3]; T->max_geo = hmeta[4]; T->max_blas_height = hmeta[5];
+    for (int k = 0; k < 3; ++k) { T->lo[k] = hbo[k]; T->hi[k] = hbo[3 + k]; }
+    memset(&ctx->timing, 0, sizeof(ctx->timing));
+    ctx->timing.primitives = n;
+    cudaEventElapsedTime(&ctx->timing.total_ms, ctx->ev[0], ctx->ev[5]);
+    ctx->dbg_n = 0;
+    return RT_SUCCESS;
+}
+
+int rt_build_tlas(rt_context* ctx, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags, rt_tlas** out) {
+    if (!ctx || !out || (n_instances && !instances)) return RT_ERROR_INVALID_ARG;
+    *out = nullptr;
+    if (n_instances > MAX_PRIMS) return RT_ERROR_INVALID_ARG;
+    rt_tlas* T = new rt_tlas();
+    int rc = tlas_build_into(ctx, T, instances, n_instances, build_flags);
+    if (rc != RT_SUCCESS) { if (T->dev) cudaFree(T->dev); delete T; return rc; }
+    *out = T;
+    return RT_SUCCESS;
+}
+
+int rt_update_tlas(rt_context* ctx, rt_tlas* tlas, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags) {
+    if (!ctx || !tlas || (n_instances && !instances)) return RT_ERROR_INVALID_ARG;
+    return tlas_build_into(ctx, tlas, instances, n_instances, build_flags);
+}
+
+void rt_free_tlas(rt_context* ctx, rt_tlas* tlas) {
+    if (!tlas) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    if (tlas->dev) cudaFree(tlas->dev);
+    delete tlas;
+}
+
+int rt_tlas_get_info(rt_context* ctx, const rt_tlas* tlas, rt_tlas_info* out) {
+    if (!ctx || !tlas || !out) return RT_ERROR_INVALID_ARG;
+    out->instance_count = tlas->n; out->node_count = tlas->n; out->root_ref = tlas->root; out->max_depth = tlas->height;
+    for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = tlas->lo[k]; out->bounds_hi[k] = tlas->hi[k]; }
+    return RT_SUCCESS;
+}
+
+// ---- shader data ---------------------------------------------------------------------------------------
+int rt_set_hit_records(rt_context* ctx, const float* rgb, uint32_t count) {
+    if (!ctx || (count && !rgb)) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_hit_records) { cudaFree(ctx->d_hit_records); ctx->d_hit_records = nullptr; }
+    ctx->n_records = 0;
+    if (count) {
+        RT_CUDA(ctx, cudaMalloc(&ctx->d_hit_records, 12ull * count));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_hit_records, rgb, 12ull * count, cudaMemcpyHostToDevice));
+        ctx->n_records = count;
+    }
+    return RT_SUCCESS;
+}
+
+int rt_set_miss_color(rt_context* ctx, const float rgb[3]) {
+    if (!ctx || !rgb) return RT_ERROR_INVALID_ARG;
+    ctx->miss[0] = rgb[0]; ctx->miss[1] = rgb[1]; ctx->miss[2] = rgb[2];
+    return RT_SUCCESS;
+}
+
+int rt_set_ray_params(rt_context* ctx, const rt_ray_params* params) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    if (params) ctx->rp = *params; else ctx->rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u};
+    return RT_SUCCESS;
+}
+
+// ---- dispatch ------------------------------------------------------------------------------------------
+uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_rows, uint32_t part_count) {
+    if (!block_rows || !part_count) return 0;
+    const uint64_t bands = (height + block_rows - 1) / block_rows;
+    return ((bands + part_count - 1) / part_count) * block_rows * (uint64_t)width;
+}
+
+int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+                  uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count,
+                  uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
+    if (!ctx || !tlas || !cam || !width || !height || !rgba_out) return RT_ERROR_INVALID_ARG;
+    if (!block_rows || (block_rows & 3u) || !part_count || part_index >= part_count) return fail(ctx, RT_ERROR_INVALID_ARG, "block_rows must be a positive multiple of 4 and part_index < part_count");
+    if ((uint64_t)width * height > 0xFFFFFFFFull) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (bounces > 1) bounces = 1;
+    // static SBT range check (Vulkan leaves out-of-range records undefined; we refuse)
+    if (tlas->n) {
+        const uint64_t bound = ctx->rp.sbt_record_stride == 1
+                                   ? (uint64_t)tlas->max_sbt_plus_geo + ctx->rp.sbt_record_offset
+                                   : (uint64_t)tlas->max_sbt + (uint64_t)tlas->max_geo * ctx->rp.sbt_record_stride + ctx->rp.sbt_record_offset;
+        if (bound >= ctx->n_records) return fail(ctx, RT_ERROR_SBT_RANGE, "hit record %llu addressed but only %u set", (unsigned long long)bound, ctx->n_records);
+    }
+    const int stack_needed = (int)tlas->height + tlas->max_blas_height + 4;
+    if (stack_needed > 160) return fail(ctx, RT_ERROR_STACK_DEPTH, "BVH depth %d exceeds the traversal stack", stack_needed);
+
+    // one part = the plain width x height image; several parts = equal-sized packed band buffers
+    const uint64_t pixels = part_count == 1 ? (uint64_t)width * height : rt_rows_packed_pixels(width, height, block_rows, part_count);
+    const bool dev_out = (flags & RT_TRACE_OUT_DEVICE) != 0;
+    TraceParams P{};
+    P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
+    for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[k]; }
+    // raygen constants of main.cpp:1038-1039; tan is evaluated once on the host in fp32
+    P.aspect_y = tanf((cam->yfov_deg * 0.017453292519943295f) * 0.5f);
+    P.aspect_x = P.aspect_y * (float)width / (float)height;
+    P.width = width; P.height = height; P.block_rows = block_rows; P.part_index = part_index; P.part_count = part_count;
+    P.local_rows = (uint32_t)(pixels / width);
+    P.tmin = ctx->rp.tmin; P.tmax = ctx->rp.tmax; P.cull_mask = ctx->rp.cull_mask; P.sbt_offset = ctx->rp.sbt_record_offset;
+    P.sbt_stride = ctx->rp.sbt_record_stride; P.bounce_seed = ctx->rp.bounce_seed; P.bounces = bounces;
+    P.hit_records = ctx->d_hit_records; P.n_records = ctx->n_records;
+    int rc;
+    if (dev_out) { P.rgba = rgba_out; P.primary_hits = primary_hits_out; P.secondary_hits = secondary_hits_out; }
+    else {
+        if ((rc = ensure(ctx, &ctx->fb, &ctx->fb_cap, pixels * 4)) != RT_SUCCESS) return rc;
+        P.rgba = (uint8_t*)ctx->fb;
+        if (primary_hits_out) { if ((rc = ensure(ctx, &ctx->hits1, &ctx->hits1_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.primary_hits = (rt_hit*)ctx->hits1; }
+        if (secondary_hits_out) { if ((rc = ensure(ctx, &ctx->hits2, &ctx->hits2_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.secondary_hits = (rt_hit*)ctx->hits2; }
+    }
+    const bool stats = (flags & RT_TRACE_STATS) != 0;
+    if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int l = launch_trace(P, stats, stack_needed, ctx->prop.multiProcessorCount, ctx->stream);
+    if (l < 0) return fail(ctx, RT_ERROR_CUDA, "trace launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += (uint64_t)l;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    if (!dev_out) {
+        RT_CUDA(ctx, cudaMemcpyAsync(rgba_out, P.rgba, pixels * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out, P.primary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out, P.secondary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    if (stats) RT_CUDA(ctx, cudaMemcpyAsync(&ctx->last_stats, ctx->d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);
+    if (!stats) memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
+    return RT_SUCCESS;
+}
+
+int rt_trace(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+             uint32_t flags, uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
+    if (!height) return RT_ERROR_INVALID_ARG;
+    const uint32_t block_rows = (height + 3u) & ~3u;     // one band = the whole image
+    return rt_trace_rows(ctx, tlas, cam, width, height, bounces, flags, block_rows, 0, 1, rgba_out, primary_hits_out, secondary_hits_out);
+}
+
+int rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,
+                   uint32_t part_count, uint8_t* rgba_out_device) {
+    if (!ctx || !packed_all || !rgba_out_device || !width || !height || !block_rows || !part_count) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    int l = launch_unpack_rows(packed_all, width, height, block_rows, part_count, rgba_out_device, ctx->stream);
+    if (l < 0) return fail(ctx, RT_ERROR_CUDA, "unpack launch failed");
+    ctx->launches += (uint64_t)l;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);
+    return RT_SUCCESS;
+}
+
+int rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out) {
+    if (!ctx || !out) return RT_ERROR_INVALID_ARG;
+    *out = ctx->last_stats;
+    return RT_SUCCESS;
+}
+float rt_last_trace_ms(const rt_context* ctx) { return ctx ? ctx->last_trace_ms : 0.0f; }
+uint64_t rt_kernel_launch_count(const rt_context* ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

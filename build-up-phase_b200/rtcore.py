@@ -1,0 +1,439 @@
+"""ctypes mirror of the C ABI in include/rtcore.h (librtcore.so, CUDA sm_100a).
+
+The calls map 1:1 onto the reference sample's setup steps (vulkan-raytracing-basic/main.cpp):
+createBLAS -> Context.build_blas, createTLAS -> Context.build_tlas, createUniformBuffer /
+createShaderBindingTable -> camera argument / Context.set_hit_records, render -> Context.trace.
+
+There is no CPU fallback: loading fails loudly if librtcore.so is missing, and Context() raises if
+no CUDA device is usable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+RT_SUCCESS = 0
+RT_ERROR_INVALID_ARG, RT_ERROR_CUDA, RT_ERROR_OUT_OF_MEMORY = -1, -2, -3
+RT_ERROR_STACK_DEPTH, RT_ERROR_SBT_RANGE, RT_ERROR_INTERNAL = -4, -5, -6
+RT_GEOMETRY_OPAQUE = 0x1
+RT_GEOMETRY_DEVICE_POINTERS = 0x100
+RT_BUILD_PREFER_FAST_TRACE = 0x4
+RT_BUILD_INSTANCES_ON_DEVICE = 0x100
+RT_TRACE_OUT_DEVICE = 0x1
+RT_TRACE_STATS = 0x2
+RT_REF_EMPTY = 0x7FFFFFFD
+
+EXPORTED_SYMBOLS = [
+    "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync",
+    "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
+    "rt_update_tlas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
+    "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
+    "rt_set_hit_records", "rt_set_miss_color", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
+    "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
+    "rt_kernel_launch_count", "rt_version",
+]
+
+
+class RtGeometry(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("vertex_count", C.c_uint32), ("vertex_stride_bytes", C.c_uint32),
+                ("indices", C.c_void_p), ("triangle_count", C.c_uint32), ("transform3x4", C.c_void_p),
+                ("flags", C.c_uint32)]
+
+
+class RtInstance(C.Structure):
+    # bit-fields of rt_instance packed by hand: custom_index:24 | mask:8, sbt_offset:24 | flags:8
+    _fields_ = [("transform", C.c_float * 12), ("custom_index_and_mask", C.c_uint32),
+                ("sbt_offset_and_flags", C.c_uint32), ("blas", C.c_void_p)]
+
+
+assert C.sizeof(RtInstance) == 64
+
+
+class RtCamera(C.Structure):
+    _fields_ = [("pos", C.c_float * 3), ("yfov_deg", C.c_float)]
+
+
+class RtRayParams(C.Structure):
+    _fields_ = [("tmin", C.c_float), ("tmax", C.c_float), ("cull_mask", C.c_uint32),
+                ("sbt_record_offset", C.c_uint32), ("sbt_record_stride", C.c_uint32), ("bounce_seed", C.c_uint32)]
+
+
+class RtBuildSizes(C.Structure):
+    _fields_ = [("acceleration_structure_size", C.c_uint64), ("build_scratch_size", C.c_uint64)]
+
+
+class RtTraceStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested",
+                                          "instances_entered", "primary_hits", "secondary_hits", "near_edge_hits")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+class RtBuildTiming(C.Structure):
+    _fields_ = [("total_ms", C.c_float), ("setup_ms", C.c_float), ("morton_ms", C.c_float), ("sort_ms", C.c_float),
+                ("hierarchy_ms", C.c_float), ("refit_ms", C.c_float), ("h2d_ms", C.c_float), ("primitives", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: (float(getattr(self, n)) if n != "primitives" else int(self.primitives)) for n, _ in self._fields_}
+
+
+class RtBlasInfo(C.Structure):
+    _fields_ = [("triangle_count", C.c_uint32), ("node_count", C.c_uint32), ("root_ref", C.c_int32),
+                ("max_depth", C.c_uint32), ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3),
+                ("storage_bytes", C.c_uint64), ("device_storage", C.c_void_p)]
+
+
+class RtTlasInfo(C.Structure):
+    _fields_ = [("instance_count", C.c_uint32), ("node_count", C.c_uint32), ("root_ref", C.c_int32),
+                ("max_depth", C.c_uint32), ("bounds_lo", C.c_float * 3), ("bounds_hi", C.c_float * 3)]
+
+
+HIT_DTYPE = np.dtype([("instance_id", "<u4"), ("geometry_index", "<u4"), ("primitive_id", "<u4"),
+                      ("custom_index", "<u4"), ("t", "<f4"), ("u", "<f4"), ("v", "<f4")])
+assert HIT_DTYPE.itemsize == 28
+
+
+class RtError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"rtcore error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Loads librtcore.so (building it with nvcc first when absent/stale). Raises if that fails."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if build_if_missing and _build.needs_build():
+        _build.build_rtcore()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: the CUDA extension must be built (python -m build_up_phase_b200.build); there is no CPU fallback")
+    L = C.CDLL(path)
+    vp, u32, i32, u64 = C.c_void_p, C.c_uint32, C.c_int, C.c_uint64
+    L.rt_create.argtypes = [i32, C.POINTER(vp)]
+    L.rt_destroy.argtypes = [vp]
+    L.rt_destroy.restype = None
+    L.rt_last_error.argtypes = [vp]
+    L.rt_last_error.restype = C.c_char_p
+    L.rt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)]
+    L.rt_set_stream.argtypes = [vp, vp]
+    L.rt_sync.argtypes = [vp]
+    L.rt_blas_build_sizes.argtypes = [vp, C.POINTER(u32), u32, C.POINTER(RtBuildSizes)]
+    L.rt_tlas_build_sizes.argtypes = [vp, u32, C.POINTER(RtBuildSizes)]
+    L.rt_build_blas.argtypes = [vp, C.POINTER(RtGeometry), u32, u32, C.POINTER(vp)]
+    L.rt_build_blas_batch.argtypes = [vp, C.POINTER(RtGeometry), C.POINTER(u32), u32, u32, C.POINTER(vp)]
+    L.rt_build_tlas.argtypes = [vp, vp, u32, u32, C.POINTER(vp)]
+    L.rt_update_tlas.argtypes = [vp, vp, vp, u32, u32]
+    L.rt_free_blas.argtypes = [vp, vp]
+    L.rt_free_blas.restype = None
+    L.rt_free_tlas.argtypes = [vp, vp]
+    L.rt_free_tlas.restype = None
+    L.rt_last_build_timing.argtypes = [vp, C.POINTER(RtBuildTiming)]
+    L.rt_last_build_ms.argtypes = [vp]
+    L.rt_last_build_ms.restype = C.c_float
+    L.rt_blas_get_info.argtypes = [vp, vp, C.POINTER(RtBlasInfo)]
+    L.rt_blas_export.argtypes = [vp, vp, vp, vp]
+    L.rt_debug_last_sorted_keys.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]
+    L.rt_blas_import.argtypes = [vp, C.POINTER(RtBlasInfo), vp, C.POINTER(vp)]
+    L.rt_tlas_get_info.argtypes = [vp, vp, C.POINTER(RtTlasInfo)]
+    L.rt_set_hit_records.argtypes = [vp, vp, u32]
+    L.rt_set_miss_color.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rt_set_ray_params.argtypes = [vp, C.POINTER(RtRayParams)]
+    L.rt_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, vp, vp, vp]
+    L.rt_trace_rows.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
+    L.rt_rows_packed_pixels.argtypes = [u32, u32, u32, u32]
+    L.rt_rows_packed_pixels.restype = u64
+    L.rt_unpack_rows.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+    L.rt_last_trace_stats.argtypes = [vp, C.POINTER(RtTraceStats)]
+    L.rt_last_trace_ms.argtypes = [vp]
+    L.rt_last_trace_ms.restype = C.c_float
+    L.rt_kernel_launch_count.argtypes = [vp]
+    L.rt_kernel_launch_count.restype = u64
+    L.rt_version.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _ptr(x) -> Optional[int]:
+    """numpy array -> host pointer; torch tensor / int -> raw pointer."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    if isinstance(x, int):
+        return x
+    if hasattr(x, "data_ptr"):
+        return int(x.data_ptr())
+    raise TypeError(type(x))
+
+
+class Blas:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def info(self) -> RtBlasInfo:
+        info = RtBlasInfo()
+        self.ctx._check(self.ctx.L.rt_blas_get_info(self.ctx.h, self.handle, C.byref(info)))
+        return info
+
+    def export(self):
+        """(nodes uint32[n,16], tris uint32[n,12]) raw 64-B nodes and 48-B triangles."""
+        info = self.info()
+        nodes = np.zeros((info.node_count, 16), dtype=np.uint32)
+        tris = np.zeros((info.triangle_count, 12), dtype=np.uint32)
+        self.ctx._check(self.ctx.L.rt_blas_export(self.ctx.h, self.handle, nodes.ctypes.data, tris.ctypes.data))
+        return nodes, tris
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.rt_free_blas(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Tlas:
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self.handle = ctx, handle
+
+    def info(self) -> RtTlasInfo:
+        info = RtTlasInfo()
+        self.ctx._check(self.ctx.L.rt_tlas_get_info(self.ctx.h, self.handle, C.byref(info)))
+        return info
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.rt_free_tlas(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Context:
+    """rt_context: one CUDA device, one stream."""
+
+    def __init__(self, device: int = 0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.rt_create(device, C.byref(h))
+        if rc != RT_SUCCESS:
+            raise RtError(rc, "rt_create failed (no usable CUDA device? there is no CPU fallback)")
+        self.h = h
+        self.device = device
+        self._keep: list = []
+
+    # -- plumbing -------------------------------------------------------------------------------
+    def _check(self, rc: int):
+        if rc != RT_SUCCESS:
+            raise RtError(rc, self.L.rt_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rt_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def device_info(self):
+        sm, ma, mi, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        self._check(self.L.rt_device_info(self.h, C.byref(sm), C.byref(ma), C.byref(mi), C.byref(mem)))
+        return {"sm_count": sm.value, "cc": (ma.value, mi.value), "total_mem": mem.value}
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self.L.rt_set_stream(self.h, cuda_stream))
+
+    def launch_count(self) -> int:
+        return int(self.L.rt_kernel_launch_count(self.h))
+
+    # -- acceleration structures --------------------------------------------------------------------
+    def _geom_array(self, geoms, keep: list, device: bool = False):
+        arr = (RtGeometry * max(1, len(geoms)))()
+        for i, g in enumerate(geoms):
+            if device:
+                v, idx, t = g.vertices, g.indices, g.transform
+                arr[i].vertices = _ptr(v)
+                arr[i].vertex_count = int(v.shape[0])
+                arr[i].indices = _ptr(idx)
+                arr[i].triangle_count = int(idx.shape[0]) if idx is not None else int(v.shape[0]) // 3
+                arr[i].transform3x4 = _ptr(t)
+                arr[i].flags = RT_GEOMETRY_OPAQUE | RT_GEOMETRY_DEVICE_POINTERS
+                keep.extend([v, idx, t])
+            else:
+                v = np.ascontiguousarray(g.vertices, dtype=np.float32)
+                keep.append(v)
+                arr[i].vertices = v.ctypes.data
+                arr[i].vertex_count = v.shape[0]
+                if g.indices is not None:
+                    idx = np.ascontiguousarray(g.indices, dtype=np.uint32)
+                    keep.append(idx)
+                    arr[i].indices = idx.ctypes.data
+                arr[i].triangle_count = g.triangle_count
+                if g.transform is not None:
+                    t = np.ascontiguousarray(g.transform, dtype=np.float32)
+                    keep.append(t)
+                    arr[i].transform3x4 = t.ctypes.data
+                arr[i].flags = RT_GEOMETRY_OPAQUE
+            arr[i].vertex_stride_bytes = 12
+        return arr
+
+    def blas_build_sizes(self, max_triangle_counts: Sequence[int]) -> RtBuildSizes:
+        arr = (C.c_uint32 * len(max_triangle_counts))(*max_triangle_counts)
+        out = RtBuildSizes()
+        self._check(self.L.rt_blas_build_sizes(self.h, arr, len(max_triangle_counts), C.byref(out)))
+        return out
+
+    def tlas_build_sizes(self, max_instances: int) -> RtBuildSizes:
+        out = RtBuildSizes()
+        self._check(self.L.rt_tlas_build_sizes(self.h, max_instances, C.byref(out)))
+        return out
+
+    def build_blas(self, geoms, device: bool = False) -> Blas:
+        keep: list = []
+        arr = self._geom_array(geoms, keep, device)
+        h = C.c_void_p()
+        self._check(self.L.rt_build_blas(self.h, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE, C.byref(h)))
+        return Blas(self, h.value)
+
+    def build_blas_batch(self, blases, device: bool = False) -> List[Blas]:
+        keep: list = []
+        flat = [g for b in blases for g in b]
+        arr = self._geom_array(flat, keep, device)
+        counts = (C.c_uint32 * len(blases))(*[len(b) for b in blases])
+        out = (C.c_void_p * len(blases))()
+        self._check(self.L.rt_build_blas_batch(self.h, arr, counts, len(blases), RT_BUILD_PREFER_FAST_TRACE, out))
+        return [Blas(self, out[i]) for i in range(len(blases))]
+
+    @staticmethod
+    def instance_array(instances, blas_handles: Sequence[Blas]):
+        arr = (RtInstance * max(1, len(instances)))()
+        for i, I in enumerate(instances):
+            for k in range(12):
+                arr[i].transform[k] = float(I.transform[k])
+            arr[i].custom_index_and_mask = (I.custom_index & 0xFFFFFF) | ((I.mask & 0xFF) << 24)
+            arr[i].sbt_offset_and_flags = (I.sbt_offset & 0xFFFFFF) | ((I.flags & 0xFF) << 24)
+            arr[i].blas = blas_handles[I.blas].handle if I.blas is not None and I.blas >= 0 else None
+        return arr
+
+    def build_tlas(self, instances, blas_handles: Sequence[Blas]) -> Tlas:
+        arr = self.instance_array(instances, blas_handles)
+        h = C.c_void_p()
+        self._check(self.L.rt_build_tlas(self.h, C.addressof(arr), len(instances), RT_BUILD_PREFER_FAST_TRACE, C.byref(h)))
+        return Tlas(self, h.value)
+
+    def update_tlas(self, tlas: Tlas, instances, blas_handles: Sequence[Blas]):
+        arr = self.instance_array(instances, blas_handles)
+        self._check(self.L.rt_update_tlas(self.h, tlas.handle, C.addressof(arr), len(instances), RT_BUILD_PREFER_FAST_TRACE))
+
+    def build_timing(self) -> dict:
+        t = RtBuildTiming()
+        self._check(self.L.rt_last_build_timing(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def last_sorted_keys(self):
+        n = C.c_uint32()
+        self._check(self.L.rt_debug_last_sorted_keys(self.h, None, None, 0, C.byref(n)))
+        keys = np.zeros(n.value, dtype=np.uint64)
+        prims = np.zeros(n.value, dtype=np.uint32)
+        self._check(self.L.rt_debug_last_sorted_keys(self.h, keys.ctypes.data, prims.ctypes.data, n.value, C.byref(n)))
+        return keys, prims
+
+    # -- shader data ----------------------------------------------------------------------------------
+    def set_hit_records(self, rgb: np.ndarray):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
+        self._check(self.L.rt_set_hit_records(self.h, rgb.ctypes.data, rgb.shape[0]))
+
+    def set_miss_color(self, rgb):
+        arr = (C.c_float * 3)(*[float(x) for x in rgb])
+        self._check(self.L.rt_set_miss_color(self.h, arr))
+
+    def set_ray_params(self, tmin=0.0, tmax=100.0, cull_mask=0xFF, sbt_record_offset=0, sbt_record_stride=1, bounce_seed=1):
+        p = RtRayParams(tmin, tmax, cull_mask, sbt_record_offset, sbt_record_stride, bounce_seed)
+        self._check(self.L.rt_set_ray_params(self.h, C.byref(p)))
+
+    # -- dispatch -----------------------------------------------------------------------------------------
+    @staticmethod
+    def camera(pos, yfov_deg) -> RtCamera:
+        cam = RtCamera()
+        for k in range(3):
+            cam.pos[k] = float(pos[k])
+        cam.yfov_deg = float(yfov_deg)
+        return cam
+
+    def trace(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int = 0, want_hits: bool = False,
+              stats: bool = False, rgba_out: Optional[np.ndarray] = None):
+        """Host-buffer trace (the reference-facing call): returns (rgba[h,w,4], primary hits, secondary hits)."""
+        rgba = rgba_out if rgba_out is not None else np.empty((height, width, 4), dtype=np.uint8)
+        prim = np.empty((height, width), dtype=HIT_DTYPE) if want_hits else None
+        sec = np.empty((height, width), dtype=HIT_DTYPE) if want_hits else None
+        flags = RT_TRACE_STATS if stats else 0
+        self._check(self.L.rt_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, _ptr(rgba), _ptr(prim), _ptr(sec)))
+        return rgba, prim, sec
+
+    def trace_device(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, rgba_dev, prim_dev=None,
+                     sec_dev=None, stats: bool = False):
+        flags = RT_TRACE_OUT_DEVICE | (RT_TRACE_STATS if stats else 0)
+        self._check(self.L.rt_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, _ptr(rgba_dev), _ptr(prim_dev), _ptr(sec_dev)))
+
+    def trace_rows(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, block_rows: int, part_index: int,
+                   part_count: int, rgba, prim=None, sec=None, device: bool = False, stats: bool = False):
+        flags = (RT_TRACE_OUT_DEVICE if device else 0) | (RT_TRACE_STATS if stats else 0)
+        self._check(self.L.rt_trace_rows(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, block_rows, part_index,
+                                         part_count, _ptr(rgba), _ptr(prim), _ptr(sec)))
+
+    def rows_packed_pixels(self, width: int, height: int, block_rows: int, part_count: int) -> int:
+        return int(self.L.rt_rows_packed_pixels(width, height, block_rows, part_count))
+
+    def unpack_rows(self, packed_all_dev, width: int, height: int, block_rows: int, part_count: int, rgba_out_dev):
+        self._check(self.L.rt_unpack_rows(self.h, _ptr(packed_all_dev), width, height, block_rows, part_count, _ptr(rgba_out_dev)))
+
+    def trace_stats(self) -> dict:
+        s = RtTraceStats()
+        self._check(self.L.rt_last_trace_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def trace_ms(self) -> float:
+        return float(self.L.rt_last_trace_ms(self.h))
+
+
+class SceneHandles:
+    """Builds a scenes.Scene on a Context the way the sample's main() does: BLASes (batched when there is
+    more than one), TLAS, hit records, miss colour."""
+
+    def __init__(self, ctx: Context, scene, batch: bool = True):
+        self.ctx, self.scene = ctx, scene
+        if len(scene.blases) > 1 and batch:
+            self.blases = ctx.build_blas_batch(scene.blases)
+        else:
+            self.blases = [ctx.build_blas(g) for g in scene.blases]
+        self.blas_timing = ctx.build_timing()
+        self.tlas = ctx.build_tlas(scene.instances, self.blases)
+        self.tlas_timing = ctx.build_timing()
+        ctx.set_hit_records(scene.hit_records)
+        ctx.set_miss_color(scene.miss_color)
+        self.cam = ctx.camera(scene.camera_pos, scene.yfov_deg)
+
+    def trace(self, width=None, height=None, bounces=None, want_hits=True, stats=False):
+        s = self.scene
+        return self.ctx.trace(self.tlas, self.cam, width or s.width, height or s.height,
+                              s.bounces if bounces is None else bounces, want_hits=want_hits, stats=stats)
+
+    def free(self):
+        self.tlas.free()
+        for b in self.blases:
+            b.free()

@@ -3,7 +3,7 @@ vulkan-raytracing-basic/main.cpp) and the synthetic procedural scenes of BASELIN
 
 A Scene is plain numpy data — exactly what the reference's createBLAS/createTLAS/createUniformBuffer/
 createShaderBindingTable put into host-visible buffers — and is consumed unchanged by the CUDA
-product (rtcore.py) and by the CPU oracle binding (oracle/oracle_binding.py). Nothing here
+product (rtcore.py) and by the CPU checker used in tests. Nothing here
 computes ray tracing.
 """
 from __future__ import annotations

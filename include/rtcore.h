@@ -234,7 +234,7 @@ RT_API int  rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t 
                            uint32_t block_rows, uint32_t part_count, uint8_t* rgba_out_device);
 
 RT_API int  rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out);
-/* CUDA-event milliseconds of the kernels of the most recent rt_trace*/rt_unpack call (no copies). */
+/* CUDA-event milliseconds of the kernels of the most recent rt_trace / rt_trace_rows / rt_unpack_rows call (no copies). */
 RT_API float rt_last_trace_ms(const rt_context* ctx);
 /* Number of kernels this library has launched on the context since creation. */
 RT_API uint64_t rt_kernel_launch_count(const rt_context* ctx);

@@ -1,0 +1,260 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI, host buffers) against the CPU oracle.
+
+Bar: hit/miss masks and (instance, geometry, primitive, customIndex) ids bit-exact, t/u/v bit-exact,
+RGBA8 within +-1 LSB. Rays within 2^-20 (barycentric) of a shared edge are counted and reported.
+"""
+import numpy as np
+import pytest
+
+from build_up_phase_b200 import scenes
+from parity import MISS, assert_parity, compare_hits, walk_compare_bvh
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(rt, ctx, oracle, scene, mode, rows=(0, None, 1), batch=True, stats=False):
+    sh = rt.SceneHandles(ctx, scene, batch=batch)
+    try:
+        g = sh.trace(want_hits=True, stats=stats)
+        gstats = ctx.trace_stats() if stats else None
+    finally:
+        sh.free()
+    o = oracle.OracleScene(scene)
+    r = o.trace(mode=mode, rows=rows)
+    o.close()
+    return g, r, gstats
+
+
+@pytest.mark.parametrize("wh", [(1200, 800), (1920, 1080)])
+def test_sample_scene(rt, ctx, oracle, wh):
+    """BASELINE configs[0] and configs[1]: the samples' scene at 1200x800 and 1920x1080."""
+    scene = scenes.sample_scene(*wh)
+    g, r, gs = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE, stats=True)
+    rp, _, rc = assert_parity(g, r, what=f"sample{wh}")
+    rgba, prim, _ = g
+    hit = prim["instance_id"] != MISS
+    if wh == (1200, 800):    # the known answers of SURVEY §8(c), checked on the GPU output itself
+        assert hit.sum() == 77284
+        assert tuple(rgba[0, 0]) == (0, 0, 51, 0)
+        m = hit & (prim["instance_id"] == 0) & (prim["geometry_index"] == 0)
+        ys, xs = np.nonzero(m)
+        assert (xs.min(), xs.max(), ys.min(), ys.max()) == (392, 530, 192, 330)
+        assert np.all(rgba[m] == np.array((153, 26, 51, 0), dtype=np.uint8))
+    assert gs["rays_primary"] == wh[0] * wh[1] and gs["primary_hits"] == hit.sum()
+    assert gs["near_edge_hits"] == r[3]["near_edge_hits"]
+    print("sample", wh, rp, rc)
+
+
+def test_single_triangle(rt, ctx, oracle):
+    scene = scenes.single_triangle_scene(640, 400)
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE)
+    assert_parity(g, r, what="triangle")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+def test_random_scenes_vs_brute_force(rt, ctx, oracle, seed):
+    """Fuzz: several BLASes x geometries x transformed instances, masks, one diffuse bounce; the oracle
+    tests EVERY triangle of EVERY instance for every ray (no BVH on the reference side)."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=200 + 150 * seed, n_instances=9, seed=seed, width=320, height=200,
+                                bounces=1, shared_edges=(seed % 2 == 1))
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE, batch=(seed % 2 == 0))
+    rp, rs, rc = assert_parity(g, r, what=f"random{seed}")
+    assert rp["hits"] > 1000 and rs["hits"] > 50
+    print("random", seed, rp, rs, rc)
+
+
+def test_tess_mesh_shared_edges(rt, ctx, oracle):
+    """Tessellated height field (every interior edge shared by two triangles): brute force at low
+    resolution, BVH oracle at higher resolution, one bounce."""
+    scene = scenes.tess_scene(nx=60, ny=30, width=400, height=224, bounces=1)
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE)
+    rp, rs, rc = assert_parity(g, r, what="tess-brute")
+    print("tess-brute", rp, rs)
+    scene = scenes.tess_scene(nx=400, ny=200, width=1280, height=720, bounces=1)
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BVH)
+    rp, rs, rc = assert_parity(g, r, what="tess-bvh")
+    assert rp["hits"] > 100000
+    print("tess-bvh", rp, rs)
+
+
+def test_instanced_batched_scene(rt, ctx, oracle):
+    """cfg4 in miniature: 64 distinct BLASes built in ONE batched launch set, 64 rotated instances."""
+    scene = scenes.instanced_scene(n_side=8, quads=20, width=960, height=540, bounces=1)
+    g, r, gs = _run(rt, ctx, oracle, scene, oracle.MODE_BVH, stats=True)
+    rp, rs, rc = assert_parity(g, r, what="inst-batched")
+    # batched build == one-by-one builds
+    sh = rt.SceneHandles(ctx, scene, batch=False)
+    g2 = sh.trace(want_hits=True)
+    sh.free()
+    assert g[1].tobytes() == g2[1].tobytes() and np.array_equal(g[0], g2[0])
+    assert gs["rays_secondary"] == rp["hits"]
+    print("inst-batched", rp, rs, gs)
+
+
+def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle):
+    """Integer/byte work must be bit-exact: sorted Morton keys, primitive order, tree topology and
+    every node box of the GPU LBVH equal the CPU restatement's."""
+    scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
+    blas = ctx.build_blas(scene.blases[0])
+    keys, prims = ctx.last_sorted_keys()
+    info = blas.info()
+    nodes, tris = blas.export()
+    blas.free()
+    o = oracle.OracleScene(scene)
+    oinfo, onodes, otris, okeys, oprims = o.blas_export(0)
+    assert info.triangle_count == oinfo.triangle_count == 120 * 70 * 2
+    assert np.array_equal(keys, okeys), "sorted Morton keys differ"
+    assert np.array_equal(prims, oprims), "sorted primitive order differs (sort not stable?)"
+    assert np.array_equal(tris[:, :11], otris[:, :11]), "sorted triangle records differ"
+    assert info.root_ref == oinfo.root_ref and info.max_depth == oinfo.max_depth
+    assert list(info.bounds_lo) == list(oinfo.bounds_lo) and list(info.bounds_hi) == list(oinfo.bounds_hi)
+    n = walk_compare_bvh(nodes, info.root_ref, onodes, oinfo.root_ref)
+    assert n > info.triangle_count // 8
+    print("lbvh nodes compared:", n, "depth", info.max_depth)
+
+
+def test_build_invariants_large(rt, ctx):
+    """Size-independent properties at 2M triangles (no oracle needed): keys sorted, values a permutation,
+    every triangle in exactly one leaf, parent boxes contain children."""
+    scene = scenes.tess_scene(nx=1000, ny=1000, width=64, height=64, bounces=0)
+    blas = ctx.build_blas(scene.blases[0])
+    t = ctx.build_timing()
+    keys, prims = ctx.last_sorted_keys()
+    info = blas.info()
+    nodes, tris = blas.export()
+    blas.free()
+    n = info.triangle_count
+    assert n == 2_000_000
+    assert np.all(keys[1:] >= keys[:-1])
+    assert np.array_equal(np.sort(prims), np.arange(n, dtype=np.uint32))
+    # walk the tree: vectorised level-by-level
+    f = nodes.view(np.float32)
+    covered = np.zeros(n, dtype=np.int32)
+    frontier = np.array([info.root_ref], dtype=np.int64)
+    box_lo = np.array([info.bounds_lo], dtype=np.float32)
+    box_hi = np.array([info.bounds_hi], dtype=np.float32)
+    depth = 0
+    while frontier.size:
+        nd = nodes[frontier]
+        fl = f[frontier]
+        nxt, nlo, nhi = [], [], []
+        for half in (0, 1):
+            lo = fl[:, 8 * half:8 * half + 3]
+            hi = fl[:, 8 * half + 3:8 * half + 6]
+            assert np.all(lo >= box_lo) and np.all(hi <= box_hi), "child box escapes parent box"
+            ref = nd[:, 8 * half + 6].view(np.int32).astype(np.int64)
+            leaf = ref < 0
+            x = (~ref[leaf]).astype(np.int64)
+            first, cnt = x >> 3, (x & 7) + 1
+            for k in range(4):
+                sel = cnt > k
+                np.add.at(covered, first[sel] + k, 1)
+            tl = f.dtype  # noqa
+            nxt.append(ref[~leaf]); nlo.append(lo[~leaf]); nhi.append(hi[~leaf])
+        frontier = np.concatenate(nxt); box_lo = np.concatenate(nlo); box_hi = np.concatenate(nhi)
+        depth += 1
+        assert depth < 200
+    assert np.all(covered == 1), "a triangle is not in exactly one leaf"
+    assert depth == info.max_depth
+    print("build 2M tris:", t)
+
+
+def test_edge_cases(rt, ctx, oracle):
+    """Empty geometry, empty TLAS, masked instance, singular instance transform, duplicate coincident
+    triangles (equal-t tie-break), degenerate triangles, ray parameters."""
+    S = scenes
+    quad_v = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], dtype=np.float32)
+    quad_i = np.array([[0, 1, 3], [1, 2, 3]], dtype=np.uint32)
+    empty = S.Geometry(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), None)
+    degenerate = S.Geometry(np.array([[0, 0, 1], [0, 0, 1], [0, 0, 1], [0, 0, 1], [1, 1, 1], [2, 2, 1]], dtype=np.float32), None, None)
+    dup = [S.Geometry(quad_v, quad_i, None), S.Geometry(quad_v.copy(), quad_i.copy(), None)]      # coincident geometries
+    singular = np.array([1, 0, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0], dtype=np.float32)
+    inst = [
+        S.Instance(S.translation(-2.5, 0, 0), 1, 0xFF, 0, 1, 0),      # duplicate quads: geometry 0 must win the tie
+        S.Instance(S.translation(-2.5, 0, 0), 2, 0xFF, 0, 1, 0),      # coincident instance: instance 0 must win
+        S.Instance(S.translation(2.5, 0, 0), 3, 0x00, 0, 1, 0),       # masked out
+        S.Instance(singular, 4, 0xFF, 0, 1, 0),                       # singular transform: never hit
+        S.Instance(S.translation(0, 2.5, 0), 5, 0xFF, 1, 1, 1),       # BLAS with an empty + a degenerate geometry + a quad
+        S.Instance(S.translation(0, -2.5, 0), 6, 0xFF, 0, 1, 2),      # completely empty BLAS
+    ]
+    scene = S.Scene("edge", [dup, [empty, degenerate, S.Geometry(quad_v, quad_i, None)], [empty]], inst,
+                    S.SAMPLE_HIT_RECORDS.copy(), width=400, height=300, bounces=1)
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE)
+    rp, rs, rc = assert_parity(g, r, what="edge")
+    prim = g[1]
+    hit = prim["instance_id"] != MISS
+    assert set(np.unique(prim["instance_id"][hit])) == {0, 4}
+    m0 = prim["instance_id"] == 0
+    assert np.all(prim["geometry_index"][m0] == 0)
+    assert np.all(prim["geometry_index"][prim["instance_id"] == 4] == 2)
+    # empty TLAS: every ray misses
+    tl = ctx.build_tlas([], [])
+    ctx.set_hit_records(scene.hit_records)
+    rgba, p, _ = ctx.trace(tl, ctx.camera((0, 0, 10), 60), 64, 48, 0, want_hits=True)
+    tl.free()
+    assert np.all(p["instance_id"] == MISS) and np.all(rgba == np.array((0, 0, 51, 0), dtype=np.uint8))
+    # ray parameters: tmax just short of the plane -> all miss; cull mask 0x00 -> all miss; then restore
+    sh = rt.SceneHandles(ctx, S.sample_scene(300, 200))
+    ctx.set_ray_params(tmax=9.99)
+    _, p, _ = sh.trace(want_hits=True)
+    assert np.all(p["instance_id"] == MISS)
+    ctx.set_ray_params(tmin=10.5)
+    _, p, _ = sh.trace(want_hits=True)
+    assert np.all(p["instance_id"] == MISS)
+    ctx.set_ray_params(cull_mask=0x00)
+    _, p, _ = sh.trace(want_hits=True)
+    assert np.all(p["instance_id"] == MISS)
+    ctx.set_ray_params()
+    _, p, _ = sh.trace(want_hits=True)
+    assert (p["instance_id"] != MISS).sum() > 1000
+    # SBT range: fewer records than addressed -> refused, never silently wrong
+    ctx.set_hit_records(S.SAMPLE_HIT_RECORDS[:3])
+    with pytest.raises(rt.RtError) as e:
+        sh.trace()
+    assert e.value.code == rt.RT_ERROR_SBT_RANGE
+    sh.free()
+
+
+def test_row_partition_and_unpack(rt, ctx, oracle):
+    """Image-space split used for multi-GPU: the packed bands of every part, unpacked, equal the full frame."""
+    import torch
+    scene = scenes.instanced_scene(n_side=4, quads=12, width=322, height=250, bounces=1)
+    sh = rt.SceneHandles(ctx, scene)
+    full, _, _ = sh.trace(want_hits=False)
+    for parts in (2, 3, 8):
+        px = ctx.rows_packed_pixels(scene.width, scene.height, 8, parts)
+        packed = torch.zeros((parts, px, 4), dtype=torch.uint8, device="cuda:0")
+        for p in range(parts):
+            ctx.trace_rows(sh.tlas, sh.cam, scene.width, scene.height, 1, 8, p, parts, packed[p], device=True)
+        out = torch.zeros((scene.height, scene.width, 4), dtype=torch.uint8, device="cuda:0")
+        ctx.unpack_rows(packed, scene.width, scene.height, 8, parts, out)
+        torch.cuda.synchronize()
+        assert np.array_equal(out.cpu().numpy(), full), f"parts={parts}"
+    sh.free()
+
+
+def test_tlas_update_and_device_inputs(rt, ctx, oracle):
+    """Per-frame path: rt_update_tlas with moved instances; device-pointer geometry inputs."""
+    import torch
+    scene = scenes.sample_scene(300, 200)
+    sh = rt.SceneHandles(ctx, scene)
+    moved = [scenes.Instance(scenes.translation(0.5, 2, 0), 100, 0xFF, 0, 1, 0), scenes.Instance(scenes.translation(-0.5, -2, 0), 100, 0xFF, 2, 1, 0)]
+    ctx.update_tlas(sh.tlas, moved, sh.blases)
+    g = sh.trace(want_hits=True)
+    sh.free()
+    scene2 = scenes.sample_scene(300, 200)
+    scene2.instances = moved
+    o = oracle.OracleScene(scene2)
+    r = o.trace(mode=oracle.MODE_BRUTE)
+    assert_parity(g, r, what="tlas-update")
+    # device-resident vertex/index buffers (torch tensors) feed the same build
+    geo = scenes.heightfield(40, 30, -3, 3, -2, 2, 0.8, 5)
+    dv = torch.from_numpy(geo.vertices).cuda()
+    di = torch.from_numpy(geo.indices.astype(np.int32)).cuda()
+    b_dev = ctx.build_blas([scenes.Geometry(dv, di, None)], device=True)
+    n_dev, t_dev = b_dev.export()
+    b_host = ctx.build_blas([geo])
+    n_host, t_host = b_host.export()
+    assert np.array_equal(t_dev, t_host) and b_dev.info().root_ref == b_host.info().root_ref
+    walk_compare_bvh(n_dev, b_dev.info().root_ref, n_host, b_host.info().root_ref)
+    b_dev.free(); b_host.free()
