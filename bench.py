@@ -1,0 +1,418 @@
+#!/usr/bin/env python
+"""bench.py — the driver-facing benchmark of the hot path (BASELINE.json metric).
+
+A "step" is one vkCmdTraceRaysKHR-equivalent pass over the full frame of the workload (primary rays +
+one diffuse bounce), with the acceleration structures already resident in HBM. At N GPUs the frame is
+split into interleaved 8-scanline bands (scene replicated), gathered to rank 0 with NCCL and unpacked.
+
+  python bench.py                         # N=1, inst10m (BASELINE configs[3], the config the metric is quoted on)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N
+  python bench.py --impl reference        # the CPU arm: the scalar oracle on all host cores, bounded sample
+
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+from build_up_phase_b200 import scenes  # noqa: E402
+
+BLOCK_ROWS = 8
+B_TRI_BUILD = 356.0          # algorithmic bytes per triangle of the LBVH build (SURVEY §8(d), 32-bit-key contract figure)
+
+
+def make_workload(name: str, width: int | None, height: int | None):
+    if name == "inst10m":
+        s = scenes.instanced_scene(32, 70, 3840, 2160, 1)
+    elif name == "inst640k":                       # CPU-container-sized variant of the same generator
+        s = scenes.instanced_scene(8, 70, 1920, 1080, 1)
+    elif name == "tess1m":
+        s = scenes.tess_scene(1000, 500, 3840, 2160, 1)
+    elif name == "sample":
+        s = scenes.sample_scene(1920, 1080)
+    elif name == "soup100m":
+        s = scenes.soup_scene(100_000_000, 7680, 4320, 0)
+    elif name == "soup10m":
+        s = scenes.soup_scene(10_000_000, 3840, 2160, 0)
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    if width:
+        s.width = width
+    if height:
+        s.height = height
+    return s
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def b_ray_bytes(st: dict, pixels: int) -> float:
+    """B_ray = 64*nodes + 56*triangles + 64*instances + 4 per pixel."""
+    return 64.0 * st["nodes_visited"] + 56.0 * st["triangles_tested"] + 64.0 * st["instances_entered"] + 4.0 * pixels
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(gpu_index)],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle): only here and in cpu_baseline may bench.py execute anything under oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_arm(scene, target_seconds: float, steps: int, warmup: int):
+    import oracle_binding as ob
+    t0 = time.time()
+    o = ob.OracleScene(scene, build_bvh=True)
+    setup_s = time.time() - t0
+    w, h = scene.width, scene.height
+    # calibrate the row stride so that one step is ~target_seconds of CPU work
+    probe_rows = (0, h, max(1, h // 16))
+    t0 = time.time()
+    _, _, _, st = o.trace(rows=probe_rows, want_hits=False)
+    dt = time.time() - t0
+    rays_probe = st["rays_primary"] + st["rays_secondary"]
+    rate = rays_probe / max(dt, 1e-9)
+    total_rays_est = rays_probe * (h / max(1, len(range(*probe_rows))))
+    stride = max(1, int(np.ceil(total_rays_est / max(rate * target_seconds, 1.0))))
+    rows = (0, h, stride)
+    times, rays = [], 0
+    for i in range(warmup + steps):
+        t0 = time.time()
+        _, _, _, st = o.trace(rows=rows, want_hits=False)
+        dt = time.time() - t0
+        if i >= warmup:
+            times.append(dt)
+            rays = st["rays_primary"] + st["rays_secondary"]
+    ms = 1000.0 * float(np.mean(times))
+    return {"mrays_per_s": rays / (ms * 1e-3) / 1e6, "ms_per_step": ms, "rays_per_step": rays, "rows": rows, "threads": ob.num_threads(),
+            "setup_s": setup_s, "oracle": o}
+
+
+def cpu_build_baseline(scene, max_tris: int = 1_500_000):
+    """CPU LBVH build (std::stable_sort + Karras + atomic refit, OpenMP) of a bounded subset of the BLASes."""
+    import oracle_binding as ob
+    tris, secs = 0, 0.0
+    for geoms in scene.blases:
+        n = sum(g.triangle_count for g in geoms)
+        if tris and tris + n > max_tris:
+            break
+        secs += ob.time_blas_build(geoms)
+        tris += n
+    return {"mtris_per_s": tris / max(secs, 1e-9) / 1e6, "triangles": tris}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    scene = make_workload(args.workload, args.width, args.height)
+    steps = args.steps if args.steps else 2
+    warmup = args.warmup if args.warmup is not None else 1
+    res = cpu_arm(scene, args.cpu_seconds, steps, warmup)
+    line = {
+        "impl": "reference", "metric": "Mrays/s (primary+secondary rays per second)", "value": res["mrays_per_s"], "unit": "Mrays/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(scene, args, 1),
+        "cpu_baseline": {"value": res["mrays_per_s"], "unit": "Mrays/s", "cores": res["threads"], "kind": "port",
+                         "sample": f"rows {res['rows'][0]}..{res['rows'][1]} step {res['rows'][2]} of the {scene.width}x{scene.height} frame "
+                                   f"({res['rays_per_step']} rays/step), oracle LBVH traversal, OpenMP"},
+        "e2e": {"value": res["mrays_per_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(scene, args, n_gpus):
+    return {"workload": f"{args.workload}: {scene.name}, {scene.triangle_count} triangles in {len(scene.blases)} BLAS, "
+                        f"{len(scene.instances)} instances, {scene.width}x{scene.height} primary + {scene.bounces} diffuse bounce",
+            "triangles": scene.triangle_count, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
+            "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated",
+            "l2_policy": "inputs larger than L2 (BVH nodes + triangles >> 126 MB); no flush between iterations"
+                         if scene.triangle_count * 112 > 2 * 126e6 else "scene fits in L2: numbers are L2-resident (parity config)"}
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from build_up_phase_b200 import rtcore
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch with torch.distributed.run for --gpus > 1")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    steps = args.steps if args.steps else 20
+    warmup = args.warmup if args.warmup is not None else 3
+    if warmup < 3:
+        warmup = 3
+
+    scene = make_workload(args.workload, args.width, args.height)
+    W, H, bounces = scene.width, scene.height, scene.bounces
+    ctx = rtcore.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- scene upload (untimed) and acceleration-structure build (timed separately: Mtri/s) ----
+    dev_blases = []
+    keep = []
+    for geoms in scene.blases:
+        dg = []
+        for g in geoms:
+            v = torch.from_numpy(np.ascontiguousarray(g.vertices)).to(dev)
+            i = torch.from_numpy(np.ascontiguousarray(g.indices).view(np.int32)).to(dev) if g.indices is not None else None
+            t = torch.from_numpy(np.ascontiguousarray(g.transform)).to(dev) if g.transform is not None else None
+            keep += [v, i, t]
+            dg.append(scenes.Geometry(v, i, t))
+        dev_blases.append(dg)
+    torch.cuda.synchronize()
+    build_ms = []
+    blases = None
+    for rep in range(args.build_reps + 1):
+        if blases is not None:
+            for b in blases:
+                b.free()
+        blases = ctx.build_blas_batch(dev_blases, device=True) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True)]
+        if rep > 0:
+            build_ms.append(ctx.build_timing())
+    bt = min(build_ms, key=lambda t: t["total_ms"])
+    tlas = ctx.build_tlas(scene.instances, blases)
+    tlas_t = ctx.build_timing()
+    ctx.set_hit_records(scene.hit_records)
+    ctx.set_miss_color(scene.miss_color)
+    cam = ctx.camera(scene.camera_pos, scene.yfov_deg)
+
+    # ---- buffers ----
+    px_packed = ctx.rows_packed_pixels(W, H, BLOCK_ROWS, world)
+    if world > 1:
+        packed = torch.zeros((px_packed, 4), dtype=torch.uint8, device=dev)
+        gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+        gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    host_np = host_frame.numpy()
+
+    def step_device():
+        if world == 1:
+            ctx.trace_device(tlas, cam, W, H, bounces, frame, async_=True)
+        else:
+            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
+            dist.gather(packed, gather_list, dst=0)
+            if rank == 0:
+                ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
+
+    def step_e2e():
+        # reference-facing call with HOST buffers: camera struct in (16 B), RGBA8 framebuffer out (pinned host memory)
+        if world == 1:
+            ctx.trace(tlas, cam, W, H, bounces, rgba_out=host_np)
+        else:
+            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
+            dist.gather(packed, gather_list, dst=0)
+            if rank == 0:
+                ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
+                host_frame.copy_(frame, non_blocking=True)
+            torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- one stats pass: ray counts + traversal counters for the byte model (untimed, slower kernel) ----
+    if world == 1:
+        ctx.trace_device(tlas, cam, W, H, bounces, frame, stats=True)
+    else:
+        ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, stats=True)
+    st = ctx.trace_stats()
+    cnt = torch.tensor([st[k] for k in ("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested", "instances_entered",
+                                        "primary_hits", "secondary_hits", "near_edge_hits")], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(cnt)
+    tot = dict(zip(("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested", "instances_entered",
+                    "primary_hits", "secondary_hits", "near_edge_hits"), [int(x) for x in cnt.tolist()]))
+    total_rays = tot["rays_primary"] + tot["rays_secondary"]
+
+    # ---- timed region: device-resident ----
+    for _ in range(warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step_device()
+    e1.record()
+    barrier()
+    l1 = ctx.launch_count()
+    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_step = float(ms_total.item()) / steps
+
+    # trace-kernel-only time on this rank (CUDA events on the launching stream, inside the library)
+    k_ms = []
+    for _ in range(min(steps, 10)):
+        if world == 1:
+            ctx.trace_device(tlas, cam, W, H, bounces, frame)
+        else:
+            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True)
+        k_ms.append(ctx.trace_ms())
+    kern = torch.tensor([float(np.mean(k_ms))], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
+    kernel_ms = float(kern.item())
+
+    # ---- timed region: end to end through the host-buffer call ----
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, steps // 2)
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1000.0 / e2e_steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        hbm, peak_src = peaks()
+        algo_bytes = b_ray_bytes(tot, W * H)
+        # per launch on one GPU: this rank's share of the frame (1/world of the bytes) over its kernel time
+        achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9
+        n_tris = scene.triangle_count
+        build_gbs = n_tris * B_TRI_BUILD / (bt["total_ms"] * 1e-3) / 1e9
+        line = {
+            "metric": "Mrays/s (primary+secondary rays per second)", "value": total_rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(scene, args, world),
+            "rays_per_step": total_rays, "rays_primary": tot["rays_primary"], "rays_secondary": tot["rays_secondary"],
+            "trace_kernel_ms": kernel_ms,
+            "e2e": {"value": total_rays / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_ms.item()),
+                    "h2d_bytes_per_step": 16, "d2h_bytes_per_step": W * H * 4,
+                    "note": "rt_trace with a pinned host framebuffer: camera struct in, RGBA8 frame out"},
+            "gpu_launches": int(l1 - l0),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
+                         "kernel": "k_trace", "peak_source": peak_src,
+                         "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass",
+                         "algorithmic_bytes_per_launch": algo_bytes / world,
+                         "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
+                                     "instances": tot["instances_entered"] / total_rays, "bytes": algo_bytes / total_rays}},
+            "build": {"metric": "LBVH build Mtri/s (first setup kernel .. last refit kernel, CUDA events)",
+                      "value": n_tris / (bt["total_ms"] * 1e-3) / 1e6, "unit": "Mtri/s", "ms": bt["total_ms"], "phases_ms": bt,
+                      "tlas_ms": tlas_t["total_ms"],
+                      "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
+                                   "bytes_per_triangle": B_TRI_BUILD}},
+            "traversal": tot,
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            res = cpu_arm(scene, args.cpu_seconds, 1, 0)
+            cb = cpu_build_baseline(scene)
+            line["cpu_baseline"] = {"value": res["mrays_per_s"], "unit": "Mrays/s", "cores": res["threads"], "kind": "port",
+                                    "sample": f"rows 0..{H} step {res['rows'][2]} of the frame ({res['rays_per_step']} rays), oracle LBVH traversal; "
+                                              f"CPU LBVH build of {cb['triangles']} triangles: {cb['mtris_per_s']:.2f} Mtri/s",
+                                    "build_mtris_per_s": cb["mtris_per_s"]}
+            # parity of the rows the CPU traced, same run (hit ids bit-exact, RGBA within 1 LSB)
+            from parity import compare_hits, compare_rgba
+            prim = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
+            sec = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
+            ctx.trace_device(tlas, cam, W, H, bounces, frame, prim, sec)
+            rows = slice(*res["rows"])
+            rgba_o, prim_o, sec_o, _ = res["oracle"].trace(rows=res["rows"], want_hits=True)
+            gp = prim.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
+            gs = sec.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
+            rp, rs = compare_hits(gp, prim_o, rows), compare_hits(gs, sec_o, rows)
+            rc = compare_rgba(frame.cpu().numpy(), rgba_o, rows)
+            line["parity"] = {"rows_checked": len(range(*res["rows"])), "primary": {k: rp[k] for k in ("rays", "hits", "id_mismatches", "near_edge_rays", "t_bit_mismatches")},
+                              "secondary": {k: rs[k] for k in ("rays", "hits", "id_mismatches", "near_edge_rays", "t_bit_mismatches")}, "rgba": rc}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=0)
+    ap.add_argument("--warmup", type=int, default=None)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="inst10m")
+    ap.add_argument("--width", type=int, default=0)
+    ap.add_argument("--height", type=int, default=0)
+    ap.add_argument("--build-reps", type=int, default=3)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle step (bounded sample)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

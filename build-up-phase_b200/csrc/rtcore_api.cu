@@ -653,6 +653,7 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out, P.primary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
         if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out, P.secondary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    if ((flags & RT_TRACE_ASYNC) && dev_out && !stats) return RT_SUCCESS;
     if (stats) RT_CUDA(ctx, cudaMemcpyAsync(&ctx->last_stats, ctx->d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);

@@ -108,7 +108,8 @@ __device__ __forceinline__ bool woop_test(const Woop& w, const float4 q0, const 
     const float Az = w.Sz * Akz, Bz = w.Sz * Bkz, Cz = w.Sz * Ckz;
     const float T = (U * Az + V * Bz) + W * Cz;
     const float rcp = 1.0f / det;
-    t = T * rcp; bu = V * rcp; bv = W * rcp; bw0 = U * rcp;
+    // "+ 0.0f" turns -0 into +0: omitting the kx/ky swap flips the sign of exactly-zero results only
+    t = T * rcp + 0.0f; bu = V * rcp + 0.0f; bv = W * rcp + 0.0f; bw0 = U * rcp + 0.0f;
     return true;
 }
 

@@ -28,6 +28,7 @@ RT_BUILD_PREFER_FAST_TRACE = 0x4
 RT_BUILD_INSTANCES_ON_DEVICE = 0x100
 RT_TRACE_OUT_DEVICE = 0x1
 RT_TRACE_STATS = 0x2
+RT_TRACE_ASYNC = 0x4
 RT_REF_EMPTY = 0x7FFFFFFD
 
 EXPORTED_SYMBOLS = [
@@ -258,6 +259,9 @@ class Context:
     def set_stream(self, cuda_stream: int):
         self._check(self.L.rt_set_stream(self.h, cuda_stream))
 
+    def sync(self):
+        self._check(self.L.rt_sync(self.h))
+
     def launch_count(self) -> int:
         return int(self.L.rt_kernel_launch_count(self.h))
 
@@ -386,13 +390,14 @@ class Context:
         return rgba, prim, sec
 
     def trace_device(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, rgba_dev, prim_dev=None,
-                     sec_dev=None, stats: bool = False):
-        flags = RT_TRACE_OUT_DEVICE | (RT_TRACE_STATS if stats else 0)
+                     sec_dev=None, stats: bool = False, async_: bool = False):
+        flags = RT_TRACE_OUT_DEVICE | (RT_TRACE_STATS if stats else 0) | (RT_TRACE_ASYNC if async_ else 0)
         self._check(self.L.rt_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, _ptr(rgba_dev), _ptr(prim_dev), _ptr(sec_dev)))
 
     def trace_rows(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, block_rows: int, part_index: int,
-                   part_count: int, rgba, prim=None, sec=None, device: bool = False, stats: bool = False):
-        flags = (RT_TRACE_OUT_DEVICE if device else 0) | (RT_TRACE_STATS if stats else 0)
+                   part_count: int, rgba, prim=None, sec=None, device: bool = False, stats: bool = False,
+                   async_: bool = False):
+        flags = (RT_TRACE_OUT_DEVICE if device else 0) | (RT_TRACE_STATS if stats else 0) | (RT_TRACE_ASYNC if async_ else 0)
         self._check(self.L.rt_trace_rows(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, block_rows, part_index,
                                          part_count, _ptr(rgba), _ptr(prim), _ptr(sec)))
 

@@ -57,6 +57,7 @@ enum {
 /* ---- rt_trace output flags -------------------------------------------------------------- */
 #define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
 #define RT_TRACE_STATS      0x2u  /* also accumulate traversal counters (slower kernel variant) */
+#define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait) */
 
 typedef struct rt_context rt_context;
 typedef struct rt_blas    rt_blas;

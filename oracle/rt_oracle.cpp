@@ -348,7 +348,9 @@ static inline bool woop(const RayPre& r, const Tri& tr, float& t, float& bu, flo
     float Az = r.Sz * Akz, Bz = r.Sz * Bkz, Cz = r.Sz * Ckz;
     float T = (U * Az + V * Bz) + W * Cz;
     float rcp = 1.0f / det;
-    t = T * rcp; bu = V * rcp; bv = W * rcp; bw0 = U * rcp;
+    // "+ 0.0f" canonicalises -0 to +0: the sign of an exactly-zero t/u/v depends on the kx/ky swap above,
+    // which has no meaning without face culling (a faster implementation may omit the swap).
+    t = T * rcp + 0.0f; bu = V * rcp + 0.0f; bv = W * rcp + 0.0f; bw0 = U * rcp + 0.0f;
     return true;
 }
 

@@ -24,9 +24,15 @@ def compare_hits(gpu, ref, rows=None):
     rep["id_mismatches_near_edge"] = int((bad & near).sum())
     for f in ("t", "u", "v"):
         rep[f + "_bit_mismatches"] = int((gpu[f].view(np.uint32) != ref[f].view(np.uint32)).sum())
-    if rep["id_mismatches"]:
-        ys, xs = np.nonzero(bad)
-        rep["first_mismatches"] = [(int(y), int(x), tuple(gpu[y, x].tolist()), tuple(ref[y, x].tolist())) for y, x in list(zip(ys, xs))[:5]]
+    anybad = bad.copy()
+    for f in ("t", "u", "v"):
+        anybad |= gpu[f].view(np.uint32) != ref[f].view(np.uint32)
+    if anybad.any():
+        ys, xs = np.nonzero(anybad)
+        rep["first_mismatches"] = [(int(y), int(x), tuple(gpu[y, x].tolist()), tuple(ref[y, x].tolist()),
+                                    [hex(int(v)) for v in gpu[y, x].tolist()[:0]] + [hex(int(np.float32(gpu[y, x][f]).view(np.uint32))) for f in ("t", "u", "v")],
+                                    [hex(int(np.float32(ref[y, x][f]).view(np.uint32))) for f in ("t", "u", "v")])
+                                   for y, x in list(zip(ys, xs))[:5]]
     return rep
 
 
