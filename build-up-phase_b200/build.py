@@ -59,7 +59,7 @@ def build_rtcore(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [_nvcc(), "-ccbin", ccbin, "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
     subprocess.check_call(cmd)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
@@ -68,5 +68,18 @@ def build_rtcore(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+def build_host_sample() -> str:
+    """Compiles the headless C++ host program (host/sample_scene.cpp) against librtcore.so."""
+    src = os.path.join(HERE, "host", "sample_scene.cpp")
+    out = os.path.join(HERE, "host", "sample_scene")
+    if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
+        return out
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    subprocess.check_call([cxx, "-O2", "-std=c++17", src, "-I", os.path.join(HERE, "..", "include"), "-L", HERE, "-lrtcore",
+                           "-Wl,-rpath," + HERE, "-Wl,-rpath,/usr/local/cuda/lib64", "-o", out])
+    return out
+
+
 if __name__ == "__main__":
     print(build_rtcore(force="--force" in sys.argv, verbose=True))
+    print(build_host_sample())
