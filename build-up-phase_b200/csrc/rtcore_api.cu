@@ -34,6 +34,8 @@ struct rt_context {
     void* fb = nullptr; size_t fb_cap = 0;
     void* hits1 = nullptr; size_t hits1_cap = 0;
     void* hits2 = nullptr; size_t hits2_cap = 0;
+    void* queue = nullptr; size_t queue_cap = 0;       // bounce queue of the two-stage wavefront
+    uint32_t* d_counters = nullptr;                    // ray-fetch / queue counters of the persistent trace kernels
     unsigned long long* d_stats = nullptr;
     int* d_error = nullptr;
     cudaEvent_t ev[8]{};
@@ -140,7 +142,8 @@ int rt_create(int device_ordinal, rt_context** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     ctx->own_stream = true;
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess ||
+        cudaMalloc(&ctx->d_counters, 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     cudaMemset(ctx->d_error, 0, 64);
     *out = ctx;
     return RT_SUCCESS;
@@ -151,7 +154,7 @@ void rt_destroy(rt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
-    cudaFree(ctx->d_stats); cudaFree(ctx->d_error);
+    cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -640,6 +643,11 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         P.rgba = (uint8_t*)ctx->fb;
         if (primary_hits_out) { if ((rc = ensure(ctx, &ctx->hits1, &ctx->hits1_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.primary_hits = (rt_hit*)ctx->hits1; }
         if (secondary_hits_out) { if ((rc = ensure(ctx, &ctx->hits2, &ctx->hits2_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.secondary_hits = (rt_hit*)ctx->hits2; }
+    }
+    P.counters = ctx->d_counters;
+    if (bounces > 0) {
+        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, pixels * TRACE_QUEUE_ENTRY_BYTES)) != RT_SUCCESS) return rc;
+        P.queue = (float4*)ctx->queue;
     }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }

@@ -1,10 +1,18 @@
 // trace.cu — vkCmdTraceRaysKHR(W,H,1) for sm_100a (reference dispatch: main.cpp:1349-1355).
 //
-// One launch = raygen prologue (main.cpp:1033-1052) -> two-level TLAS->BLAS while-while traversal
+// One call = raygen prologue (main.cpp:1033-1052) -> two-level TLAS->BLAS while-while traversal
 // (what traceRayEXT hands to the driver / RT cores; B200 has none, so this runs on the SMs) ->
-// closest-hit / miss epilogue (main.cpp:1063-1066,1080-1091) -> rgba8 imageStore (main.cpp:1054),
-// optionally followed in the same thread by one deterministic diffuse bounce.
+// closest-hit / miss epilogue (main.cpp:1063-1066,1080-1091) -> rgba8 imageStore (main.cpp:1054).
+// With one diffuse bounce the work is a two-stage wavefront: stage 0 traces the primary rays and
+// appends a secondary ray per hit to a queue in HBM; stage 1 traces the queue and blends.
 //
+//  * Persistent warps: the grid is sized to the SMs (occupancy x 148), every warp pulls rays from a
+//    global counter. When fewer than REFILL_THRESHOLD lanes of a warp are still traversing, the
+//    warp leaves the traversal loop, finished lanes run their epilogue and the idle lanes are
+//    refilled with one ballot + one atomicAdd + one shuffle (warp-level ray compaction), so SIMD
+//    lanes stay busy although ray lengths differ by orders of magnitude.
+//  * Rays are numbered tile-major (8x4-pixel tiles) so the 32 rays a warp fetches together are
+//    neighbours and concurrently running warps work on neighbouring tiles (L1/L2 reuse of nodes).
 //  * 64-byte nodes fetched as 4 x LDG.128 through the read-only path; 48-byte triangles as 3 x LDG.128.
 //  * Box test: conservative slabs in FMA form (pad derived per ray/space from |origin| + |bounds|),
 //    so a box is never culled when the exact-arithmetic triangle test could still report a hit.
@@ -13,7 +21,6 @@
 //    the sample uses gl_RayFlagsOpaqueEXT only and TRIANGLE_FACING_CULL_DISABLE (main.cpp:852,1048).
 //  * Closest hit = smallest t in (tmin, tmax); equal t resolved by lowest (instance, geometry,
 //    primitive) so the result does not depend on BVH shape or traversal order.
-//  * Each warp owns an 8x4-pixel tile so primary rays of a warp stay coherent.
 #include <float.h>
 
 #include "rt_device.cuh"
@@ -22,7 +29,10 @@ namespace rt {
 
 namespace {
 
-constexpr int TRACE_THREADS = 256;
+constexpr int TRACE_THREADS = 128;
+constexpr int TRACE_MIN_BLOCKS = 5;          // register cap 65536 / (128 * 5) = 102
+constexpr int REFILL_THRESHOLD = 20;         // leave the traversal loop when fewer lanes are active
+constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 
 struct Slab {
     float rdx, rdy, rdz;     // 1/d (zero components replaced by +-1e-20)
@@ -63,8 +73,8 @@ struct Woop {
     bool z0, z1;             // kz == 0, kz == 1
 };
 // kz = dominant axis (lowest index wins ties), kx = kz+1, ky = kz+2 (mod 3). The kx/ky swap of the
-// paper (for d[kz] < 0) only negates U, V, W and det together, which leaves the hit decision and
-// t, u, v bit-identical when there is no face culling, so it is omitted.
+// paper (for d[kz] < 0) only negates U, V, W and det together; without face culling that leaves the
+// hit decision and t, u, v unchanged except for the sign of exact zeros, which is canonicalised.
 __device__ __forceinline__ void woop_setup(Woop& w, V3 o, V3 d) {
     int kz = 0; float m = fabsf(d.x);
     if (fabsf(d.y) > m) { kz = 1; m = fabsf(d.y); }
@@ -113,12 +123,6 @@ __device__ __forceinline__ bool woop_test(const Woop& w, const float4 q0, const 
     return true;
 }
 
-struct Hit {
-    float t, u, v, w0;
-    uint32_t inst_id, geo, prim;     // tie-break ids (0xFFFFFFFF = miss)
-    uint32_t slot, tri;              // TLAS slot (sorted) and triangle index inside its BLAS
-};
-
 __device__ __forceinline__ float u01(uint32_t h) { return (float)(h >> 8) * 5.9604644775390625e-08f; }
 
 __device__ __forceinline__ unsigned char unorm8(float c) {
@@ -128,211 +132,284 @@ __device__ __forceinline__ unsigned char unorm8(float c) {
     return (unsigned char)__float2int_rn(v * 255.0f);
 }
 
-template <bool STATS, int STACK>
-__global__ void __launch_bounds__(TRACE_THREADS) k_trace(const TraceParams P) {
+__device__ __forceinline__ void load_w2o(const InstanceRec* R, float* w2o) {
+    const float4* m4 = reinterpret_cast<const float4*>(R);
+    const float4 m0 = __ldg(m4), m1 = __ldg(m4 + 1), m2 = __ldg(m4 + 2);
+    w2o[0] = m0.x; w2o[1] = m0.y; w2o[2] = m0.z; w2o[3] = m0.w;
+    w2o[4] = m1.x; w2o[5] = m1.y; w2o[6] = m1.z; w2o[7] = m1.w;
+    w2o[8] = m2.x; w2o[9] = m2.y; w2o[10] = m2.z; w2o[11] = m2.w;
+}
+
+__device__ __forceinline__ rt_hit miss_record(float tmax) {
+    rt_hit r;
+    r.instance_id = r.geometry_index = r.primitive_id = r.custom_index = NO_HIT;
+    r.t = tmax; r.u = 0.0f; r.v = 0.0f;
+    return r;
+}
+
+// STAGE 0: primary rays generated from pixel ids. STAGE 1: secondary rays read from the bounce queue.
+template <int STAGE, bool STATS, int STACK>
+__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
-    const uint32_t warp_global = blockIdx.x * (TRACE_THREADS / 32) + (threadIdx.x >> 5);
+    const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tiles_x = (P.width + 7u) >> 3;
     const uint32_t tiles_y = (P.local_rows + 3u) >> 2;
-    if (warp_global >= tiles_x * tiles_y) return;
-    const uint32_t x = (warp_global % tiles_x) * 8u + (lane & 7);
-    const uint32_t lr = (warp_global / tiles_x) * 4u + (lane >> 3);
-    const uint32_t band = lr / P.block_rows;
-    const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
-    const bool in_buffer = x < P.width && lr < P.local_rows;
-    const bool valid = in_buffer && y < P.height;
+    const uint32_t total = STAGE == 0 ? tiles_x * tiles_y * 32u : P.counters[2];
+    uint32_t* fetch_counter = P.counters + STAGE;
 
-    unsigned long long c_nodes = 0, c_tris = 0, c_insts = 0, c_ph = 0, c_sh = 0, c_sec = 0, c_edge = 0, c_prim = 0;
-    float col[3] = {0.0f, 0.0f, 0.0f};
-    Hit h1, h2;
-    h1.t = P.tmax; h1.u = h1.v = h1.w0 = 0.0f; h1.inst_id = h1.geo = h1.prim = 0xFFFFFFFFu; h1.slot = h1.tri = 0;
-    h2 = h1;
+    unsigned long long c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0, c_rays = 0, c_edge = 0;
 
-    if (valid) {
-        // ---- raygen (main.cpp:1033-1046); aspect_x/aspect_y are computed once on the host (tanf) ----
-        const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
-        const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
-        const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
-        const float ax = ndcx * P.aspect_x, ay = ndcy * P.aspect_y;
-        V3 o = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
-        V3 d = {(ax * 1.0f + ay * 0.0f) + 0.0f, (ax * 0.0f + ay * -1.0f) + 0.0f, (ax * 0.0f + ay * 0.0f) + -1.0f};
-        const uint32_t pixel = y * P.width + x;
-        V3 prim_o = o, prim_d = d;
+    // ---- per-lane ray state ----
+    bool have_ray = false, exhausted = false;
+    bool in_buffer = false, valid = false;
+    uint32_t lidx = 0, pixel = 0;
+    V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
+    float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
+    int32_t cur = REF_DONE;
+    int sp = 0;
+    bool in_blas = false;
+    const BvhNode* nodes = P.tlas_nodes;
+    const TriRec* tris = nullptr;
+    Slab sl; Woop wp;
+    sl.rdx = sl.rdy = sl.rdz = sl.cnx = sl.cny = sl.cnz = sl.cfx = sl.cfy = sl.cfz = 0.0f; sl.px = sl.py = sl.pz = false;
+    wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
+    uint32_t cur_slot = 0;
+    float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
+    uint32_t best_slot = NO_HIT, best_tri = 0;
+    int32_t stack[STACK];
 
-#pragma unroll 1
-        for (uint32_t stage = 0; stage <= P.bounces; ++stage) {
-            Hit best;
-            best.t = P.tmax; best.u = best.v = best.w0 = 0.0f; best.inst_id = best.geo = best.prim = 0xFFFFFFFFu; best.slot = best.tri = 0;
-            // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
-            int32_t stack[STACK];
-            int sp = 0;
-            stack[sp++] = REF_DONE;
-            const BvhNode* nodes = P.tlas_nodes;
-            const TriRec* tris = nullptr;
-            Slab sl; Woop wp;
-            slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
-            wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
-            bool in_blas = false;
-            uint32_t cur_slot = 0, cur_inst_id = 0;
-            int32_t cur = P.tlas_root;
-            for (;;) {
-                while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {           // internal node
-                    const float4* n4 = reinterpret_cast<const float4*>(nodes + cur);
-                    const float4 a0 = __ldg(n4), a1 = __ldg(n4 + 1), b0 = __ldg(n4 + 2), b1 = __ldg(n4 + 3);
-                    if (STATS) ++c_nodes;
-                    float t0, t1;
-                    const bool hit0 = slab_test(sl, a0, a1, P.tmin, best.t, t0);
-                    const bool hit1 = slab_test(sl, b0, b1, P.tmin, best.t, t1);
-                    const int32_t r0 = __float_as_int(a1.z), r1 = __float_as_int(b1.z);
-                    if (hit0 && hit1) {
-                        const bool swap = t1 < t0;
-                        stack[sp++] = swap ? r0 : r1;
-                        cur = swap ? r1 : r0;
-                    } else if (hit0) cur = r0;
-                    else if (hit1) cur = r1;
-                    else cur = stack[--sp];
-                }
-                if (cur < 0) {                                                   // leaf
-                    const uint32_t first = leaf_first(cur), count = leaf_count(cur);
-                    if (!in_blas) {
-                        // TLAS leaf: one instance. Cull mask (main.cpp:851,1048), then enter its BLAS in object space.
-                        const InstanceRec* R = P.instances + first;
-                        const uint32_t cm = __ldg(&R->custom_mask);
-                        const int32_t root = __ldg(&R->root);
-                        if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
-                            if (STATS) ++c_insts;
-                            const float4* m4 = reinterpret_cast<const float4*>(R);
-                            const float4 m0 = __ldg(m4), m1 = __ldg(m4 + 1), m2 = __ldg(m4 + 2);
-                            const float w2o[12] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
-                            const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
-                            slab_setup(sl, oo, od, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
-                            woop_setup(wp, oo, od);
-                            nodes = R->nodes; tris = R->tris;
-                            cur_slot = first; cur_inst_id = __ldg(&R->instance_id);
-                            in_blas = true;
-                            stack[sp++] = REF_POP_INSTANCE;
-                            cur = root;
-                        } else cur = stack[--sp];
+    for (;;) {
+        // ================= refill idle lanes: ballot + one atomic + shuffle =================
+        const unsigned need = __ballot_sync(0xffffffffu, !have_ray && !exhausted);
+        if (need) {
+            const int leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (!have_ray && !exhausted) {
+                const uint32_t idx = base + __popc(need & lt_mask);
+                if (idx >= total) exhausted = true;
+                else {
+                    have_ray = true;
+                    if (STAGE == 0) {
+                        const uint32_t tile = idx >> 5, within = idx & 31u;
+                        const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
+                        const uint32_t lr = (tile / tiles_x) * 4u + (within >> 3);
+                        const uint32_t band = lr / P.block_rows;
+                        const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
+                        in_buffer = x < P.width && lr < P.local_rows;
+                        valid = in_buffer && y < P.height;
+                        lidx = lr * P.width + x;
+                        pixel = y * P.width + x;
+                        // ---- raygen (main.cpp:1033-1046); aspect_x/aspect_y computed once on the host (tanf) ----
+                        const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
+                        const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
+                        const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
+                        const float ax = ndcx * P.aspect_x, ay = ndcy * P.aspect_y;
+                        o = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
+                        d = {(ax * 1.0f + ay * 0.0f) + 0.0f, (ax * 0.0f + ay * -1.0f) + 0.0f, (ax * 0.0f + ay * 0.0f) + -1.0f};
                     } else {
-                        for (uint32_t k = 0; k < count; ++k) {
-                            const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
-                            const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
-                            if (STATS) ++c_tris;
-                            float t, bu, bv, bw0;
-                            if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
-                                const uint32_t geo = __float_as_uint(q2.y), prim = __float_as_uint(q2.z);
-                                bool better = t < best.t;
-                                if (t == best.t) {
-                                    better = cur_inst_id != best.inst_id ? cur_inst_id < best.inst_id
-                                             : (geo != best.geo ? geo < best.geo : prim < best.prim);
-                                }
-                                if (better) {
-                                    best.t = t; best.u = bu; best.v = bv; best.w0 = bw0;
-                                    best.inst_id = cur_inst_id; best.geo = geo; best.prim = prim;
-                                    best.slot = cur_slot; best.tri = first + k;
-                                }
-                            }
-                        }
-                        cur = stack[--sp];
+                        const float4* q = P.queue + 3 * (size_t)idx;
+                        const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
+                        lidx = __float_as_uint(q0.x);
+                        o = {q0.y, q0.z, q0.w};
+                        d = {q1.x, q1.y, q1.z};
+                        col0 = q1.w; col1 = q2.x; col2 = q2.y;
+                        in_buffer = valid = true;
                     }
-                } else if (cur == REF_POP_INSTANCE) {                            // back to world space
+                    // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
+                    best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
+                    sp = 0;
+                    stack[sp++] = REF_DONE;
                     in_blas = false;
                     nodes = P.tlas_nodes;
+                    cur = valid ? P.tlas_root : REF_DONE;
+                    if (cur == REF_EMPTY) cur = REF_DONE;
                     slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
-                    cur = stack[--sp];
-                } else if (cur == REF_EMPTY) {
-                    cur = stack[--sp];
-                } else break;                                                     // REF_DONE
+                }
             }
+        }
+        if (__ballot_sync(0xffffffffu, have_ray) == 0u) break;
+        const bool warp_exhausted = __ballot_sync(0xffffffffu, exhausted) != 0u;
 
-            if (stage == 0) { h1 = best; if (STATS) ++c_prim; } else { h2 = best; if (STATS) ++c_sec; }
-            float sc[3];
-            const bool hit = best.inst_id != 0xFFFFFFFFu;
-            const InstanceRec* R = P.instances + best.slot;
-            uint32_t custom = 0;
-            if (hit) {
-                // ---- closest-hit (main.cpp:1080-1091) with the SBT rule of main.cpp:1260-1262 ----
-                const uint32_t cm = __ldg(&R->custom_mask), sf = __ldg(&R->sbt_flags);
-                custom = cm & 0xFFFFFFu;
-                if (best.prim == 1u && best.inst_id == 1u && custom == 100u && best.geo == 1u) {
-                    sc[0] = 1.0f - best.u - best.v; sc[1] = best.u; sc[2] = best.v;
+        // ================= two-level while-while traversal =================
+        while (cur != REF_DONE) {
+            while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {               // internal node
+                const float4* n4 = reinterpret_cast<const float4*>(nodes + cur);
+                const float4 a0 = __ldg(n4), a1 = __ldg(n4 + 1), b0 = __ldg(n4 + 2), b1 = __ldg(n4 + 3);
+                if (STATS) ++c_nodes;
+                float t0, t1;
+                const bool hit0 = slab_test(sl, a0, a1, P.tmin, best_t, t0);
+                const bool hit1 = slab_test(sl, b0, b1, P.tmin, best_t, t1);
+                const int32_t r0 = __float_as_int(a1.z), r1 = __float_as_int(b1.z);
+                if (hit0 && hit1) {
+                    const bool swap = t1 < t0;
+                    stack[sp++] = swap ? r0 : r1;
+                    cur = swap ? r1 : r0;
+                } else if (hit0) cur = r0;
+                else if (hit1) cur = r1;
+                else cur = stack[--sp];
+            }
+            if (cur < 0) {                                                       // leaf
+                const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+                if (!in_blas) {
+                    // TLAS leaf = one instance: cull mask (main.cpp:851,1048), then enter its BLAS in object space
+                    const InstanceRec* R = P.instances + first;
+                    const uint32_t cm = __ldg(&R->custom_mask);
+                    const int32_t root = __ldg(&R->root);
+                    if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
+                        if (STATS) ++c_insts;
+                        float w2o[12];
+                        load_w2o(R, w2o);
+                        const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
+                        slab_setup(sl, oo, od, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
+                        woop_setup(wp, oo, od);
+                        nodes = R->nodes; tris = R->tris;
+                        cur_slot = first;
+                        in_blas = true;
+                        stack[sp++] = REF_POP_INSTANCE;
+                        cur = root;
+                    } else cur = stack[--sp];
                 } else {
-                    const uint32_t rec = (sf & 0xFFFFFFu) + best.geo * P.sbt_stride + P.sbt_offset;
-                    if (rec < P.n_records) { sc[0] = __ldg(P.hit_records + 3 * rec); sc[1] = __ldg(P.hit_records + 3 * rec + 1); sc[2] = __ldg(P.hit_records + 3 * rec + 2); }
-                    else { sc[0] = sc[1] = sc[2] = 0.0f; }
+                    for (uint32_t k = 0; k < count; ++k) {
+                        const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
+                        const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
+                        if (STATS) ++c_tris;
+                        float t, bu, bv, bw0;
+                        if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
+                            bool better = t < best_t;
+                            if (t == best_t && best_slot != NO_HIT) {
+                                // equal t: lowest (instance, geometry, primitive) wins; rare, so the ids of the
+                                // current best are re-read from memory instead of living in registers
+                                const InstanceRec* Rb = P.instances + best_slot;
+                                const uint32_t bi = __ldg(&Rb->instance_id), ci = __ldg(&(P.instances + cur_slot)->instance_id);
+                                const TriRec* bt = Rb->tris + best_tri;
+                                const uint32_t bg = __ldg(&bt->geo), bp = __ldg(&bt->prim);
+                                const uint32_t geo = __float_as_uint(q2.y), prim = __float_as_uint(q2.z);
+                                better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
+                            }
+                            if (better) { best_t = t; best_u = bu; best_v = bv; best_w0 = bw0; best_slot = cur_slot; best_tri = first + k; }
+                        }
+                    }
+                    cur = stack[--sp];
                 }
-                if (STATS) { if (stage == 0) { ++c_ph; if (fminf(fminf(best.u, best.v), best.w0) < 9.5367431640625e-07f) ++c_edge; } else ++c_sh; }
+            } else if (cur == REF_POP_INSTANCE) {                                // back to world space
+                in_blas = false;
+                nodes = P.tlas_nodes;
+                slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
+                cur = stack[--sp];
+            } else if (cur == REF_EMPTY) {
+                cur = stack[--sp];
+            }
+            // warp-level compaction trigger: too few lanes still traversing -> go refill the idle ones
+            if (!warp_exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
+        }
+
+        // ================= epilogue of the lanes whose ray just finished =================
+        const bool finish = have_ray && cur == REF_DONE;
+        bool enqueue = false;
+        float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
+        if (finish) {
+            have_ray = false;
+            if (!valid) {
+                if (in_buffer) {
+                    reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(0, 0, 0, 0);
+                    if (P.primary_hits) P.primary_hits[lidx] = miss_record(P.tmax);
+                    if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
+                }
             } else {
-                sc[0] = P.miss[0]; sc[1] = P.miss[1]; sc[2] = P.miss[2];          // miss shader (main.cpp:1063-1066)
-            }
-            rt_hit* hout = stage == 0 ? P.primary_hits : P.secondary_hits;
-            if (hout) {
-                rt_hit r;
-                r.instance_id = best.inst_id; r.geometry_index = best.geo; r.primitive_id = best.prim;
-                r.custom_index = hit ? custom : 0xFFFFFFFFu; r.t = hit ? best.t : P.tmax; r.u = best.u; r.v = best.v;
-                hout[(size_t)lr * P.width + x] = r;
-            }
-            if (stage == 0) { col[0] = sc[0]; col[1] = sc[1]; col[2] = sc[2]; }
-            else { col[0] = 0.5f * col[0] + 0.5f * sc[0]; col[1] = 0.5f * col[1] + 0.5f * sc[1]; col[2] = 0.5f * col[2] + 0.5f * sc[2]; }
-            if (!hit || stage == P.bounces) break;
-
-            // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
-            {
-                const V3 p = {prim_o.x + best.t * prim_d.x, prim_o.y + best.t * prim_d.y, prim_o.z + best.t * prim_d.z};
-                const float4* m4 = reinterpret_cast<const float4*>(R);
-                const float4 m0 = __ldg(m4), m1 = __ldg(m4 + 1), m2 = __ldg(m4 + 2);
-                const float w2o[12] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w, m2.x, m2.y, m2.z, m2.w};
-                const float4* t4 = reinterpret_cast<const float4*>(R->tris + best.tri);
-                const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
-                const V3 e1 = {q0.w - q0.x, q1.x - q0.y, q1.y - q0.z};
-                const V3 e2 = {q1.z - q0.x, q1.w - q0.y, q2.x - q0.z};
-                V3 n = xform_normal(w2o, cross3(e1, e2));
-                const float l2 = dot3(n, n);
-                if (l2 > 0.0f && l2 < INFINITY) { const float l = sqrtf(l2); n = {n.x / l, n.y / l, n.z / l}; }
-                else { const float dl = sqrtf(dot3(prim_d, prim_d)); n = {-prim_d.x / dl, -prim_d.y / dl, -prim_d.z / dl}; }
-                if (dot3(n, prim_d) > 0.0f) n = {-n.x, -n.y, -n.z};
-                uint32_t h = pcg_hash(pixel + pcg_hash(P.bounce_seed + 0x9E3779B9u));
-                V3 s = {0.0f, 0.0f, 0.0f};
-                for (int tries = 0; tries < 8; ++tries) {
-                    const uint32_t ha = pcg_hash(h), hb = pcg_hash(ha), hc = pcg_hash(hb);
-                    h = hc;
-                    const V3 q = {u01(ha) * 2.0f - 1.0f, u01(hb) * 2.0f - 1.0f, u01(hc) * 2.0f - 1.0f};
-                    const float qq = dot3(q, q);
-                    if (qq <= 1.0f && qq > 1e-8f) { const float ql = sqrtf(qq); s = {q.x / ql, q.y / ql, q.z / ql}; break; }
+                if (STATS) ++c_rays;
+                const bool hit = best_slot != NO_HIT;
+                const InstanceRec* R = P.instances + (hit ? best_slot : 0u);
+                float sc0, sc1, sc2;
+                rt_hit rec = miss_record(P.tmax);
+                float4 tq0 = make_float4(0.f, 0.f, 0.f, 0.f), tq1 = tq0, tq2 = tq0;
+                if (hit) {
+                    // ---- closest-hit (main.cpp:1080-1091) with the SBT rule of main.cpp:1260-1262 ----
+                    const uint32_t cm = __ldg(&R->custom_mask), sf = __ldg(&R->sbt_flags), inst_id = __ldg(&R->instance_id);
+                    const float4* t4 = reinterpret_cast<const float4*>(R->tris + best_tri);
+                    tq0 = __ldg(t4); tq1 = __ldg(t4 + 1); tq2 = __ldg(t4 + 2);
+                    const uint32_t geo = __float_as_uint(tq2.y), prim = __float_as_uint(tq2.z), custom = cm & 0xFFFFFFu;
+                    if (prim == 1u && inst_id == 1u && custom == 100u && geo == 1u) {
+                        sc0 = 1.0f - best_u - best_v; sc1 = best_u; sc2 = best_v;
+                    } else {
+                        const uint32_t r = (sf & 0xFFFFFFu) + geo * P.sbt_stride + P.sbt_offset;
+                        if (r < P.n_records) { sc0 = __ldg(P.hit_records + 3 * r); sc1 = __ldg(P.hit_records + 3 * r + 1); sc2 = __ldg(P.hit_records + 3 * r + 2); }
+                        else { sc0 = sc1 = sc2 = 0.0f; }
+                    }
+                    rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
+                    rec.t = best_t; rec.u = best_u; rec.v = best_v;
+                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c_edge; }
+                } else {
+                    sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];                 // miss shader (main.cpp:1063-1066)
                 }
-                V3 dir = {n.x + s.x, n.y + s.y, n.z + s.z};
-                const float dl2 = dot3(dir, dir);
-                if (dl2 < 1e-12f) dir = n;
-                else { const float dl = sqrtf(dl2); dir = {dir.x / dl, dir.y / dl, dir.z / dl}; }
-                const float eps = 0.0009765625f;
-                o = {p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps};
-                d = dir;
+                if (STAGE == 0) {
+                    if (P.primary_hits) P.primary_hits[lidx] = rec;
+                    if (hit && P.bounces > 0u) {
+                        // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
+                        const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
+                        float w2o[12];
+                        load_w2o(R, w2o);
+                        const V3 ed1 = {tq0.w - tq0.x, tq1.x - tq0.y, tq1.y - tq0.z};
+                        const V3 ed2 = {tq1.z - tq0.x, tq1.w - tq0.y, tq2.x - tq0.z};
+                        V3 n = xform_normal(w2o, cross3(ed1, ed2));
+                        const float l2 = dot3(n, n);
+                        if (l2 > 0.0f && l2 < INFINITY) { const float l = sqrtf(l2); n = {n.x / l, n.y / l, n.z / l}; }
+                        else { const float dl = sqrtf(dot3(d, d)); n = {-d.x / dl, -d.y / dl, -d.z / dl}; }
+                        if (dot3(n, d) > 0.0f) n = {-n.x, -n.y, -n.z};
+                        uint32_t h = pcg_hash(pixel + pcg_hash(P.bounce_seed + 0x9E3779B9u));
+                        V3 s = {0.0f, 0.0f, 0.0f};
+                        for (int tries = 0; tries < 8; ++tries) {
+                            const uint32_t ha = pcg_hash(h), hb = pcg_hash(ha), hc = pcg_hash(hb);
+                            h = hc;
+                            const V3 q = {u01(ha) * 2.0f - 1.0f, u01(hb) * 2.0f - 1.0f, u01(hc) * 2.0f - 1.0f};
+                            const float qq = dot3(q, q);
+                            if (qq <= 1.0f && qq > 1e-8f) { const float ql = sqrtf(qq); s = {q.x / ql, q.y / ql, q.z / ql}; break; }
+                        }
+                        V3 dir = {n.x + s.x, n.y + s.y, n.z + s.z};
+                        const float dl2 = dot3(dir, dir);
+                        if (dl2 < 1e-12f) dir = n;
+                        else { const float dl = sqrtf(dl2); dir = {dir.x / dl, dir.y / dl, dir.z / dl}; }
+                        const float eps = 0.0009765625f;
+                        enqueue = true;
+                        e0 = make_float4(__uint_as_float(lidx), p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps);
+                        e1 = make_float4(dir.x, dir.y, dir.z, sc0);
+                        e2 = make_float4(sc1, sc2, 0.0f, 0.0f);
+                    } else {
+                        reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(sc0), unorm8(sc1), unorm8(sc2), 0);   // imageStore, main.cpp:1054
+                        if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
+                    }
+                } else {
+                    if (P.secondary_hits) P.secondary_hits[lidx] = rec;
+                    const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
+                    reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
+                }
+            }
+        }
+        if (STAGE == 0) {
+            // warp-aggregated append to the bounce queue
+            const unsigned em = __ballot_sync(0xffffffffu, enqueue);
+            if (em) {
+                const int leader = __ffs(em) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(P.counters + 2, (uint32_t)__popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (enqueue) {
+                    float4* q = P.queue + 3 * (size_t)(base + __popc(em & lt_mask));
+                    __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
+                }
             }
         }
     }
 
-    if (in_buffer) {
-        const size_t idx = (size_t)lr * P.width + x;
-        uchar4 px = valid ? make_uchar4(unorm8(col[0]), unorm8(col[1]), unorm8(col[2]), 0) : make_uchar4(0, 0, 0, 0);
-        reinterpret_cast<uchar4*>(P.rgba)[idx] = px;                              // imageStore(vec4(hitValue, 0.0)), main.cpp:1054
-        if (!valid) {
-            rt_hit r; r.instance_id = r.geometry_index = r.primitive_id = r.custom_index = 0xFFFFFFFFu; r.t = P.tmax; r.u = r.v = 0.0f;
-            if (P.primary_hits) P.primary_hits[idx] = r;
-            if (P.secondary_hits) P.secondary_hits[idx] = r;
-        } else if (P.secondary_hits && h1.inst_id == 0xFFFFFFFFu) {
-            rt_hit r; r.instance_id = r.geometry_index = r.primitive_id = r.custom_index = 0xFFFFFFFFu; r.t = P.tmax; r.u = r.v = 0.0f;
-            P.secondary_hits[idx] = r;
-        } else if (P.secondary_hits && P.bounces == 0) {
-            rt_hit r; r.instance_id = r.geometry_index = r.primitive_id = r.custom_index = 0xFFFFFFFFu; r.t = P.tmax; r.u = r.v = 0.0f;
-            P.secondary_hits[idx] = r;
-        }
-    }
     if (STATS && P.stats) {
-        unsigned long long v[8] = {c_prim, c_sec, c_nodes, c_tris, c_insts, c_ph, c_sh, c_edge};
+        // rt_trace_stats order: rays_primary, rays_secondary, nodes, tris, insts, primary_hits, secondary_hits, near_edge
+        unsigned long long v[8] = {STAGE == 0 ? c_rays : 0ull, STAGE == 1 ? c_rays : 0ull, c_nodes, c_tris, c_insts,
+                                   STAGE == 0 ? c_hits : 0ull, STAGE == 1 ? c_hits : 0ull, c_edge};
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+            for (int ofs = 16; ofs > 0; ofs >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], ofs);
             if (lane == 0 && v[k]) atomicAdd(P.stats + k, v[k]);
         }
     }
@@ -348,21 +425,41 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ 
     out[(size_t)y * width + x] = packed_all[((size_t)part * rows_per_part + lr) * width + x];
 }
 
+template <int STAGE, bool STATS, int STACK>
+int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
+    static int blocks_per_sm = 0;       // same for every device of this process (one device per process)
+    if (blocks_per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK>, TRACE_THREADS, 0) != cudaSuccess || blocks_per_sm < 1)
+            blocks_per_sm = 1;
+    }
+    const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
+    uint32_t blocks = (uint32_t)(sm_count * blocks_per_sm);            // persistent: a multiple of the SM count
+    const uint32_t max_useful = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
+    if (STAGE == 0 && blocks > max_useful) blocks = max_useful;
+    if (blocks == 0) return 0;
+    k_trace<STAGE, STATS, STACK><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    return 1;
+}
+
+template <bool STATS, int STACK>
+int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
+    int n = launch_stage<0, STATS, STACK>(p, sm_count, st);
+    if (p.bounces > 0) n += launch_stage<1, STATS, STACK>(p, sm_count, st);
+    return n;
+}
+
 }  // namespace
 
-int launch_trace(const TraceParams& p, bool stats, int stack_needed, int /*sm_count*/, cudaStream_t st) {
+int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st) {
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     if (tiles == 0) return 0;
-    const uint32_t blocks = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
-    if (stack_needed <= 64) {
-        if (stats) k_trace<true, 64><<<blocks, TRACE_THREADS, 0, st>>>(p);
-        else k_trace<false, 64><<<blocks, TRACE_THREADS, 0, st>>>(p);
-    } else if (stack_needed <= 160) {
-        if (stats) k_trace<true, 160><<<blocks, TRACE_THREADS, 0, st>>>(p);
-        else k_trace<false, 160><<<blocks, TRACE_THREADS, 0, st>>>(p);
-    } else return -2;
+    if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
+    int n;
+    if (stack_needed <= 64) n = stats ? launch_both<true, 64>(p, sm_count, st) : launch_both<false, 64>(p, sm_count, st);
+    else if (stack_needed <= 160) n = stats ? launch_both<true, 160>(p, sm_count, st) : launch_both<false, 160>(p, sm_count, st);
+    else return -2;
     if (cudaGetLastError() != cudaSuccess) return -1;
-    return 1;
+    return n;
 }
 
 int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,
