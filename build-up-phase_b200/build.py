@@ -39,6 +39,18 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in files)
 
 
+def build_variant(name: str, defines) -> str:
+    """Tuning aid: builds build/librtcore_<name>.so with extra -D flags (select it with RTCORE_LIB=<path>)."""
+    out = os.path.join(HERE, "build", f"librtcore_{name}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    cmd = [_nvcc(), "-ccbin", ccbin, *flags, *[f"-D{d}" for d in defines], "-shared", "-o", out,
+           *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    subprocess.check_call(cmd)
+    return out
+
+
 def build_rtcore(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

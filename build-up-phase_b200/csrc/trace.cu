@@ -29,9 +29,15 @@ namespace rt {
 
 namespace {
 
+#ifndef RT_TRACE_MIN_BLOCKS
+#define RT_TRACE_MIN_BLOCKS 5
+#endif
+#ifndef RT_REFILL_THRESHOLD
+#define RT_REFILL_THRESHOLD 20
+#endif
 constexpr int TRACE_THREADS = 128;
-constexpr int TRACE_MIN_BLOCKS = 5;          // register cap 65536 / (128 * 5) = 102
-constexpr int REFILL_THRESHOLD = 20;         // leave the traversal loop when fewer lanes are active
+constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 5) = 102
+constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 
 struct Slab {

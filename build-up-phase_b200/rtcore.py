@@ -120,8 +120,8 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    path = lib_path()
-    if build_if_missing and _build.needs_build():
+    path = os.environ.get("RTCORE_LIB") or lib_path()      # RTCORE_LIB: tuning variants built by build.build_variant()
+    if build_if_missing and not os.environ.get("RTCORE_LIB") and _build.needs_build():
         _build.build_rtcore()
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: the CUDA extension must be built (python -m build_up_phase_b200.build); there is no CPU fallback")
