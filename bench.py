@@ -408,6 +408,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    # torchrun exports OMP_NUM_THREADS=1 to its children; the CPU legs (reference arm, cpu_baseline) are specified to use
+    # all host threads, so undo that before the OpenMP runtime of the oracle library is loaded.
+    if os.environ.get("OMP_NUM_THREADS") == "1" and "RT_KEEP_OMP" not in os.environ:
+        os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -30,14 +30,35 @@ namespace rt {
 namespace {
 
 #ifndef RT_TRACE_MIN_BLOCKS
-#define RT_TRACE_MIN_BLOCKS 5
+#define RT_TRACE_MIN_BLOCKS 8
 #endif
 #ifndef RT_REFILL_THRESHOLD
-#define RT_REFILL_THRESHOLD 20
+#define RT_REFILL_THRESHOLD 12
 #endif
 constexpr int TRACE_THREADS = 128;
-constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 5) = 102
+constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
 constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
+#ifndef RT_NODE_CAP
+#define RT_NODE_CAP 4
+#endif
+constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner node loop when fewer lanes are still in it (0 = never)
+#ifndef RT_LDG256
+#define RT_LDG256 0
+#endif
+
+// Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
+// on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void* p) {
+    F8 r;
+#if RT_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#else
+    r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+    return r;
+}
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 
 struct Slab {
@@ -241,8 +262,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         // ================= two-level while-while traversal =================
         while (cur != REF_DONE) {
             while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {               // internal node
-                const float4* n4 = reinterpret_cast<const float4*>(nodes + cur);
-                const float4 a0 = __ldg(n4), a1 = __ldg(n4 + 1), b0 = __ldg(n4 + 2), b1 = __ldg(n4 + 3);
+                const F8 na = ldg256(&nodes[cur].c[0]), nb = ldg256(&nodes[cur].c[1]);
+                const float4 a0 = na.a, a1 = na.b, b0 = nb.a, b1 = nb.b;
                 if (STATS) ++c_nodes;
                 float t0, t1;
                 const bool hit0 = slab_test(sl, a0, a1, P.tmin, best_t, t0);
@@ -255,6 +276,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
                 else cur = stack[--sp];
+                if (NODE_CAP > 0 && __popc(__activemask()) < NODE_CAP) break;   // do not idle the warp behind a few long node chains
             }
             if (cur < 0) {                                                       // leaf
                 const uint32_t first = leaf_first(cur), count = leaf_count(cur);

@@ -5,12 +5,13 @@ from build_up_phase_b200 import build as b
 
 VARIANTS = {
     "base": [],
-    "mb6": ["RT_TRACE_MIN_BLOCKS=6"],
-    "mb8": ["RT_TRACE_MIN_BLOCKS=8"],
-    "mb8_thr12": ["RT_TRACE_MIN_BLOCKS=8", "RT_REFILL_THRESHOLD=12"],
-    "mb8_thr26": ["RT_TRACE_MIN_BLOCKS=8", "RT_REFILL_THRESHOLD=26"],
     "thr12": ["RT_REFILL_THRESHOLD=12"],
-    "thr26": ["RT_REFILL_THRESHOLD=26"],
+    "thr16": ["RT_REFILL_THRESHOLD=16"],
+    "cap0": ["RT_NODE_CAP=0"],
+    "cap4": ["RT_NODE_CAP=4"],
+    "cap4_thr12": ["RT_NODE_CAP=4", "RT_REFILL_THRESHOLD=12"],
+    "cap8_thr12": ["RT_NODE_CAP=8", "RT_REFILL_THRESHOLD=12"],
+    "cap12_thr12": ["RT_NODE_CAP=12", "RT_REFILL_THRESHOLD=12"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
