@@ -34,7 +34,10 @@ BLOCK_ROWS = 8
 B_TRI_BUILD = 356.0          # algorithmic bytes per triangle of the LBVH build (SURVEY §8(d), 32-bit-key contract figure)
 
 
-def make_workload(name: str, width: int | None, height: int | None):
+SOUP_SIZES = {"soup100m": (100_000_000, 7680, 4320), "soup10m": (10_000_000, 3840, 2160), "soup1m": (1_000_000, 1920, 1080)}
+
+
+def make_workload(name: str, width: int | None, height: int | None, only_parts=None, soup_split: str = "slab"):
     if name == "inst10m":
         s = scenes.instanced_scene(32, 70, 3840, 2160, 1)
     elif name == "inst640k":                       # CPU-container-sized variant of the same generator
@@ -43,10 +46,9 @@ def make_workload(name: str, width: int | None, height: int | None):
         s = scenes.tess_scene(1000, 500, 3840, 2160, 1)
     elif name == "sample":
         s = scenes.sample_scene(1920, 1080)
-    elif name == "soup100m":
-        s = scenes.soup_scene(100_000_000, 7680, 4320, 0)
-    elif name == "soup10m":
-        s = scenes.soup_scene(10_000_000, 3840, 2160, 0)
+    elif name in SOUP_SIZES:
+        n, w, h = SOUP_SIZES[name]
+        s = scenes.soup_scene(n, w, h, 0, only_parts=only_parts, split=soup_split)
     else:
         raise SystemExit(f"unknown workload {name}")
     if width:
@@ -160,7 +162,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    scene = make_workload(args.workload, args.width, args.height)
+    scene = make_workload(args.workload, args.width, args.height, soup_split=args.soup_split)
     steps = args.steps if args.steps else 2
     warmup = args.warmup if args.warmup is not None else 1
     res = cpu_arm(scene, args.cpu_seconds, steps, warmup)
@@ -178,12 +180,13 @@ def run_reference(args):
 
 
 def workload_config(scene, args, n_gpus):
-    return {"workload": f"{args.workload}: {scene.name}, {scene.triangle_count} triangles in {len(scene.blases)} BLAS, "
+    n_tris = SOUP_SIZES[args.workload][0] if args.workload in SOUP_SIZES else scene.triangle_count
+    return {"workload": f"{args.workload}: {scene.name}, {n_tris} triangles in {len(scene.blases)} BLAS, "
                         f"{len(scene.instances)} instances, {scene.width}x{scene.height} primary + {scene.bounces} diffuse bounce",
-            "triangles": scene.triangle_count, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
+            "triangles": n_tris, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
             "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated",
             "l2_policy": "inputs larger than L2 (BVH nodes + triangles >> 126 MB); no flush between iterations"
-                         if scene.triangle_count * 112 > 2 * 126e6 else "scene fits in L2: numbers are L2-resident (parity config)"}
+                         if n_tris * 112 > 2 * 126e6 else "scene fits in L2: numbers are L2-resident (parity config)"}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,34 +211,106 @@ def run_gpu(args):
     if warmup < 3:
         warmup = 3
 
-    scene = make_workload(args.workload, args.width, args.height)
+    is_soup = args.workload in SOUP_SIZES
+    my_parts = [p for p in range(scenes.SOUP_PARTS) if p % world == rank] if is_soup else None
+    scene = make_workload(args.workload, args.width, args.height, only_parts=my_parts, soup_split=args.soup_split)
     W, H, bounces = scene.width, scene.height, scene.bounces
     ctx = rtcore.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
     # ---- scene upload (untimed) and acceleration-structure build (timed separately: Mtri/s) ----
-    dev_blases = []
-    keep = []
-    for geoms in scene.blases:
+    def upload(geoms):
         dg = []
         for g in geoms:
             v = torch.from_numpy(np.ascontiguousarray(g.vertices)).to(dev)
             i = torch.from_numpy(np.ascontiguousarray(g.indices).view(np.int32)).to(dev) if g.indices is not None else None
             t = torch.from_numpy(np.ascontiguousarray(g.transform)).to(dev) if g.transform is not None else None
-            keep += [v, i, t]
             dg.append(scenes.Geometry(v, i, t))
-        dev_blases.append(dg)
-    torch.cuda.synchronize()
-    build_ms = []
-    blases = None
-    for rep in range(args.build_reps + 1):
-        if blases is not None:
-            for b in blases:
-                b.free()
-        blases = ctx.build_blas_batch(dev_blases, device=True) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True)]
-        if rep > 0:
-            build_ms.append(ctx.build_timing())
-    bt = min(build_ms, key=lambda t: t["total_ms"])
+        return dg
+
+    n_tris_total = SOUP_SIZES[args.workload][0] if is_soup else scene.triangle_count
+    bcast_ms = 0.0
+    if not is_soup:
+        dev_blases = [upload(geoms) for geoms in scene.blases]
+        torch.cuda.synchronize()
+        build_ms = []
+        blases = None
+        for rep in range(args.build_reps + 1):
+            if blases is not None:
+                for b in blases:
+                    b.free()
+            blases = ctx.build_blas_batch(dev_blases, device=True) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True)]
+            if rep > 0:
+                build_ms.append(ctx.build_timing())
+        bt = min(build_ms, key=lambda t: t["total_ms"])
+        build_note = "one batched build of all BLASes on every GPU (scene replicated)"
+    else:
+        # cfg5: the soup is 8 index ranges = 8 BLASes; rank r builds parts p with p % N == r, then every BLAS
+        # blob is broadcast (NCCL over NVLink) from its builder and adopted by the other ranks.
+        own = {}
+        phase_keys = ("total_ms", "setup_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms")
+        bt = {k: 0.0 for k in phase_keys}
+        for p in my_parts:
+            dg = upload(scene.blases[p])
+            torch.cuda.synchronize()
+            best, b = None, None
+            for rep in range(args.build_reps + 1):
+                if b is not None:
+                    b.free()
+                b = ctx.build_blas(dg, device=True)
+                t = ctx.build_timing()
+                if rep > 0 or args.build_reps == 0:
+                    best = t if best is None or t["total_ms"] < best["total_ms"] else best
+            own[p] = b
+            for k in phase_keys:
+                bt[k] += best[k]
+            del dg
+        bt["primitives"] = n_tris_total
+        infos = {p: own[p].info() for p in my_parts}
+        blases = [None] * scenes.SOUP_PARTS
+        for p in my_parts:
+            blases[p] = own[p]
+        if world > 1:
+            tms = torch.tensor([bt[k] for k in phase_keys], dtype=torch.float64, device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)          # the slowest rank's build defines the build time
+            bt.update(dict(zip(phase_keys, [float(x) for x in tms.tolist()])))
+            meta = [None] * scenes.SOUP_PARTS
+            for p in range(scenes.SOUP_PARTS):
+                obj = [None]
+                if p in infos:
+                    i = infos[p]
+                    obj = [dict(triangle_count=i.triangle_count, node_count=i.node_count, root_ref=i.root_ref, max_depth=i.max_depth,
+                                lo=list(i.bounds_lo), hi=list(i.bounds_hi), storage_bytes=i.storage_bytes)]
+                dist.broadcast_object_list(obj, src=p % world)
+                meta[p] = obj[0]
+            bufs = {}
+            for p in range(scenes.SOUP_PARTS):
+                if p in own:
+                    bufs[p] = rtcore.device_view(infos[p].device_storage, int(infos[p].storage_bytes), dev)
+                else:
+                    bufs[p] = torch.empty(int(meta[p]["storage_bytes"]), dtype=torch.uint8, device=dev)
+            dist.barrier(); torch.cuda.synchronize()
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            b0.record()
+            for p in range(scenes.SOUP_PARTS):
+                dist.broadcast(bufs[p], src=p % world)
+            b1.record()
+            torch.cuda.synchronize()
+            bc = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
+            dist.all_reduce(bc, op=dist.ReduceOp.MAX)
+            bcast_ms = float(bc.item())
+            for p in range(scenes.SOUP_PARTS):
+                if p not in own:
+                    m = meta[p]
+                    info = rtcore.RtBlasInfo()
+                    info.triangle_count, info.node_count, info.root_ref, info.max_depth = m["triangle_count"], m["node_count"], m["root_ref"], m["max_depth"]
+                    for k in range(3):
+                        info.bounds_lo[k], info.bounds_hi[k] = m["lo"][k], m["hi"][k]
+                    info.storage_bytes = m["storage_bytes"]
+                    blases[p] = ctx.import_blas(info, bufs[p])
+            del bufs
+        build_note = (f"{scenes.SOUP_PARTS} BLASes of {n_tris_total // scenes.SOUP_PARTS} triangles, {len(my_parts)} built per GPU, "
+                      f"blobs broadcast with NCCL ({bcast_ms:.2f} ms); build time = slowest rank's builds + broadcast")
     tlas = ctx.build_tlas(scene.instances, blases)
     tlas_t = ctx.build_timing()
     ctx.set_hit_records(scene.hit_records)
@@ -342,8 +417,9 @@ def run_gpu(args):
         algo_bytes = b_ray_bytes(tot, W * H)
         # per launch on one GPU: this rank's share of the frame (1/world of the bytes) over its kernel time
         achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9
-        n_tris = scene.triangle_count
-        build_gbs = n_tris * B_TRI_BUILD / (bt["total_ms"] * 1e-3) / 1e9
+        n_tris = n_tris_total
+        build_total_ms = bt["total_ms"] + bcast_ms
+        build_gbs = n_tris * B_TRI_BUILD / (build_total_ms * 1e-3) / 1e9
         line = {
             "metric": "Mrays/s (primary+secondary rays per second)", "value": total_rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -362,8 +438,8 @@ def run_gpu(args):
                          "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
                                      "instances": tot["instances_entered"] / total_rays, "bytes": algo_bytes / total_rays}},
             "build": {"metric": "LBVH build Mtri/s (first setup kernel .. last refit kernel, CUDA events)",
-                      "value": n_tris / (bt["total_ms"] * 1e-3) / 1e6, "unit": "Mtri/s", "ms": bt["total_ms"], "phases_ms": bt,
-                      "tlas_ms": tlas_t["total_ms"],
+                      "value": n_tris / (build_total_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms": build_total_ms, "phases_ms": bt,
+                      "broadcast_ms": bcast_ms, "note": build_note, "tlas_ms": tlas_t["total_ms"],
                       "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
                                    "bytes_per_triangle": B_TRI_BUILD}},
             "traversal": tot,
@@ -407,6 +483,8 @@ def main():
     ap.add_argument("--build-reps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
+                    help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()
     # torchrun exports OMP_NUM_THREADS=1 to its children; the CPU legs (reference arm, cpu_baseline) are specified to use
     # all host threads, so undo that before the OpenMP runtime of the oracle library is loaded.

@@ -184,6 +184,19 @@ def _ptr(x) -> Optional[int]:
     raise TypeError(type(x))
 
 
+class _CudaPtr:
+    """Minimal __cuda_array_interface__ holder: lets torch alias raw device memory owned by librtcore."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(ptr: int, nbytes: int, device):
+    """uint8 torch tensor aliasing [ptr, ptr+nbytes) on `device` (no copy) — e.g. a BLAS blob handed to NCCL."""
+    import torch
+    return torch.as_tensor(_CudaPtr(ptr, nbytes), device=device)
+
+
 class Blas:
     def __init__(self, ctx: "Context", handle: int):
         self.ctx, self.handle = ctx, handle
@@ -322,6 +335,12 @@ class Context:
         out = (C.c_void_p * len(blases))()
         self._check(self.L.rt_build_blas_batch(self.h, arr, counts, len(blases), RT_BUILD_PREFER_FAST_TRACE, out))
         return [Blas(self, out[i]) for i in range(len(blases))]
+
+    def import_blas(self, info: RtBlasInfo, device_blob) -> Blas:
+        """rt_blas_import: adopt (copy) a relocatable BLAS blob that another GPU built and broadcast."""
+        h = C.c_void_p()
+        self._check(self.L.rt_blas_import(self.h, C.byref(info), _ptr(device_blob), C.byref(h)))
+        return Blas(self, h.value)
 
     @staticmethod
     def instance_array(instances, blas_handles: Sequence[Blas]):

@@ -234,26 +234,54 @@ def instanced_scene(n_side: int = 32, quads: int = 70, width: int = 3840, height
                  width=width, height=height, bounces=bounces)
 
 
-def soup_scene(n_tris: int = 100_000_000, width: int = 7680, height: int = 4320, bounces: int = 0, seed: int = 7,
-               edge: float = 0.01) -> Scene:
-    """cfg5 "soup100m": n independent triangles; centroid uniform in a [-10,10] x [-5.6,5.6] x [-6,2] slab in
-    front of the camera, two edge vectors uniform in [-edge, edge]^3; non-indexed (indices = None)."""
-    rng = np.random.default_rng(seed)
-    verts = np.empty((n_tris, 3, 3), dtype=np.float32)
+SOUP_PARTS = 8     # cfg5 is always cut into 8 contiguous index ranges = 8 BLASes, whatever the GPU count
+
+
+def soup_part(n_tris: int, part: int, parts: int = SOUP_PARTS, seed: int = 7, edge: float = 0.01, split: str = "slab") -> Geometry:
+    """Triangles [part*n/parts, (part+1)*n/parts) of the cfg5 soup as one non-indexed geometry. Every part has its own
+    generator stream, so a rank can generate just the parts it builds and the scene is identical for every GPU count.
+    split="slab": part p holds the triangles whose centroid lies in the p-th of `parts` equal x-slabs of the volume (a
+    spatially partitioned data set: the BLASes do not overlap, the overall density is still uniform). split="index":
+    every part is uniform over the whole volume (all BLASes overlap completely; every ray has to traverse all of them)."""
+    first, last = part * n_tris // parts, (part + 1) * n_tris // parts
+    n = last - first
+    rng = np.random.default_rng([seed, part])
+    verts = np.empty((n, 3, 3), dtype=np.float32)
     chunk = 4_000_000
     lo = np.array([-10.0, -5.6, -6.0], dtype=np.float32)
     hi = np.array([10.0, 5.6, 2.0], dtype=np.float32)
-    for s in range(0, n_tris, chunk):
-        e = min(n_tris, s + chunk)
+    if split == "slab":
+        w = (hi[0] - lo[0]) / np.float32(parts)
+        lo, hi = lo.copy(), hi.copy()
+        lo[0], hi[0] = lo[0] + np.float32(part) * w, lo[0] + np.float32(part + 1) * w
+    elif split != "index":
+        raise ValueError(split)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk)
         c = rng.random((e - s, 3), dtype=np.float32) * (hi - lo) + lo
         e1 = (rng.random((e - s, 3), dtype=np.float32) * np.float32(2) - np.float32(1)) * np.float32(edge)
         e2 = (rng.random((e - s, 3), dtype=np.float32) * np.float32(2) - np.float32(1)) * np.float32(edge)
         verts[s:e, 0] = c
         verts[s:e, 1] = c + e1
         verts[s:e, 2] = c + e2
-    geo = Geometry(verts.reshape(-1, 3), None, None)
-    inst = Instance(IDENTITY_3X4.copy(), 5, 0xFF, 0, INSTANCE_TRIANGLE_FACING_CULL_DISABLE, 0)
-    return Scene(f"soup{n_tris}", [[geo]], [inst], SAMPLE_HIT_RECORDS[3:4].copy(), width=width, height=height, bounces=bounces)
+    return Geometry(verts.reshape(-1, 3), None, None)
+
+
+def soup_scene(n_tris: int = 100_000_000, width: int = 7680, height: int = 4320, bounces: int = 0, seed: int = 7,
+               edge: float = 0.01, parts: int = SOUP_PARTS, only_parts=None, split: str = "slab") -> Scene:
+    """cfg5 "soup100m": n independent triangles; centroid uniform in a [-10,10] x [-5.6,5.6] x [-6,2] slab in
+    front of the camera, two edge vectors uniform in [-edge, edge]^3; non-indexed (indices = None). The soup is
+    cut into `parts` contiguous index ranges, one BLAS each (per-GPU BLAS builds), instanced with
+    the identity. only_parts: generate just these parts (the others get an empty placeholder geometry)."""
+    blases, instances = [], []
+    for p in range(parts):
+        if only_parts is None or p in only_parts:
+            geo = soup_part(n_tris, p, parts, seed, edge, split)
+        else:
+            geo = Geometry(np.zeros((0, 3), dtype=np.float32), None, None)
+        blases.append([geo])
+        instances.append(Instance(IDENTITY_3X4.copy(), 5, 0xFF, 0, INSTANCE_TRIANGLE_FACING_CULL_DISABLE, p))
+    return Scene(f"soup{n_tris}-{split}", blases, instances, SAMPLE_HIT_RECORDS[3:4].copy(), width=width, height=height, bounces=bounces)
 
 
 def random_scene(n_blas: int, tris_per_blas: int, n_instances: int, seed: int, width: int = 256, height: int = 160,
