@@ -5,13 +5,11 @@ from build_up_phase_b200 import build as b
 
 VARIANTS = {
     "base": [],
-    "thr12": ["RT_REFILL_THRESHOLD=12"],
-    "thr16": ["RT_REFILL_THRESHOLD=16"],
-    "cap0": ["RT_NODE_CAP=0"],
-    "cap4": ["RT_NODE_CAP=4"],
-    "cap4_thr12": ["RT_NODE_CAP=4", "RT_REFILL_THRESHOLD=12"],
-    "cap8_thr12": ["RT_NODE_CAP=8", "RT_REFILL_THRESHOLD=12"],
-    "cap12_thr12": ["RT_NODE_CAP=12", "RT_REFILL_THRESHOLD=12"],
+    "mb6": ["RT_TRACE_MIN_BLOCKS=6"],
+    "mb5": ["RT_TRACE_MIN_BLOCKS=5"],
+    "thr8": ["RT_REFILL_THRESHOLD=8"],
+    "thr20": ["RT_REFILL_THRESHOLD=20"],
+    "thr26": ["RT_REFILL_THRESHOLD=26"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
