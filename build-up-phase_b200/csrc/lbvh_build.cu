@@ -391,8 +391,7 @@ __global__ void __launch_bounds__(128) k_widen(const WidenParams<Prim> P) {
                 const uint32_t base = end + atomicAdd(next_count, (uint32_t)em.n_internal);
                 if (base + (uint32_t)em.n_internal > P.wnode_cap || level + 1 >= (uint32_t)WIDEN_MAX_LEVELS) {
                     atomicExch(overflow, 1u);                            // host retries with a larger node pool
-                    node.imask = 0;
-                    for (int s = 0; s < WIDE; ++s) if ((node.meta[s] & 0x1Fu) >= 24u) node.meta[s] = 0;
+                    node.imask = 0;                                     // the dropped slots own no prim_valid bits: never visited
                 } else {
                     node.child_base = base;
                     for (int k = 0; k < em.n_internal; ++k) { P.w.src[base + k] = em.internal_ref[k]; P.w.seg[base + k] = seg; }

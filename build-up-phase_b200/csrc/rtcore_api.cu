@@ -680,8 +680,8 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
                                    : (uint64_t)tlas->max_sbt + (uint64_t)tlas->max_geo * ctx->rp.sbt_record_stride + ctx->rp.sbt_record_offset;
         if (bound >= ctx->n_records) return fail(ctx, RT_ERROR_SBT_RANGE, "hit record %llu addressed but only %u set", (unsigned long long)bound, ctx->n_records);
     }
-    // one group entry per wide level (siblings still to visit) + the three entries an instance transition pushes
-    const int stack_needed = (int)tlas->height + tlas->max_blas_height + 6;
+    // per wide level: one node group (siblings still to visit) + one deferred primitive group; + the three entries an instance transition pushes
+    const int stack_needed = 2 * ((int)tlas->height + tlas->max_blas_height) + 6;
     if (stack_needed > 160) return fail(ctx, RT_ERROR_STACK_DEPTH, "BVH depth %d exceeds the traversal stack", stack_needed);
 
     // one part = the plain width x height image; several parts = equal-sized packed band buffers

@@ -41,6 +41,10 @@ namespace {
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
 constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
+#ifndef RT_PRIM_MIN
+#define RT_PRIM_MIN 8
+#endif
+constexpr int PRIM_MIN = RT_PRIM_MIN;                     // run the primitive step once this many lanes have primitives pending
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
 
 struct Woop {
@@ -125,9 +129,17 @@ __device__ __forceinline__ rt_hit miss_record(float tmax) {
 
 constexpr uint32_t GROUP_PRIM_BITS = 0x00FFFFFFu;     // y <= this: the group holds primitive bits only
 
+// Per-ray state that is touched only at instance transitions, triangle tests and in the epilogue lives in shared
+// memory ([field][thread]: conflict-free), not in registers: the node step then fits 64 registers without spilling
+// and 8 CTAs stay resident per SM. 20 words x 128 threads = 10 KB per CTA.
+enum ColdField { C_OX, C_OY, C_OZ, C_DX, C_DY, C_DZ, C_WOKX, C_WOKY, C_WOKZ, C_WSX, C_WSY, C_WSZ, C_WKZ, C_BU, C_BV, C_BW0,
+                 C_COL0, C_COL1, C_COL2, C_PIXEL, COLD_WORDS };
+
 // STAGE 0: primary rays generated from pixel ids. STAGE 1: secondary rays read from the bounce queue.
 template <int STAGE, bool STATS, int STACK>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
+    __shared__ float s_cold[COLD_WORDS][TRACE_THREADS];
+#define COLD(k) s_cold[k][threadIdx.x]
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tiles_x = (P.width + 7u) >> 3;
@@ -141,21 +153,18 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     bool have_ray = false, exhausted = false;
     bool in_buffer = false, valid = false;
     bool traversing = false;             // the ray still has groups to visit
-    uint32_t lidx = 0, pixel = 0;
-    V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
-    float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
+    uint32_t lidx = 0;
     // node group: x = index of the first internal child, y = hit bits 31..24 | imask 7..0   (y > GROUP_PRIM_BITS)
-    // prim group: x = index of the first primitive,      y = hit bits 23..0
+    // prim group: x = index of the wide node,            y = hit bits 23..0 (subset of the node's prim_valid)
     uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
     int sp = 0;
     bool in_blas = false;
     const WNode* nodes = P.tlas_nodes;
     const TriRec* tris = nullptr;
-    RayBox rb; Woop wp;
+    RayBox rb;
     rb.idx = rb.idy = rb.idz = rb.cnx = rb.cny = rb.cnz = rb.cfx = rb.cfy = rb.cfz = 0.0f; rb.oct = 0u;
-    wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
     uint32_t cur_slot = 0;
-    float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
+    float best_t = P.tmax;
     uint32_t best_slot = NO_HIT, best_tri = 0;
     uint2 stack[STACK];
 
@@ -172,6 +181,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 if (idx >= total) exhausted = true;
                 else {
                     have_ray = true;
+                    V3 o, d;
                     if (STAGE == 0) {
                         const uint32_t tile = idx >> 5, within = idx & 31u;
                         const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
@@ -181,7 +191,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         in_buffer = x < P.width && lr < P.local_rows;
                         valid = in_buffer && y < P.height;
                         lidx = lr * P.width + x;
-                        pixel = y * P.width + x;
+                        COLD(C_PIXEL) = __uint_as_float(y * P.width + x);
                         // ---- raygen (main.cpp:1033-1046); aspect_x/aspect_y computed once on the host (tanf) ----
                         const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
                         const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
@@ -195,11 +205,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         lidx = __float_as_uint(q0.x);
                         o = {q0.y, q0.z, q0.w};
                         d = {q1.x, q1.y, q1.z};
-                        col0 = q1.w; col1 = q2.x; col2 = q2.y;
+                        COLD(C_COL0) = q1.w; COLD(C_COL1) = q2.x; COLD(C_COL2) = q2.y;
                         in_buffer = valid = true;
                     }
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
-                    best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
+                    COLD(C_OX) = o.x; COLD(C_OY) = o.y; COLD(C_OZ) = o.z; COLD(C_DX) = d.x; COLD(C_DY) = d.y; COLD(C_DZ) = d.z;
+                    best_t = P.tmax; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
                     in_blas = false;
                     nodes = P.tlas_nodes;
@@ -215,9 +226,80 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         const bool warp_exhausted = __ballot_sync(0xffffffffu, exhausted) != 0u;
 
         // ================= two-level traversal over node groups =================
-        while (traversing) {
-            // ---------- one wide node: the highest-priority hit child of the current node group ----------
-            if (ng.y > GROUP_PRIM_BITS) {
+        // Warp-uniform loop. A lane with a ray either has primitives pending (tg), or children pending (ng), or
+        // has to pop its stack. Every iteration the warp runs ONE of the two heavy steps for all lanes that want it:
+        // the primitive step (one triangle test or one instance entry per lane) once at least PRIM_MIN lanes have
+        // primitives pending or nobody has node work, else the node step; lanes waiting for the other step idle.
+        // This keeps the expensive rare paths (exact triangle test, instance transform with IEEE divisions) from
+        // running with two or three lanes after every node step.
+        for (;;) {
+            const unsigned m_act = __ballot_sync(0xffffffffu, traversing);
+            if (m_act == 0u || (!warp_exhausted && __popc(m_act) < REFILL_THRESHOLD)) break;
+            const bool want_p = traversing && tg.y != 0u;
+            const bool want_n = traversing && !want_p && ng.y > GROUP_PRIM_BITS;
+            const int n_p = __popc(__ballot_sync(0xffffffffu, want_p));
+            const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));
+            if (n_p >= PRIM_MIN || n_n == 0) {
+                // ---------- one primitive of the hit leaf slots ----------
+                if (want_p) {
+                    // primitive index = prim_base + rank of the bit inside the node's prim_valid (word 1 of the node, L1-hot)
+                    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(nodes + tg.x) + 1);      // child_base prim_base prim_valid spare
+                    const uint32_t bit = 31u - (uint32_t)__clz((int)tg.y);
+                    tg.y &= ~(1u << bit);
+                    const uint32_t pidx = w1.y + (uint32_t)__popc(w1.z & ~(0xFFFFFFFFu << bit));
+                    if (in_blas) {
+                        const float4* t4 = reinterpret_cast<const float4*>(tris + pidx);
+                        const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
+                        if (STATS) ++c_tris;
+                        float t, bu, bv, bw0;
+                        Woop wp;
+                        wp.okx = COLD(C_WOKX); wp.oky = COLD(C_WOKY); wp.okz = COLD(C_WOKZ);
+                        wp.Sx = COLD(C_WSX); wp.Sy = COLD(C_WSY); wp.Sz = COLD(C_WSZ);
+                        { const uint32_t kz = __float_as_uint(COLD(C_WKZ)); wp.z0 = kz == 0u; wp.z1 = kz == 1u; }
+                        if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
+                            bool better = t < best_t;
+                            if (t == best_t && best_slot != NO_HIT) {
+                                // equal t: lowest (instance, geometry, primitive) wins; rare, so the ids of the
+                                // current best are re-read from memory instead of living in registers
+                                const InstanceRec* Rb = P.instances + best_slot;
+                                const uint32_t bi = __ldg(&Rb->instance_id), ci = __ldg(&(P.instances + cur_slot)->instance_id);
+                                const TriRec* bt = Rb->tris + best_tri;
+                                const uint32_t bg = __ldg(&bt->geo), bp = __ldg(&bt->prim);
+                                const uint32_t geo = __float_as_uint(q2.y), prim = __float_as_uint(q2.z);
+                                better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
+                            }
+                            if (better) { best_t = t; COLD(C_BU) = bu; COLD(C_BV) = bv; if (STATS) COLD(C_BW0) = bw0; best_slot = cur_slot; best_tri = pidx; }
+                        }
+                    } else {
+                        // TLAS primitive = one instance: cull mask (main.cpp:851,1048), then enter its BLAS in object space
+                        const InstanceRec* R = P.instances + pidx;
+                        const uint32_t cm = __ldg(&R->custom_mask);
+                        const int32_t root = __ldg(&R->root);
+                        if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
+                            if (STATS) ++c_insts;
+                            if (tg.y) stack[sp++] = tg;                                  // other instances of this TLAS node
+                            if (ng.y > GROUP_PRIM_BITS) stack[sp++] = ng;                // pending TLAS children
+                            stack[sp++] = make_uint2(0u, 0u);                            // sentinel: back to world space
+                            float w2o[12];
+                            load_w2o(R, w2o);
+                            const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
+                            const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
+                            raybox_setup(rb, &oo.x, &od.x, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
+                            Woop wp;
+                            woop_setup(wp, oo, od);
+                            COLD(C_WOKX) = wp.okx; COLD(C_WOKY) = wp.oky; COLD(C_WOKZ) = wp.okz;
+                            COLD(C_WSX) = wp.Sx; COLD(C_WSY) = wp.Sy; COLD(C_WSZ) = wp.Sz;
+                            COLD(C_WKZ) = __uint_as_float(wp.z0 ? 0u : (wp.z1 ? 1u : 2u));
+                            nodes = R->nodes; tris = R->tris;
+                            cur_slot = pidx;
+                            in_blas = true;
+                            ng = make_uint2((uint32_t)root, 0x80000000u);
+                            tg = make_uint2(0u, 0u);
+                        }
+                    }
+                }
+            } else if (want_n) {
+                // ---------- one wide node: the highest-priority hit child of the current node group ----------
                 const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
                 const uint32_t imask = ng.y & 0xFFu;
                 ng.y &= ~(1u << bit);
@@ -227,74 +309,26 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 const uint4* n4 = reinterpret_cast<const uint4*>(nodes + child);
                 const uint4 n0 = __ldg(n4), n1 = __ldg(n4 + 1), n2 = __ldg(n4 + 2), n3 = __ldg(n4 + 3), n4w = __ldg(n4 + 4);
                 if (STATS) ++c_nodes;
-                const uint32_t hits = wide_node_hits(rb, n0, n1, n2, n3, n4w, P.tmin, best_t);
-                ng = make_uint2(n1.x, (hits & 0xFF000000u) | (n0.w >> 24));
-                tg = make_uint2(n1.y, hits & GROUP_PRIM_BITS);
-            }
-            // ---------- primitives of the hit leaf slots ----------
-            while (tg.y) {
-                const uint32_t bit = 31u - (uint32_t)__clz((int)tg.y);
-                tg.y &= ~(1u << bit);
-                if (in_blas) {
-                    const uint32_t ti = tg.x + bit;
-                    const float4* t4 = reinterpret_cast<const float4*>(tris + ti);
-                    const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
-                    if (STATS) ++c_tris;
-                    float t, bu, bv, bw0;
-                    if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
-                        bool better = t < best_t;
-                        if (t == best_t && best_slot != NO_HIT) {
-                            // equal t: lowest (instance, geometry, primitive) wins; rare, so the ids of the
-                            // current best are re-read from memory instead of living in registers
-                            const InstanceRec* Rb = P.instances + best_slot;
-                            const uint32_t bi = __ldg(&Rb->instance_id), ci = __ldg(&(P.instances + cur_slot)->instance_id);
-                            const TriRec* bt = Rb->tris + best_tri;
-                            const uint32_t bg = __ldg(&bt->geo), bp = __ldg(&bt->prim);
-                            const uint32_t geo = __float_as_uint(q2.y), prim = __float_as_uint(q2.z);
-                            better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
-                        }
-                        if (better) { best_t = t; best_u = bu; best_v = bv; if (STATS) best_w0 = bw0; best_slot = cur_slot; best_tri = ti; }
-                    }
-                } else {
-                    // TLAS primitive = one instance: cull mask (main.cpp:851,1048), then enter its BLAS in object space
-                    const uint32_t ii = tg.x + bit;
-                    const InstanceRec* R = P.instances + ii;
-                    const uint32_t cm = __ldg(&R->custom_mask);
-                    const int32_t root = __ldg(&R->root);
-                    if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
-                        if (STATS) ++c_insts;
-                        if (tg.y) stack[sp++] = tg;                                  // other instances of this TLAS node
-                        if (ng.y > GROUP_PRIM_BITS) stack[sp++] = ng;                // pending TLAS children
-                        stack[sp++] = make_uint2(0u, 0u);                            // sentinel: back to world space
-                        float w2o[12];
-                        load_w2o(R, w2o);
-                        const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
-                        raybox_setup(rb, &oo.x, &od.x, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
-                        woop_setup(wp, oo, od);
-                        nodes = R->nodes; tris = R->tris;
-                        cur_slot = ii;
-                        in_blas = true;
-                        ng = make_uint2((uint32_t)root, 0x80000000u);
-                        tg = make_uint2(0u, 0u);
-                    }
-                }
+                uint32_t inner, prims;
+                wide_node_hits(rb, n0, n1, n2, n3, n4w, P.tmin, best_t, inner, prims);
+                ng = make_uint2(n1.x, inner | (n0.w >> 24));
+                tg = make_uint2(child, prims);
             }
             // ---------- nothing pending in the current groups: pop ----------
-            if (ng.y <= GROUP_PRIM_BITS) {
+            if (traversing && tg.y == 0u && ng.y <= GROUP_PRIM_BITS) {
                 if (sp == 0) traversing = false;
                 else {
                     const uint2 e = stack[--sp];
                     if (e.y == 0u) {                                                 // sentinel: leave the instance
                         in_blas = false;
                         nodes = P.tlas_nodes;
+                        const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
                         raybox_setup(rb, &o.x, &d.x, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
                         ng = make_uint2(0u, 0u);
                     } else if (e.y > GROUP_PRIM_BITS) ng = e;
                     else { tg = e; ng = make_uint2(0u, 0u); }
                 }
             }
-            // warp-level compaction trigger: too few lanes still traversing -> go refill the idle ones
-            if (!warp_exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
         }
 
         // ================= epilogue of the lanes whose ray just finished =================
@@ -312,6 +346,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             } else {
                 if (STATS) ++c_rays;
                 const bool hit = best_slot != NO_HIT;
+                const float best_u = hit ? COLD(C_BU) : 0.0f, best_v = hit ? COLD(C_BV) : 0.0f;
                 const InstanceRec* R = P.instances + (hit ? best_slot : 0u);
                 float sc0, sc1, sc2;
                 rt_hit rec = miss_record(P.tmax);
@@ -331,7 +366,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     }
                     rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
                     rec.t = best_t; rec.u = best_u; rec.v = best_v;
-                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c_edge; }
+                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), COLD(C_BW0)) < 9.5367431640625e-07f) ++c_edge; }
                 } else {
                     sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];                 // miss shader (main.cpp:1063-1066)
                 }
@@ -339,6 +374,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     if (P.primary_hits) P.primary_hits[lidx] = rec;
                     if (hit && P.bounces > 0u) {
                         // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
+                        const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
+                        const uint32_t pixel = __float_as_uint(COLD(C_PIXEL));
                         const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
                         float w2o[12];
                         load_w2o(R, w2o);
@@ -373,7 +410,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     }
                 } else {
                     if (P.secondary_hits) P.secondary_hits[lidx] = rec;
-                    const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
+                    const float f0 = 0.5f * COLD(C_COL0) + 0.5f * sc0, f1 = 0.5f * COLD(C_COL1) + 0.5f * sc1, f2 = 0.5f * COLD(C_COL2) + 0.5f * sc2;
                     reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
                 }
             }
@@ -394,6 +431,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         }
     }
 
+#undef COLD
     if (STATS && P.stats) {
         // rt_trace_stats order: rays_primary, rays_secondary, nodes, tris, insts, primary_hits, secondary_hits, near_edge
         unsigned long long v[8] = {STAGE == 0 ? c_rays : 0ull, STAGE == 1 ? c_rays : 0ull, c_nodes, c_tris, c_insts,

@@ -10,15 +10,15 @@
 // Layout (80 B, five 16-byte words; same idea as Ylitie/Karras/Laine 2017, own implementation):
 //   w0  px py pz | ex ey ez imask      origin of the node's quantisation grid; biased fp32 exponents of the
 //                                      grid steps (step_k = 2^(e_k-127)); bit s of imask = slot s is internal
-//   w1  child_base prim_base meta[8]   internal children are consecutive wide nodes child_base + rank(slot);
-//                                      leaf slots reference primitives prim_base + offset .. + count-1
+//   w1  child_base prim_base           internal children are consecutive wide nodes child_base + rank(slot among internal);
+//       prim_valid spare               leaf slot s owns bits 3s..3s+2 of prim_valid, one bit per primitive it holds (1..3);
+//                                      the primitives of a node are consecutive: index = prim_base + rank(bit in prim_valid)
 //   w2  qlo.x[8] qlo.y[8]              child boxes: lo = p + qlo*step (rounded down), hi = p + qhi*step (rounded up)
 //   w3  qlo.z[8] qhi.x[8]
 //   w4  qhi.y[8] qhi.z[8]
-// meta[s]: 0 = empty slot; internal = 0b001_11sss (low 5 bits 24+s); leaf = unary(count)<<5 | offset with
-// count 1..3 -> 0b001/0b011/0b111 and offset < 24. Slots are assigned so that slot bit 2/1/0 set means the
-// child lies towards +x/+y/+z of the node centre: visiting hit slots in descending (slot XOR octant) order
-// is then approximately front to back for every ray octant, without sorting distances.
+// Slots are assigned so that slot bit 2/1/0 set means the child lies towards +x/+y/+z of the node centre:
+// visiting hit slots in descending (slot XOR octant) order is then approximately front to back for every ray
+// octant, without sorting distances. Empty slots carry an inverted box (qlo 255, qhi 0) and no prim_valid bits.
 //
 // This header is also compiled as plain C++ by tests/wide_host.cpp (host emulation of the collapse and of
 // the node test) so that the logic is checked on CPU against brute force without a GPU.
@@ -39,13 +39,13 @@ struct alignas(16) WNode {
     float px, py, pz;
     uint8_t ex, ey, ez, imask;
     uint32_t child_base, prim_base;
-    uint8_t meta[8];
+    uint32_t prim_valid, spare;
     uint8_t qlox[8], qloy[8], qloz[8], qhix[8], qhiy[8], qhiz[8];
 };
 static_assert(sizeof(WNode) == 80, "WNode must be 80 B");
 
 constexpr int WIDE = 8;
-constexpr int WIDE_TRI_LEAF_MAX = 3;     // unary count in 3 meta bits; 8 slots x 3 = 24 primitive bits of the hit mask
+constexpr int WIDE_TRI_LEAF_MAX = 3;     // 8 slots x 3 = the 24 primitive bits of a hit mask
 constexpr uint32_t WNODE_NONE = 0xFFFFFFFFu;
 
 // Binary node half as produced by the refit: {lo.xyz, hi.xyz, ref, height}; refs: >= 0 internal (segment
@@ -151,14 +151,13 @@ RT_HD void widen_one(int32_t src, const float* src_lo, const float* src_hi, Fetc
     const uint32_t E[3] = {wide_step_exponent(hi[0] - lo[0]), wide_step_exponent(hi[1] - lo[1]), wide_step_exponent(hi[2] - lo[2])};
     out.px = lo[0]; out.py = lo[1]; out.pz = lo[2];
     out.ex = (uint8_t)E[0]; out.ey = (uint8_t)E[1]; out.ez = (uint8_t)E[2];
-    out.imask = 0; out.child_base = 0; out.prim_base = 0;
+    out.imask = 0; out.child_base = 0; out.prim_base = 0; out.prim_valid = 0; out.spare = 0;
     em.n_internal = 0; em.n_leaf = 0; em.n_prims = 0;
     uint8_t* qlo[3] = {out.qlox, out.qloy, out.qloz};
     uint8_t* qhi[3] = {out.qhix, out.qhiy, out.qhiz};
     for (int s = 0; s < WIDE; ++s) {
         const int i = child_in[s];
         if (i < 0 || !valid[i]) {                    // empty slot, or a subtree without any active primitive
-            out.meta[s] = 0;
             for (int k = 0; k < 3; ++k) { qlo[k][s] = 255; qhi[k][s] = 0; }
             continue;
         }
@@ -174,13 +173,11 @@ RT_HD void widen_one(int32_t src, const float* src_lo, const float* src_hi, Fetc
         }
         if (ch[i].ref >= 0) {
             out.imask |= (uint8_t)(1u << s);
-            out.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
             em.internal_ref[em.n_internal++] = ch[i].ref;
         } else {
             const uint32_t u = (uint32_t)~ch[i].ref;
             const uint32_t first = u >> 3, count = (u & 7u) + 1u;             // count <= 3 by construction of the binary tree
-            const uint32_t unary = (1u << count) - 1u;
-            out.meta[s] = (uint8_t)((unary << 5) | em.n_prims);
+            out.prim_valid |= ((1u << count) - 1u) << (3 * s);
             em.leaf_first[em.n_leaf] = first; em.leaf_count[em.n_leaf] = count; ++em.n_leaf;
             em.n_prims += count;
         }
@@ -196,6 +193,7 @@ RT_HD uint32_t rt_prmt(uint32_t a, uint32_t b, uint32_t s) { return __byte_perm(
 RT_HD float rt_fma_rn(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 RT_HD float rt_fma_rd(float a, float b, float c) { return __fmaf_rd(a, b, c); }
 RT_HD float rt_fma_ru(float a, float b, float c) { return __fmaf_ru(a, b, c); }
+RT_HD float rt_rcp(float x) { float r; asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 #else
 #ifdef __CUDACC__
 typedef uint4 WWord;
@@ -213,6 +211,7 @@ inline uint32_t rt_prmt(uint32_t a, uint32_t b, uint32_t s) {
     }
     return r;
 }
+inline float rt_rcp(float x) { return 1.0f / x; }
 inline float rt_fma_rn(float a, float b, float c) { return (float)fma((double)a, (double)b, (double)c); }   // double-rounding is irrelevant for the emulation
 inline float rt_fma_rd(float a, float b, float c) { const double e = fma((double)a, (double)b, (double)c); float f = (float)e; return (double)f > e ? nextafterf(f, -INFINITY) : f; }
 inline float rt_fma_ru(float a, float b, float c) { const double e = fma((double)a, (double)b, (double)c); float f = (float)e; return (double)f < e ? nextafterf(f, INFINITY) : f; }
@@ -234,7 +233,9 @@ RT_HD void raybox_setup(RayBox& s, const float* o, const float* d, float ax, flo
     const float dz = fabsf(d[2]) < 1e-20f ? copysignf(1e-20f, d[2]) : d[2];
     const bool px = dx > 0.0f, py = dy > 0.0f, pz = dz > 0.0f;
     s.oct = (px ? 4u : 0u) | (py ? 2u : 0u) | (pz ? 1u : 0u);
-    s.idx = 1.0f / dx; s.idy = 1.0f / dy; s.idz = 1.0f / dz;
+    // the box test only has to be conservative: a 1-ulp-class reciprocal (MUFU.RCP, rel. error 2^-22) is covered 4x by the
+    // 2^-19 pad (|plane - o| <= 2M, so the induced error in t is below M*|id|*2^-21), and saves three IEEE divisions
+    s.idx = rt_rcp(dx); s.idy = rt_rcp(dy); s.idz = rt_rcp(dz);
     s.cnx = -((px ? o[0] + e : o[0] - e) * s.idx); s.cfx = -((px ? o[0] - e : o[0] + e) * s.idx);
     s.cny = -((py ? o[1] + e : o[1] - e) * s.idy); s.cfy = -((py ? o[1] - e : o[1] + e) * s.idy);
     s.cnz = -((pz ? o[2] + e : o[2] - e) * s.idz); s.cfz = -((pz ? o[2] - e : o[2] + e) * s.idz);
@@ -244,10 +245,10 @@ RT_HD void raybox_setup(RayBox& s, const float* o, const float* d, float ax, flo
 template <int K>
 RT_HD float q2f(uint32_t word) { return rt_u2f(rt_prmt(word, 0x47000000u, 0x7404u | (K << 4))); }
 
-// Tests the 8 children of one wide node. Returns the hit mask: bits 31..24 = internal children, bit 24 + (slot ^ oct)
-// (highest bit = nearest in octant order); bits 23..0 = primitives of the hit leaf slots (prim_base + bit).
-RT_HD uint32_t wide_node_hits(const RayBox& rb, const WWord n0, const WWord n1, const WWord n2, const WWord n3,
-                                  const WWord n4, float tmin, float tbest) {
+// Tests the 8 children of one wide node. inner: bits 31..24, bit 24 + (slot ^ oct) set for every hit internal slot
+// (highest bit = nearest in octant order). prims: the prim_valid bits of the hit leaf slots.
+RT_HD void wide_node_hits(const RayBox& rb, const WWord n0, const WWord n1, const WWord n2, const WWord n3, const WWord n4,
+                          float tmin, float tbest, uint32_t& inner, uint32_t& prims) {
     const uint32_t ew = n0.w;
     const float ax = rt_u2f((ew & 0xFFu) << 23) * rb.idx;
     const float ay = rt_u2f(((ew >> 8) & 0xFFu) << 23) * rb.idy;
@@ -259,9 +260,8 @@ RT_HD uint32_t wide_node_hits(const RayBox& rb, const WWord n0, const WWord n1, 
     const float bny = rt_fma_rd(-32768.0f, ay, rt_fma_rn(py, rb.idy, rb.cny)), bfy = rt_fma_ru(-32768.0f, ay, rt_fma_rn(py, rb.idy, rb.cfy));
     const float bnz = rt_fma_rd(-32768.0f, az, rt_fma_rn(pz, rb.idz, rb.cnz)), bfz = rt_fma_ru(-32768.0f, az, rt_fma_rn(pz, rb.idz, rb.cfz));
     const bool dpx = (rb.oct & 4u) != 0u, dpy = (rb.oct & 2u) != 0u, dpz = (rb.oct & 1u) != 0u;
-    // n2 = {qlo[0][0..3], qlo[0][4..7], qlo[1][0..3], qlo[1][4..7]}  n3 = {qlo[2].., qlo[2].., qhi.x.., qhi.x..}  n4 = {qhi.y.., qhi.y.., qhi.z.., qhi.z..}
-    const uint32_t oct4 = rb.oct * 0x01010101u;
-    uint32_t hits = 0;
+    // n2 = {qlo.x[0..3], qlo.x[4..7], qlo.y[0..3], qlo.y[4..7]}  n3 = {qlo.z.., qlo.z.., qhi.x.., qhi.x..}  n4 = {qhi.y.., qhi.y.., qhi.z.., qhi.z..}
+    uint32_t hit8 = 0;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         const uint32_t lox = h ? n2.y : n2.x, loy = h ? n2.w : n2.z, loz = h ? n3.y : n3.x;
@@ -269,11 +269,6 @@ RT_HD uint32_t wide_node_hits(const RayBox& rb, const WWord n0, const WWord n1, 
         const uint32_t nx = dpx ? lox : hix, fx = dpx ? hix : lox;
         const uint32_t ny = dpy ? loy : hiy, fy = dpy ? hiy : loy;
         const uint32_t nz = dpz ? loz : hiz, fz = dpz ? hiz : loz;
-        const uint32_t meta4 = h ? n1.w : n1.z;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = (is_inner4 >> 4) * 7u;                          // 0x07 in the bytes of internal slots (oct < 8)
-        const uint32_t bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1F1F1F1Fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
 #define RT_WIDE_CHILD(J)                                                                                        \
         {                                                                                                       \
             const float tnx = rt_fma_rn(q2f<J>(nx), ax, bnx), tfx = rt_fma_rn(q2f<J>(fx), ax, bfx);             \
@@ -281,13 +276,24 @@ RT_HD uint32_t wide_node_hits(const RayBox& rb, const WWord n0, const WWord n1, 
             const float tnz = rt_fma_rn(q2f<J>(nz), az, bnz), tfz = rt_fma_rn(q2f<J>(fz), az, bfz);             \
             const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                          \
             const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));                                         \
-            const uint32_t bits = rt_prmt(child_bits4, 0u, 0x4440u | J) << (rt_prmt(bit_index4, 0u, 0x4440u | J));   \
-            if (tn <= tf) hits |= bits;                                                                         \
+            if (tn <= tf) hit8 |= 1u << (4 * h + J);                                                            \
         }
         RT_WIDE_CHILD(0) RT_WIDE_CHILD(1) RT_WIDE_CHILD(2) RT_WIDE_CHILD(3)
 #undef RT_WIDE_CHILD
     }
-    return hits;
+    const uint32_t imask = ew >> 24;
+    // internal slots: move bit s to bit s ^ oct (three conditional swaps), then up to bits 31..24
+    uint32_t ih = hit8 & imask;
+    { const uint32_t t = ((ih & 0x55u) << 1) | ((ih >> 1) & 0x55u); ih = (rb.oct & 1u) ? t : ih; }
+    { const uint32_t t = ((ih & 0x33u) << 2) | ((ih >> 2) & 0x33u); ih = (rb.oct & 2u) ? t : ih; }
+    { const uint32_t t = ((ih & 0x0Fu) << 4) | ((ih >> 4) & 0x0Fu); ih = (rb.oct & 4u) ? t : ih; }
+    inner = ih << 24;
+    // leaf slots: spread bit s to bit 3s, widen to the slot's three primitive bits, keep the primitives that exist
+    uint32_t x = hit8 & ~imask;
+    x = (x | (x << 8)) & 0x00F00Fu;
+    x = (x | (x << 4)) & 0x0C30C3u;
+    x = (x | (x << 2)) & 0x249249u;
+    prims = (x * 7u) & n1.z;
 }
 
 }  // namespace rt

@@ -81,9 +81,17 @@ def walk_compare_bvh(nodes_a, root_a, nodes_b, root_b):
     return count
 
 
+def _popcount24(v):
+    v = v.astype(np.int64)
+    c = np.zeros(v.shape, dtype=np.int64)
+    for b in range(24):
+        c += (v >> b) & 1
+    return c
+
+
 def check_wide_bvh(wnodes, tris, root, bounds_lo, bounds_hi):
     """Structural invariants of an exported 8-wide BVH (uint32[n,20] nodes, uint32[m,12] triangles in wide order):
-    every node referenced exactly once, every triangle in exactly one leaf slot, meta/imask consistent, and every
+    every node referenced exactly once, every triangle in exactly one leaf slot, imask/prim_valid consistent, and every
     triangle inside the dequantised box of EVERY ancestor slot on its path (so no conservative box can cull it).
     Returns the number of reachable nodes. Vectorised level by level."""
     n_nodes, n_tris = wnodes.shape[0], tris.shape[0]
@@ -96,7 +104,7 @@ def check_wide_bvh(wnodes, tris, root, bounds_lo, bounds_hi):
     step = np.ldexp(1.0, e - 127)
     imask = b[:, 15].astype(np.int64)
     child_base, prim_base = wnodes[:, 4].astype(np.int64), wnodes[:, 5].astype(np.int64)
-    meta = b[:, 24:32].astype(np.int64)
+    prim_valid = wnodes[:, 6].astype(np.int64)
     q = b[:, 32:80].reshape(n_nodes, 6, 8).astype(np.float64)          # qlo.x qlo.y qlo.z qhi.x qhi.y qhi.z  x 8 slots
     lo = p[:, :, None] + q[:, 0:3, :] * step[:, :, None]               # [n, 3, 8]
     hi = p[:, :, None] + q[:, 3:6, :] * step[:, :, None]
@@ -112,19 +120,19 @@ def check_wide_bvh(wnodes, tris, root, bounds_lo, bounds_hi):
         np.add.at(seen_nodes, frontier, 1)
         nxt, nlo, nhi = [], [], []
         rank = np.zeros(frontier.size, dtype=np.int64)
+        pv = prim_valid[frontier]
+        assert np.all(pv < (1 << 24))
         for s in range(8):
-            m = meta[frontier, s]
-            used = m != 0
-            inner = used & ((m & 0x1F) >= 24)
-            leaf = used & ~inner
+            inner = ((imask[frontier] >> s) & 1) == 1
+            f3 = (pv >> (3 * s)) & 7
+            assert np.all(np.isin(f3, (0, 1, 3, 7))), "bad primitive field"
+            assert np.all(f3[inner] == 0), "internal slot with primitive bits"
+            leaf = f3 != 0
             clo = np.maximum(lo[frontier, :, s], acc_lo)
             chi = np.minimum(hi[frontier, :, s], acc_hi)
-            assert np.all(((imask[frontier] >> s) & 1) == inner), "imask disagrees with meta"
-            assert np.all(m[inner] == (0x20 | (24 + s))), "bad internal meta"
-            mm = m >> 5
-            assert np.all(np.isin(mm[leaf], (1, 3, 7))), "bad unary triangle count"
-            cnt = np.where(mm == 1, 1, np.where(mm == 3, 2, 3))
-            off = m & 0x1F
+            cnt = np.where(f3 == 1, 1, np.where(f3 == 3, 2, np.where(f3 == 7, 3, 0)))
+            below = pv & ((1 << (3 * s)) - 1)
+            off = _popcount24(below)
             for k in range(3):
                 sel = leaf & (cnt > k)
                 ti = prim_base[frontier][sel] + off[sel] + k

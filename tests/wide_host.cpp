@@ -83,15 +83,20 @@ int wide_host_reach(const uint32_t* wnodes, uint32_t root, const float* absmax, 
                 const uint32_t child = ng.x + (uint32_t)__builtin_popcount(imask & ~(0xFFFFFFFFu << slot));
                 const WWord* w = reinterpret_cast<const WWord*>(wn + child);
                 ++visited;
-                const uint32_t hits = wide_node_hits(rb, w[0], w[1], w[2], w[3], w[4], tmin, tmax);
-                ng = G{w[1].x, (hits & 0xFF000000u) | (w[0].w >> 24)};
-                tg = G{w[1].y, hits & 0x00FFFFFFu};
+                uint32_t inner, prims;
+                wide_node_hits(rb, w[0], w[1], w[2], w[3], w[4], tmin, tmax, inner, prims);
+                ng = G{w[1].x, inner | (w[0].w >> 24)};
+                tg = G{child, prims};
             }
-            while (tg.y) {
-                const uint32_t bit = 31u - (uint32_t)__builtin_clz(tg.y);
-                tg.y &= ~(1u << bit);
-                ++tested;
-                if ((int32_t)(tg.x + bit) == expect[r]) found = true;
+            if (tg.y) {
+                const WNode& N = wn[tg.x];
+                while (tg.y) {
+                    const uint32_t bit = 31u - (uint32_t)__builtin_clz(tg.y);
+                    tg.y &= ~(1u << bit);
+                    ++tested;
+                    const uint32_t pidx = N.prim_base + (uint32_t)__builtin_popcount(N.prim_valid & ~(0xFFFFFFFFu << bit));
+                    if ((int32_t)pidx == expect[r]) found = true;
+                }
             }
             if (ng.y <= 0x00FFFFFFu) {
                 if (stack.empty()) traversing = false;

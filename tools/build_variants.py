@@ -5,11 +5,11 @@ from build_up_phase_b200 import build as b
 
 VARIANTS = {
     "base": [],
-    "mb6": ["RT_TRACE_MIN_BLOCKS=6"],
-    "mb5": ["RT_TRACE_MIN_BLOCKS=5"],
-    "thr8": ["RT_REFILL_THRESHOLD=8"],
-    "thr20": ["RT_REFILL_THRESHOLD=20"],
-    "thr26": ["RT_REFILL_THRESHOLD=26"],
+    "pm1": ["RT_PRIM_MIN=1"],
+    "pm4": ["RT_PRIM_MIN=4"],
+    "pm12": ["RT_PRIM_MIN=12"],
+    "pm16": ["RT_PRIM_MIN=16"],
+    "pm12_thr20": ["RT_PRIM_MIN=12", "RT_REFILL_THRESHOLD=20"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
