@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtcore.so")
 SOURCES = ["rtcore_api.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu"]
-HEADERS = ["rt_internal.h", "rt_device.cuh", "wide_bvh.cuh", os.path.join("..", "..", "include", "rtcore.h")]
+HEADERS = ["rt_internal.h", "rt_device.cuh", os.path.join("..", "..", "include", "rtcore.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -20,12 +20,9 @@
 // All kernels are HBM-bound streaming passes: coalesced 128-bit accesses, grids sized from the
 // problem (multiples of 148 SMs x resident CTAs for the big ones), no tensor cores (nothing here
 // is a contraction).
-#include <cooperative_groups.h>
 #include <float.h>
 
 #include "rt_device.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace rt {
 
@@ -205,7 +202,7 @@ __device__ __forceinline__ bool climb(BvhNode* __restrict__ nodes, const uint32_
 }
 
 __global__ void __launch_bounds__(256) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
-                                                   const TriRec* __restrict__ unsorted,
+                                                   const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
                                                    BvhNode* __restrict__ nodes, BlasRecord* __restrict__ records,
                                                    const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
                                                    const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
@@ -214,7 +211,11 @@ __global__ void __launch_bounds__(256) k_refit_tris(const uint64_t* __restrict__
     const uint32_t blas = (uint32_t)(__ldg(keys + leaf) >> MORTON_BITS);
     const uint32_t src_i = __ldg(vals + leaf);
     const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
-    const float4 q0 = __ldg(src), q1 = __ldg(src + 1), q2 = __ldg(src + 2);   // the triangle itself is emitted by k_widen
+    const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
+    float4 q2 = __ldg(src + 2);
+    q2.w = 0.0f;                                          // pad (carried the BLAS id through the sort)
+    float4* dst = reinterpret_cast<float4*>(sorted + leaf);
+    dst[0] = q0; dst[1] = q1; dst[2] = q2;
     Box3 b;
     b.lo[0] = fminf(fminf(q0.x, q0.w), q1.z); b.lo[1] = fminf(fminf(q0.y, q1.x), q1.w); b.lo[2] = fminf(fminf(q0.z, q1.y), q2.x);
     b.hi[0] = fmaxf(fmaxf(q0.x, q0.w), q1.z); b.hi[1] = fmaxf(fmaxf(q0.y, q1.x), q1.w); b.hi[2] = fmaxf(fmaxf(q0.z, q1.y), q2.x);
@@ -299,14 +300,18 @@ __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restri
     vals[i] = i;
 }
 
-__global__ void __launch_bounds__(256) k_refit_inst(const uint32_t* __restrict__ vals, uint32_t n,
-                                                   const float* __restrict__ boxes, BlasRecord* __restrict__ seg,
+__global__ void __launch_bounds__(256) k_refit_inst(const uint32_t* __restrict__ vals, uint32_t n, const InstanceRec* __restrict__ unsorted,
+                                                   const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
                                                    BvhNode* __restrict__ nodes, int32_t* __restrict__ meta, float* __restrict__ bounds_out,
                                                    const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
                                                    const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
     const uint32_t src_i = __ldg(vals + leaf);
+    const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
+    float4* dst = reinterpret_cast<float4*>(sorted + leaf);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) dst[k] = __ldg(src + k);
     const float* bx = boxes + 6 * (size_t)src_i;
     Box3 b = {{bx[0], bx[1], bx[2]}, {bx[3], bx[4], bx[5]}};
     int32_t ref; uint32_t height;
@@ -314,147 +319,14 @@ __global__ void __launch_bounds__(256) k_refit_inst(const uint32_t* __restrict__
         meta[0] = ref; meta[1] = (int32_t)height;
         bounds_out[0] = b.lo[0]; bounds_out[1] = b.lo[1]; bounds_out[2] = b.lo[2];
         bounds_out[3] = b.hi[0]; bounds_out[4] = b.hi[1]; bounds_out[5] = b.hi[2];
-        seg->root = ref; seg->height = height;            // the one segment k_widen collapses
-        seg->lo[0] = b.lo[0]; seg->lo[1] = b.lo[1]; seg->lo[2] = b.lo[2];
-        seg->hi[0] = b.hi[0]; seg->hi[1] = b.hi[1]; seg->hi[2] = b.hi[2];
     }
-}
-
-// ---- binary LBVH -> 8-wide compressed BVH (wide_bvh.cuh) ---------------------------------------------
-// Level-synchronous top-down collapse in ONE cooperative launch: level 0 = the segment roots (wide node s
-// belongs to segment s: one BLAS of a batched build, or the whole TLAS); a thread expands one wide node
-// (widen_one), reserves consecutive node slots for its internal children with one atomicAdd on the NEXT
-// level's counter (node index = end of this level + reservation, so the children of all nodes of a level
-// form one contiguous index range = the next level), reserves primitive slots in its segment, writes the
-// 80-byte node and gathers its <= 24 primitives from the unsorted array. One grid.sync() per level.
-template <class Prim>
-struct WidenParams {
-    const BvhNode* bnodes;            // binary nodes, segment s at bnodes + segs[s].first
-    BlasRecord* segs;                 // first, tri_count (= primitive count), root/height (binary in, wide out), lo/hi
-    uint32_t n_segs;
-    WNode* wnodes; uint32_t wnode_cap;
-    WidenScratch w;
-    const Prim* prim_unsorted;        // primitive records in input order
-    const uint32_t* vals;             // sorted position (global) -> input index
-    Prim* prim_out;                   // global array; segment s at prim_out + segs[s].first
-};
-
-struct FetchHalves {
-    const BvhNode* seg_nodes;
-    __device__ __forceinline__ void operator()(int32_t ref, WChild* out) const {
-        const float4* n4 = reinterpret_cast<const float4*>(seg_nodes + ref);
-        const float4 a0 = __ldcg(n4), a1 = __ldcg(n4 + 1), b0 = __ldcg(n4 + 2), b1 = __ldcg(n4 + 3);
-        out[0].lo[0] = a0.x; out[0].lo[1] = a0.y; out[0].lo[2] = a0.z; out[0].hi[0] = a0.w; out[0].hi[1] = a1.x; out[0].hi[2] = a1.y;
-        out[0].ref = __float_as_int(a1.z);
-        out[1].lo[0] = b0.x; out[1].lo[1] = b0.y; out[1].lo[2] = b0.z; out[1].hi[0] = b0.w; out[1].hi[1] = b1.x; out[1].hi[2] = b1.y;
-        out[1].ref = __float_as_int(b1.z);
-    }
-};
-
-__device__ __forceinline__ void emit_prim(const TriRec* __restrict__ src, TriRec* __restrict__ dst, uint32_t sorted_pos) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4 q0 = __ldg(s4), q1 = __ldg(s4 + 1), q2 = __ldg(s4 + 2);
-    q2.w = __uint_as_float(sorted_pos);                  // was: the BLAS id carried through the sort
-    float4* d4 = reinterpret_cast<float4*>(dst);
-    d4[0] = q0; d4[1] = q1; d4[2] = q2;
-}
-__device__ __forceinline__ void emit_prim(const InstanceRec* __restrict__ src, InstanceRec* __restrict__ dst, uint32_t) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int k = 0; k < 6; ++k) d4[k] = __ldg(s4 + k);
-}
-
-template <class Prim>
-__global__ void __launch_bounds__(128) k_widen(const WidenParams<Prim> P) {
-    cg::grid_group grid = cg::this_grid();
-    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-    uint32_t begin = 0, end = P.n_segs, level = 0;
-    uint32_t* overflow = P.w.level_count + WIDEN_MAX_LEVELS;
-    if (tid == 0) {                                          // debug/parity view of the binary tree (segment 0)
-        P.w.level_count[WIDEN_MAX_LEVELS + 3] = (uint32_t)P.segs[0].root;
-        P.w.level_count[WIDEN_MAX_LEVELS + 4] = P.segs[0].height;
-    }
-    while (begin < end) {
-        uint32_t* next_count = P.w.level_count + (level + 1 < (uint32_t)WIDEN_MAX_LEVELS ? level + 1 : WIDEN_MAX_LEVELS - 1);
-        for (uint32_t wi = begin + tid; wi < end; wi += nthreads) {
-            // work items were written by other SMs during the previous level: read them past the (non-coherent) L1
-            const uint32_t seg = level == 0 ? wi : __ldcg(P.w.seg + wi);
-            BlasRecord& S = P.segs[seg];
-            const uint32_t seg_first = S.first;
-            if (level == 0 && S.tri_count == 0) continue;            // empty segment: no root node (root stays REF_EMPTY)
-            const int32_t src = level == 0 ? S.root : __ldcg(P.w.src + wi);
-            WNode node; WideEmit em;
-            FetchHalves fetch{P.bnodes + seg_first};
-            widen_one(src, S.lo, S.hi, fetch, node, em);
-            if (em.n_internal) {
-                const uint32_t base = end + atomicAdd(next_count, (uint32_t)em.n_internal);
-                if (base + (uint32_t)em.n_internal > P.wnode_cap || level + 1 >= (uint32_t)WIDEN_MAX_LEVELS) {
-                    atomicExch(overflow, 1u);                            // host retries with a larger node pool
-                    node.imask = 0;                                     // the dropped slots own no prim_valid bits: never visited
-                } else {
-                    node.child_base = base;
-                    for (int k = 0; k < em.n_internal; ++k) { P.w.src[base + k] = em.internal_ref[k]; P.w.seg[base + k] = seg; }
-                }
-            }
-            if (em.n_prims) {
-                const uint32_t pbase = atomicAdd(P.w.seg_cursor + seg, em.n_prims);
-                node.prim_base = pbase;
-                uint32_t o = pbase;
-                for (int l = 0; l < em.n_leaf; ++l)
-                    for (uint32_t k = 0; k < em.leaf_count[l]; ++k, ++o) {
-                        const uint32_t sorted_pos = em.leaf_first[l] + k;                 // segment relative
-                        const uint32_t in_idx = __ldg(P.vals + seg_first + sorted_pos);
-                        emit_prim(P.prim_unsorted + in_idx, P.prim_out + seg_first + o, sorted_pos);
-                    }
-            }
-            uint4* dst = reinterpret_cast<uint4*>(P.wnodes + wi);
-            const uint4* srcw = reinterpret_cast<const uint4*>(&node);
-#pragma unroll
-            for (int k = 0; k < 5; ++k) dst[k] = srcw[k];
-        }
-        grid.sync();
-        begin = end;
-        uint32_t add = *reinterpret_cast<volatile uint32_t*>(next_count);
-        if (end + add > P.wnode_cap) add = P.wnode_cap - end;
-        end += add;
-        ++level;
-        if (level >= (uint32_t)WIDEN_MAX_LEVELS) break;
-    }
-    // publish: wide root index (= segment index) and wide depth; total node count
-    for (uint32_t s = tid; s < P.n_segs; s += nthreads) {
-        BlasRecord& S = P.segs[s];
-        S.root = S.tri_count ? (int32_t)s : REF_EMPTY;
-        S.height = level;
-    }
-    if (tid == 0) { P.w.level_count[WIDEN_MAX_LEVELS + 1] = level; P.w.level_count[WIDEN_MAX_LEVELS + 2] = end; }
-}
-
-template <class Prim>
-int launch_widen(const WidenParams<Prim>& p, int sm_count, cudaStream_t st) {
-    static int blocks_per_sm = 0;
-    if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_widen<Prim>, 128, 0) != cudaSuccess || blocks_per_sm < 1) blocks_per_sm = 1;
-        if (blocks_per_sm > 8) blocks_per_sm = 8;
-    }
-    if (cudaMemsetAsync(p.w.level_count, 0, sizeof(uint32_t) * (WIDEN_MAX_LEVELS + 8), st) != cudaSuccess) return -1;
-    if (cudaMemsetAsync(p.w.seg_cursor, 0, sizeof(uint32_t) * (size_t)p.n_segs, st) != cudaSuccess) return -1;
-    // small builds do not need the whole machine: one thread per wide node of the widest plausible level
-    uint32_t want_blocks = (p.wnode_cap + 127u) / 128u;
-    uint32_t blocks = (uint32_t)(sm_count * blocks_per_sm);
-    if (blocks > want_blocks) blocks = want_blocks;
-    if (blocks < 1) blocks = 1;
-    WidenParams<Prim> pc = p;
-    void* args[] = {&pc};
-    if (cudaLaunchCooperativeKernel((const void*)k_widen<Prim>, dim3(blocks), dim3(128), args, 0, st) != cudaSuccess) return -1;
-    return 1;
 }
 
 inline int div_up(uint32_t a, uint32_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
 
-int launch_blas_build(const BlasBuildArgs& a, int sm_count, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b) {
+int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b) {
     int launches = 0;
     *sorted_in_b = false;
     if (a.n_tris == 0) return 0;
@@ -477,23 +349,15 @@ int launch_blas_build(const BlasBuildArgs& a, int sm_count, cudaStream_t st, con
         ++launches;
     }
     if (ev) cudaEventRecord(ev->e[4], st);
-    k_refit_tris<<<div_up(a.n_tris, 256), 256, 0, st>>>(keys, vals, a.n_tris, a.tris_unsorted, a.nodes, a.records,
+    k_refit_tris<<<div_up(a.n_tris, 256), 256, 0, st>>>(keys, vals, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, a.records,
                                                        a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
     ++launches;
     if (ev) cudaEventRecord(ev->e[5], st);
-    {
-        WidenParams<TriRec> w{};
-        w.bnodes = a.nodes; w.segs = a.records; w.n_segs = a.n_blas; w.wnodes = a.wnodes; w.wnode_cap = a.wnode_cap; w.w = a.w;
-        w.prim_unsorted = a.tris_unsorted; w.vals = vals; w.prim_out = a.tris_out;
-        if (launch_widen(w, sm_count, st) < 0) return -1;
-        ++launches;
-    }
-    if (ev) cudaEventRecord(ev->e[6], st);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }
 
-int launch_tlas_build(const TlasBuildArgs& a, int sm_count, cudaStream_t st) {
+int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st) {
     int launches = 0;
     if (a.n == 0) return 0;
     k_inst_setup<<<div_up(a.n, 128), 128, 0, st>>>(a.instances, a.n, a.inst_unsorted, a.boxes_unsorted, a.bounds_ordered, a.root_out);
@@ -510,16 +374,9 @@ int launch_tlas_build(const TlasBuildArgs& a, int sm_count, cudaStream_t st) {
         k_karras<<<div_up(a.n - 1, 256), 256, 0, st>>>(keys, (int)a.n, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
         ++launches;
     }
-    k_refit_inst<<<div_up(a.n, 256), 256, 0, st>>>(vals, a.n, a.boxes_unsorted, a.seg, a.nodes, a.root_out,
+    k_refit_inst<<<div_up(a.n, 256), 256, 0, st>>>(vals, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, a.root_out,
                                                   a.bounds_out, a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
     ++launches;
-    {
-        WidenParams<InstanceRec> w{};
-        w.bnodes = a.nodes; w.segs = a.seg; w.n_segs = 1; w.wnodes = a.wnodes; w.wnode_cap = a.wnode_cap; w.w = a.w;
-        w.prim_unsorted = a.inst_unsorted; w.vals = vals; w.prim_out = a.inst_out;
-        if (launch_widen(w, sm_count, st) < 0) return -1;
-        ++launches;
-    }
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }

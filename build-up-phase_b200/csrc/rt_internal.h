@@ -17,7 +17,6 @@
 #include <stdint.h>
 
 #include "../../include/rtcore.h"
-#include "wide_bvh.cuh"
 
 namespace rt {
 
@@ -25,7 +24,7 @@ constexpr int32_t REF_DONE  = 0x7FFFFFFF;
 constexpr int32_t REF_POP_INSTANCE = 0x7FFFFFFE;
 constexpr int32_t REF_EMPTY = RT_REF_EMPTY;      // 0x7FFFFFFD
 constexpr int32_t REF_SENTINEL_MIN = 0x7FFFFFF0;
-constexpr int BLAS_LEAF_MAX = WIDE_TRI_LEAF_MAX;   // 3: a leaf slot of the wide node encodes its count in unary in 3 bits
+constexpr int BLAS_LEAF_MAX = 4;
 constexpr int TLAS_LEAF_MAX = 1;
 constexpr uint32_t MORTON_BITS = 30;
 constexpr uint32_t MAX_PRIMS = 1u << 28;         // leaf ref packs (first << 3) into 31 bits
@@ -34,14 +33,14 @@ struct __align__(32) BvhNodeHalf { float lo[3]; float hi[3]; int32_t ref; uint32
 struct __align__(64) BvhNode { BvhNodeHalf c[2]; };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
 
-struct __align__(16) TriRec { float v[9]; uint32_t geo, prim, sorted_pos; };   // sorted_pos: position in Morton order (BLAS-relative)
+struct __align__(16) TriRec { float v[9]; uint32_t geo, prim, pad; };
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 B");
 
 struct __align__(16) InstanceRec {
     float w2o[12];              // 48
-    const WNode*  nodes;        // 56   wide nodes of the BLAS storage
-    const TriRec* tris;         // 64   triangles of this BLAS (wide-node order)
-    int32_t  root;              // 68   wide-node index of the BLAS root, or REF_EMPTY
+    const BvhNode* nodes;       // 56
+    const TriRec*  tris;        // 64
+    int32_t  root;              // 68
     uint32_t custom_mask;       // 72   custom_index:24 | mask:8
     uint32_t sbt_flags;         // 76   sbt_offset:24 | flags:8
     uint32_t instance_id;       // 80   slot in the caller's rt_instance array (gl_InstanceID)
@@ -52,10 +51,10 @@ static_assert(sizeof(InstanceRec) == 96, "InstanceRec must be 96 B");
 
 // What accelerationStructureReference points at: one record per BLAS in device memory.
 struct __align__(16) BlasRecord {
-    const WNode*  nodes;        // wide nodes of the storage this BLAS lives in (indices are storage-global)
-    const TriRec* tris;         // first triangle of this BLAS
-    int32_t  root;              // during the build: binary root ref; after k_widen: wide root index or REF_EMPTY
-    uint32_t height;            // during the build: binary height; after k_widen: wide depth (levels)
+    const BvhNode* nodes;
+    const TriRec*  tris;
+    int32_t  root;
+    uint32_t height;
     float    lo[3], hi[3];
     uint32_t tri_count;
     uint32_t n_geoms;
@@ -102,57 +101,42 @@ struct BuildScratch {           // all device pointers, sized for n primitives
     int*      error_flag;       // 1 int
 };
 
-// ---- binary -> 8-wide collapse (k_widen) ----
-constexpr int WIDEN_MAX_LEVELS = 128;
-struct WidenScratch {
-    int32_t*  src;              // wnode_cap: binary ref each wide node expands
-    uint32_t* seg;              // wnode_cap: segment (BLAS) of each wide node
-    uint32_t* seg_cursor;       // n_segments: primitives emitted so far per segment
-    uint32_t* level_count;      // WIDEN_MAX_LEVELS + 8: nodes allocated per level; [MAX] = overflow flag, [MAX+1] = levels, [MAX+2] = nodes, [MAX+3/4] = binary root/height of segment 0
-};
 struct BlasBuildArgs {
     const GeomDesc* geoms; uint32_t n_geoms;
     const uint32_t* geom_tri_first;   // n_geoms+1 prefix array (device) for the binary search
     uint32_t n_tris; uint32_t n_blas;
     uint32_t seg_bits;                // ceil(log2(n_blas))
     TriRec*   tris_unsorted;          // scratch, n_tris
-    TriRec*   tris_out;               // output: triangles in wide-node order (per BLAS contiguous)
-    BvhNode*  nodes;                  // scratch: binary LBVH, n_tris slots
-    WNode*    wnodes;                 // output: wide nodes (storage-global indices), capacity wnode_cap
-    uint32_t  wnode_cap;
-    WidenScratch w;
+    TriRec*   tris_sorted;            // output
+    BvhNode*  nodes;                  // output, n_tris slots
     BlasRecord* records;              // n_blas (device), nodes/tris/first/tri_count/n_geoms pre-filled by the host
     int*      bounds_ordered;         // n_blas * 6 ints (ordered-int encoded floats), pre-initialised
     BuildScratch s;
     SortPlan  sort;
 };
-struct BuildEvents { cudaEvent_t e[7]; };  // setup | morton | sort | hierarchy | refit | widen | end
-int launch_blas_build(const BlasBuildArgs& a, int sm_count, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b);
+struct BuildEvents { cudaEvent_t e[6]; };  // setup | morton | sort | hierarchy | refit | end
+int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b);
 
 struct TlasBuildArgs {
     const rt_instance* instances;     // device copy of the caller's 64-byte records (blas field = BlasRecord device address)
     uint32_t n;
     InstanceRec* inst_unsorted;       // scratch
-    InstanceRec* inst_out;            // output: instance records in wide-node order
+    InstanceRec* inst_sorted;         // output
     float*       boxes_unsorted;      // scratch n*6
-    BvhNode*     nodes;               // scratch: binary LBVH over the instance boxes
-    WNode*       wnodes;              // output, capacity wnode_cap
-    uint32_t     wnode_cap;
-    WidenScratch w;
-    BlasRecord*  seg;                 // scratch: one segment record {first 0, count n, root, bounds} driving k_widen
+    BvhNode*     nodes;               // output
     int*         bounds_ordered;      // 6 ints
-    int32_t*     root_out;            // {binary root, binary height, max_sbt_plus_geo, max_sbt, max_geo, max_blas_height}  (6 ints, device)
+    int32_t*     root_out;            // {root, height, max_sbt_plus_geo, max_sbt, max_geo, max_blas_height}  (6 ints, device)
     float*       bounds_out;          // 6 floats (device)
     BuildScratch s;
     SortPlan     sort;
 };
-int launch_tlas_build(const TlasBuildArgs& a, int sm_count, cudaStream_t st);
+int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st);
 
 // ---- trace (csrc/trace.cu) -----------------------------------------------------------------------
 struct TraceParams {
-    const WNode* tlas_nodes;
+    const BvhNode* tlas_nodes;
     const InstanceRec* instances;
-    int32_t tlas_root;          // wide root index, or REF_EMPTY
+    int32_t tlas_root;
     float tlas_absmax[3];
     float cam_pos[3];
     float aspect_x, aspect_y;

@@ -38,24 +38,21 @@ struct rt_context {
     uint32_t* d_counters = nullptr;                    // ray-fetch / queue counters of the persistent trace kernels
     unsigned long long* d_stats = nullptr;
     int* d_error = nullptr;
-    cudaEvent_t ev[10]{};
+    cudaEvent_t ev[8]{};
     rt_build_timing timing{};
     float last_trace_ms = 0.0f;
     rt_trace_stats last_stats{};
     uint64_t launches = 0;
     // debug view of the last BLAS build's sorted keys (lives in scratch until the next build)
     const uint64_t* dbg_keys = nullptr; const uint32_t* dbg_vals = nullptr; uint32_t dbg_n = 0;
-    // debug view of the last single-BLAS build's intermediate binary LBVH (scratch as well)
-    const BvhNode* dbg_bnodes = nullptr; int32_t dbg_broot = REF_EMPTY; uint32_t dbg_bheight = 0;
 };
 
 struct BlasStorage {
     int refs = 0;
-    void* dev = nullptr;            // tris[N] | records[n_blas] | wnodes[cap]   (only relative references inside)
-    size_t bytes = 0;               // allocated
-    size_t used_bytes = 0;          // prefix that holds data: tris | records | wnodes[n_wnodes]  (the relocatable blob)
-    WNode* wnodes = nullptr; TriRec* tris = nullptr; BlasRecord* records = nullptr;
-    uint32_t n_tris = 0, n_blas = 0, n_wnodes = 0, wnode_cap = 0, depth = 0;
+    void* dev = nullptr;            // nodes[N] | tris[N] | records[n_blas]
+    size_t bytes = 0;
+    BvhNode* nodes = nullptr; TriRec* tris = nullptr; BlasRecord* records = nullptr;
+    uint32_t n_tris = 0, n_blas = 0;
 };
 struct rt_blas {
     BlasStorage* st = nullptr;
@@ -64,8 +61,8 @@ struct rt_blas {
 };
 struct rt_tlas {
     void* dev = nullptr; size_t bytes = 0;
-    InstanceRec* inst = nullptr; WNode* nodes = nullptr;
-    uint32_t n = 0, n_wnodes = 0;
+    InstanceRec* inst = nullptr; BvhNode* nodes = nullptr;
+    uint32_t n = 0;
     int32_t root = REF_EMPTY; uint32_t height = 0;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     int32_t max_sbt_plus_geo = 0, max_sbt = 0, max_geo = 0, max_blas_height = 0;
@@ -106,26 +103,15 @@ struct Carver {
     template <typename T> T* take(size_t count) { off = align_up(off, 256); T* p = (T*)(base + off); off += sizeof(T) * count; return p; }
 };
 
-// wide-node pool of a build over n primitives in n_seg segments: typical use is ~n/6; n/2 is generous, the
-// (pathological) overflow case is detected by k_widen and retried with the safe bound n + n_seg.
-uint32_t wnode_capacity(uint32_t n, uint32_t n_seg, bool safe) {
-    const uint64_t c = (safe ? (uint64_t)n : (uint64_t)n / 2 + 64) + n_seg;
-    return (uint32_t)(c > 0xFFFFFFF0ull ? 0xFFFFFFF0ull : c);
-}
-
 size_t build_scratch_bytes(uint32_t n, const SortPlan& sp, bool tris, uint32_t n_geoms, uint32_t n_blas) {
     size_t b = 0;
     auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
-    const uint32_t n_seg = tris ? n_blas : 1u;
-    const size_t cap = wnode_capacity(n, n_seg, true);
     add(8ull * n); add(8ull * n); add(4ull * n); add(4ull * n);          // keys a/b, vals a/b
     add(4ull * n); add(4ull * n); add(4ull * n); add(4ull * n);          // parent_leaf, parent_node, other_end, arrived
     add(sp.scratch_bytes);
-    add(64ull * n);                                                      // binary LBVH nodes
-    add(4ull * cap); add(4ull * cap); add(4ull * n_seg); add(4ull * (WIDEN_MAX_LEVELS + 8));   // k_widen work items + counters
     if (tris) { add(48ull * n); add(sizeof(GeomDesc) * (size_t)n_geoms); add(4ull * (n_geoms + 1)); add(24ull * n_blas); }
-    else { add(96ull * n); add(24ull * n); add(64ull * n); add(64); add(64); add(64); add(64); }
-    return b + 8192;
+    else { add(96ull * n); add(24ull * n); add(64ull * n); add(64); add(64); }
+    return b + 4096;
 }
 
 void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
@@ -134,13 +120,6 @@ void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
     s.parent_leaf = c.take<uint32_t>(n); s.parent_node = c.take<uint32_t>(n);
     s.other_end = c.take<int32_t>(n); s.arrived = c.take<uint32_t>(n);
     s.sort_scratch = c.take<uint8_t>(sp.scratch_bytes);
-}
-
-void carve_widen(Carver& c, uint32_t n, uint32_t n_seg, BvhNode** bnodes, WidenScratch& w) {
-    const size_t cap = wnode_capacity(n, n_seg, true);
-    *bnodes = c.take<BvhNode>(n);
-    w.src = c.take<int32_t>(cap); w.seg = c.take<uint32_t>(cap);
-    w.seg_cursor = c.take<uint32_t>(n_seg); w.level_count = c.take<uint32_t>(WIDEN_MAX_LEVELS + 8);
 }
 
 uint32_t ceil_log2(uint32_t v) { uint32_t b = 0; while ((1ull << b) < v) ++b; return b; }
@@ -214,7 +193,7 @@ int rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, ui
     for (uint32_t g = 0; g < n_geoms; ++g) n += max_triangle_counts[g];
     if (n > MAX_PRIMS) return fail(ctx, RT_ERROR_INVALID_ARG, "too many triangles (%llu > %u)", (unsigned long long)n, MAX_PRIMS);
     SortPlan sp = sort_plan((uint32_t)n, MORTON_BITS);
-    out->acceleration_structure_size = n * sizeof(TriRec) + (uint64_t)wnode_capacity((uint32_t)n, 1, false) * sizeof(WNode) + sizeof(BlasRecord) + 1024;
+    out->acceleration_structure_size = n * (sizeof(BvhNode) + sizeof(TriRec)) + sizeof(BlasRecord) + 512;
     out->build_scratch_size = build_scratch_bytes((uint32_t)n, sp, true, n_geoms, 1);
     return RT_SUCCESS;
 }
@@ -222,7 +201,7 @@ int rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, ui
 int rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes* out) {
     if (!ctx || !out) return RT_ERROR_INVALID_ARG;
     SortPlan sp = sort_plan(max_instances, MORTON_BITS);
-    out->acceleration_structure_size = (uint64_t)max_instances * sizeof(InstanceRec) + (uint64_t)wnode_capacity(max_instances, 1, true) * sizeof(WNode) + 1024;
+    out->acceleration_structure_size = (uint64_t)max_instances * (sizeof(BvhNode) + sizeof(InstanceRec)) + 512;
     out->build_scratch_size = build_scratch_bytes(max_instances, sp, false, 0, 0);
     return RT_SUCCESS;
 }
@@ -283,6 +262,18 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     if (seg_bits + MORTON_BITS > 64) return RT_ERROR_INVALID_ARG;
     const SortPlan sp = sort_plan(N, (int)(MORTON_BITS + seg_bits));
 
+    // ---- output storage: nodes | tris | records ----
+    BlasStorage* st = new BlasStorage();
+    st->n_tris = N; st->n_blas = n_blas;
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    st->bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
+    cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
+    if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", st->bytes, cudaGetErrorString(ce)); }
+    st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
+    for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->nodes + recs[b].first; recs[b].tris = st->tris + recs[b].first; }
+    st->refs = 1;   // held by this function until handles exist
+    struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{st};
+
     // ---- scratch ----
     const size_t need = build_scratch_bytes(N ? N : 1, sp, true, n_geoms, n_blas) + align_up(stage_bytes, 256) + 4096;
     int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
@@ -290,7 +281,6 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     Carver c(ctx->scratch);
     BlasBuildArgs a{};
     carve_common(c, N ? N : 1, sp, a.s);
-    carve_widen(c, N ? N : 1, n_blas, &a.nodes, a.w);
     a.s.error_flag = ctx->d_error;
     a.tris_unsorted = c.take<TriRec>(N ? N : 1);
     GeomDesc* d_descs = c.take<GeomDesc>(n_geoms ? n_geoms : 1);
@@ -299,7 +289,7 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     uint8_t* d_stage = c.take<uint8_t>(stage_bytes + 16);
 
     // ---- stage host inputs (H2D, timed separately) ----
-    RT_CUDA(ctx, cudaEventRecord(ctx->ev[8], ctx->stream));
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
     {
         std::vector<uint8_t> pack;           // small arrays are packed into one copy; large ones go directly
         const size_t DIRECT = 1u << 20;
@@ -348,74 +338,45 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
         }
         if (n_geoms) RT_CUDA(ctx, cudaMemcpyAsync(d_descs, descs.data(), sizeof(GeomDesc) * n_geoms, cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(d_prefix, prefix.data(), 4ull * (n_geoms + 1), cudaMemcpyHostToDevice, ctx->stream));
-        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // pack/descs are host temporaries
-    }
-    RT_CUDA(ctx, cudaEventRecord(ctx->ev[9], ctx->stream));
-
-    // ---- output storage (tris | records | wide nodes) and device build; a second attempt only if the wide-node
-    //      pool of the first one overflowed (pathological trees) ----
-    BlasStorage* st = nullptr;
-    struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{nullptr};
-    BuildEvents be; for (int k = 0; k < 7; ++k) be.e[k] = ctx->ev[k];
-    bool in_b = false;
-    std::vector<BlasRecord> recs_out(n_blas);
-    uint32_t wstat[8] = {0, 0, 0, 0, 0, 0, 0, 0};      // overflow flag, levels, node count, binary root, binary height
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        if (st) { storage_release(st); guard.s = nullptr; st = nullptr; }
-        st = new BlasStorage();
-        st->n_tris = N; st->n_blas = n_blas;
-        st->wnode_cap = wnode_capacity(N ? N : 1, n_blas, attempt == 1);
-        const size_t tris_b = align_up(sizeof(TriRec) * (size_t)(N ? N : 1), 256), recs_b = align_up(sizeof(BlasRecord) * (size_t)n_blas, 256);
-        st->bytes = tris_b + recs_b + sizeof(WNode) * (size_t)st->wnode_cap + 256;
-        cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
-        if (ce != cudaSuccess) { size_t want = st->bytes; delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", want, cudaGetErrorString(ce)); }
-        st->tris = (TriRec*)st->dev; st->records = (BlasRecord*)((uint8_t*)st->dev + tris_b); st->wnodes = (WNode*)((uint8_t*)st->dev + tris_b + recs_b);
-        st->refs = 1;   // held by this function until handles exist
-        guard.s = st;
-        for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->wnodes; recs[b].tris = st->tris + recs[b].first; }
         RT_CUDA(ctx, cudaMemcpyAsync(d_bounds, bounds.data(), 24ull * n_blas, cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemcpyAsync(st->records, recs.data(), sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyHostToDevice, ctx->stream));
         RT_CUDA(ctx, cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream));
-        a.geoms = d_descs; a.n_geoms = n_geoms; a.geom_tri_first = d_prefix; a.n_tris = N; a.n_blas = n_blas; a.seg_bits = seg_bits;
-        a.tris_out = st->tris; a.wnodes = st->wnodes; a.wnode_cap = st->wnode_cap; a.records = st->records; a.bounds_ordered = d_bounds; a.sort = sp;
-        int launches = 0;
-        if (N > 0) {
-            launches = launch_blas_build(a, ctx->prop.multiProcessorCount, ctx->stream, &be, &in_b);
-            if (launches < 0) return fail(ctx, RT_ERROR_CUDA, "BLAS build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-            ctx->launches += (uint64_t)launches;
-            RT_CUDA(ctx, cudaMemcpyAsync(wstat, a.w.level_count + WIDEN_MAX_LEVELS, 20, cudaMemcpyDeviceToHost, ctx->stream));
-        }
-        int h_err = 0;
-        RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        RT_CUDA(ctx, cudaMemcpyAsync(recs_out.data(), st->records, sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyDeviceToHost, ctx->stream));
-        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
-        if (N == 0 || wstat[0] == 0) break;
-        if (attempt == 1) return fail(ctx, RT_ERROR_INTERNAL, "wide-node pool overflow (tree deeper than %d levels?)", WIDEN_MAX_LEVELS);
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));     // pack/descs are host temporaries
     }
-    st->n_wnodes = N ? wstat[2] : 0; st->depth = N ? wstat[1] : 0;
-    {
-        const size_t tris_b = align_up(sizeof(TriRec) * (size_t)(N ? N : 1), 256), recs_b = align_up(sizeof(BlasRecord) * (size_t)n_blas, 256);
-        st->used_bytes = tris_b + recs_b + sizeof(WNode) * (size_t)st->n_wnodes;
+    RT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+
+    // ---- device build ----
+    a.geoms = d_descs; a.n_geoms = n_geoms; a.geom_tri_first = d_prefix; a.n_tris = N; a.n_blas = n_blas; a.seg_bits = seg_bits;
+    a.tris_sorted = st->tris; a.nodes = st->nodes; a.records = st->records; a.bounds_ordered = d_bounds; a.sort = sp;
+    BuildEvents be; for (int k = 0; k < 6; ++k) be.e[k] = ctx->ev[k];
+    bool in_b = false;
+    int launches = 0;
+    if (N > 0) {
+        launches = launch_blas_build(a, ctx->stream, &be, &in_b);
+        if (launches < 0) return fail(ctx, RT_ERROR_CUDA, "BLAS build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->launches += (uint64_t)launches;
     }
+    int h_err = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaMemcpyAsync(recs.data(), st->records, sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     ctx->timing.primitives = N;
-    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[8], ctx->ev[9]);
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, ctx->ev[6], ctx->ev[7]);
     if (N > 0) {
         cudaEventElapsedTime(&ctx->timing.setup_ms, be.e[0], be.e[1]);
         cudaEventElapsedTime(&ctx->timing.morton_ms, be.e[1], be.e[2]);
         cudaEventElapsedTime(&ctx->timing.sort_ms, be.e[2], be.e[3]);
         cudaEventElapsedTime(&ctx->timing.hierarchy_ms, be.e[3], be.e[4]);
         cudaEventElapsedTime(&ctx->timing.refit_ms, be.e[4], be.e[5]);
-        cudaEventElapsedTime(&ctx->timing.widen_ms, be.e[5], be.e[6]);
-        cudaEventElapsedTime(&ctx->timing.total_ms, be.e[0], be.e[6]);
+        cudaEventElapsedTime(&ctx->timing.total_ms, be.e[0], be.e[5]);
     }
     ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N;
-    ctx->dbg_bnodes = a.nodes; ctx->dbg_broot = N ? (int32_t)wstat[3] : REF_EMPTY; ctx->dbg_bheight = wstat[4];
 
     for (uint32_t b = 0; b < n_blas; ++b) {
         rt_blas* h = new rt_blas();
-        h->st = st; h->index = b; h->rec = recs_out[b];
+        h->st = st; h->index = b; h->rec = recs[b];
         ++st->refs;
         out_array[b] = h;
     }
@@ -445,11 +406,11 @@ float rt_last_build_ms(const rt_context* ctx) { return ctx ? ctx->timing.total_m
 int rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out) {
     if (!ctx || !blas || !out) return RT_ERROR_INVALID_ARG;
     out->triangle_count = blas->rec.tri_count;
-    out->node_count = blas->st->n_wnodes;      // 80-byte wide nodes of the storage this BLAS lives in
+    out->node_count = blas->rec.tri_count;     // Karras slots [0, n); slot indices are BLAS-relative
     out->root_ref = blas->rec.root;
     out->max_depth = blas->rec.height;
     for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = blas->rec.lo[k]; out->bounds_hi[k] = blas->rec.hi[k]; }
-    out->storage_bytes = blas->st->n_blas == 1 ? (uint64_t)blas->st->used_bytes : 0;
+    out->storage_bytes = blas->st->n_blas == 1 ? (uint64_t)blas->st->bytes : 0;
     out->device_storage = blas->st->n_blas == 1 ? blas->st->dev : nullptr;
     return RT_SUCCESS;
 }
@@ -458,8 +419,8 @@ int rt_blas_export(rt_context* ctx, const rt_blas* blas, void* nodes_out, void* 
     if (!ctx || !blas) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const size_t n = blas->rec.tri_count, nn = blas->st->n_wnodes;
-    if (nodes_out && nn) RT_CUDA(ctx, cudaMemcpy(nodes_out, blas->st->wnodes, sizeof(WNode) * nn, cudaMemcpyDeviceToHost));
+    const size_t n = blas->rec.tri_count;
+    if (nodes_out && n) RT_CUDA(ctx, cudaMemcpy(nodes_out, blas->rec.nodes, sizeof(BvhNode) * n, cudaMemcpyDeviceToHost));
     if (tris_out && n) RT_CUDA(ctx, cudaMemcpy(tris_out, blas->rec.tris, sizeof(TriRec) * n, cudaMemcpyDeviceToHost));
     return RT_SUCCESS;
 }
@@ -474,44 +435,33 @@ int rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* pri
     return RT_SUCCESS;
 }
 
-int rt_debug_last_binary_bvh(rt_context* ctx, void* nodes_out, uint32_t capacity, int32_t* root_out, uint32_t* height_out) {
-    if (!ctx) return RT_ERROR_INVALID_ARG;
-    if (root_out) *root_out = ctx->dbg_broot;
-    if (height_out) *height_out = ctx->dbg_bheight;
-    const uint32_t n = ctx->dbg_n < capacity ? ctx->dbg_n : capacity;
-    RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    if (n && nodes_out && ctx->dbg_bnodes) RT_CUDA(ctx, cudaMemcpy(nodes_out, ctx->dbg_bnodes, sizeof(BvhNode) * (size_t)n, cudaMemcpyDeviceToHost));
-    return RT_SUCCESS;
-}
-
 int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device_blob, rt_blas** out) {
     if (!ctx || !info || !device_blob || !out) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint32_t N = info->triangle_count;
     BlasStorage* st = new BlasStorage();
-    st->n_tris = N; st->n_blas = 1; st->n_wnodes = info->node_count; st->wnode_cap = info->node_count; st->depth = info->max_depth;
-    const size_t tris_b = align_up(sizeof(TriRec) * (size_t)(N ? N : 1), 256), recs_b = align_up(sizeof(BlasRecord), 256);
-    st->used_bytes = tris_b + recs_b + sizeof(WNode) * (size_t)st->n_wnodes;
-    st->bytes = st->used_bytes + 256;
-    if (info->storage_bytes != st->used_bytes) { delete st; return fail(ctx, RT_ERROR_INVALID_ARG, "blob size mismatch"); }
+    st->n_tris = N; st->n_blas = 1;
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    st->bytes = nodes_b + tris_b + sizeof(BlasRecord) + 256;
+    if (info->storage_bytes != st->bytes) { delete st; return fail(ctx, RT_ERROR_INVALID_ARG, "blob size mismatch"); }
     cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
     if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc failed"); }
-    st->tris = (TriRec*)st->dev; st->records = (BlasRecord*)((uint8_t*)st->dev + tris_b); st->wnodes = (WNode*)((uint8_t*)st->dev + tris_b + recs_b);
+    st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
     st->refs = 1;
     rt_blas* h = new rt_blas();
     h->st = st; h->index = 0;
     BlasRecord& R = h->rec;
     memset(&R, 0, sizeof(R));
-    cudaError_t e1 = cudaMemcpyAsync(st->dev, device_blob, st->used_bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    R.nodes = st->nodes; R.tris = st->tris; R.root = info->root_ref; R.height = info->max_depth; R.tri_count = N; R.n_geoms = 0; R.first = 0;
+    for (int k = 0; k < 3; ++k) { R.lo[k] = info->bounds_lo[k]; R.hi[k] = info->bounds_hi[k]; }
+    cudaError_t e1 = cudaMemcpyAsync(st->dev, device_blob, nodes_b + tris_b, cudaMemcpyDeviceToDevice, ctx->stream);
     // n_geoms travels in the source record
     BlasRecord src{};
-    cudaError_t e2 = cudaMemcpyAsync(&src, (const uint8_t*)device_blob + tris_b, sizeof(BlasRecord), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e2 = cudaMemcpyAsync(&src, (const uint8_t*)device_blob + nodes_b + tris_b, sizeof(BlasRecord), cudaMemcpyDeviceToHost, ctx->stream);
     cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
-    R = src;
-    R.nodes = st->wnodes; R.tris = st->tris; R.first = 0;        // only the two base pointers are not relocatable
+    R.n_geoms = src.n_geoms;
     cudaError_t e4 = cudaMemcpy(st->records, &R, sizeof(BlasRecord), cudaMemcpyHostToDevice);
     if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess || e4 != cudaSuccess) { rt_free_blas(ctx, h); return fail(ctx, RT_ERROR_CUDA, "blob import copy failed"); }
-    if (R.tri_count != N || R.root != info->root_ref) { rt_free_blas(ctx, h); return fail(ctx, RT_ERROR_INVALID_ARG, "blob does not match its info"); }
     *out = h;
     return RT_SUCCESS;
 }
@@ -520,8 +470,7 @@ int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device
 static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* instances, uint32_t n, uint32_t build_flags) {
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     const SortPlan sp = sort_plan(n, MORTON_BITS);
-    const uint32_t wcap = wnode_capacity(n ? n : 1, 1, true);
-    const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(WNode) * (size_t)wcap, 256);
+    const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256);
     const size_t bytes = inst_b + nodes_b + 256;
     if (T->bytes < bytes) {
         if (T->dev) cudaFree(T->dev);
@@ -529,8 +478,8 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
         RT_CUDA(ctx, cudaMalloc(&T->dev, bytes));
         T->bytes = bytes;
     }
-    T->inst = (InstanceRec*)T->dev; T->nodes = (WNode*)((uint8_t*)T->dev + inst_b);
-    T->n = n; T->n_wnodes = 0; T->root = REF_EMPTY; T->height = 0;
+    T->inst = (InstanceRec*)T->dev; T->nodes = (BvhNode*)((uint8_t*)T->dev + inst_b);
+    T->n = n; T->root = REF_EMPTY; T->height = 0;
     for (int k = 0; k < 3; ++k) { T->lo[k] = FLT_MAX; T->hi[k] = -FLT_MAX; }
     T->max_sbt_plus_geo = T->max_sbt = T->max_geo = T->max_blas_height = 0;
     if (n == 0) return RT_SUCCESS;
@@ -541,9 +490,7 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
     Carver c(ctx->scratch);
     TlasBuildArgs a{};
     carve_common(c, n, sp, a.s);
-    carve_widen(c, n, 1, &a.nodes, a.w);
     a.s.error_flag = ctx->d_error;
-    a.seg = c.take<BlasRecord>(1);
     a.inst_unsorted = c.take<InstanceRec>(n);
     a.boxes_unsorted = c.take<float>(6 * (size_t)n);
     rt_instance* d_inst = c.take<rt_instance>(n);
@@ -571,27 +518,19 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
     RT_CUDA(ctx, cudaMemcpyAsync(a.root_out, hmeta, 32, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, cudaMemcpyAsync(a.bounds_out, hbo, 32, cudaMemcpyHostToDevice, ctx->stream));
     RT_CUDA(ctx, cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream));
-    BlasRecord hseg; memset(&hseg, 0, sizeof(hseg));
-    hseg.first = 0; hseg.tri_count = n; hseg.root = REF_EMPTY;
-    for (int k = 0; k < 3; ++k) { hseg.lo[k] = FLT_MAX; hseg.hi[k] = -FLT_MAX; }
-    RT_CUDA(ctx, cudaMemcpyAsync(a.seg, &hseg, sizeof(hseg), cudaMemcpyHostToDevice, ctx->stream));
-    a.n = n; a.inst_out = T->inst; a.wnodes = T->nodes; a.wnode_cap = wcap; a.sort = sp;
+    a.n = n; a.inst_sorted = T->inst; a.nodes = T->nodes; a.sort = sp;
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    int launches = launch_tlas_build(a, ctx->prop.multiProcessorCount, ctx->stream);
+    int launches = launch_tlas_build(a, ctx->stream);
     if (launches < 0) return fail(ctx, RT_ERROR_CUDA, "TLAS build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     ctx->launches += (uint64_t)launches;
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[5], ctx->stream));
     int h_err = 0;
     RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    uint32_t wstat[4] = {0, 0, 0, 0};
     RT_CUDA(ctx, cudaMemcpyAsync(hmeta, a.root_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaMemcpyAsync(hbo, a.bounds_out, 32, cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(&hseg, a.seg, sizeof(hseg), cudaMemcpyDeviceToHost, ctx->stream));
-    RT_CUDA(ctx, cudaMemcpyAsync(wstat, a.w.level_count + WIDEN_MAX_LEVELS, 12, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
-    if (wstat[0]) return fail(ctx, RT_ERROR_INTERNAL, "TLAS wide-node pool overflow");
-    T->root = hseg.root; T->height = hseg.height; T->n_wnodes = wstat[2];
+    T->root = hmeta[0]; T->height = (uint32_t)hmeta[1];
     T->max_sbt_plus_geo = hmeta[2]; T->max_sbt = hmeta[3]; T->max_geo = hmeta[4]; T->max_blas_height = hmeta[5];
     for (int k = 0; k < 3; ++k) { T->lo[k] = hbo[k]; T->hi[k] = hbo[3 + k]; }
     memset(&ctx->timing, 0, sizeof(ctx->timing));
@@ -626,7 +565,7 @@ void rt_free_tlas(rt_context* ctx, rt_tlas* tlas) {
 
 int rt_tlas_get_info(rt_context* ctx, const rt_tlas* tlas, rt_tlas_info* out) {
     if (!ctx || !tlas || !out) return RT_ERROR_INVALID_ARG;
-    out->instance_count = tlas->n; out->node_count = tlas->n_wnodes; out->root_ref = tlas->root; out->max_depth = tlas->height;
+    out->instance_count = tlas->n; out->node_count = tlas->n; out->root_ref = tlas->root; out->max_depth = tlas->height;
     for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = tlas->lo[k]; out->bounds_hi[k] = tlas->hi[k]; }
     return RT_SUCCESS;
 }
@@ -680,8 +619,7 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
                                    : (uint64_t)tlas->max_sbt + (uint64_t)tlas->max_geo * ctx->rp.sbt_record_stride + ctx->rp.sbt_record_offset;
         if (bound >= ctx->n_records) return fail(ctx, RT_ERROR_SBT_RANGE, "hit record %llu addressed but only %u set", (unsigned long long)bound, ctx->n_records);
     }
-    // per wide level: one node group (siblings still to visit) + one deferred primitive group; + the three entries an instance transition pushes
-    const int stack_needed = 2 * ((int)tlas->height + tlas->max_blas_height) + 6;
+    const int stack_needed = (int)tlas->height + tlas->max_blas_height + 4;
     if (stack_needed > 160) return fail(ctx, RT_ERROR_STACK_DEPTH, "BVH depth %d exceeds the traversal stack", stack_needed);
 
     // one part = the plain width x height image; several parts = equal-sized packed band buffers

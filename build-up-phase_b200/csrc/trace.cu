@@ -1,24 +1,21 @@
 // trace.cu — vkCmdTraceRaysKHR(W,H,1) for sm_100a (reference dispatch: main.cpp:1349-1355).
 //
-// One call = raygen prologue (main.cpp:1033-1052) -> two-level TLAS->BLAS traversal (what traceRayEXT
-// hands to the driver / RT cores; B200 has none, so this runs on the SMs) -> closest-hit / miss
-// epilogue (main.cpp:1063-1066,1080-1091) -> rgba8 imageStore (main.cpp:1054).
+// One call = raygen prologue (main.cpp:1033-1052) -> two-level TLAS->BLAS while-while traversal
+// (what traceRayEXT hands to the driver / RT cores; B200 has none, so this runs on the SMs) ->
+// closest-hit / miss epilogue (main.cpp:1063-1066,1080-1091) -> rgba8 imageStore (main.cpp:1054).
 // With one diffuse bounce the work is a two-stage wavefront: stage 0 traces the primary rays and
 // appends a secondary ray per hit to a queue in HBM; stage 1 traces the queue and blends.
 //
 //  * Persistent warps: the grid is sized to the SMs (occupancy x 148), every warp pulls rays from a
 //    global counter. When fewer than REFILL_THRESHOLD lanes of a warp are still traversing, the
 //    warp leaves the traversal loop, finished lanes run their epilogue and the idle lanes are
-//    refilled with one ballot + one atomicAdd + one shuffle (warp-level ray compaction).
+//    refilled with one ballot + one atomicAdd + one shuffle (warp-level ray compaction), so SIMD
+//    lanes stay busy although ray lengths differ by orders of magnitude.
 //  * Rays are numbered tile-major (8x4-pixel tiles) so the 32 rays a warp fetches together are
 //    neighbours and concurrently running warps work on neighbouring tiles (L1/L2 reuse of nodes).
-//  * 8-wide compressed nodes (wide_bvh.cuh): one 80-byte node = 5 x LDG.128 decides 8 children. Child
-//    planes are 8-bit offsets on a power-of-two grid; they are turned into floats with one PRMT each
-//    (byte -> mantissa of 32768.0f) and the slab test is one FFMA per plane. Hit slots are visited in
-//    (slot XOR ray octant) order, i.e. approximately front to back, without sorting. The traversal stack
-//    holds node GROUPS (child base + hit bits), so a node with k hit children costs one entry.
-//  * Box test: conservative by construction — quantised boxes contain the exact ones, the ray origin is
-//    padded per space (2^-19 relative), the dequantisation constants are rounded outwards (fma.rd/.ru).
+//  * 64-byte nodes fetched as 4 x LDG.128 through the read-only path; 48-byte triangles as 3 x LDG.128.
+//  * Box test: conservative slabs in FMA form (pad derived per ray/space from |origin| + |bounds|),
+//    so a box is never culled when the exact-arithmetic triangle test could still report a hit.
 //  * Triangle test: watertight Woop/Benthin/Wald 2013, plain IEEE mul/add (no contraction; the
 //    file is compiled with -fmad=false), fp64 fallback on exact-zero edge functions. No culling:
 //    the sample uses gl_RayFlagsOpaqueEXT only and TRIANGLE_FACING_CULL_DISABLE (main.cpp:852,1048).
@@ -41,11 +38,61 @@ namespace {
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
 constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
-#ifndef RT_PRIM_MIN
-#define RT_PRIM_MIN 8
+#ifndef RT_NODE_CAP
+#define RT_NODE_CAP 4
 #endif
-constexpr int PRIM_MIN = RT_PRIM_MIN;                     // run the primitive step once this many lanes have primitives pending
+constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner node loop when fewer lanes are still in it (0 = never)
+#ifndef RT_LDG256
+#define RT_LDG256 0
+#endif
+
+// Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
+// on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ldg256(const void* p) {
+    F8 r;
+#if RT_LDG256
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
+#else
+    r.a = __ldg(reinterpret_cast<const float4*>(p)); r.b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+#endif
+    return r;
+}
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
+
+struct Slab {
+    float rdx, rdy, rdz;     // 1/d (zero components replaced by +-1e-20)
+    float cnx, cny, cnz;     // -(o +- e) * rd for the near planes
+    float cfx, cfy, cfz;     // -(o -+ e) * rd for the far planes
+    bool px, py, pz;         // d > 0
+};
+
+__device__ __forceinline__ void slab_setup(Slab& s, V3 o, V3 d, float ax, float ay, float az) {
+    const float M = fmaxf(fmaxf(ax + fabsf(o.x), ay + fabsf(o.y)), az + fabsf(o.z));
+    const float e = M * 1.9073486328125e-06f;   // 2^-19 relative spatial pad
+    const float dx = fabsf(d.x) < 1e-20f ? copysignf(1e-20f, d.x) : d.x;
+    const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
+    const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
+    s.px = dx > 0.0f; s.py = dy > 0.0f; s.pz = dz > 0.0f;
+    s.rdx = 1.0f / dx; s.rdy = 1.0f / dy; s.rdz = 1.0f / dz;
+    s.cnx = -((s.px ? o.x + e : o.x - e) * s.rdx); s.cfx = -((s.px ? o.x - e : o.x + e) * s.rdx);
+    s.cny = -((s.py ? o.y + e : o.y - e) * s.rdy); s.cfy = -((s.py ? o.y - e : o.y + e) * s.rdy);
+    s.cnz = -((s.pz ? o.z + e : o.z - e) * s.rdz); s.cfz = -((s.pz ? o.z - e : o.z + e) * s.rdz);
+}
+
+// half = {lo.x lo.y lo.z hi.x} {hi.y hi.z ref height}
+__device__ __forceinline__ bool slab_test(const Slab& s, const float4 h0, const float4 h1, float tmin, float tbest, float& tn) {
+    const float nx = s.px ? h0.x : h0.w, fx = s.px ? h0.w : h0.x;
+    const float ny = s.py ? h0.y : h1.x, fy = s.py ? h1.x : h0.y;
+    const float nz = s.pz ? h0.z : h1.y, fz = s.pz ? h1.y : h0.z;
+    const float tnx = __fmaf_rn(nx, s.rdx, s.cnx), tfx = __fmaf_rn(fx, s.rdx, s.cfx);
+    const float tny = __fmaf_rn(ny, s.rdy, s.cny), tfy = __fmaf_rn(fy, s.rdy, s.cfy);
+    const float tnz = __fmaf_rn(nz, s.rdz, s.cnz), tfz = __fmaf_rn(fz, s.rdz, s.cfz);
+    tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+    const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
+    return tn <= tf;
+}
 
 struct Woop {
     float okx, oky, okz;     // origin permuted to (kx, ky, kz)
@@ -127,19 +174,9 @@ __device__ __forceinline__ rt_hit miss_record(float tmax) {
     return r;
 }
 
-constexpr uint32_t GROUP_PRIM_BITS = 0x00FFFFFFu;     // y <= this: the group holds primitive bits only
-
-// Per-ray state that is touched only at instance transitions, triangle tests and in the epilogue lives in shared
-// memory ([field][thread]: conflict-free), not in registers: the node step then fits 64 registers without spilling
-// and 8 CTAs stay resident per SM. 20 words x 128 threads = 10 KB per CTA.
-enum ColdField { C_OX, C_OY, C_OZ, C_DX, C_DY, C_DZ, C_WOKX, C_WOKY, C_WOKZ, C_WSX, C_WSY, C_WSZ, C_WKZ, C_BU, C_BV, C_BW0,
-                 C_COL0, C_COL1, C_COL2, C_PIXEL, COLD_WORDS };
-
 // STAGE 0: primary rays generated from pixel ids. STAGE 1: secondary rays read from the bounce queue.
 template <int STAGE, bool STATS, int STACK>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
-    __shared__ float s_cold[COLD_WORDS][TRACE_THREADS];
-#define COLD(k) s_cold[k][threadIdx.x]
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tiles_x = (P.width + 7u) >> 3;
@@ -152,21 +189,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     // ---- per-lane ray state ----
     bool have_ray = false, exhausted = false;
     bool in_buffer = false, valid = false;
-    bool traversing = false;             // the ray still has groups to visit
-    uint32_t lidx = 0;
-    // node group: x = index of the first internal child, y = hit bits 31..24 | imask 7..0   (y > GROUP_PRIM_BITS)
-    // prim group: x = index of the wide node,            y = hit bits 23..0 (subset of the node's prim_valid)
-    uint2 ng = make_uint2(0u, 0u), tg = make_uint2(0u, 0u);
+    uint32_t lidx = 0, pixel = 0;
+    V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
+    float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
+    int32_t cur = REF_DONE;
     int sp = 0;
     bool in_blas = false;
-    const WNode* nodes = P.tlas_nodes;
+    const BvhNode* nodes = P.tlas_nodes;
     const TriRec* tris = nullptr;
-    RayBox rb;
-    rb.idx = rb.idy = rb.idz = rb.cnx = rb.cny = rb.cnz = rb.cfx = rb.cfy = rb.cfz = 0.0f; rb.oct = 0u;
+    Slab sl; Woop wp;
+    sl.rdx = sl.rdy = sl.rdz = sl.cnx = sl.cny = sl.cnz = sl.cfx = sl.cfy = sl.cfz = 0.0f; sl.px = sl.py = sl.pz = false;
+    wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
     uint32_t cur_slot = 0;
-    float best_t = P.tmax;
+    float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
     uint32_t best_slot = NO_HIT, best_tri = 0;
-    uint2 stack[STACK];
+    int32_t stack[STACK];
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
@@ -181,7 +218,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 if (idx >= total) exhausted = true;
                 else {
                     have_ray = true;
-                    V3 o, d;
                     if (STAGE == 0) {
                         const uint32_t tile = idx >> 5, within = idx & 31u;
                         const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
@@ -191,7 +227,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         in_buffer = x < P.width && lr < P.local_rows;
                         valid = in_buffer && y < P.height;
                         lidx = lr * P.width + x;
-                        COLD(C_PIXEL) = __uint_as_float(y * P.width + x);
+                        pixel = y * P.width + x;
                         // ---- raygen (main.cpp:1033-1046); aspect_x/aspect_y computed once on the host (tanf) ----
                         const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
                         const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
@@ -205,57 +241,69 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         lidx = __float_as_uint(q0.x);
                         o = {q0.y, q0.z, q0.w};
                         d = {q1.x, q1.y, q1.z};
-                        COLD(C_COL0) = q1.w; COLD(C_COL1) = q2.x; COLD(C_COL2) = q2.y;
+                        col0 = q1.w; col1 = q2.x; col2 = q2.y;
                         in_buffer = valid = true;
                     }
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
-                    COLD(C_OX) = o.x; COLD(C_OY) = o.y; COLD(C_OZ) = o.z; COLD(C_DX) = d.x; COLD(C_DY) = d.y; COLD(C_DZ) = d.z;
-                    best_t = P.tmax; best_slot = NO_HIT; best_tri = 0;
+                    best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
+                    stack[sp++] = REF_DONE;
                     in_blas = false;
                     nodes = P.tlas_nodes;
-                    traversing = valid && P.tlas_root != REF_EMPTY;
-                    // the root is "the only hit child of a group whose first child is the root": bit 31, imask 0
-                    ng = make_uint2((uint32_t)P.tlas_root, traversing ? 0x80000000u : 0u);
-                    tg = make_uint2(0u, 0u);
-                    raybox_setup(rb, &o.x, &d.x, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
+                    cur = valid ? P.tlas_root : REF_DONE;
+                    if (cur == REF_EMPTY) cur = REF_DONE;
+                    slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
                 }
             }
         }
         if (__ballot_sync(0xffffffffu, have_ray) == 0u) break;
         const bool warp_exhausted = __ballot_sync(0xffffffffu, exhausted) != 0u;
 
-        // ================= two-level traversal over node groups =================
-        // Warp-uniform loop. A lane with a ray either has primitives pending (tg), or children pending (ng), or
-        // has to pop its stack. Every iteration the warp runs ONE of the two heavy steps for all lanes that want it:
-        // the primitive step (one triangle test or one instance entry per lane) once at least PRIM_MIN lanes have
-        // primitives pending or nobody has node work, else the node step; lanes waiting for the other step idle.
-        // This keeps the expensive rare paths (exact triangle test, instance transform with IEEE divisions) from
-        // running with two or three lanes after every node step.
-        for (;;) {
-            const unsigned m_act = __ballot_sync(0xffffffffu, traversing);
-            if (m_act == 0u || (!warp_exhausted && __popc(m_act) < REFILL_THRESHOLD)) break;
-            const bool want_p = traversing && tg.y != 0u;
-            const bool want_n = traversing && !want_p && ng.y > GROUP_PRIM_BITS;
-            const int n_p = __popc(__ballot_sync(0xffffffffu, want_p));
-            const int n_n = __popc(__ballot_sync(0xffffffffu, want_n));
-            if (n_p >= PRIM_MIN || n_n == 0) {
-                // ---------- one primitive of the hit leaf slots ----------
-                if (want_p) {
-                    // primitive index = prim_base + rank of the bit inside the node's prim_valid (word 1 of the node, L1-hot)
-                    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(nodes + tg.x) + 1);      // child_base prim_base prim_valid spare
-                    const uint32_t bit = 31u - (uint32_t)__clz((int)tg.y);
-                    tg.y &= ~(1u << bit);
-                    const uint32_t pidx = w1.y + (uint32_t)__popc(w1.z & ~(0xFFFFFFFFu << bit));
-                    if (in_blas) {
-                        const float4* t4 = reinterpret_cast<const float4*>(tris + pidx);
+        // ================= two-level while-while traversal =================
+        while (cur != REF_DONE) {
+            while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {               // internal node
+                const F8 na = ldg256(&nodes[cur].c[0]), nb = ldg256(&nodes[cur].c[1]);
+                const float4 a0 = na.a, a1 = na.b, b0 = nb.a, b1 = nb.b;
+                if (STATS) ++c_nodes;
+                float t0, t1;
+                const bool hit0 = slab_test(sl, a0, a1, P.tmin, best_t, t0);
+                const bool hit1 = slab_test(sl, b0, b1, P.tmin, best_t, t1);
+                const int32_t r0 = __float_as_int(a1.z), r1 = __float_as_int(b1.z);
+                if (hit0 && hit1) {
+                    const bool swap = t1 < t0;
+                    stack[sp++] = swap ? r0 : r1;
+                    cur = swap ? r1 : r0;
+                } else if (hit0) cur = r0;
+                else if (hit1) cur = r1;
+                else cur = stack[--sp];
+                if (NODE_CAP > 0 && __popc(__activemask()) < NODE_CAP) break;   // do not idle the warp behind a few long node chains
+            }
+            if (cur < 0) {                                                       // leaf
+                const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+                if (!in_blas) {
+                    // TLAS leaf = one instance: cull mask (main.cpp:851,1048), then enter its BLAS in object space
+                    const InstanceRec* R = P.instances + first;
+                    const uint32_t cm = __ldg(&R->custom_mask);
+                    const int32_t root = __ldg(&R->root);
+                    if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
+                        if (STATS) ++c_insts;
+                        float w2o[12];
+                        load_w2o(R, w2o);
+                        const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
+                        slab_setup(sl, oo, od, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
+                        woop_setup(wp, oo, od);
+                        nodes = R->nodes; tris = R->tris;
+                        cur_slot = first;
+                        in_blas = true;
+                        stack[sp++] = REF_POP_INSTANCE;
+                        cur = root;
+                    } else cur = stack[--sp];
+                } else {
+                    for (uint32_t k = 0; k < count; ++k) {
+                        const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
                         const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
                         if (STATS) ++c_tris;
                         float t, bu, bv, bw0;
-                        Woop wp;
-                        wp.okx = COLD(C_WOKX); wp.oky = COLD(C_WOKY); wp.okz = COLD(C_WOKZ);
-                        wp.Sx = COLD(C_WSX); wp.Sy = COLD(C_WSY); wp.Sz = COLD(C_WSZ);
-                        { const uint32_t kz = __float_as_uint(COLD(C_WKZ)); wp.z0 = kz == 0u; wp.z1 = kz == 1u; }
                         if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
                             bool better = t < best_t;
                             if (t == best_t && best_slot != NO_HIT) {
@@ -268,71 +316,25 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                                 const uint32_t geo = __float_as_uint(q2.y), prim = __float_as_uint(q2.z);
                                 better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
                             }
-                            if (better) { best_t = t; COLD(C_BU) = bu; COLD(C_BV) = bv; if (STATS) COLD(C_BW0) = bw0; best_slot = cur_slot; best_tri = pidx; }
-                        }
-                    } else {
-                        // TLAS primitive = one instance: cull mask (main.cpp:851,1048), then enter its BLAS in object space
-                        const InstanceRec* R = P.instances + pidx;
-                        const uint32_t cm = __ldg(&R->custom_mask);
-                        const int32_t root = __ldg(&R->root);
-                        if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
-                            if (STATS) ++c_insts;
-                            if (tg.y) stack[sp++] = tg;                                  // other instances of this TLAS node
-                            if (ng.y > GROUP_PRIM_BITS) stack[sp++] = ng;                // pending TLAS children
-                            stack[sp++] = make_uint2(0u, 0u);                            // sentinel: back to world space
-                            float w2o[12];
-                            load_w2o(R, w2o);
-                            const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
-                            const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
-                            raybox_setup(rb, &oo.x, &od.x, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
-                            Woop wp;
-                            woop_setup(wp, oo, od);
-                            COLD(C_WOKX) = wp.okx; COLD(C_WOKY) = wp.oky; COLD(C_WOKZ) = wp.okz;
-                            COLD(C_WSX) = wp.Sx; COLD(C_WSY) = wp.Sy; COLD(C_WSZ) = wp.Sz;
-                            COLD(C_WKZ) = __uint_as_float(wp.z0 ? 0u : (wp.z1 ? 1u : 2u));
-                            nodes = R->nodes; tris = R->tris;
-                            cur_slot = pidx;
-                            in_blas = true;
-                            ng = make_uint2((uint32_t)root, 0x80000000u);
-                            tg = make_uint2(0u, 0u);
+                            if (better) { best_t = t; best_u = bu; best_v = bv; best_w0 = bw0; best_slot = cur_slot; best_tri = first + k; }
                         }
                     }
+                    cur = stack[--sp];
                 }
-            } else if (want_n) {
-                // ---------- one wide node: the highest-priority hit child of the current node group ----------
-                const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
-                const uint32_t imask = ng.y & 0xFFu;
-                ng.y &= ~(1u << bit);
-                if (ng.y > GROUP_PRIM_BITS) stack[sp++] = ng;                       // siblings still to visit
-                const uint32_t slot = (bit - 24u) ^ rb.oct;
-                const uint32_t child = ng.x + (uint32_t)__popc(imask & ~(0xFFFFFFFFu << slot));
-                const uint4* n4 = reinterpret_cast<const uint4*>(nodes + child);
-                const uint4 n0 = __ldg(n4), n1 = __ldg(n4 + 1), n2 = __ldg(n4 + 2), n3 = __ldg(n4 + 3), n4w = __ldg(n4 + 4);
-                if (STATS) ++c_nodes;
-                uint32_t inner, prims;
-                wide_node_hits(rb, n0, n1, n2, n3, n4w, P.tmin, best_t, inner, prims);
-                ng = make_uint2(n1.x, inner | (n0.w >> 24));
-                tg = make_uint2(child, prims);
+            } else if (cur == REF_POP_INSTANCE) {                                // back to world space
+                in_blas = false;
+                nodes = P.tlas_nodes;
+                slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
+                cur = stack[--sp];
+            } else if (cur == REF_EMPTY) {
+                cur = stack[--sp];
             }
-            // ---------- nothing pending in the current groups: pop ----------
-            if (traversing && tg.y == 0u && ng.y <= GROUP_PRIM_BITS) {
-                if (sp == 0) traversing = false;
-                else {
-                    const uint2 e = stack[--sp];
-                    if (e.y == 0u) {                                                 // sentinel: leave the instance
-                        in_blas = false;
-                        nodes = P.tlas_nodes;
-                        const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
-                        raybox_setup(rb, &o.x, &d.x, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
-                        ng = make_uint2(0u, 0u);
-                    } else if (e.y > GROUP_PRIM_BITS) ng = e;
-                    else { tg = e; ng = make_uint2(0u, 0u); }
-                }
-            }
+            // warp-level compaction trigger: too few lanes still traversing -> go refill the idle ones
+            if (!warp_exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
         }
 
         // ================= epilogue of the lanes whose ray just finished =================
-        const bool finish = have_ray && !traversing;
+        const bool finish = have_ray && cur == REF_DONE;
         bool enqueue = false;
         float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
         if (finish) {
@@ -346,7 +348,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             } else {
                 if (STATS) ++c_rays;
                 const bool hit = best_slot != NO_HIT;
-                const float best_u = hit ? COLD(C_BU) : 0.0f, best_v = hit ? COLD(C_BV) : 0.0f;
                 const InstanceRec* R = P.instances + (hit ? best_slot : 0u);
                 float sc0, sc1, sc2;
                 rt_hit rec = miss_record(P.tmax);
@@ -366,7 +367,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     }
                     rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
                     rec.t = best_t; rec.u = best_u; rec.v = best_v;
-                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), COLD(C_BW0)) < 9.5367431640625e-07f) ++c_edge; }
+                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c_edge; }
                 } else {
                     sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];                 // miss shader (main.cpp:1063-1066)
                 }
@@ -374,8 +375,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     if (P.primary_hits) P.primary_hits[lidx] = rec;
                     if (hit && P.bounces > 0u) {
                         // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
-                        const V3 o = {COLD(C_OX), COLD(C_OY), COLD(C_OZ)}, d = {COLD(C_DX), COLD(C_DY), COLD(C_DZ)};
-                        const uint32_t pixel = __float_as_uint(COLD(C_PIXEL));
                         const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
                         float w2o[12];
                         load_w2o(R, w2o);
@@ -410,7 +409,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     }
                 } else {
                     if (P.secondary_hits) P.secondary_hits[lidx] = rec;
-                    const float f0 = 0.5f * COLD(C_COL0) + 0.5f * sc0, f1 = 0.5f * COLD(C_COL1) + 0.5f * sc1, f2 = 0.5f * COLD(C_COL2) + 0.5f * sc2;
+                    const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
                     reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
                 }
             }
@@ -431,7 +430,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         }
     }
 
-#undef COLD
     if (STATS && P.stats) {
         // rt_trace_stats order: rays_primary, rays_secondary, nodes, tris, insts, primary_hits, secondary_hits, near_edge
         unsigned long long v[8] = {STAGE == 0 ? c_rays : 0ull, STAGE == 1 ? c_rays : 0ull, c_nodes, c_tris, c_insts,
@@ -485,7 +483,7 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     if (tiles == 0) return 0;
     if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
     int n;
-    if (stack_needed <= 32) n = stats ? launch_both<true, 32>(p, sm_count, st) : launch_both<false, 32>(p, sm_count, st);
+    if (stack_needed <= 64) n = stats ? launch_both<true, 64>(p, sm_count, st) : launch_both<false, 64>(p, sm_count, st);
     else if (stack_needed <= 160) n = stats ? launch_both<true, 160>(p, sm_count, st) : launch_both<false, 160>(p, sm_count, st);
     else return -2;
     if (cudaGetLastError() != cudaSuccess) return -1;

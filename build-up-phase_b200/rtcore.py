@@ -35,7 +35,7 @@ EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync",
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
     "rt_update_tlas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
-    "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_debug_last_binary_bvh", "rt_blas_import", "rt_tlas_get_info",
+    "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
@@ -80,8 +80,7 @@ class RtTraceStats(C.Structure):
 
 class RtBuildTiming(C.Structure):
     _fields_ = [("total_ms", C.c_float), ("setup_ms", C.c_float), ("morton_ms", C.c_float), ("sort_ms", C.c_float),
-                ("hierarchy_ms", C.c_float), ("refit_ms", C.c_float), ("h2d_ms", C.c_float), ("widen_ms", C.c_float),
-                ("reserved", C.c_float), ("primitives", C.c_uint64)]
+                ("hierarchy_ms", C.c_float), ("refit_ms", C.c_float), ("h2d_ms", C.c_float), ("primitives", C.c_uint64)]
 
     def as_dict(self):
         return {n: (float(getattr(self, n)) if n != "primitives" else int(self.primitives)) for n, _ in self._fields_}
@@ -152,7 +151,6 @@ def load(build_if_missing: bool = True):
     L.rt_blas_get_info.argtypes = [vp, vp, C.POINTER(RtBlasInfo)]
     L.rt_blas_export.argtypes = [vp, vp, vp, vp]
     L.rt_debug_last_sorted_keys.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]
-    L.rt_debug_last_binary_bvh.argtypes = [vp, vp, u32, C.POINTER(C.c_int32), C.POINTER(u32)]
     L.rt_blas_import.argtypes = [vp, C.POINTER(RtBlasInfo), vp, C.POINTER(vp)]
     L.rt_tlas_get_info.argtypes = [vp, vp, C.POINTER(RtTlasInfo)]
     L.rt_set_hit_records.argtypes = [vp, vp, u32]
@@ -209,10 +207,9 @@ class Blas:
         return info
 
     def export(self):
-        """(wide nodes uint32[n_nodes,20], tris uint32[n,12]): raw 80-B 8-wide nodes and 48-B triangles in wide-node
-        order (word 11 of a triangle = its position in Morton order)."""
+        """(nodes uint32[n,16], tris uint32[n,12]) raw 64-B nodes and 48-B triangles."""
         info = self.info()
-        nodes = np.zeros((info.node_count, 20), dtype=np.uint32)
+        nodes = np.zeros((info.node_count, 16), dtype=np.uint32)
         tris = np.zeros((info.triangle_count, 12), dtype=np.uint32)
         self.ctx._check(self.ctx.L.rt_blas_export(self.ctx.h, self.handle, nodes.ctypes.data, tris.ctypes.data))
         return nodes, tris
@@ -378,15 +375,6 @@ class Context:
         prims = np.zeros(n.value, dtype=np.uint32)
         self._check(self.L.rt_debug_last_sorted_keys(self.h, keys.ctypes.data, prims.ctypes.data, n.value, C.byref(n)))
         return keys, prims
-
-    def last_binary_bvh(self):
-        """(nodes uint32[n,16], root_ref, height) of the intermediate binary LBVH of the most recent single-BLAS build."""
-        n = C.c_uint32()
-        self._check(self.L.rt_debug_last_sorted_keys(self.h, None, None, 0, C.byref(n)))
-        nodes = np.zeros((n.value, 16), dtype=np.uint32)
-        root, height = C.c_int32(), C.c_uint32()
-        self._check(self.L.rt_debug_last_binary_bvh(self.h, nodes.ctypes.data, n.value, C.byref(root), C.byref(height)))
-        return nodes, root.value, height.value
 
     # -- shader data ----------------------------------------------------------------------------------
     def set_hit_records(self, rgb: np.ndarray):

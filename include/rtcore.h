@@ -133,15 +133,13 @@ typedef struct rt_trace_stats {
 
 /* Phase timings of the most recent build on this context, CUDA-event milliseconds. */
 typedef struct rt_build_timing {
-    float total_ms;        /* first setup kernel .. end of the wide-node collapse (no H2D) */
+    float total_ms;        /* first setup kernel .. last refit kernel (no H2D) */
     float setup_ms;        /* triangle fetch + transform + bounds */
     float morton_ms;
     float sort_ms;
     float hierarchy_ms;
-    float refit_ms;        /* atomic bottom-up AABB refit of the binary LBVH */
+    float refit_ms;        /* leaf emit + atomic bottom-up refit */
     float h2d_ms;          /* staging copies of host inputs (outside total_ms) */
-    float widen_ms;        /* collapse into 8-wide compressed nodes + triangle emit (inside total_ms) */
-    float reserved;
     uint64_t primitives;
 } rt_build_timing;
 
@@ -180,23 +178,19 @@ RT_API float rt_last_build_ms(const rt_context* ctx);
 /* Introspection used by the parity tests (build invariants) and by multi-GPU BLAS broadcast. */
 typedef struct rt_blas_info {
     uint32_t triangle_count;
-    uint32_t node_count;        /* 80-byte 8-wide nodes stored (of the whole storage for a batched build) */
-    int32_t  root_ref;          /* index of the root wide node, RT_REF_EMPTY for an empty BLAS */
-    uint32_t max_depth;         /* levels of the wide tree */
+    uint32_t node_count;        /* 64-byte internal nodes stored */
+    int32_t  root_ref;          /* >=0 internal node, <0 leaf, RT_REF_EMPTY for an empty BLAS */
+    uint32_t max_depth;
     float    bounds_lo[3], bounds_hi[3];
-    uint64_t storage_bytes;     /* relocatable device blob: triangles | record | wide nodes (0 for a batched build) */
+    uint64_t storage_bytes;     /* relocatable device blob: nodes then triangles */
     void*    device_storage;    /* device pointer of that blob */
 } rt_blas_info;
 #define RT_REF_EMPTY 0x7FFFFFFD
 RT_API int  rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out);
-/* Copies wide nodes (node_count x 80 B) and triangles (triangle_count x 48 B, wide-node order; the last word of a
- * record is its position in Morton order) to host buffers; either may be NULL. */
+/* Copies nodes (node_count x 64 B) and triangles (triangle_count x 48 B) to host buffers; either may be NULL. */
 RT_API int  rt_blas_export(rt_context* ctx, const rt_blas* blas, void* nodes_out, void* tris_out);
 /* Debug/parity export of the sorted Morton keys+primitive ids of the most recent single-BLAS build. */
 RT_API int  rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* prim_out, uint32_t capacity, uint32_t* n_out);
-/* Debug/parity export of the intermediate binary LBVH (Karras topology + refitted boxes, 64-byte nodes) of the most
- * recent single-BLAS build; leaf refs index the Morton-sorted primitive order. */
-RT_API int  rt_debug_last_binary_bvh(rt_context* ctx, void* nodes_out, uint32_t capacity, int32_t* root_out, uint32_t* height_out);
 /* Wraps a device blob produced by another context/GPU's rt_blas_get_info().device_storage
  * (after ncclBroadcast) as a BLAS on this context. The blob is copied. */
 RT_API int  rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device_blob, rt_blas** out);

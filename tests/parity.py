@@ -79,72 +79,3 @@ def walk_compare_bvh(nodes_a, root_a, nodes_b, root_b):
                 stack.append(ref)
         count += 1
     return count
-
-
-def _popcount24(v):
-    v = v.astype(np.int64)
-    c = np.zeros(v.shape, dtype=np.int64)
-    for b in range(24):
-        c += (v >> b) & 1
-    return c
-
-
-def check_wide_bvh(wnodes, tris, root, bounds_lo, bounds_hi):
-    """Structural invariants of an exported 8-wide BVH (uint32[n,20] nodes, uint32[m,12] triangles in wide order):
-    every node referenced exactly once, every triangle in exactly one leaf slot, imask/prim_valid consistent, and every
-    triangle inside the dequantised box of EVERY ancestor slot on its path (so no conservative box can cull it).
-    Returns the number of reachable nodes. Vectorised level by level."""
-    n_nodes, n_tris = wnodes.shape[0], tris.shape[0]
-    if root < 0 or root >= 0x7FFFFFF0:
-        assert n_tris == 0
-        return 0
-    b = np.ascontiguousarray(wnodes).view(np.uint8).reshape(n_nodes, 80)
-    p = np.ascontiguousarray(wnodes[:, 0:3]).view(np.float32).astype(np.float64)
-    e = b[:, 12:15].astype(np.int64)
-    step = np.ldexp(1.0, e - 127)
-    imask = b[:, 15].astype(np.int64)
-    child_base, prim_base = wnodes[:, 4].astype(np.int64), wnodes[:, 5].astype(np.int64)
-    prim_valid = wnodes[:, 6].astype(np.int64)
-    q = b[:, 32:80].reshape(n_nodes, 6, 8).astype(np.float64)          # qlo.x qlo.y qlo.z qhi.x qhi.y qhi.z  x 8 slots
-    lo = p[:, :, None] + q[:, 0:3, :] * step[:, :, None]               # [n, 3, 8]
-    hi = p[:, :, None] + q[:, 3:6, :] * step[:, :, None]
-    tv = np.ascontiguousarray(tris[:, :9]).view(np.float32).reshape(n_tris, 3, 3).astype(np.float64)
-    tlo, thi = tv.min(axis=1), tv.max(axis=1)
-    seen_nodes = np.zeros(n_nodes, dtype=np.int32)
-    seen_tris = np.zeros(n_tris, dtype=np.int32)
-    frontier = np.array([root], dtype=np.int64)
-    acc_lo = np.array([bounds_lo], dtype=np.float64)
-    acc_hi = np.array([bounds_hi], dtype=np.float64)
-    depth = 0
-    while frontier.size:
-        np.add.at(seen_nodes, frontier, 1)
-        nxt, nlo, nhi = [], [], []
-        rank = np.zeros(frontier.size, dtype=np.int64)
-        pv = prim_valid[frontier]
-        assert np.all(pv < (1 << 24))
-        for s in range(8):
-            inner = ((imask[frontier] >> s) & 1) == 1
-            f3 = (pv >> (3 * s)) & 7
-            assert np.all(np.isin(f3, (0, 1, 3, 7))), "bad primitive field"
-            assert np.all(f3[inner] == 0), "internal slot with primitive bits"
-            leaf = f3 != 0
-            clo = np.maximum(lo[frontier, :, s], acc_lo)
-            chi = np.minimum(hi[frontier, :, s], acc_hi)
-            cnt = np.where(f3 == 1, 1, np.where(f3 == 3, 2, np.where(f3 == 7, 3, 0)))
-            below = pv & ((1 << (3 * s)) - 1)
-            off = _popcount24(below)
-            for k in range(3):
-                sel = leaf & (cnt > k)
-                ti = prim_base[frontier][sel] + off[sel] + k
-                assert np.all(ti < n_tris)
-                np.add.at(seen_tris, ti, 1)
-                assert np.all(tlo[ti] >= clo[sel]) and np.all(thi[ti] <= chi[sel]), "a triangle escapes a box on its path"
-            nxt.append(child_base[frontier][inner] + rank[inner]); nlo.append(clo[inner]); nhi.append(chi[inner])
-            rank += inner
-        frontier = np.concatenate(nxt); acc_lo = np.concatenate(nlo); acc_hi = np.concatenate(nhi)
-        assert np.all(frontier < n_nodes)
-        depth += 1
-        assert depth < 200
-    assert np.all(seen_tris == 1), "a triangle is not in exactly one leaf slot"
-    assert np.all(seen_nodes <= 1), "a wide node is referenced twice"
-    return int((seen_nodes > 0).sum())

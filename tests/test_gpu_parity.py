@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from build_up_phase_b200 import scenes
-from parity import check_wide_bvh, MISS, assert_parity, compare_hits, walk_compare_bvh
+from parity import MISS, assert_parity, compare_hits, walk_compare_bvh
 
 pytestmark = pytest.mark.gpu
 
@@ -97,26 +97,20 @@ def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle):
     scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
     blas = ctx.build_blas(scene.blases[0])
     keys, prims = ctx.last_sorted_keys()
-    nodes, root, height = ctx.last_binary_bvh()          # the intermediate binary LBVH (Karras + refit)
     info = blas.info()
-    wnodes, tris = blas.export()                         # what the trace kernel walks: 8-wide nodes, triangles in wide order
+    nodes, tris = blas.export()
     blas.free()
     o = oracle.OracleScene(scene)
     oinfo, onodes, otris, okeys, oprims = o.blas_export(0)
     assert info.triangle_count == oinfo.triangle_count == 120 * 70 * 2
     assert np.array_equal(keys, okeys), "sorted Morton keys differ"
     assert np.array_equal(prims, oprims), "sorted primitive order differs (sort not stable?)"
-    sorted_tris = np.zeros_like(tris)
-    assert np.array_equal(np.sort(tris[:, 11]), np.arange(tris.shape[0], dtype=np.uint32)), "wide-order triangles are not a permutation"
-    sorted_tris[tris[:, 11]] = tris
-    assert np.array_equal(sorted_tris[:, :11], otris[:, :11]), "sorted triangle records differ"
-    assert root == oinfo.root_ref and height == oinfo.max_depth
+    assert np.array_equal(tris[:, :11], otris[:, :11]), "sorted triangle records differ"
+    assert info.root_ref == oinfo.root_ref and info.max_depth == oinfo.max_depth
     assert list(info.bounds_lo) == list(oinfo.bounds_lo) and list(info.bounds_hi) == list(oinfo.bounds_hi)
-    n = walk_compare_bvh(nodes, root, onodes, oinfo.root_ref)
+    n = walk_compare_bvh(nodes, info.root_ref, onodes, oinfo.root_ref)
     assert n > info.triangle_count // 8
-    wn = check_wide_bvh(wnodes, tris, info.root_ref, info.bounds_lo, info.bounds_hi)
-    assert wn == info.node_count
-    print("lbvh nodes compared:", n, "depth", height, "| wide nodes", wn, "wide depth", info.max_depth)
+    print("lbvh nodes compared:", n, "depth", info.max_depth)
 
 
 def test_build_invariants_large(rt, ctx):
@@ -126,19 +120,17 @@ def test_build_invariants_large(rt, ctx):
     blas = ctx.build_blas(scene.blases[0])
     t = ctx.build_timing()
     keys, prims = ctx.last_sorted_keys()
-    nodes, root, height = ctx.last_binary_bvh()
     info = blas.info()
-    wnodes, tris = blas.export()
+    nodes, tris = blas.export()
     blas.free()
     n = info.triangle_count
     assert n == 2_000_000
     assert np.all(keys[1:] >= keys[:-1])
     assert np.array_equal(np.sort(prims), np.arange(n, dtype=np.uint32))
-    assert check_wide_bvh(wnodes, tris, info.root_ref, info.bounds_lo, info.bounds_hi) == info.node_count
-    # walk the binary tree: vectorised level-by-level
+    # walk the tree: vectorised level-by-level
     f = nodes.view(np.float32)
     covered = np.zeros(n, dtype=np.int32)
-    frontier = np.array([root], dtype=np.int64)
+    frontier = np.array([info.root_ref], dtype=np.int64)
     box_lo = np.array([info.bounds_lo], dtype=np.float32)
     box_hi = np.array([info.bounds_hi], dtype=np.float32)
     depth = 0
@@ -163,7 +155,7 @@ def test_build_invariants_large(rt, ctx):
         depth += 1
         assert depth < 200
     assert np.all(covered == 1), "a triangle is not in exactly one leaf"
-    assert depth == height
+    assert depth == info.max_depth
     print("build 2M tris:", t)
 
 
@@ -263,15 +255,6 @@ def test_tlas_update_and_device_inputs(rt, ctx, oracle):
     n_dev, t_dev = b_dev.export()
     b_host = ctx.build_blas([geo])
     n_host, t_host = b_host.export()
-    i_dev, i_host = b_dev.info(), b_host.info()
-
-    def canon(t):          # wide-node order depends on the order of atomic slot reservations; Morton order does not
-        s = np.zeros_like(t)
-        s[t[:, 11]] = t
-        return s
-    assert np.array_equal(canon(t_dev), canon(t_host))
-    assert i_dev.root_ref == i_host.root_ref and i_dev.node_count == i_host.node_count and i_dev.max_depth == i_host.max_depth
-    assert list(i_dev.bounds_lo) == list(i_host.bounds_lo) and list(i_dev.bounds_hi) == list(i_host.bounds_hi)
-    assert check_wide_bvh(n_dev, t_dev, i_dev.root_ref, i_dev.bounds_lo, i_dev.bounds_hi) == i_dev.node_count
-    assert check_wide_bvh(n_host, t_host, i_host.root_ref, i_host.bounds_lo, i_host.bounds_hi) == i_host.node_count
+    assert np.array_equal(t_dev, t_host) and b_dev.info().root_ref == b_host.info().root_ref
+    walk_compare_bvh(n_dev, b_dev.info().root_ref, n_host, b_host.info().root_ref)
     b_dev.free(); b_host.free()

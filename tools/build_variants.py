@@ -5,11 +5,13 @@ from build_up_phase_b200 import build as b
 
 VARIANTS = {
     "base": [],
-    "pm1": ["RT_PRIM_MIN=1"],
-    "pm4": ["RT_PRIM_MIN=4"],
-    "pm12": ["RT_PRIM_MIN=12"],
-    "pm16": ["RT_PRIM_MIN=16"],
-    "pm12_thr20": ["RT_PRIM_MIN=12", "RT_REFILL_THRESHOLD=20"],
+    "thr12": ["RT_REFILL_THRESHOLD=12"],
+    "thr16": ["RT_REFILL_THRESHOLD=16"],
+    "cap0": ["RT_NODE_CAP=0"],
+    "cap4": ["RT_NODE_CAP=4"],
+    "cap4_thr12": ["RT_NODE_CAP=4", "RT_REFILL_THRESHOLD=12"],
+    "cap8_thr12": ["RT_NODE_CAP=8", "RT_REFILL_THRESHOLD=12"],
+    "cap12_thr12": ["RT_NODE_CAP=12", "RT_REFILL_THRESHOLD=12"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
