@@ -412,6 +412,17 @@ def run_gpu(args):
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
 
+    # checksums of the full frame and of the hit records (primary + secondary): variants of the kernels must reproduce them exactly
+    crc = None
+    if world == 1:
+        import zlib
+        prim_c = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
+        sec_c = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
+        ctx.trace_device(tlas, cam, W, H, bounces, frame, prim_c, sec_c)
+        crc = {"rgba": zlib.crc32(frame.cpu().numpy().tobytes()), "primary_hits": zlib.crc32(prim_c.cpu().numpy().tobytes()),
+               "secondary_hits": zlib.crc32(sec_c.cpu().numpy().tobytes())}
+        del prim_c, sec_c
+
     if rank == 0:
         hbm, peak_src = peaks()
         algo_bytes = b_ray_bytes(tot, W * H)
@@ -443,6 +454,7 @@ def run_gpu(args):
                       "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
                                    "bytes_per_triangle": B_TRI_BUILD}},
             "traversal": tot,
+            "crc32": crc,
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

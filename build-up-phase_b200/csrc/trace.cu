@@ -45,6 +45,12 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 #ifndef RT_LDG256
 #define RT_LDG256 0
 #endif
+#ifndef RT_FAST_SLAB
+#define RT_FAST_SLAB 0
+#endif
+#ifndef RT_POSTPONE_LEAF
+#define RT_POSTPONE_LEAF 0
+#endif
 
 // Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
 // on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
@@ -75,7 +81,14 @@ __device__ __forceinline__ void slab_setup(Slab& s, V3 o, V3 d, float ax, float 
     const float dy = fabsf(d.y) < 1e-20f ? copysignf(1e-20f, d.y) : d.y;
     const float dz = fabsf(d.z) < 1e-20f ? copysignf(1e-20f, d.z) : d.z;
     s.px = dx > 0.0f; s.py = dy > 0.0f; s.pz = dz > 0.0f;
+#if RT_FAST_SLAB
+    // MUFU.RCP (<= 1 ulp): the box test only has to be conservative and the 2^-19 spatial pad dwarfs a 2^-23 scale error of t
+    asm("rcp.approx.f32 %0, %1;" : "=f"(s.rdx) : "f"(dx));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(s.rdy) : "f"(dy));
+    asm("rcp.approx.f32 %0, %1;" : "=f"(s.rdz) : "f"(dz));
+#else
     s.rdx = 1.0f / dx; s.rdy = 1.0f / dy; s.rdz = 1.0f / dz;
+#endif
     s.cnx = -((s.px ? o.x + e : o.x - e) * s.rdx); s.cfx = -((s.px ? o.x - e : o.x + e) * s.rdx);
     s.cny = -((s.py ? o.y + e : o.y - e) * s.rdy); s.cfy = -((s.py ? o.y - e : o.y + e) * s.rdy);
     s.cnz = -((s.pz ? o.z + e : o.z - e) * s.rdz); s.cfz = -((s.pz ? o.z - e : o.z + e) * s.rdz);
@@ -204,6 +217,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
     uint32_t best_slot = NO_HIT, best_tri = 0;
     int32_t stack[STACK];
+#if RT_POSTPONE_LEAF
+    int32_t postponed = 0;            // leaf refs are negative, so 0 = none
+#endif
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
@@ -276,8 +292,14 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
                 else cur = stack[--sp];
+#if RT_POSTPONE_LEAF
+                if (cur < 0 && postponed == 0) { postponed = cur; cur = stack[--sp]; }   // speculative traversal: one leaf may wait
+#endif
                 if (NODE_CAP > 0 && __popc(__activemask()) < NODE_CAP) break;   // do not idle the warp behind a few long node chains
             }
+#if RT_POSTPONE_LEAF
+            if (postponed != 0) { stack[sp++] = cur; cur = postponed; postponed = 0; }
+#endif
             if (cur < 0) {                                                       // leaf
                 const uint32_t first = leaf_first(cur), count = leaf_count(cur);
                 if (!in_blas) {

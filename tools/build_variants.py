@@ -5,13 +5,9 @@ from build_up_phase_b200 import build as b
 
 VARIANTS = {
     "base": [],
-    "thr12": ["RT_REFILL_THRESHOLD=12"],
-    "thr16": ["RT_REFILL_THRESHOLD=16"],
-    "cap0": ["RT_NODE_CAP=0"],
-    "cap4": ["RT_NODE_CAP=4"],
-    "cap4_thr12": ["RT_NODE_CAP=4", "RT_REFILL_THRESHOLD=12"],
-    "cap8_thr12": ["RT_NODE_CAP=8", "RT_REFILL_THRESHOLD=12"],
-    "cap12_thr12": ["RT_NODE_CAP=12", "RT_REFILL_THRESHOLD=12"],
+    "fastslab": ["RT_FAST_SLAB=1"],
+    "postpone": ["RT_POSTPONE_LEAF=1"],
+    "fastslab_postpone": ["RT_FAST_SLAB=1", "RT_POSTPONE_LEAF=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or list(VARIANTS)
