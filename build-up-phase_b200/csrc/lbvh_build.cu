@@ -106,8 +106,9 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const GeomDesc* __r
     }
 }
 
+// vb > 0: packed record `key << vb | triangle id` (vals unused)
 __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ tris, uint32_t n_tris, const int* __restrict__ bounds,
-                                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                   uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int vb) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n_tris) return;
     const float4* src = reinterpret_cast<const float4*>(tris + t);
@@ -118,37 +119,38 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
     const int* b = bounds + 6 * (size_t)blas;
     float slo[3] = {ordered_to_float(__ldg(b)), ordered_to_float(__ldg(b + 1)), ordered_to_float(__ldg(b + 2))};
     float shi[3] = {ordered_to_float(__ldg(b + 3)), ordered_to_float(__ldg(b + 4)), ordered_to_float(__ldg(b + 5))};
-    keys[t] = ((uint64_t)blas << MORTON_BITS) | (uint64_t)morton30(plo, phi, slo, shi);
-    vals[t] = t;
+    const uint64_t key = ((uint64_t)blas << MORTON_BITS) | (uint64_t)morton30(plo, phi, slo, shi);
+    if (vb) keys[t] = (key << vb) | (uint64_t)t;
+    else { keys[t] = key; vals[t] = t; }
 }
 
 // ---- Karras 2012 ------------------------------------------------------------------------------
-__device__ __forceinline__ int karras_delta(const uint64_t* __restrict__ keys, int n, int i, uint64_t ki, int j) {
+__device__ __forceinline__ int karras_delta(const uint64_t* __restrict__ keys, int vb, int n, int i, uint64_t ki, int j) {
     if (j < 0 || j >= n) return -1;
-    const uint64_t kj = __ldg(keys + j);
+    const uint64_t kj = __ldg(keys + j) >> vb;
     if (ki == kj) return 64 + __clz(i ^ j);
     return __clzll((long long)(ki ^ kj));
 }
 
-__global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ keys, int n, int32_t* __restrict__ other_end,
+__global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ keys, int vb, int n, int32_t* __restrict__ other_end,
                                                uint32_t* __restrict__ parent_node, uint32_t* __restrict__ parent_leaf) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
-    const uint64_t ki = __ldg(keys + i);
-    int d = (karras_delta(keys, n, i, ki, i + 1) - karras_delta(keys, n, i, ki, i - 1)) >= 0 ? 1 : -1;
+    const uint64_t ki = __ldg(keys + i) >> vb;
+    int d = (karras_delta(keys, vb, n, i, ki, i + 1) - karras_delta(keys, vb, n, i, ki, i - 1)) >= 0 ? 1 : -1;
     if (i == 0) d = 1;
-    const int dmin = karras_delta(keys, n, i, ki, i - d);
+    const int dmin = karras_delta(keys, vb, n, i, ki, i - d);
     int lmax = 2;
-    while (karras_delta(keys, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
+    while (karras_delta(keys, vb, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
     int l = 0;
     for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (karras_delta(keys, n, i, ki, i + (l + t) * d) > dmin) l += t;
+        if (karras_delta(keys, vb, n, i, ki, i + (l + t) * d) > dmin) l += t;
     const int j = i + l * d;
-    const int dnode = karras_delta(keys, n, i, ki, j);
+    const int dnode = karras_delta(keys, vb, n, i, ki, j);
     int s = 0, t = l;
     do {
         t = (t + 1) >> 1;
-        if (karras_delta(keys, n, i, ki, i + (s + t) * d) > dnode) s += t;
+        if (karras_delta(keys, vb, n, i, ki, i + (s + t) * d) > dnode) s += t;
     } while (t > 1);
     const int gamma = i + s * d + min(d, 0);
     const int first = min(i, j), last = max(i, j);
@@ -201,15 +203,16 @@ __device__ __forceinline__ bool climb(BvhNode* __restrict__ nodes, const uint32_
     }
 }
 
-__global__ void __launch_bounds__(256) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, uint32_t n,
+__global__ void __launch_bounds__(256) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
                                                    const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
                                                    BvhNode* __restrict__ nodes, BlasRecord* __restrict__ records,
                                                    const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
                                                    const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
-    const uint32_t blas = (uint32_t)(__ldg(keys + leaf) >> MORTON_BITS);
-    const uint32_t src_i = __ldg(vals + leaf);
+    const uint64_t rec = __ldg(keys + leaf);
+    const uint32_t blas = (uint32_t)(rec >> (MORTON_BITS + vb));
+    const uint32_t src_i = vb ? (uint32_t)(rec & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
     const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
     const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
     float4 q2 = __ldg(src + 2);
@@ -289,25 +292,26 @@ __global__ void __launch_bounds__(128) k_inst_setup(const rt_instance* __restric
 }
 
 __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restrict__ inst, const float* __restrict__ boxes, uint32_t n,
-                                                    const int* __restrict__ bounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                    const int* __restrict__ bounds, uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int vb) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float* bx = boxes + 6 * (size_t)i;
     float plo[3] = {bx[0], bx[1], bx[2]}, phi[3] = {bx[3], bx[4], bx[5]};
     float slo[3] = {ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2])};
     float shi[3] = {ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5])};
-    keys[i] = inst[i].active ? (uint64_t)morton30(plo, phi, slo, shi) : 0x3FFFFFFFull;
-    vals[i] = i;
+    const uint64_t key = inst[i].active ? (uint64_t)morton30(plo, phi, slo, shi) : 0x3FFFFFFFull;
+    if (vb) keys[i] = (key << vb) | (uint64_t)i;
+    else { keys[i] = key; vals[i] = i; }
 }
 
-__global__ void __launch_bounds__(256) k_refit_inst(const uint32_t* __restrict__ vals, uint32_t n, const InstanceRec* __restrict__ unsorted,
+__global__ void __launch_bounds__(256) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
                                                    const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
                                                    BvhNode* __restrict__ nodes, int32_t* __restrict__ meta, float* __restrict__ bounds_out,
                                                    const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
                                                    const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     if (leaf >= n) return;
-    const uint32_t src_i = __ldg(vals + leaf);
+    const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
     const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
     float4* dst = reinterpret_cast<float4*>(sorted + leaf);
 #pragma unroll
@@ -334,10 +338,11 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
     k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
     ++launches;
     if (ev) cudaEventRecord(ev->e[1], st);
-    k_tri_morton<<<div_up(a.n_tris, 256), 256, 0, st>>>(a.tris_unsorted, a.n_tris, a.bounds_ordered, a.s.keys_a, a.s.vals_a);
+    const int vb = a.sort.packed_val_bits;
+    k_tri_morton<<<div_up(a.n_tris, 256), 256, 0, st>>>(a.tris_unsorted, a.n_tris, a.bounds_ordered, a.s.keys_a, a.s.vals_a, vb);
     ++launches;
     if (ev) cudaEventRecord(ev->e[2], st);
-    int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, a.s.vals_a, a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, sorted_in_b);
+    int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, vb ? nullptr : a.s.vals_a, vb ? nullptr : a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, sorted_in_b);
     if (sl < 0) return -1;
     launches += sl;
     const uint64_t* keys = *sorted_in_b ? a.s.keys_b : a.s.keys_a;
@@ -345,11 +350,11 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
     if (ev) cudaEventRecord(ev->e[3], st);
     if (a.n_tris > 1) {
         if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * (size_t)a.n_tris, st) != cudaSuccess) return -1;
-        k_karras<<<div_up(a.n_tris - 1, 256), 256, 0, st>>>(keys, (int)a.n_tris, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
+        k_karras<<<div_up(a.n_tris - 1, 256), 256, 0, st>>>(keys, vb, (int)a.n_tris, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
         ++launches;
     }
     if (ev) cudaEventRecord(ev->e[4], st);
-    k_refit_tris<<<div_up(a.n_tris, 256), 256, 0, st>>>(keys, vals, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, a.records,
+    k_refit_tris<<<div_up(a.n_tris, 256), 256, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, a.records,
                                                        a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
     ++launches;
     if (ev) cudaEventRecord(ev->e[5], st);
@@ -361,20 +366,21 @@ int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st) {
     int launches = 0;
     if (a.n == 0) return 0;
     k_inst_setup<<<div_up(a.n, 128), 128, 0, st>>>(a.instances, a.n, a.inst_unsorted, a.boxes_unsorted, a.bounds_ordered, a.root_out);
-    k_inst_morton<<<div_up(a.n, 256), 256, 0, st>>>(a.inst_unsorted, a.boxes_unsorted, a.n, a.bounds_ordered, a.s.keys_a, a.s.vals_a);
+    const int vb = a.sort.packed_val_bits;
+    k_inst_morton<<<div_up(a.n, 256), 256, 0, st>>>(a.inst_unsorted, a.boxes_unsorted, a.n, a.bounds_ordered, a.s.keys_a, a.s.vals_a, vb);
     launches += 2;
     bool in_b = false;
-    int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, a.s.vals_a, a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, &in_b);
+    int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, vb ? nullptr : a.s.vals_a, vb ? nullptr : a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, &in_b);
     if (sl < 0) return -1;
     launches += sl;
     const uint64_t* keys = in_b ? a.s.keys_b : a.s.keys_a;
     const uint32_t* vals = in_b ? a.s.vals_b : a.s.vals_a;
     if (a.n > 1) {
         if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * (size_t)a.n, st) != cudaSuccess) return -1;
-        k_karras<<<div_up(a.n - 1, 256), 256, 0, st>>>(keys, (int)a.n, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
+        k_karras<<<div_up(a.n - 1, 256), 256, 0, st>>>(keys, vb, (int)a.n, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
         ++launches;
     }
-    k_refit_inst<<<div_up(a.n, 256), 256, 0, st>>>(vals, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, a.root_out,
+    k_refit_inst<<<div_up(a.n, 256), 256, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, a.root_out,
                                                   a.bounds_out, a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
     ++launches;
     if (cudaGetLastError() != cudaSuccess) return -1;

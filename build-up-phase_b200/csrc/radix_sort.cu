@@ -1,5 +1,8 @@
 // radix_sort.cu — "onesweep" LSD radix sort of (u64 Morton key, u32 primitive id) pairs for sm_100a.
 //
+// Two record formats: (u64 key, u32 value) pairs, or PACKED 64-bit words `key << val_bits | value` when
+// key_bits + val_bits <= 64 (every configuration of BASELINE.json): then only 8 B are read and 8 B written per
+// element and pass instead of 12 + 12.
 // One up-front histogram kernel reads the keys once and produces the global digit histogram of
 // EVERY 8-bit pass; each pass is then a single kernel: a tile (3072 pairs) is ranked in
 // shared memory with warp-level match_any multi-split, its per-digit counts are published to a
@@ -37,14 +40,14 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// hist[p][d] += number of keys whose p-th 8-bit digit is d
-__global__ void __launch_bounds__(512) k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int passes, uint32_t* __restrict__ hist) {
+// hist[p][d] += number of keys whose p-th 8-bit digit (counted from bit base_shift) is d
+__global__ void __launch_bounds__(512) k_sort_hist(const uint64_t* __restrict__ keys, uint32_t n, int passes, int base_shift, uint32_t* __restrict__ hist) {
     __shared__ uint32_t sh[MAX_PASSES * RADIX];
     for (int j = threadIdx.x; j < passes * RADIX; j += blockDim.x) sh[j] = 0;
     __syncthreads();
     const uint32_t stride = gridDim.x * blockDim.x;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        uint64_t k = keys[i];
+        uint64_t k = keys[i] >> base_shift;
         for (int p = 0; p < passes; ++p) atomicAdd(&sh[p * RADIX + (uint32_t)((k >> (8 * p)) & 255u)], 1u);
     }
     __syncthreads();
@@ -67,6 +70,8 @@ __global__ void __launch_bounds__(RADIX) k_sort_scan_hist(uint32_t* hist) {
     h[d] = base + inc - v;
 }
 
+// HAS_VALS = false: the primitive id rides in the low bits of the 64-bit word (below `shift`), nothing else is moved
+template <bool HAS_VALS>
 __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
     const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
@@ -74,7 +79,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
     uint32_t* tile_state, uint32_t* tile_counter, int* error_flag) {
     __shared__ uint32_t s_cnt[SORT_WARPS * RADIX];   // per-warp digit counts -> per-warp exclusive offsets
     __shared__ uint64_t s_keys[SORT_TILE];
-    __shared__ uint32_t s_vals[SORT_TILE];
+    __shared__ uint32_t s_vals[HAS_VALS ? SORT_TILE : 1];
     __shared__ uint32_t s_loff[RADIX];               // start of digit d inside the tile-local order
     __shared__ uint32_t s_goff[RADIX];               // global position of local slot p with digit d = s_goff[d] + p
     __shared__ uint32_t s_wtot[SORT_WARPS];
@@ -168,10 +173,12 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
             s_keys[lpos[i]] = key[i];
         } else lpos[i] = 0xFFFFFFFFu;
     }
+    if (HAS_VALS) {
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        uint32_t li = wbase + i * 32;
-        if (li < tile_n) s_vals[lpos[i]] = vals_in[base + li];
+        for (int i = 0; i < SORT_ITEMS; ++i) {
+            uint32_t li = wbase + i * 32;
+            if (li < tile_n) s_vals[lpos[i]] = vals_in[base + li];
+        }
     }
     __syncthreads();
 #pragma unroll
@@ -182,7 +189,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
             const uint32_t d = (uint32_t)((k >> shift) & 255u);
             const uint32_t g = s_goff[d] + p;
             keys_out[g] = k;
-            vals_out[g] = s_vals[p];
+            if (HAS_VALS) vals_out[g] = s_vals[p];
         }
     }
 }
@@ -202,6 +209,8 @@ SortPlan sort_plan(uint32_t n, int key_bits) {
 
 int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                void* scratch, int* device_error_flag, cudaStream_t stream, bool* result_in_b) {
+    const bool has_vals = vals_a != nullptr;
+    const int base_shift = has_vals ? 0 : plan.packed_val_bits;
     *result_in_b = false;
     if (plan.n == 0) return 0;
     uint32_t* hist = (uint32_t*)scratch;
@@ -212,15 +221,20 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
     int hist_blocks = (int)((plan.n + 512 * 16 - 1) / (512 * 16));
     if (hist_blocks > 148 * 4) hist_blocks = 148 * 4;
     if (hist_blocks < 1) hist_blocks = 1;
-    k_sort_hist<<<hist_blocks, 512, 0, stream>>>(keys_a, plan.n, plan.passes, hist);
+    k_sort_hist<<<hist_blocks, 512, 0, stream>>>(keys_a, plan.n, plan.passes, base_shift, hist);
     k_sort_scan_hist<<<plan.passes, RADIX, 0, stream>>>(hist);
     launches += 2;
     uint64_t* kin = keys_a; uint64_t* kout = keys_b;
     uint32_t* vin = vals_a; uint32_t* vout = vals_b;
     for (int p = 0; p < plan.passes; ++p) {
-        k_onesweep_pass<<<plan.tiles, SORT_THREADS, 0, stream>>>(kin, kout, vin, vout, plan.n, 8 * p, hist + p * RADIX,
-                                                                 states + (size_t)p * plan.tiles * RADIX, counters + p,
-                                                                 device_error_flag);
+        if (has_vals)
+            k_onesweep_pass<true><<<plan.tiles, SORT_THREADS, 0, stream>>>(kin, kout, vin, vout, plan.n, 8 * p, hist + p * RADIX,
+                                                                           states + (size_t)p * plan.tiles * RADIX, counters + p,
+                                                                           device_error_flag);
+        else
+            k_onesweep_pass<false><<<plan.tiles, SORT_THREADS, 0, stream>>>(kin, kout, nullptr, nullptr, plan.n, base_shift + 8 * p, hist + p * RADIX,
+                                                                            states + (size_t)p * plan.tiles * RADIX, counters + p,
+                                                                            device_error_flag);
         ++launches;
         uint64_t* tk = kin; kin = kout; kout = tk;
         uint32_t* tv = vin; vin = vout; vout = tv;

@@ -82,9 +82,10 @@ struct SortPlan {
     int passes = 0;             // 8-bit digits
     uint32_t tiles = 0;
     size_t scratch_bytes = 0;   // histogram + look-back state
+    int packed_val_bits = 0;    // > 0: records are 64-bit words `key << packed_val_bits | value` (vals arrays unused)
 };
 SortPlan sort_plan(uint32_t n, int key_bits);
-// Sorts (keys, vals) by the low key_bits of the key, stable. Result ends in keys_a/vals_a or keys_b/vals_b;
+// Sorts (keys, vals) by the low key_bits of the key, stable. vals_a == nullptr selects the packed format. Result ends in keys_a/vals_a or keys_b/vals_b;
 // *result_in_b tells which. Returns the number of kernels launched, or <0 on a launch error.
 int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,
                void* scratch, int* device_error_flag, cudaStream_t stream, bool* result_in_b);

@@ -44,7 +44,7 @@ struct rt_context {
     rt_trace_stats last_stats{};
     uint64_t launches = 0;
     // debug view of the last BLAS build's sorted keys (lives in scratch until the next build)
-    const uint64_t* dbg_keys = nullptr; const uint32_t* dbg_vals = nullptr; uint32_t dbg_n = 0;
+    const uint64_t* dbg_keys = nullptr; const uint32_t* dbg_vals = nullptr; uint32_t dbg_n = 0; int dbg_vb = 0;
 };
 
 struct BlasStorage {
@@ -123,6 +123,12 @@ void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
 }
 
 uint32_t ceil_log2(uint32_t v) { uint32_t b = 0; while ((1ull << b) < v) ++b; return b; }
+
+// Packed sort records `key << vb | id` whenever key and id fit one 64-bit word (8 B instead of 12 B moved per element and pass).
+void choose_record_format(SortPlan& sp, uint32_t n, uint32_t key_bits, uint32_t build_flags) {
+    const uint32_t vb = ceil_log2(n) ? ceil_log2(n) : 1u;
+    sp.packed_val_bits = (!(build_flags & RT_BUILD_NO_PACKED_SORT) && key_bits + vb <= 64u) ? (int)vb : 0;
+}
 
 }  // namespace
 
@@ -212,7 +218,7 @@ static void storage_release(BlasStorage* st) {
 }
 
 int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
-                        uint32_t /*build_flags*/, rt_blas** out_array) {
+                        uint32_t build_flags, rt_blas** out_array) {
     if (!ctx || !out_array || n_blas == 0 || !geom_counts) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     for (uint32_t b = 0; b < n_blas; ++b) out_array[b] = nullptr;
@@ -260,7 +266,8 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     const uint32_t N = (uint32_t)total;
     const uint32_t seg_bits = ceil_log2(n_blas);
     if (seg_bits + MORTON_BITS > 64) return RT_ERROR_INVALID_ARG;
-    const SortPlan sp = sort_plan(N, (int)(MORTON_BITS + seg_bits));
+    SortPlan sp = sort_plan(N, (int)(MORTON_BITS + seg_bits));
+    choose_record_format(sp, N, MORTON_BITS + seg_bits, build_flags);
 
     // ---- output storage: nodes | tris | records ----
     BlasStorage* st = new BlasStorage();
@@ -372,7 +379,7 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
         cudaEventElapsedTime(&ctx->timing.refit_ms, be.e[4], be.e[5]);
         cudaEventElapsedTime(&ctx->timing.total_ms, be.e[0], be.e[5]);
     }
-    ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N;
+    ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N; ctx->dbg_vb = sp.packed_val_bits;
 
     for (uint32_t b = 0; b < n_blas; ++b) {
         rt_blas* h = new rt_blas();
@@ -430,6 +437,16 @@ int rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* pri
     if (n_out) *n_out = ctx->dbg_n;
     const uint32_t n = ctx->dbg_n < capacity ? ctx->dbg_n : capacity;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->dbg_vb) {                                   // packed records: split `key << vb | id` on the host
+        std::vector<uint64_t> rec(n);
+        if (n) RT_CUDA(ctx, cudaMemcpy(rec.data(), ctx->dbg_keys, 8ull * n, cudaMemcpyDeviceToHost));
+        const uint64_t mask = (1ull << ctx->dbg_vb) - 1ull;
+        for (uint32_t i = 0; i < n; ++i) {
+            if (keys_out) keys_out[i] = rec[i] >> ctx->dbg_vb;
+            if (prim_out) prim_out[i] = (uint32_t)(rec[i] & mask);
+        }
+        return RT_SUCCESS;
+    }
     if (n && keys_out) RT_CUDA(ctx, cudaMemcpy(keys_out, ctx->dbg_keys, 8ull * n, cudaMemcpyDeviceToHost));
     if (n && prim_out) RT_CUDA(ctx, cudaMemcpy(prim_out, ctx->dbg_vals, 4ull * n, cudaMemcpyDeviceToHost));
     return RT_SUCCESS;
@@ -469,7 +486,8 @@ int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device
 // ---- TLAS -------------------------------------------------------------------------------------------
 static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* instances, uint32_t n, uint32_t build_flags) {
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    const SortPlan sp = sort_plan(n, MORTON_BITS);
+    SortPlan sp = sort_plan(n, MORTON_BITS);
+    choose_record_format(sp, n, MORTON_BITS, build_flags);
     const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256);
     const size_t bytes = inst_b + nodes_b + 256;
     if (T->bytes < bytes) {

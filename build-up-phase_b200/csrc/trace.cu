@@ -48,9 +48,6 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 #ifndef RT_FAST_SLAB
 #define RT_FAST_SLAB 0
 #endif
-#ifndef RT_POSTPONE_LEAF
-#define RT_POSTPONE_LEAF 0
-#endif
 
 // Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
 // on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
@@ -187,7 +184,149 @@ __device__ __forceinline__ rt_hit miss_record(float tmax) {
     return r;
 }
 
+// ---- ray identity ---------------------------------------------------------------------------------------
+struct RayId { bool in_buffer, valid; uint32_t lidx, pixel; };
+
+// Primary ray `idx` (tile-major numbering: 8x4-pixel tiles, 32 consecutive ids per tile) -> raygen shader
+// (main.cpp:1033-1046); aspect_x/aspect_y are computed once on the host (tanf).
+__device__ __forceinline__ RayId primary_ray(const TraceParams& P, uint32_t idx, uint32_t tiles_x, V3& o, V3& d) {
+    RayId id;
+    const uint32_t tile = idx >> 5, within = idx & 31u;
+    const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
+    const uint32_t lr = (tile / tiles_x) * 4u + (within >> 3);
+    const uint32_t band = lr / P.block_rows;
+    const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
+    id.in_buffer = x < P.width && lr < P.local_rows;
+    id.valid = id.in_buffer && y < P.height;
+    id.lidx = lr * P.width + x;
+    id.pixel = y * P.width + x;
+    const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
+    const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
+    const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
+    const float ax = ndcx * P.aspect_x, ay = ndcy * P.aspect_y;
+    o = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
+    d = {(ax * 1.0f + ay * 0.0f) + 0.0f, (ax * 0.0f + ay * -1.0f) + 0.0f, (ax * 0.0f + ay * 0.0f) + -1.0f};
+    return id;
+}
+
+struct Counters { unsigned long long nodes = 0, tris = 0, insts = 0, hits = 0, rays = 0, edge = 0; };
+
+template <int STAGE>
+__device__ __forceinline__ void flush_stats(const TraceParams& P, const Counters& c, int lane) {
+    if (!P.stats) return;
+    // rt_trace_stats order: rays_primary, rays_secondary, nodes, tris, insts, primary_hits, secondary_hits, near_edge
+    unsigned long long v[8] = {STAGE == 0 ? c.rays : 0ull, STAGE == 1 ? c.rays : 0ull, c.nodes, c.tris, c.insts,
+                               STAGE == 0 ? c.hits : 0ull, STAGE == 1 ? c.hits : 0ull, c.edge};
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], ofs);
+        if (lane == 0 && v[k]) atomicAdd(P.stats + k, v[k]);
+    }
+}
+
+// ---- the shaders' epilogue: closest-hit (main.cpp:1080-1091, SBT rule main.cpp:1260-1262) / miss (main.cpp:1063-1066)
+// / imageStore (main.cpp:1054), plus the generation of the diffuse bounce ray (stage 0) or the blend (stage 1).
+template <int STAGE, bool STATS>
+__device__ __forceinline__ void shade(const TraceParams& P, const RayId id, const V3 o, const V3 d, float col0, float col1, float col2,
+                                      float best_t, float best_u, float best_v, float best_w0, uint32_t best_slot, uint32_t best_tri,
+                                      bool& enqueue, float4& e0, float4& e1, float4& e2, Counters& c) {
+    const uint32_t lidx = id.lidx;
+    if (!id.valid) {
+        if (id.in_buffer) {
+            reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(0, 0, 0, 0);
+            if (P.primary_hits) P.primary_hits[lidx] = miss_record(P.tmax);
+            if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
+        }
+        return;
+    }
+    if (STATS) ++c.rays;
+    const bool hit = best_slot != NO_HIT;
+    const InstanceRec* R = P.instances + (hit ? best_slot : 0u);
+    float sc0, sc1, sc2;
+    rt_hit rec = miss_record(P.tmax);
+    float4 tq0 = make_float4(0.f, 0.f, 0.f, 0.f), tq1 = tq0, tq2 = tq0;
+    if (hit) {
+        const uint32_t cm = __ldg(&R->custom_mask), sf = __ldg(&R->sbt_flags), inst_id = __ldg(&R->instance_id);
+        const float4* t4 = reinterpret_cast<const float4*>(R->tris + best_tri);
+        tq0 = __ldg(t4); tq1 = __ldg(t4 + 1); tq2 = __ldg(t4 + 2);
+        const uint32_t geo = __float_as_uint(tq2.y), prim = __float_as_uint(tq2.z), custom = cm & 0xFFFFFFu;
+        if (prim == 1u && inst_id == 1u && custom == 100u && geo == 1u) {
+            sc0 = 1.0f - best_u - best_v; sc1 = best_u; sc2 = best_v;
+        } else {
+            const uint32_t r = (sf & 0xFFFFFFu) + geo * P.sbt_stride + P.sbt_offset;
+            if (r < P.n_records) { sc0 = __ldg(P.hit_records + 3 * r); sc1 = __ldg(P.hit_records + 3 * r + 1); sc2 = __ldg(P.hit_records + 3 * r + 2); }
+            else { sc0 = sc1 = sc2 = 0.0f; }
+        }
+        rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
+        rec.t = best_t; rec.u = best_u; rec.v = best_v;
+        if (STATS) { ++c.hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c.edge; }
+    } else {
+        sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];
+    }
+    if (STAGE == 0) {
+        if (P.primary_hits) P.primary_hits[lidx] = rec;
+        if (hit && P.bounces > 0u) {
+            // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
+            const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
+            float w2o[12];
+            load_w2o(R, w2o);
+            const V3 ed1 = {tq0.w - tq0.x, tq1.x - tq0.y, tq1.y - tq0.z};
+            const V3 ed2 = {tq1.z - tq0.x, tq1.w - tq0.y, tq2.x - tq0.z};
+            V3 n = xform_normal(w2o, cross3(ed1, ed2));
+            const float l2 = dot3(n, n);
+            if (l2 > 0.0f && l2 < INFINITY) { const float l = sqrtf(l2); n = {n.x / l, n.y / l, n.z / l}; }
+            else { const float dl = sqrtf(dot3(d, d)); n = {-d.x / dl, -d.y / dl, -d.z / dl}; }
+            if (dot3(n, d) > 0.0f) n = {-n.x, -n.y, -n.z};
+            uint32_t h = pcg_hash(id.pixel + pcg_hash(P.bounce_seed + 0x9E3779B9u));
+            V3 s = {0.0f, 0.0f, 0.0f};
+            for (int tries = 0; tries < 8; ++tries) {
+                const uint32_t ha = pcg_hash(h), hb = pcg_hash(ha), hc = pcg_hash(hb);
+                h = hc;
+                const V3 q = {u01(ha) * 2.0f - 1.0f, u01(hb) * 2.0f - 1.0f, u01(hc) * 2.0f - 1.0f};
+                const float qq = dot3(q, q);
+                if (qq <= 1.0f && qq > 1e-8f) { const float ql = sqrtf(qq); s = {q.x / ql, q.y / ql, q.z / ql}; break; }
+            }
+            V3 dir = {n.x + s.x, n.y + s.y, n.z + s.z};
+            const float dl2 = dot3(dir, dir);
+            if (dl2 < 1e-12f) dir = n;
+            else { const float dl = sqrtf(dl2); dir = {dir.x / dl, dir.y / dl, dir.z / dl}; }
+            const float eps = 0.0009765625f;
+            enqueue = true;
+            e0 = make_float4(__uint_as_float(lidx), p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps);
+            e1 = make_float4(dir.x, dir.y, dir.z, sc0);
+            e2 = make_float4(sc1, sc2, 0.0f, 0.0f);
+        } else {
+            reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(sc0), unorm8(sc1), unorm8(sc2), 0);   // imageStore, main.cpp:1054
+            if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
+        }
+    } else {
+        if (P.secondary_hits) P.secondary_hits[lidx] = rec;
+        const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
+        reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
+    }
+}
+
+// warp-aggregated append to the bounce queue (all 32 lanes must call)
+__device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueue, const float4& e0, const float4& e1, const float4& e2,
+                                               int lane, uint32_t lt_mask) {
+    const unsigned em = __ballot_sync(0xffffffffu, enqueue);
+    if (em) {
+        const int leader = __ffs(em) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(P.counters + 2, (uint32_t)__popc(em));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (enqueue) {
+            float4* q = P.queue + 3 * (size_t)(base + __popc(em & lt_mask));
+            __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
+        }
+    }
+}
+
 // STAGE 0: primary rays generated from pixel ids. STAGE 1: secondary rays read from the bounce queue.
+// The shaders' epilogue runs inside this kernel for the lanes whose ray just finished. (Measured alternatives, both
+// slower on B200 - profiles/README.md r01h: a separate warp-convergent shading kernel with refill thresholds 16..28,
+// and speculative traversal with one postponed leaf.)
 template <int STAGE, bool STATS, int STACK>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
@@ -196,13 +335,13 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     const uint32_t tiles_y = (P.local_rows + 3u) >> 2;
     const uint32_t total = STAGE == 0 ? tiles_x * tiles_y * 32u : P.counters[2];
     uint32_t* fetch_counter = P.counters + STAGE;
+    constexpr int THRESHOLD = REFILL_THRESHOLD;
 
-    unsigned long long c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0, c_rays = 0, c_edge = 0;
+    Counters c;
 
     // ---- per-lane ray state ----
     bool have_ray = false, exhausted = false;
-    bool in_buffer = false, valid = false;
-    uint32_t lidx = 0, pixel = 0;
+    RayId id = {false, false, 0u, 0u};
     V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
     float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
     int32_t cur = REF_DONE;
@@ -217,9 +356,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
     uint32_t best_slot = NO_HIT, best_tri = 0;
     int32_t stack[STACK];
-#if RT_POSTPONE_LEAF
-    int32_t postponed = 0;            // leaf refs are negative, so 0 = none
-#endif
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
@@ -235,30 +371,15 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 else {
                     have_ray = true;
                     if (STAGE == 0) {
-                        const uint32_t tile = idx >> 5, within = idx & 31u;
-                        const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
-                        const uint32_t lr = (tile / tiles_x) * 4u + (within >> 3);
-                        const uint32_t band = lr / P.block_rows;
-                        const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
-                        in_buffer = x < P.width && lr < P.local_rows;
-                        valid = in_buffer && y < P.height;
-                        lidx = lr * P.width + x;
-                        pixel = y * P.width + x;
-                        // ---- raygen (main.cpp:1033-1046); aspect_x/aspect_y computed once on the host (tanf) ----
-                        const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
-                        const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
-                        const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
-                        const float ax = ndcx * P.aspect_x, ay = ndcy * P.aspect_y;
-                        o = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
-                        d = {(ax * 1.0f + ay * 0.0f) + 0.0f, (ax * 0.0f + ay * -1.0f) + 0.0f, (ax * 0.0f + ay * 0.0f) + -1.0f};
+                        id = primary_ray(P, idx, tiles_x, o, d);
                     } else {
                         const float4* q = P.queue + 3 * (size_t)idx;
                         const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
-                        lidx = __float_as_uint(q0.x);
+                        id.lidx = __float_as_uint(q0.x);
                         o = {q0.y, q0.z, q0.w};
                         d = {q1.x, q1.y, q1.z};
                         col0 = q1.w; col1 = q2.x; col2 = q2.y;
-                        in_buffer = valid = true;
+                        id.in_buffer = id.valid = true;
                     }
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
@@ -266,7 +387,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     stack[sp++] = REF_DONE;
                     in_blas = false;
                     nodes = P.tlas_nodes;
-                    cur = valid ? P.tlas_root : REF_DONE;
+                    cur = id.valid ? P.tlas_root : REF_DONE;
                     if (cur == REF_EMPTY) cur = REF_DONE;
                     slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
                 }
@@ -280,7 +401,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {               // internal node
                 const F8 na = ldg256(&nodes[cur].c[0]), nb = ldg256(&nodes[cur].c[1]);
                 const float4 a0 = na.a, a1 = na.b, b0 = nb.a, b1 = nb.b;
-                if (STATS) ++c_nodes;
+                if (STATS) ++c.nodes;
                 float t0, t1;
                 const bool hit0 = slab_test(sl, a0, a1, P.tmin, best_t, t0);
                 const bool hit1 = slab_test(sl, b0, b1, P.tmin, best_t, t1);
@@ -292,14 +413,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
                 else cur = stack[--sp];
-#if RT_POSTPONE_LEAF
-                if (cur < 0 && postponed == 0) { postponed = cur; cur = stack[--sp]; }   // speculative traversal: one leaf may wait
-#endif
                 if (NODE_CAP > 0 && __popc(__activemask()) < NODE_CAP) break;   // do not idle the warp behind a few long node chains
             }
-#if RT_POSTPONE_LEAF
-            if (postponed != 0) { stack[sp++] = cur; cur = postponed; postponed = 0; }
-#endif
             if (cur < 0) {                                                       // leaf
                 const uint32_t first = leaf_first(cur), count = leaf_count(cur);
                 if (!in_blas) {
@@ -308,7 +423,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     const uint32_t cm = __ldg(&R->custom_mask);
                     const int32_t root = __ldg(&R->root);
                     if (((cm >> 24) & P.cull_mask) != 0u && root != REF_EMPTY) {
-                        if (STATS) ++c_insts;
+                        if (STATS) ++c.insts;
                         float w2o[12];
                         load_w2o(R, w2o);
                         const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
@@ -324,7 +439,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     for (uint32_t k = 0; k < count; ++k) {
                         const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
                         const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
-                        if (STATS) ++c_tris;
+                        if (STATS) ++c.tris;
                         float t, bu, bv, bw0;
                         if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
                             bool better = t < best_t;
@@ -352,7 +467,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 cur = stack[--sp];
             }
             // warp-level compaction trigger: too few lanes still traversing -> go refill the idle ones
-            if (!warp_exhausted && __popc(__activemask()) < REFILL_THRESHOLD) break;
+            if (!warp_exhausted && __popc(__activemask()) < THRESHOLD) break;
         }
 
         // ================= epilogue of the lanes whose ray just finished =================
@@ -361,108 +476,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
         if (finish) {
             have_ray = false;
-            if (!valid) {
-                if (in_buffer) {
-                    reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(0, 0, 0, 0);
-                    if (P.primary_hits) P.primary_hits[lidx] = miss_record(P.tmax);
-                    if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
-                }
-            } else {
-                if (STATS) ++c_rays;
-                const bool hit = best_slot != NO_HIT;
-                const InstanceRec* R = P.instances + (hit ? best_slot : 0u);
-                float sc0, sc1, sc2;
-                rt_hit rec = miss_record(P.tmax);
-                float4 tq0 = make_float4(0.f, 0.f, 0.f, 0.f), tq1 = tq0, tq2 = tq0;
-                if (hit) {
-                    // ---- closest-hit (main.cpp:1080-1091) with the SBT rule of main.cpp:1260-1262 ----
-                    const uint32_t cm = __ldg(&R->custom_mask), sf = __ldg(&R->sbt_flags), inst_id = __ldg(&R->instance_id);
-                    const float4* t4 = reinterpret_cast<const float4*>(R->tris + best_tri);
-                    tq0 = __ldg(t4); tq1 = __ldg(t4 + 1); tq2 = __ldg(t4 + 2);
-                    const uint32_t geo = __float_as_uint(tq2.y), prim = __float_as_uint(tq2.z), custom = cm & 0xFFFFFFu;
-                    if (prim == 1u && inst_id == 1u && custom == 100u && geo == 1u) {
-                        sc0 = 1.0f - best_u - best_v; sc1 = best_u; sc2 = best_v;
-                    } else {
-                        const uint32_t r = (sf & 0xFFFFFFu) + geo * P.sbt_stride + P.sbt_offset;
-                        if (r < P.n_records) { sc0 = __ldg(P.hit_records + 3 * r); sc1 = __ldg(P.hit_records + 3 * r + 1); sc2 = __ldg(P.hit_records + 3 * r + 2); }
-                        else { sc0 = sc1 = sc2 = 0.0f; }
-                    }
-                    rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
-                    rec.t = best_t; rec.u = best_u; rec.v = best_v;
-                    if (STATS) { ++c_hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c_edge; }
-                } else {
-                    sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];                 // miss shader (main.cpp:1063-1066)
-                }
-                if (STAGE == 0) {
-                    if (P.primary_hits) P.primary_hits[lidx] = rec;
-                    if (hit && P.bounces > 0u) {
-                        // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
-                        const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
-                        float w2o[12];
-                        load_w2o(R, w2o);
-                        const V3 ed1 = {tq0.w - tq0.x, tq1.x - tq0.y, tq1.y - tq0.z};
-                        const V3 ed2 = {tq1.z - tq0.x, tq1.w - tq0.y, tq2.x - tq0.z};
-                        V3 n = xform_normal(w2o, cross3(ed1, ed2));
-                        const float l2 = dot3(n, n);
-                        if (l2 > 0.0f && l2 < INFINITY) { const float l = sqrtf(l2); n = {n.x / l, n.y / l, n.z / l}; }
-                        else { const float dl = sqrtf(dot3(d, d)); n = {-d.x / dl, -d.y / dl, -d.z / dl}; }
-                        if (dot3(n, d) > 0.0f) n = {-n.x, -n.y, -n.z};
-                        uint32_t h = pcg_hash(pixel + pcg_hash(P.bounce_seed + 0x9E3779B9u));
-                        V3 s = {0.0f, 0.0f, 0.0f};
-                        for (int tries = 0; tries < 8; ++tries) {
-                            const uint32_t ha = pcg_hash(h), hb = pcg_hash(ha), hc = pcg_hash(hb);
-                            h = hc;
-                            const V3 q = {u01(ha) * 2.0f - 1.0f, u01(hb) * 2.0f - 1.0f, u01(hc) * 2.0f - 1.0f};
-                            const float qq = dot3(q, q);
-                            if (qq <= 1.0f && qq > 1e-8f) { const float ql = sqrtf(qq); s = {q.x / ql, q.y / ql, q.z / ql}; break; }
-                        }
-                        V3 dir = {n.x + s.x, n.y + s.y, n.z + s.z};
-                        const float dl2 = dot3(dir, dir);
-                        if (dl2 < 1e-12f) dir = n;
-                        else { const float dl = sqrtf(dl2); dir = {dir.x / dl, dir.y / dl, dir.z / dl}; }
-                        const float eps = 0.0009765625f;
-                        enqueue = true;
-                        e0 = make_float4(__uint_as_float(lidx), p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps);
-                        e1 = make_float4(dir.x, dir.y, dir.z, sc0);
-                        e2 = make_float4(sc1, sc2, 0.0f, 0.0f);
-                    } else {
-                        reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(sc0), unorm8(sc1), unorm8(sc2), 0);   // imageStore, main.cpp:1054
-                        if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
-                    }
-                } else {
-                    if (P.secondary_hits) P.secondary_hits[lidx] = rec;
-                    const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
-                    reinterpret_cast<uchar4*>(P.rgba)[lidx] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
-                }
-            }
+            shade<STAGE, STATS>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
         }
-        if (STAGE == 0) {
-            // warp-aggregated append to the bounce queue
-            const unsigned em = __ballot_sync(0xffffffffu, enqueue);
-            if (em) {
-                const int leader = __ffs(em) - 1;
-                uint32_t base = 0;
-                if (lane == leader) base = atomicAdd(P.counters + 2, (uint32_t)__popc(em));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (enqueue) {
-                    float4* q = P.queue + 3 * (size_t)(base + __popc(em & lt_mask));
-                    __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
-                }
-            }
-        }
+        if (STAGE == 0) enqueue_bounce(P, enqueue, e0, e1, e2, lane, lt_mask);
     }
-
-    if (STATS && P.stats) {
-        // rt_trace_stats order: rays_primary, rays_secondary, nodes, tris, insts, primary_hits, secondary_hits, near_edge
-        unsigned long long v[8] = {STAGE == 0 ? c_rays : 0ull, STAGE == 1 ? c_rays : 0ull, c_nodes, c_tris, c_insts,
-                                   STAGE == 0 ? c_hits : 0ull, STAGE == 1 ? c_hits : 0ull, c_edge};
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-#pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], ofs);
-            if (lane == 0 && v[k]) atomicAdd(P.stats + k, v[k]);
-        }
-    }
+    if (STATS) flush_stats<STAGE>(P, c, lane);
 }
 
 __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ packed_all, uint32_t width, uint32_t height,

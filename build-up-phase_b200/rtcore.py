@@ -26,6 +26,7 @@ RT_GEOMETRY_OPAQUE = 0x1
 RT_GEOMETRY_DEVICE_POINTERS = 0x100
 RT_BUILD_PREFER_FAST_TRACE = 0x4
 RT_BUILD_INSTANCES_ON_DEVICE = 0x100
+RT_BUILD_NO_PACKED_SORT = 0x200
 RT_TRACE_OUT_DEVICE = 0x1
 RT_TRACE_STATS = 0x2
 RT_TRACE_ASYNC = 0x4
@@ -320,20 +321,20 @@ class Context:
         self._check(self.L.rt_tlas_build_sizes(self.h, max_instances, C.byref(out)))
         return out
 
-    def build_blas(self, geoms, device: bool = False) -> Blas:
+    def build_blas(self, geoms, device: bool = False, flags: int = 0) -> Blas:
         keep: list = []
         arr = self._geom_array(geoms, keep, device)
         h = C.c_void_p()
-        self._check(self.L.rt_build_blas(self.h, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE, C.byref(h)))
+        self._check(self.L.rt_build_blas(self.h, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE | flags, C.byref(h)))
         return Blas(self, h.value)
 
-    def build_blas_batch(self, blases, device: bool = False) -> List[Blas]:
+    def build_blas_batch(self, blases, device: bool = False, flags: int = 0) -> List[Blas]:
         keep: list = []
         flat = [g for b in blases for g in b]
         arr = self._geom_array(flat, keep, device)
         counts = (C.c_uint32 * len(blases))(*[len(b) for b in blases])
         out = (C.c_void_p * len(blases))()
-        self._check(self.L.rt_build_blas_batch(self.h, arr, counts, len(blases), RT_BUILD_PREFER_FAST_TRACE, out))
+        self._check(self.L.rt_build_blas_batch(self.h, arr, counts, len(blases), RT_BUILD_PREFER_FAST_TRACE | flags, out))
         return [Blas(self, out[i]) for i in range(len(blases))]
 
     def import_blas(self, info: RtBlasInfo, device_blob) -> Blas:

@@ -91,11 +91,12 @@ def test_instanced_batched_scene(rt, ctx, oracle):
     print("inst-batched", rp, rs, gs)
 
 
-def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle):
+@pytest.mark.parametrize("flags", [0, 0x200], ids=["packed-sort", "pair-sort"])
+def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags):
     """Integer/byte work must be bit-exact: sorted Morton keys, primitive order, tree topology and
-    every node box of the GPU LBVH equal the CPU restatement's."""
+    every node box of the GPU LBVH equal the CPU restatement's (both sort record formats)."""
     scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
-    blas = ctx.build_blas(scene.blases[0])
+    blas = ctx.build_blas(scene.blases[0], flags=flags)
     keys, prims = ctx.last_sorted_keys()
     info = blas.info()
     nodes, tris = blas.export()
