@@ -8,13 +8,14 @@
 //   k_tri_morton  30-bit Morton code of the triangle-box centre inside its BLAS bounds;
 //                 key = (blas << 30) | morton, value = triangle id
 //   sort_pairs    onesweep radix sort (radix_sort.cu), only the significant key bytes
-//   k_karras      Karras 2012: one thread per internal node finds its range and split with clz on
-//                 key XOR (index-augmented for duplicate keys). Because the BLAS id is the key
-//                 prefix, every BLAS is exactly one subtree of the global radix tree.
-//   k_refit_tris  one thread per sorted leaf: emits the sorted triangle, then climbs; each node has
-//                 an arrival counter, the second thread to arrive unions the two child halves and
-//                 continues (atomic bottom-up refit). Subtrees of <= 4 triangles collapse into a
-//                 leaf. The thread that completes a BLAS's subtree publishes its root/bounds/height.
+//   k_refit_tris  hierarchy emission AND refit in one bottom-up pass over Karras' radix tree (clz on
+//                 key XOR, index-augmented for duplicate keys; found bottom-up as in Apetrei 2014, see
+//                 build_tree_tile): one thread per sorted leaf emits the sorted triangle, then climbs;
+//                 the second child to arrive at a split unions the boxes and continues. Splits inside
+//                 a CTA's 512-leaf tile meet in shared memory, only the tile-border subtrees use global
+//                 arrival counters. Because the BLAS id is the key prefix, every BLAS of a batch is
+//                 exactly one subtree of the global radix tree; subtrees of <= 4 triangles collapse
+//                 into a leaf; the thread that completes a BLAS publishes its root/bounds/height.
 // TLAS: same machinery over instance world boxes (k_inst_setup computes world->object in fp64).
 //
 // All kernels are HBM-bound streaming passes: coalesced 128-bit accesses, grids sized from the
@@ -124,45 +125,21 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
     else { keys[t] = key; vals[t] = t; }
 }
 
-// ---- Karras 2012 ------------------------------------------------------------------------------
-__device__ __forceinline__ int karras_delta(const uint64_t* __restrict__ keys, int vb, int n, int i, uint64_t ki, int j) {
-    if (j < 0 || j >= n) return -1;
-    const uint64_t kj = __ldg(keys + j) >> vb;
-    if (ki == kj) return 64 + __clz(i ^ j);
-    return __clzll((long long)(ki ^ kj));
-}
-
-__global__ void __launch_bounds__(256) k_karras(const uint64_t* __restrict__ keys, int vb, int n, int32_t* __restrict__ other_end,
-                                               uint32_t* __restrict__ parent_node, uint32_t* __restrict__ parent_leaf) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n - 1) return;
-    const uint64_t ki = __ldg(keys + i) >> vb;
-    int d = (karras_delta(keys, vb, n, i, ki, i + 1) - karras_delta(keys, vb, n, i, ki, i - 1)) >= 0 ? 1 : -1;
-    if (i == 0) d = 1;
-    const int dmin = karras_delta(keys, vb, n, i, ki, i - d);
-    int lmax = 2;
-    while (karras_delta(keys, vb, n, i, ki, i + lmax * d) > dmin) lmax <<= 1;
-    int l = 0;
-    for (int t = lmax >> 1; t >= 1; t >>= 1)
-        if (karras_delta(keys, vb, n, i, ki, i + (l + t) * d) > dmin) l += t;
-    const int j = i + l * d;
-    const int dnode = karras_delta(keys, vb, n, i, ki, j);
-    int s = 0, t = l;
-    do {
-        t = (t + 1) >> 1;
-        if (karras_delta(keys, vb, n, i, ki, i + (s + t) * d) > dnode) s += t;
-    } while (t > 1);
-    const int gamma = i + s * d + min(d, 0);
-    const int first = min(i, j), last = max(i, j);
-    other_end[i] = j;
-    if (first == gamma) parent_leaf[gamma] = ((uint32_t)i << 1);
-    else parent_node[gamma] = ((uint32_t)i << 1);
-    if (last == gamma + 1) parent_leaf[gamma + 1] = ((uint32_t)i << 1) | 1u;
-    else parent_node[gamma + 1] = ((uint32_t)i << 1) | 1u;
-}
-
-// ---- atomic bottom-up refit ---------------------------------------------------------------------
+// ---- hierarchy emission + refit, one bottom-up pass ---------------------------------------------------
+// The tree is Karras' binary radix tree over the (key, index) strings, but it is found BOTTOM-UP (Apetrei 2014):
+// a finished subtree over sorted leaves [l, r] merges with its right neighbour when it shares the longer prefix
+// with it (delta(r) > delta(l-1)), else with the left one; the new node is stored at the slot of its SPLIT position
+// (g = r resp. l-1), which is unique per node. The first child to arrive at a split deposits {box, ref, height,
+// far end of its range} and retires; the second one unions and climbs on. No top-down Karras pass, no parent arrays.
+//
+// A CTA owns TILE consecutive leaves. Every split whose two leaves g, g+1 lie inside the tile is resolved through
+// SHARED memory (deposit slots + an atomicOr flag, CTA-scope fences only); live nodes are then written once, as a
+// full 64-B record, by the thread that completes them, and the halves of subtrees that collapse into a <= LEAF_MAX
+// leaf are never written. What is left after the CTA quiesces (subtrees that touch the tile border: ~log2(TILE)/TILE
+// of the nodes) continues through global memory with the classic fence + arrival counter.
 struct Box3 { float lo[3], hi[3]; };
+
+constexpr int TREE_TILE = 512;
 
 __device__ __forceinline__ void store_half(BvhNode* nodes, uint32_t node, uint32_t side, const Box3& b, int32_t ref, uint32_t height) {
     float4* dst = reinterpret_cast<float4*>(&nodes[node].c[side]);
@@ -170,66 +147,177 @@ __device__ __forceinline__ void store_half(BvhNode* nodes, uint32_t node, uint32
     dst[1] = make_float4(b.hi[1], b.hi[2], __int_as_float(ref), __uint_as_float(height));
 }
 
-// Climbs from a leaf whose box/ref are given. seg_first/seg_count delimit the subtree (BLAS segment or the
-// whole TLAS) whose root terminates the climb; refs are made relative to seg_first.
-// Returns true when THIS thread completed the segment root (outputs valid).
-template <int LEAF_MAX>
-__device__ __forceinline__ bool climb(BvhNode* __restrict__ nodes, const uint32_t* __restrict__ parent_leaf,
-                                      const uint32_t* __restrict__ parent_node, const int32_t* __restrict__ other_end,
-                                      uint32_t* __restrict__ arrived, uint32_t leaf, uint32_t seg_first, uint32_t seg_count,
-                                      Box3& b, int32_t& ref, uint32_t& height) {
-    ref = leaf_ref(leaf - seg_first, 1);
-    height = 0;
-    if (seg_count == 1) return true;
-    BvhNode* seg_nodes = nodes + seg_first;             // node slot of global node g is seg_nodes[g - seg_first]
-    uint32_t p = parent_leaf[leaf];
+// common-prefix length of the augmented strings (key_i, i) and (key_{i+1}, i+1)
+__device__ __forceinline__ int delta_adjacent(uint64_t ka, uint64_t kb, uint32_t i) {
+    return ka == kb ? 64 + __clz((int)(i ^ (i + 1u))) : __clzll((long long)(ka ^ kb));
+}
+__device__ __forceinline__ int delta_global(const uint64_t* __restrict__ keys, int vb, uint32_t i) {
+    return delta_adjacent(__ldg(keys + i) >> vb, __ldg(keys + i + 1) >> vb, i);
+}
+
+struct TreeJob {
+    uint32_t l, r;              // sorted-leaf range of the finished subtree
+    Box3 b;
+    int32_t ref;                // how the parent refers to this subtree (relative to the segment)
+    uint32_t height;
+    uint32_t seg_first, seg_count;
+};
+
+__device__ __forceinline__ void merge_job(TreeJob& j, bool right, uint32_t g, const float4& s0, const float4& s1, uint32_t sfar, int leaf_max) {
+    if (right) j.r = sfar; else j.l = sfar;
+    j.b.lo[0] = fminf(j.b.lo[0], s0.x); j.b.lo[1] = fminf(j.b.lo[1], s0.y); j.b.lo[2] = fminf(j.b.lo[2], s0.z);
+    j.b.hi[0] = fmaxf(j.b.hi[0], s0.w); j.b.hi[1] = fmaxf(j.b.hi[1], s1.x); j.b.hi[2] = fmaxf(j.b.hi[2], s1.y);
+    const uint32_t count = j.r - j.l + 1u;
+    if (count <= (uint32_t)leaf_max) { j.ref = leaf_ref(j.l - j.seg_first, count); j.height = 0; }
+    else { j.ref = (int32_t)(g - j.seg_first); j.height = max(j.height, __float_as_uint(s1.w)) + 1u; }
+}
+
+// Segment policies: seg_of(key) gives first/count of the segment (one BLAS of a batch, or the whole TLAS) a key belongs
+// to; on_root(job) is called by the one thread that completes a segment's root.
+struct TriSegments {
+    BlasRecord* records; const uint64_t* keys; int vb;
+    __device__ __forceinline__ void seg_of(uint64_t key, uint32_t& first, uint32_t& count) const {
+        const BlasRecord& R = records[(uint32_t)(key >> MORTON_BITS)];
+        first = R.first; count = R.tri_count;
+    }
+    __device__ __forceinline__ void on_root(const TreeJob& j) const {
+        BlasRecord& R = records[(uint32_t)((__ldg(keys + j.l) >> vb) >> MORTON_BITS)];
+        R.root = j.ref; R.height = j.height;
+        R.lo[0] = j.b.lo[0]; R.lo[1] = j.b.lo[1]; R.lo[2] = j.b.lo[2];
+        R.hi[0] = j.b.hi[0]; R.hi[1] = j.b.hi[1]; R.hi[2] = j.b.hi[2];
+    }
+};
+struct InstSegment {
+    uint32_t n; int32_t* meta; float* bounds_out;
+    __device__ __forceinline__ void seg_of(uint64_t, uint32_t& first, uint32_t& count) const { first = 0u; count = n; }
+    __device__ __forceinline__ void on_root(const TreeJob& j) const {
+        meta[0] = j.ref; meta[1] = (int32_t)j.height;
+        bounds_out[0] = j.b.lo[0]; bounds_out[1] = j.b.lo[1]; bounds_out[2] = j.b.lo[2];
+        bounds_out[3] = j.b.hi[0]; bounds_out[4] = j.b.hi[1]; bounds_out[5] = j.b.hi[2];
+    }
+};
+
+// Phase 1 (inside the leaf kernels): everything a tile can finish on its own. Unfinished subtrees (at most 2 per tile:
+// the ones whose next split lies outside it) and orphans (a child deposited in shared memory whose sibling straddles
+// the tile border: at most one per straddling ancestor of the two border leaves) are appended to the border-job queue
+// as 48-B records {lo.xyz hi.x | hi.yz ref height | l r - -}; one global atomic per CTA.
+template <int LEAF_MAX, class Seg>
+__device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+                                                float4* __restrict__ jobs, uint32_t* __restrict__ job_count,
+                                                const Box3& leaf_box, const Seg& seg) {
+    __shared__ int s_delta[TREE_TILE + 1];          // s_delta[k] = delta(L0 - 1 + k)
+    __shared__ uint32_t s_flag[TREE_TILE];          // bit side: that child of split L0 + k has been deposited
+    __shared__ float4 s_a[2 * TREE_TILE], s_b[2 * TREE_TILE];
+    __shared__ uint32_t s_far[2 * TREE_TILE];
+    __shared__ uint32_t s_njobs, s_base;
+    const uint32_t tid = threadIdx.x, L0 = blockIdx.x * (uint32_t)TREE_TILE, leaf = L0 + tid;
+    const uint64_t k0 = leaf < n ? __ldg(keys + leaf) >> vb : 0ull;
+    s_delta[tid + 1] = leaf + 1u < n ? delta_adjacent(k0, __ldg(keys + leaf + 1) >> vb, leaf) : -1;
+    if (tid == 0) { s_delta[0] = L0 > 0u ? delta_adjacent(__ldg(keys + L0 - 1) >> vb, k0, L0 - 1u) : -1; s_njobs = 0u; }
+    s_flag[tid] = 0u;
+    __syncthreads();
+
+    TreeJob j;
+    bool carried = false;
+    if (leaf < n) {
+        j.l = j.r = leaf; j.b = leaf_box; j.height = 0;
+        seg.seg_of(k0, j.seg_first, j.seg_count);
+        j.ref = leaf_ref(leaf - j.seg_first, 1);
+        for (;;) {
+            if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); break; }
+            const bool right = s_delta[j.r - L0 + 1u] > s_delta[j.l - L0];
+            const uint32_t g = right ? j.r : j.l - 1u;
+            if (g < L0 || g + 1u >= L0 + (uint32_t)TREE_TILE) { carried = true; break; }
+            const uint32_t slot = g - L0, side = right ? 0u : 1u;
+            const float4 m0 = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
+            const float4 m1 = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
+            s_a[2 * slot + side] = m0; s_b[2 * slot + side] = m1; s_far[2 * slot + side] = right ? j.l : j.r;
+            __threadfence_block();
+            if (atomicOr(&s_flag[slot], 1u << side) == 0u) break;          // first arrival: the sibling finishes this node
+            __threadfence_block();
+            const float4 s0 = s_a[2 * slot + (side ^ 1u)], s1 = s_b[2 * slot + (side ^ 1u)];
+            merge_job(j, right, g, s0, s1, s_far[2 * slot + (side ^ 1u)], LEAF_MAX);
+            if (j.ref >= 0) {                                                // live node: one thread writes the whole 64-B record
+                float4* dst = reinterpret_cast<float4*>(nodes + g);
+                dst[0] = right ? m0 : s0; dst[1] = right ? m1 : s1; dst[2] = right ? s0 : m0; dst[3] = right ? s1 : m1;
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t f = s_flag[tid];
+    const bool orphan = f == 1u || f == 2u;
+    const uint32_t ia = carried ? atomicAdd(&s_njobs, 1u) : 0u;
+    const uint32_t ib = orphan ? atomicAdd(&s_njobs, 1u) : 0u;
+    __syncthreads();
+    if (tid == 0 && s_njobs) s_base = atomicAdd(job_count, s_njobs);
+    __syncthreads();
+    if (carried) {
+        float4* q = jobs + 3 * (size_t)(s_base + ia);
+        q[0] = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
+        q[1] = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
+        q[2] = make_float4(__uint_as_float(j.l), __uint_as_float(j.r), 0.0f, 0.0f);
+    }
+    if (orphan) {
+        const uint32_t side = f - 1u, g = L0 + tid;
+        float4* q = jobs + 3 * (size_t)(s_base + ib);
+        q[0] = s_a[2 * tid + side]; q[1] = s_b[2 * tid + side];
+        const uint32_t far = s_far[2 * tid + side];
+        q[2] = side == 0u ? make_float4(__uint_as_float(far), __uint_as_float(g), 0.0f, 0.0f)
+                          : make_float4(__uint_as_float(g + 1u), __uint_as_float(far), 0.0f, 0.0f);
+    }
+}
+// capacity of the border-job queue: 2 unfinished subtrees + one orphan per straddling ancestor (tree height <= 64 key
+// bits + 32 index bits) of each border leaf, and never more than one orphan per split of the tile
+__host__ __device__ constexpr uint32_t tree_jobs_per_tile() { return 2u + 2u * 96u; }
+
+// Phase 2: one thread per border job climbs through global memory: deposit half + far end, fence, arrival counter.
+template <int LEAF_MAX, class Seg>
+__global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+                                                    const float4* __restrict__ jobs, const uint32_t* __restrict__ job_count,
+                                                    uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg seg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *job_count) return;
+    const float4 m0 = __ldg(jobs + 3 * (size_t)i), m1 = __ldg(jobs + 3 * (size_t)i + 1), m2 = __ldg(jobs + 3 * (size_t)i + 2);
+    TreeJob j;
+    j.b.lo[0] = m0.x; j.b.lo[1] = m0.y; j.b.lo[2] = m0.z; j.b.hi[0] = m0.w; j.b.hi[1] = m1.x; j.b.hi[2] = m1.y;
+    j.ref = __float_as_int(m1.z); j.height = __float_as_uint(m1.w);
+    j.l = __float_as_uint(m2.x); j.r = __float_as_uint(m2.y);
+    seg.seg_of(__ldg(keys + j.l) >> vb, j.seg_first, j.seg_count);
     for (;;) {
-        const uint32_t node = p >> 1, side = p & 1u;
-        store_half(seg_nodes, node - seg_first, side, b, ref, height);
+        if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); break; }
+        const int dl = j.l > 0u ? delta_global(keys, vb, j.l - 1u) : -1;
+        const int dr = j.r + 1u < n ? delta_global(keys, vb, j.r) : -1;
+        const bool right = dr > dl;
+        const uint32_t g = right ? j.r : j.l - 1u, side = right ? 0u : 1u;
+        store_half(nodes, g, side, j.b, j.ref, j.height);
+        far_end[2 * (size_t)g + side] = right ? j.l : j.r;
         __threadfence();
-        if (atomicAdd(arrived + node, 1u) == 0u) return false;      // first arrival: the sibling's thread finishes this node
-        const float4* sib = reinterpret_cast<const float4*>(&seg_nodes[node - seg_first].c[side ^ 1u]);
+        if (atomicAdd(arrived + g, 1u) == 0u) break;
+        __threadfence();
+        const float4* sib = reinterpret_cast<const float4*>(&nodes[g].c[side ^ 1u]);
         const float4 s0 = __ldcg(sib), s1 = __ldcg(sib + 1);
-        b.lo[0] = fminf(b.lo[0], s0.x); b.lo[1] = fminf(b.lo[1], s0.y); b.lo[2] = fminf(b.lo[2], s0.z);
-        b.hi[0] = fmaxf(b.hi[0], s0.w); b.hi[1] = fmaxf(b.hi[1], s1.x); b.hi[2] = fmaxf(b.hi[2], s1.y);
-        const uint32_t sib_height = __float_as_uint(s1.w);
-        const int32_t j = other_end[node];
-        const uint32_t first = min(node, (uint32_t)j), last = max(node, (uint32_t)j);
-        const uint32_t count = last - first + 1u;
-        if (count <= (uint32_t)LEAF_MAX) { ref = leaf_ref(first - seg_first, count); height = 0; }
-        else { ref = (int32_t)(node - seg_first); height = max(height, sib_height) + 1u; }
-        if (count == seg_count) return true;                        // completed the segment's root
-        p = parent_node[node];
+        merge_job(j, right, g, s0, s1, __ldcg(far_end + 2 * (size_t)g + (side ^ 1u)), LEAF_MAX);
     }
 }
 
-__global__ void __launch_bounds__(256) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
-                                                   const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
-                                                   BvhNode* __restrict__ nodes, BlasRecord* __restrict__ records,
-                                                   const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
-                                                   const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
+__global__ void __launch_bounds__(TREE_TILE, 3) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
+                                                         const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
+                                                         BvhNode* __restrict__ nodes, const TriSegments seg,
+                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= n) return;
-    const uint64_t rec = __ldg(keys + leaf);
-    const uint32_t blas = (uint32_t)(rec >> (MORTON_BITS + vb));
-    const uint32_t src_i = vb ? (uint32_t)(rec & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
-    const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
-    const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
-    float4 q2 = __ldg(src + 2);
-    q2.w = 0.0f;                                          // pad (carried the BLAS id through the sort)
-    float4* dst = reinterpret_cast<float4*>(sorted + leaf);
-    dst[0] = q0; dst[1] = q1; dst[2] = q2;
-    Box3 b;
-    b.lo[0] = fminf(fminf(q0.x, q0.w), q1.z); b.lo[1] = fminf(fminf(q0.y, q1.x), q1.w); b.lo[2] = fminf(fminf(q0.z, q1.y), q2.x);
-    b.hi[0] = fmaxf(fmaxf(q0.x, q0.w), q1.z); b.hi[1] = fmaxf(fmaxf(q0.y, q1.x), q1.w); b.hi[2] = fmaxf(fmaxf(q0.z, q1.y), q2.x);
-    const uint32_t seg_first = records[blas].first, seg_count = records[blas].tri_count;
-    int32_t ref; uint32_t height;
-    if (climb<BLAS_LEAF_MAX>(nodes, parent_leaf, parent_node, other_end, arrived, leaf, seg_first, seg_count, b, ref, height)) {
-        BlasRecord& R = records[blas];
-        R.root = ref; R.height = height;
-        R.lo[0] = b.lo[0]; R.lo[1] = b.lo[1]; R.lo[2] = b.lo[2];
-        R.hi[0] = b.hi[0]; R.hi[1] = b.hi[1]; R.hi[2] = b.hi[2];
+    Box3 b = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+    if (leaf < n) {
+        const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
+        const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
+        const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
+        float4 q2 = __ldg(src + 2);
+        q2.w = 0.0f;                                          // pad (carried the BLAS id through the sort)
+        float4* dst = reinterpret_cast<float4*>(sorted + leaf);
+        dst[0] = q0; dst[1] = q1; dst[2] = q2;
+        b.lo[0] = fminf(fminf(q0.x, q0.w), q1.z); b.lo[1] = fminf(fminf(q0.y, q1.x), q1.w); b.lo[2] = fminf(fminf(q0.z, q1.y), q2.x);
+        b.hi[0] = fmaxf(fmaxf(q0.x, q0.w), q1.z); b.hi[1] = fmaxf(fmaxf(q0.y, q1.x), q1.w); b.hi[2] = fmaxf(fmaxf(q0.z, q1.y), q2.x);
     }
+    build_tree_tile<BLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg);
 }
 
 // ---- TLAS ---------------------------------------------------------------------------------------
@@ -304,31 +392,34 @@ __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restri
     else { keys[i] = key; vals[i] = i; }
 }
 
-__global__ void __launch_bounds__(256) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
-                                                   const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
-                                                   BvhNode* __restrict__ nodes, int32_t* __restrict__ meta, float* __restrict__ bounds_out,
-                                                   const uint32_t* __restrict__ parent_leaf, const uint32_t* __restrict__ parent_node,
-                                                   const int32_t* __restrict__ other_end, uint32_t* __restrict__ arrived) {
+__global__ void __launch_bounds__(TREE_TILE, 3) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
+                                                         const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
+                                                         BvhNode* __restrict__ nodes, const InstSegment seg,
+                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
-    if (leaf >= n) return;
-    const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
-    const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
-    float4* dst = reinterpret_cast<float4*>(sorted + leaf);
+    Box3 b = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
+    if (leaf < n) {
+        const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
+        const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
+        float4* dst = reinterpret_cast<float4*>(sorted + leaf);
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dst[k] = __ldg(src + k);
-    const float* bx = boxes + 6 * (size_t)src_i;
-    Box3 b = {{bx[0], bx[1], bx[2]}, {bx[3], bx[4], bx[5]}};
-    int32_t ref; uint32_t height;
-    if (climb<TLAS_LEAF_MAX>(nodes, parent_leaf, parent_node, other_end, arrived, leaf, 0u, n, b, ref, height)) {
-        meta[0] = ref; meta[1] = (int32_t)height;
-        bounds_out[0] = b.lo[0]; bounds_out[1] = b.lo[1]; bounds_out[2] = b.lo[2];
-        bounds_out[3] = b.hi[0]; bounds_out[4] = b.hi[1]; bounds_out[5] = b.hi[2];
+        for (int k = 0; k < 6; ++k) dst[k] = __ldg(src + k);
+        const float* bx = boxes + 6 * (size_t)src_i;
+        b.lo[0] = bx[0]; b.lo[1] = bx[1]; b.lo[2] = bx[2]; b.hi[0] = bx[3]; b.hi[1] = bx[4]; b.hi[2] = bx[5];
     }
+    build_tree_tile<TLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg);
 }
 
 inline int div_up(uint32_t a, uint32_t b) { return (int)((a + b - 1) / b); }
 
 }  // namespace
+
+uint32_t tree_job_capacity(uint32_t n) {
+    const uint64_t tiles = ((uint64_t)n + TREE_TILE - 1) / TREE_TILE;
+    const uint64_t per_tile = tree_jobs_per_tile() < (uint32_t)TREE_TILE + 2u ? tree_jobs_per_tile() : (uint32_t)TREE_TILE + 2u;
+    const uint64_t cap = tiles * per_tile;
+    return (uint32_t)(cap < 2ull * n + 2 ? cap : 2ull * n + 2);
+}
 
 int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b) {
     int launches = 0;
@@ -348,15 +439,17 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
     const uint64_t* keys = *sorted_in_b ? a.s.keys_b : a.s.keys_a;
     const uint32_t* vals = *sorted_in_b ? a.s.vals_b : a.s.vals_a;
     if (ev) cudaEventRecord(ev->e[3], st);
-    if (a.n_tris > 1) {
-        if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * (size_t)a.n_tris, st) != cudaSuccess) return -1;
-        k_karras<<<div_up(a.n_tris - 1, 256), 256, 0, st>>>(keys, vb, (int)a.n_tris, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
-        ++launches;
-    }
+    if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * ((size_t)a.n_tris + 1), st) != cudaSuccess) return -1;   // counters + job count
     if (ev) cudaEventRecord(ev->e[4], st);
-    k_refit_tris<<<div_up(a.n_tris, 256), 256, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, a.records,
-                                                       a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
-    ++launches;
+    {
+        const TriSegments seg{a.records, keys, vb};
+        const uint32_t tiles = (uint32_t)div_up(a.n_tris, TREE_TILE);
+        uint32_t* job_count = a.s.arrived + a.n_tris;
+        k_refit_tris<<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count);
+        k_tree_border<BLAS_LEAF_MAX, TriSegments><<<div_up(tree_job_capacity(a.n_tris), 128), 128, 0, st>>>(keys, vb, a.n_tris, a.nodes, a.s.jobs, job_count,
+                                                                                                          a.s.far_end, a.s.arrived, seg);
+    }
+    launches += 2;
     if (ev) cudaEventRecord(ev->e[5], st);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
@@ -375,14 +468,15 @@ int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st) {
     launches += sl;
     const uint64_t* keys = in_b ? a.s.keys_b : a.s.keys_a;
     const uint32_t* vals = in_b ? a.s.vals_b : a.s.vals_a;
-    if (a.n > 1) {
-        if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * (size_t)a.n, st) != cudaSuccess) return -1;
-        k_karras<<<div_up(a.n - 1, 256), 256, 0, st>>>(keys, vb, (int)a.n, a.s.other_end, a.s.parent_node, a.s.parent_leaf);
-        ++launches;
+    if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * ((size_t)a.n + 1), st) != cudaSuccess) return -1;
+    {
+        const InstSegment seg{a.n, a.root_out, a.bounds_out};
+        uint32_t* job_count = a.s.arrived + a.n;
+        k_refit_inst<<<div_up(a.n, TREE_TILE), TREE_TILE, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, seg, a.s.jobs, job_count);
+        k_tree_border<TLAS_LEAF_MAX, InstSegment><<<div_up(tree_job_capacity(a.n), 128), 128, 0, st>>>(keys, vb, a.n, a.nodes, a.s.jobs, job_count,
+                                                                                                     a.s.far_end, a.s.arrived, seg);
     }
-    k_refit_inst<<<div_up(a.n, 256), 256, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, a.root_out,
-                                                  a.bounds_out, a.s.parent_leaf, a.s.parent_node, a.s.other_end, a.s.arrived);
-    ++launches;
+    launches += 2;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }

@@ -94,10 +94,9 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
 struct BuildScratch {           // all device pointers, sized for n primitives
     uint64_t* keys_a; uint64_t* keys_b;
     uint32_t* vals_a; uint32_t* vals_b;
-    uint32_t* parent_leaf;      // n
-    uint32_t* parent_node;      // n
-    int32_t*  other_end;        // n
-    uint32_t* arrived;          // n
+    uint32_t* far_end;          // 2n: far end of the range of the child deposited at (split, side), border subtrees only
+    uint32_t* arrived;          // n + 1: arrival counters of the splits resolved through global memory, then the border-job count
+    float4*   jobs;             // 3 x float4 per border job, tree_job_capacity(n) of them
     void*     sort_scratch;
     int*      error_flag;       // 1 int
 };
@@ -116,6 +115,7 @@ struct BlasBuildArgs {
     SortPlan  sort;
 };
 struct BuildEvents { cudaEvent_t e[6]; };  // setup | morton | sort | hierarchy | refit | end
+uint32_t tree_job_capacity(uint32_t n);   // upper bound of the border-job queue length for n leaves
 int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b);
 
 struct TlasBuildArgs {

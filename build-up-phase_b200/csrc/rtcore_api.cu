@@ -107,7 +107,7 @@ size_t build_scratch_bytes(uint32_t n, const SortPlan& sp, bool tris, uint32_t n
     size_t b = 0;
     auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
     add(8ull * n); add(8ull * n); add(4ull * n); add(4ull * n);          // keys a/b, vals a/b
-    add(4ull * n); add(4ull * n); add(4ull * n); add(4ull * n);          // parent_leaf, parent_node, other_end, arrived
+    add(8ull * n); add(4ull * n + 4); add(48ull * tree_job_capacity(n));    // far_end, arrived (+ job count), border jobs
     add(sp.scratch_bytes);
     if (tris) { add(48ull * n); add(sizeof(GeomDesc) * (size_t)n_geoms); add(4ull * (n_geoms + 1)); add(24ull * n_blas); }
     else { add(96ull * n); add(24ull * n); add(64ull * n); add(64); add(64); }
@@ -117,8 +117,8 @@ size_t build_scratch_bytes(uint32_t n, const SortPlan& sp, bool tris, uint32_t n
 void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
     s.keys_a = c.take<uint64_t>(n); s.keys_b = c.take<uint64_t>(n);
     s.vals_a = c.take<uint32_t>(n); s.vals_b = c.take<uint32_t>(n);
-    s.parent_leaf = c.take<uint32_t>(n); s.parent_node = c.take<uint32_t>(n);
-    s.other_end = c.take<int32_t>(n); s.arrived = c.take<uint32_t>(n);
+    s.far_end = c.take<uint32_t>(2 * (size_t)n); s.arrived = c.take<uint32_t>((size_t)n + 1);
+    s.jobs = c.take<float4>(3 * (size_t)tree_job_capacity(n));
     s.sort_scratch = c.take<uint8_t>(sp.scratch_bytes);
 }
 

@@ -284,6 +284,24 @@ def soup_scene(n_tris: int = 100_000_000, width: int = 7680, height: int = 4320,
     return Scene(f"soup{n_tris}-{split}", blases, instances, SAMPLE_HIT_RECORDS[3:4].copy(), width=width, height=height, bounces=bounces)
 
 
+def duplicate_key_scene(n_tris: int = 20_000, clusters: int = 37, seed: int = 11, width: int = 64, height: int = 64) -> Scene:
+    """Build stress case: triangles piled onto a few cluster centres, so that long runs of primitives share one Morton
+    code (the index-augmented part of the radix-tree definition decides the topology there), plus two far outliers that
+    stretch the quantisation grid."""
+    rng = np.random.default_rng(seed)
+    centres = (rng.random((clusters, 3), dtype=np.float32) * np.float32(2) - np.float32(1)).astype(np.float32)
+    which = rng.integers(0, clusters, size=n_tris)
+    c = centres[which]
+    e1 = (rng.random((n_tris, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(1e-5)
+    e2 = (rng.random((n_tris, 3), dtype=np.float32) - np.float32(0.5)) * np.float32(1e-5)
+    verts = np.empty((n_tris, 3, 3), dtype=np.float32)
+    verts[:, 0] = c; verts[:, 1] = c + e1; verts[:, 2] = c + e2
+    verts[0] += np.float32(50.0); verts[1] -= np.float32(50.0)
+    geo = Geometry(verts.reshape(-1, 3), None, None)
+    inst = Instance(IDENTITY_3X4.copy(), 1, 0xFF, 0, INSTANCE_TRIANGLE_FACING_CULL_DISABLE, 0)
+    return Scene(f"dupkeys{n_tris}", [[geo]], [inst], SAMPLE_HIT_RECORDS[:1].copy(), width=width, height=height, bounces=0)
+
+
 def random_scene(n_blas: int, tris_per_blas: int, n_instances: int, seed: int, width: int = 256, height: int = 160,
                  bounces: int = 1, n_geoms: int = 2, shared_edges: bool = True) -> Scene:
     """Small fuzz scene for brute-force parity: random triangle clusters (optionally as a connected strip

@@ -132,8 +132,12 @@ static inline uint32_t morton30(const Box& pb, const Box& scene) {
 }
 
 // Karras-2012 LBVH over N primitive boxes with keys; leaves collapsed to <= leaf_max primitives.
+// Node numbering: an internal node is stored at the slot of its SPLIT position gamma (its left child ends at
+// sorted primitive gamma, its right child starts at gamma + 1); every split position occurs exactly once, so
+// this is a permutation of Karras' own numbering. The ranges/splits are found top-down exactly as in the
+// paper; the GPU product finds the same tree bottom-up, which makes the comparison an independent check.
 struct Lbvh {
-    std::vector<Node> nodes;        // N-1 slots (Karras numbering), unreachable ones are garbage
+    std::vector<Node> nodes;        // N-1 slots (split-position numbering), unreachable ones are garbage
     std::vector<uint64_t> keys;     // sorted
     std::vector<uint32_t> prims;    // sorted position -> original primitive
     int32_t root = REF_EMPTY;
@@ -178,6 +182,7 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
     std::vector<int32_t> other_end(NI);           // j of node i; range = [min(i,j), max(i,j)]
     std::vector<uint32_t> parent_of_node(NI, 0xFFFFFFFFu), parent_of_leaf(N);  // (parent << 1) | side
     std::vector<int32_t> left_child(NI), right_child(NI);                       // >=0 internal, ~idx leaf position
+    std::vector<int32_t> slot_of(NI);                                           // Karras node i -> storage slot (its split position)
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < NI; ++i) {
         int d = (delta(i, i + 1) - delta(i, i - 1)) >= 0 ? 1 : -1;
@@ -198,6 +203,7 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
         int64_t gamma = i + s * d + std::min(d, 0);
         int64_t first = std::min(i, j), last = std::max(i, j);
         other_end[i] = (int32_t)j;
+        slot_of[i] = (int32_t)gamma;
         if (first == gamma) { left_child[i] = ~(int32_t)gamma; parent_of_leaf[gamma] = ((uint32_t)i << 1) | 0u; }
         else { left_child[i] = (int32_t)gamma; parent_of_node[gamma] = ((uint32_t)i << 1) | 0u; }
         if (last == gamma + 1) { right_child[i] = ~(int32_t)(gamma + 1); parent_of_leaf[gamma + 1] = ((uint32_t)i << 1) | 1u; }
@@ -216,17 +222,17 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
         uint32_t p = parent_of_leaf[leaf];
         for (;;) {
             uint32_t node = p >> 1, side = p & 1u;
-            NodeHalf& h = bvh.nodes[node].c[side];
+            NodeHalf& h = bvh.nodes[slot_of[node]].c[side];
             for (int k = 0; k < 3; ++k) { h.lo[k] = b.lo[k]; h.hi[k] = b.hi[k]; }
             h.ref = ref; h.height = height;
             if (arrived[node].fetch_add(1, std::memory_order_acq_rel) == 0) break;  // first: sibling will finish
-            const NodeHalf& o = bvh.nodes[node].c[side ^ 1u];
+            const NodeHalf& o = bvh.nodes[slot_of[node]].c[side ^ 1u];
             for (int k = 0; k < 3; ++k) { b.lo[k] = fminf(b.lo[k], o.lo[k]); b.hi[k] = fmaxf(b.hi[k], o.hi[k]); }
             int64_t j = other_end[node];
             int64_t first = std::min<int64_t>(node, j), last = std::max<int64_t>(node, j);
             uint32_t count = (uint32_t)(last - first + 1);
             if ((int)count <= leaf_max) { ref = leaf_ref((uint32_t)first, count); height = 0; }
-            else { ref = (int32_t)node; height = std::max(height, o.height) + 1; }
+            else { ref = slot_of[node]; height = std::max(height, o.height) + 1; }
             if (node == 0) { root_box = b; root_height = height; root_ref = ref; break; }
             p = parent_of_node[node];
         }

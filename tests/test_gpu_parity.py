@@ -92,10 +92,18 @@ def test_instanced_batched_scene(rt, ctx, oracle):
 
 
 @pytest.mark.parametrize("flags", [0, 0x200], ids=["packed-sort", "pair-sort"])
-def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags):
+@pytest.mark.parametrize("kind", ["tess", "dupkeys", "tiny"])
+def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
     """Integer/byte work must be bit-exact: sorted Morton keys, primitive order, tree topology and
-    every node box of the GPU LBVH equal the CPU restatement's (both sort record formats)."""
-    scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
+    every node box of the GPU LBVH equal the CPU restatement's (both sort record formats). The CPU side finds the
+    radix tree top-down (Karras), the GPU bottom-up in 512-leaf tiles: "dupkeys" exercises the index-augmented
+    prefix rule on long runs of equal keys, "tiny" a tree smaller than one tile."""
+    if kind == "tess":
+        scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
+    elif kind == "dupkeys":
+        scene = scenes.duplicate_key_scene(20_000)
+    else:
+        scene = scenes.tess_scene(nx=9, ny=7, width=64, height=64, bounces=0)
     blas = ctx.build_blas(scene.blases[0], flags=flags)
     keys, prims = ctx.last_sorted_keys()
     info = blas.info()
@@ -103,14 +111,16 @@ def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags):
     blas.free()
     o = oracle.OracleScene(scene)
     oinfo, onodes, otris, okeys, oprims = o.blas_export(0)
-    assert info.triangle_count == oinfo.triangle_count == 120 * 70 * 2
+    assert info.triangle_count == oinfo.triangle_count == scene.triangle_count
+    if kind == "dupkeys":
+        assert np.count_nonzero(keys[1:] == keys[:-1]) > info.triangle_count // 2
     assert np.array_equal(keys, okeys), "sorted Morton keys differ"
     assert np.array_equal(prims, oprims), "sorted primitive order differs (sort not stable?)"
     assert np.array_equal(tris[:, :11], otris[:, :11]), "sorted triangle records differ"
     assert info.root_ref == oinfo.root_ref and info.max_depth == oinfo.max_depth
     assert list(info.bounds_lo) == list(oinfo.bounds_lo) and list(info.bounds_hi) == list(oinfo.bounds_hi)
     n = walk_compare_bvh(nodes, info.root_ref, onodes, oinfo.root_ref)
-    assert n > info.triangle_count // 8
+    assert n >= info.triangle_count // 8
     print("lbvh nodes compared:", n, "depth", info.max_depth)
 
 
