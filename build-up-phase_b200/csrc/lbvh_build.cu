@@ -12,7 +12,7 @@
 //                 key XOR, index-augmented for duplicate keys; found bottom-up as in Apetrei 2014, see
 //                 build_tree_tile): one thread per sorted leaf emits the sorted triangle, then climbs;
 //                 the second child to arrive at a split unions the boxes and continues. Splits inside
-//                 a CTA's 512-leaf tile meet in shared memory, only the tile-border subtrees use global
+//                 a CTA's 128-leaf tile meet in shared memory, only the tile-border subtrees use global
 //                 arrival counters. Because the BLAS id is the key prefix, every BLAS of a batch is
 //                 exactly one subtree of the global radix tree; subtrees of <= 4 triangles collapse
 //                 into a leaf; the thread that completes a BLAS publishes its root/bounds/height.
@@ -139,7 +139,17 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
 // of the nodes) continues through global memory with the classic fence + arrival counter.
 struct Box3 { float lo[3], hi[3]; };
 
-constexpr int TREE_TILE = 512;
+#ifndef RT_TREE_TILE
+#define RT_TREE_TILE 128
+#endif
+#ifndef RT_TREE_MIN_CTAS
+#define RT_TREE_MIN_CTAS (1536 / RT_TREE_TILE)
+#endif
+constexpr int TREE_TILE = RT_TREE_TILE;            // <= 512: a tile-local range end is packed into 9 bits next to the height
+static_assert(TREE_TILE <= 512 && (TREE_TILE & (TREE_TILE - 1)) == 0, "tile");
+
+// CTA-scope acquire/release fence (cheaper than the sequentially consistent one __threadfence_block() emits)
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
 __device__ __forceinline__ void store_half(BvhNode* nodes, uint32_t node, uint32_t side, const Box3& b, int32_t ref, uint32_t height) {
     float4* dst = reinterpret_cast<float4*>(&nodes[node].c[side]);
@@ -208,7 +218,6 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
     __shared__ int s_delta[TREE_TILE + 1];          // s_delta[k] = delta(L0 - 1 + k)
     __shared__ uint32_t s_flag[TREE_TILE];          // bit side: that child of split L0 + k has been deposited
     __shared__ float4 s_a[2 * TREE_TILE], s_b[2 * TREE_TILE];
-    __shared__ uint32_t s_far[2 * TREE_TILE];
     __shared__ uint32_t s_njobs, s_base;
     const uint32_t tid = threadIdx.x, L0 = blockIdx.x * (uint32_t)TREE_TILE, leaf = L0 + tid;
     const uint64_t k0 = leaf < n ? __ldg(keys + leaf) >> vb : 0ull;
@@ -217,29 +226,40 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
     s_flag[tid] = 0u;
     __syncthreads();
 
+    // In the tile the subtree is {lt, rt} (tile-local ends), box, ref, height; a deposit is two float4:
+    // {lo.xyz hi.x} {hi.y hi.z ref height | far_end_local << 8}.
     TreeJob j;
     bool carried = false;
     if (leaf < n) {
-        j.l = j.r = leaf; j.b = leaf_box; j.height = 0;
+        j.b = leaf_box; j.height = 0;
         seg.seg_of(k0, j.seg_first, j.seg_count);
         j.ref = leaf_ref(leaf - j.seg_first, 1);
+        const uint32_t rel = L0 - j.seg_first;                               // tile-local -> segment-relative (mod 2^32)
+        uint32_t lt = tid, rt = tid;
         for (;;) {
-            if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); break; }
-            const bool right = s_delta[j.r - L0 + 1u] > s_delta[j.l - L0];
-            const uint32_t g = right ? j.r : j.l - 1u;
-            if (g < L0 || g + 1u >= L0 + (uint32_t)TREE_TILE) { carried = true; break; }
-            const uint32_t slot = g - L0, side = right ? 0u : 1u;
+            if (rt - lt + 1u == j.seg_count) { j.l = L0 + lt; j.r = L0 + rt; seg.on_root(j); break; }
+            const bool right = s_delta[rt + 1u] > s_delta[lt];
+            const uint32_t slot = right ? rt : lt - 1u;                      // split g = L0 + slot; lt - 1 wraps to 2^32-1 at the tile's left end
+            if (slot >= (uint32_t)TREE_TILE - 1u) { carried = true; j.l = L0 + lt; j.r = L0 + rt; break; }
+            const uint32_t side = right ? 0u : 1u;
             const float4 m0 = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
-            const float4 m1 = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
-            s_a[2 * slot + side] = m0; s_b[2 * slot + side] = m1; s_far[2 * slot + side] = right ? j.l : j.r;
-            __threadfence_block();
+            const float4 m1 = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height | ((right ? lt : rt) << 8)));
+            s_a[2 * slot + side] = m0; s_b[2 * slot + side] = m1;
+            fence_cta();
             if (atomicOr(&s_flag[slot], 1u << side) == 0u) break;          // first arrival: the sibling finishes this node
-            __threadfence_block();
+            fence_cta();
             const float4 s0 = s_a[2 * slot + (side ^ 1u)], s1 = s_b[2 * slot + (side ^ 1u)];
-            merge_job(j, right, g, s0, s1, s_far[2 * slot + (side ^ 1u)], LEAF_MAX);
-            if (j.ref >= 0) {                                                // live node: one thread writes the whole 64-B record
-                float4* dst = reinterpret_cast<float4*>(nodes + g);
-                dst[0] = right ? m0 : s0; dst[1] = right ? m1 : s1; dst[2] = right ? s0 : m0; dst[3] = right ? s1 : m1;
+            const uint32_t sw = __float_as_uint(s1.w);
+            if (right) rt = sw >> 8; else lt = sw >> 8;
+            j.b.lo[0] = fminf(j.b.lo[0], s0.x); j.b.lo[1] = fminf(j.b.lo[1], s0.y); j.b.lo[2] = fminf(j.b.lo[2], s0.z);
+            j.b.hi[0] = fmaxf(j.b.hi[0], s0.w); j.b.hi[1] = fmaxf(j.b.hi[1], s1.x); j.b.hi[2] = fmaxf(j.b.hi[2], s1.y);
+            const uint32_t count = rt - lt + 1u;
+            if (count <= (uint32_t)LEAF_MAX) { j.ref = leaf_ref(lt + rel, count); j.height = 0; }
+            else {                                                           // live node: one thread writes the whole 64-B record
+                j.ref = (int32_t)(slot + rel); j.height = max(j.height, sw & 255u) + 1u;
+                float4* dst = reinterpret_cast<float4*>(nodes + L0 + slot);
+                dst[2 * side] = m0; dst[2 * side + 1] = make_float4(m1.x, m1.y, m1.z, __uint_as_float(__float_as_uint(m1.w) & 255u));
+                dst[2 * (side ^ 1u)] = s0; dst[2 * (side ^ 1u) + 1] = make_float4(s1.x, s1.y, s1.z, __uint_as_float(sw & 255u));
             }
         }
     }
@@ -260,8 +280,10 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
     if (orphan) {
         const uint32_t side = f - 1u, g = L0 + tid;
         float4* q = jobs + 3 * (size_t)(s_base + ib);
-        q[0] = s_a[2 * tid + side]; q[1] = s_b[2 * tid + side];
-        const uint32_t far = s_far[2 * tid + side];
+        float4 m1 = s_b[2 * tid + side];
+        const uint32_t far = L0 + (__float_as_uint(m1.w) >> 8);
+        m1.w = __uint_as_float(__float_as_uint(m1.w) & 255u);
+        q[0] = s_a[2 * tid + side]; q[1] = m1;
         q[2] = side == 0u ? make_float4(__uint_as_float(far), __uint_as_float(g), 0.0f, 0.0f)
                           : make_float4(__uint_as_float(g + 1u), __uint_as_float(far), 0.0f, 0.0f);
     }
@@ -300,7 +322,7 @@ __global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict_
     }
 }
 
-__global__ void __launch_bounds__(TREE_TILE, 3) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
+__global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
                                                          const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
                                                          BvhNode* __restrict__ nodes, const TriSegments seg,
                                                          float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {
@@ -392,7 +414,7 @@ __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restri
     else { keys[i] = key; vals[i] = i; }
 }
 
-__global__ void __launch_bounds__(TREE_TILE, 3) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
+__global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
                                                          const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
                                                          BvhNode* __restrict__ nodes, const InstSegment seg,
                                                          float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {

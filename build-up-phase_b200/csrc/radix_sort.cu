@@ -24,12 +24,22 @@ namespace {
 constexpr int RADIX = 256;
 constexpr int SORT_THREADS = 256;            // == RADIX: thread d owns digit d in the scan / look-back
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int SORT_ITEMS = 12;
+#ifndef RT_SORT_ITEMS
+#define RT_SORT_ITEMS 12
+#endif
+#ifndef RT_SORT_MIN_CTAS
+#define RT_SORT_MIN_CTAS 4
+#endif
+constexpr int SORT_ITEMS = RT_SORT_ITEMS;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;   // 3072 pairs
 constexpr int MAX_PASSES = 8;
 
 constexpr uint32_t FLAG_AGG = 1u << 30, FLAG_PREFIX = 2u << 30, VALUE_MASK = (1u << 30) - 1u;
 constexpr uint32_t SPIN_LIMIT = 1u << 24;
+#ifndef RT_LOOKBACK_WINDOW
+#define RT_LOOKBACK_WINDOW 4
+#endif
+constexpr int LOOKBACK_WINDOW = RT_LOOKBACK_WINDOW;
 
 __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
     uint32_t v;
@@ -38,6 +48,23 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 }
 __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// Peer mask of the lanes holding the same 8-bit digit: MATCH.ANY, or (RT_SORT_USE_BALLOT) 8 ballots. Measured on B200
+// (profiles/README.md, r01l): the ballot form is not faster, MATCH.ANY is not what bounds the pass.
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid) {
+#if !defined(RT_SORT_USE_BALLOT)
+    return __match_any_sync(0xffffffffu, valid ? (d & 255u) : 0xFFFFFFFFu);
+#else
+    uint32_t m = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool bit = (d >> b) & 1u;
+        const uint32_t v = __ballot_sync(0xffffffffu, bit);
+        m &= bit ? v : ~v;
+    }
+    return m;
+#endif
 }
 
 // hist[p][d] += number of keys whose p-th 8-bit digit (counted from bit base_shift) is d
@@ -72,7 +99,7 @@ __global__ void __launch_bounds__(RADIX) k_sort_scan_hist(uint32_t* hist) {
 
 // HAS_VALS = false: the primitive id rides in the low bits of the 64-bit word (below `shift`), nothing else is moved
 template <bool HAS_VALS>
-__global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
+__global__ void __launch_bounds__(SORT_THREADS, RT_SORT_MIN_CTAS) k_onesweep_pass(
     const uint64_t* __restrict__ keys_in, uint64_t* __restrict__ keys_out,
     const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ vals_out,
     uint32_t n, int shift, const uint32_t* __restrict__ digit_base,
@@ -102,20 +129,35 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
         key[i] = li < tile_n ? keys_in[base + li] : ~0ull;
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
+    // Ranking in three software-pipelined sweeps (no dependent chain through shared memory between items):
+    // (1) the peer mask of every item (lanes holding the same digit), (2) one shared-memory atomic per distinct digit
+    // and item by the lowest peer lane — a warp's atomics are issued in program order, so item i is counted before
+    // item i + 1 and the ranking is stable —, (3) broadcast of the old counter value to the peers.
+    constexpr int RANK_BATCH = SORT_ITEMS % 6 == 0 ? 6 : 4;     // items in flight per sweep (bounds the live registers)
+    static_assert(SORT_ITEMS % RANK_BATCH == 0, "SORT_ITEMS");
 #pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const bool valid = (wbase + i * 32) < tile_n;
-        const uint32_t d = valid ? (uint32_t)((key[i] >> shift) & 255u) : 0xFFFFFFFFu;
-        const uint32_t m = __match_any_sync(0xffffffffu, d);
-        const int leader = __ffs(m) - 1;
-        uint32_t prev = 0;
-        if (valid && lane == leader) {
-            prev = s_cnt[warp * RADIX + d];
-            s_cnt[warp * RADIX + d] = prev + __popc(m);
+    for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_BATCH) {
+        uint32_t prev[RANK_BATCH];
+#pragma unroll
+        for (int k = 0; k < RANK_BATCH; ++k) {
+            const int i = i0 + k;
+            const bool valid = (wbase + i * 32) < tile_n;
+            rank[i] = match_digit((uint32_t)(key[i] >> shift), valid);
         }
-        prev = __shfl_sync(0xffffffffu, prev, leader);
-        rank[i] = prev + __popc(m & lt_mask);
-        __syncwarp();
+#pragma unroll
+        for (int k = 0; k < RANK_BATCH; ++k) {
+            const int i = i0 + k;
+            const bool valid = (wbase + i * 32) < tile_n;
+            const uint32_t m = rank[i];
+            prev[k] = 0;
+            if (valid && lane == __ffs(m) - 1) prev[k] = atomicAdd(&s_cnt[warp * RADIX + (uint32_t)((key[i] >> shift) & 255u)], (uint32_t)__popc(m));
+        }
+#pragma unroll
+        for (int k = 0; k < RANK_BATCH; ++k) {
+            const int i = i0 + k;
+            const uint32_t m = rank[i];
+            rank[i] = __shfl_sync(0xffffffffu, prev[k], __ffs(m) - 1) + __popc(m & lt_mask);
+        }
     }
     __syncthreads();
 
@@ -139,21 +181,31 @@ __global__ void __launch_bounds__(SORT_THREADS) k_onesweep_pass(
         for (int w = 0; w < warp; ++w) wb += s_wtot[w];
         const uint32_t loff = wb + inc - run;
 
+        // Decoupled look-back, LOOKBACK_WINDOW predecessor tiles per step: the window's loads are independent (one L2
+        // round trip per step instead of one per tile); they are consumed in order up to the first tile that has not
+        // published yet, or the first inclusive prefix. Tile -1 is a virtual inclusive prefix of 0.
         uint32_t excl = 0;
         if (tile > 0) {
             int t = (int)tile - 1;
             uint32_t spins = 0;
             for (;;) {
-                uint32_t s = ld_volatile_u32(tile_state + (size_t)t * RADIX + d);
-                uint32_t flag = s >> 30;
-                if (flag == 0) {
-                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1); break; }
-                    __nanosleep(32);
-                    continue;
+                uint32_t sv[LOOKBACK_WINDOW];
+#pragma unroll
+                for (int k = 0; k < LOOKBACK_WINDOW; ++k)
+                    sv[k] = t - k >= 0 ? ld_volatile_u32(tile_state + (size_t)(t - k) * RADIX + d) : FLAG_PREFIX;
+                bool done = false;
+                int adv = 0;
+#pragma unroll
+                for (int k = 0; k < LOOKBACK_WINDOW; ++k) {
+                    const uint32_t flag = sv[k] >> 30;
+                    if (!done && adv == k && flag != 0u) { excl += sv[k] & VALUE_MASK; adv = k + 1; done = flag == 2u; }
                 }
-                excl += s & VALUE_MASK;
-                if (flag == 2 || t == 0) break;
-                --t;
+                if (done) break;
+                t -= adv;
+                if (adv == 0) {
+                    if (++spins > SPIN_LIMIT) { atomicExch(error_flag, 1); break; }
+                    __nanosleep(20);
+                }
             }
             st_volatile_u32(my_state, FLAG_PREFIX | ((excl + run) & VALUE_MASK));
         }

@@ -96,7 +96,7 @@ def test_instanced_batched_scene(rt, ctx, oracle):
 def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
     """Integer/byte work must be bit-exact: sorted Morton keys, primitive order, tree topology and
     every node box of the GPU LBVH equal the CPU restatement's (both sort record formats). The CPU side finds the
-    radix tree top-down (Karras), the GPU bottom-up in 512-leaf tiles: "dupkeys" exercises the index-augmented
+    radix tree top-down (Karras), the GPU bottom-up in shared-memory tiles: "dupkeys" exercises the index-augmented
     prefix rule on long runs of equal keys, "tiny" a tree smaller than one tile."""
     if kind == "tess":
         scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)

@@ -9,6 +9,23 @@ def _split(t0, t1):
 
 VARIANTS = {
     "base": [],
+    "tile128": ["RT_TREE_TILE=128"],
+    "match": ["RT_SORT_USE_MATCH=1"],
+    "ballot_5": ["RT_SORT_MIN_CTAS=5"],
+    "ballot_6": ["RT_SORT_MIN_CTAS=6"],
+    "lb1": ["RT_LOOKBACK_WINDOW=1"],
+    "lb4": ["RT_LOOKBACK_WINDOW=4"],
+    "lb16": ["RT_LOOKBACK_WINDOW=16"],
+    "lb8_6": ["RT_LOOKBACK_WINDOW=8", "RT_SORT_MIN_CTAS=6"],
+    "sort8_5": ["RT_SORT_ITEMS=8", "RT_SORT_MIN_CTAS=5"],
+    "sort8_6": ["RT_SORT_ITEMS=8", "RT_SORT_MIN_CTAS=6"],
+    "sort12_5": ["RT_SORT_ITEMS=12", "RT_SORT_MIN_CTAS=5"],
+    "sort12_6": ["RT_SORT_ITEMS=12", "RT_SORT_MIN_CTAS=6"],
+    "sort16_4": ["RT_SORT_ITEMS=16", "RT_SORT_MIN_CTAS=4"],
+    "sort16_3": ["RT_SORT_ITEMS=16", "RT_SORT_MIN_CTAS=3"],
+    "tile256": ["RT_TREE_TILE=256"],
+    "tile256_4": ["RT_TREE_TILE=256", "RT_TREE_MIN_CTAS=4"],
+    "tile512_2": ["RT_TREE_TILE=512", "RT_TREE_MIN_CTAS=2"],
     "split_16_16": _split(16, 16),
     "split_20_20": _split(20, 20),
     "split_24_24": _split(24, 24),
