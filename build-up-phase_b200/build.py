@@ -12,8 +12,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtcore.so")
-SOURCES = ["rtcore_api.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu"]
-HEADERS = ["rt_internal.h", "rt_device.cuh", os.path.join("..", "..", "include", "rtcore.h")]
+SOURCES = ["rtcore_api.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu",
+           os.path.join("..", "host", "rtcore_io.cpp")]     # host-side .obj / image I/O (include/rtcore_io.h), no device code
+HEADERS = ["rt_internal.h", "rt_device.cuh", os.path.join("..", "..", "include", "rtcore.h"),
+           os.path.join("..", "..", "include", "rtcore_io.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -60,7 +62,7 @@ def build_rtcore(force: bool = False, verbose: bool = False) -> str:
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(objdir, s.replace(".cu", ".o"))
+        o = os.path.join(objdir, os.path.splitext(os.path.basename(s))[0] + ".o")
         objs.append(o)
         cmd = [_nvcc(), "-ccbin", ccbin, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", o]
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -40,6 +40,10 @@ EXPORTED_SYMBOLS = [
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
+    # include/rtcore_io.h
+    "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
+    "rt_obj_group_count", "rt_obj_vertices", "rt_obj_indices", "rt_obj_group_name", "rt_obj_group_first_triangle",
+    "rt_obj_group_triangle_count", "rt_obj_geometry", "rt_write_ppm", "rt_srgb8_table",
 ]
 
 
@@ -168,6 +172,29 @@ def load(build_if_missing: bool = True):
     L.rt_kernel_launch_count.argtypes = [vp]
     L.rt_kernel_launch_count.restype = u64
     L.rt_version.restype = C.c_char_p
+    # include/rtcore_io.h
+    L.rt_obj_load.argtypes = [C.c_char_p, C.POINTER(vp)]
+    L.rt_obj_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
+    L.rt_obj_free.argtypes = [vp]
+    L.rt_obj_free.restype = None
+    L.rt_obj_last_error.restype = C.c_char_p
+    for name in ("rt_obj_vertex_count", "rt_obj_triangle_count", "rt_obj_group_count"):
+        getattr(L, name).argtypes = [vp]
+        getattr(L, name).restype = u32
+    L.rt_obj_vertices.argtypes = [vp]
+    L.rt_obj_vertices.restype = C.POINTER(C.c_float)
+    L.rt_obj_indices.argtypes = [vp]
+    L.rt_obj_indices.restype = C.POINTER(u32)
+    L.rt_obj_group_name.argtypes = [vp, u32]
+    L.rt_obj_group_name.restype = C.c_char_p
+    L.rt_obj_group_first_triangle.argtypes = [vp, u32]
+    L.rt_obj_group_first_triangle.restype = u32
+    L.rt_obj_group_triangle_count.argtypes = [vp, u32]
+    L.rt_obj_group_triangle_count.restype = u32
+    L.rt_obj_geometry.argtypes = [vp, u32, C.POINTER(RtGeometry)]
+    L.rt_write_ppm.argtypes = [C.c_char_p, vp, u32, u32, u32]
+    L.rt_srgb8_table.argtypes = [vp]
+    L.rt_srgb8_table.restype = None
     _lib = L
     return L
 
@@ -462,3 +489,69 @@ class SceneHandles:
         self.tlas.free()
         for b in self.blases:
             b.free()
+
+
+# ---- include/rtcore_io.h: host-side formats either side of the path -------------------------------------------------
+IMAGE_SRGB_ENCODE = 0x1
+IMAGE_FLIP_Y = 0x2
+
+
+class ObjMesh:
+    """rt_obj_mesh: a Wavefront .obj parsed by the library (the reference's "load an obj file -> build the acceleration
+    structure" assignment, vulkan-raytracing-basic/README.md:225-226). groups() -> [(name, first_triangle, count)]."""
+
+    def __init__(self, path: Optional[str] = None, text: Optional[bytes] = None):
+        L = load()
+        h = C.c_void_p()
+        if path is not None:
+            rc = L.rt_obj_load(os.fsencode(path), C.byref(h))
+        else:
+            rc = L.rt_obj_parse(text, len(text), C.byref(h))
+        if rc != 0:
+            raise RtError(rc, L.rt_obj_last_error().decode())
+        self._h = h
+        nv, nt = L.rt_obj_vertex_count(h), L.rt_obj_triangle_count(h)
+        self.vertices = (np.ctypeslib.as_array(L.rt_obj_vertices(h), shape=(nv, 3)).copy() if nv else np.zeros((0, 3), np.float32))
+        self.indices = (np.ctypeslib.as_array(L.rt_obj_indices(h), shape=(nt, 3)).copy() if nt else np.zeros((0, 3), np.uint32))
+        self._groups = [(L.rt_obj_group_name(h, g).decode(), L.rt_obj_group_first_triangle(h, g), L.rt_obj_group_triangle_count(h, g))
+                        for g in range(L.rt_obj_group_count(h))]
+
+    def groups(self):
+        return list(self._groups)
+
+    def geometries(self):
+        """One scenes.Geometry per group (shared vertex array, the group's slice of the index array)."""
+        from . import scenes
+        return [scenes.Geometry(self.vertices, self.indices[f:f + n].copy(), None) for _, f, n in self._groups]
+
+    def c_geometry(self, group: int) -> RtGeometry:
+        g = RtGeometry()
+        rc = load().rt_obj_geometry(self._h, group, C.byref(g))
+        if rc != 0:
+            raise RtError(rc, "rt_obj_geometry")
+        return g
+
+    def free(self):
+        if self._h:
+            load().rt_obj_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def write_ppm(path: str, rgba: np.ndarray, flags: int = 0) -> None:
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = a.shape[0], a.shape[1]
+    rc = load().rt_write_ppm(os.fsencode(path), a.ctypes.data, w, h, flags)
+    if rc != 0:
+        raise RtError(rc, load().rt_obj_last_error().decode())
+
+
+def srgb8_table() -> np.ndarray:
+    t = np.zeros(256, dtype=np.uint8)
+    load().rt_srgb8_table(t.ctypes.data)
+    return t

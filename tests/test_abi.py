@@ -1,4 +1,4 @@
-"""The C-ABI library loads on a GPU-less host and exports exactly what include/rtcore.h declares."""
+"""The C-ABI library loads on a GPU-less host and exports exactly what include/*.h declare."""
 import ctypes as C
 import os
 import re
@@ -7,9 +7,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _declared():
-    src = open(os.path.join(ROOT, "include", "rtcore.h")).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"RT_API[^;(]*?\b(rt_[a-z_0-9]+)\s*\(", src)))
+    names = set()
+    inc = os.path.join(ROOT, "include")
+    for h in sorted(os.listdir(inc)):
+        if not h.endswith(".h"):
+            continue
+        src = open(os.path.join(inc, h)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names.update(re.findall(r"RT_API[^;(]*?\b(rt_[a-z_0-9]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_header_symbols_exported(rt):
@@ -17,7 +23,7 @@ def test_header_symbols_exported(rt):
     names = _declared()
     assert len(names) >= 30
     for n in names:
-        assert hasattr(L, n), f"{n} declared in rtcore.h but not exported by librtcore.so"
+        assert hasattr(L, n), f"{n} declared in include/*.h but not exported by librtcore.so"
     assert sorted(rt.EXPORTED_SYMBOLS) == names
 
 

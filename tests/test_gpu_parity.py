@@ -269,3 +269,35 @@ def test_tlas_update_and_device_inputs(rt, ctx, oracle):
     assert np.array_equal(t_dev, t_host) and b_dev.info().root_ref == b_host.info().root_ref
     walk_compare_bvh(n_dev, b_dev.info().root_ref, n_host, b_host.info().root_ref)
     b_dev.free(); b_host.free()
+
+
+def test_obj_mesh_build_and_trace(rt, ctx, oracle, tmp_path):
+    """a Wavefront .obj (two groups -> two geometries of one BLAS, quads fan-triangulated by the
+    loader) goes through rt_obj_load -> rt_build_blas -> rt_trace; the oracle brute-forces the same arrays as parsed by
+    the independent Python statement of the grammar (tests/test_io_formats.py)."""
+    from test_io_formats import py_parse_obj
+    hf = scenes.heightfield(24, 18, -3.0, 3.0, -2.0, 2.0, 0.6, 21)
+    v = hf.vertices.astype(np.float64)
+    quads = hf.indices.reshape(-1, 2, 3)                     # grid_indices emits two triangles per quad
+    lines = [f"v {x!r} {y!r} {z!r}" for x, y, z in v.tolist()]
+    half = len(quads) // 2
+    for gi, (a, b) in enumerate(((0, half), (half, len(quads)))):
+        lines.append(f"g part{gi}")
+        for q in quads[a:b]:
+            lines.append("f " + " ".join(str(int(i) + 1) for i in q[0]))
+            lines.append("f " + " ".join(f"{int(i) + 1}//1" for i in q[1]))
+    text = "\n".join(lines) + "\n"
+    path = tmp_path / "hf.obj"
+    path.write_text(text)
+    mesh = rt.ObjMesh(path=str(path))
+    pv, pt, pg = py_parse_obj(text)
+    assert np.array_equal(mesh.vertices.view(np.uint32), pv.view(np.uint32)) and np.array_equal(mesh.indices, pt) and len(pg) == 2
+    geoms = mesh.geometries()
+    assert sum(g.triangle_count for g in geoms) == hf.triangle_count
+    inst = scenes.Instance(scenes.rotation_3x4(np.array([1.0, 0.3, 0.0]), 0.4, np.array([0.0, 0.0, 0.0])), 7, 0xFF, 0,
+                           scenes.INSTANCE_TRIANGLE_FACING_CULL_DISABLE, 0)
+    scene = scenes.Scene("obj", [geoms], [inst], scenes.SAMPLE_HIT_RECORDS[:2].copy(), width=320, height=200, bounces=1)
+    g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE)
+    rp, rs, rc = assert_parity(g, r, what="obj")
+    assert rp["hits"] > 5000 and set(np.unique(g[1]["geometry_index"][g[1]["instance_id"] != MISS])) == {0, 1}
+    print("obj", rp, rs, rc)
