@@ -4,7 +4,7 @@
 //   BvhNode     64 B  = two 32-B halves {lo.xyz, hi.xyz, ref, height}, one per child. A half is
 //                       exactly one 32-B DRAM sector and is written by the ONE thread that climbs
 //                       through that child during the atomic bottom-up refit.
-//   TriRec      48 B  = v0.xyz v1.xyz v2.xyz geometryIndex primitiveIndex pad  (3 x LDG.128);
+//   TriRec      48 B  = v0.xyz v1.xyz v2.xyz geometryIndex primitiveIndex geometryFlags  (3 x LDG.128);
 //                       BLAS-space vertices with the per-geometry transform already baked in
 //                       (vkCmdBuildAccelerationStructuresKHR semantics, reference main.cpp:795-808).
 //   InstanceRec 96 B  = world->object 3x4, BLAS node/triangle base pointers, root ref, packed
@@ -33,7 +33,7 @@ struct __align__(32) BvhNodeHalf { float lo[3]; float hi[3]; int32_t ref; uint32
 struct __align__(64) BvhNode { BvhNodeHalf c[2]; };
 static_assert(sizeof(BvhNode) == 64, "BvhNode must be 64 B");
 
-struct __align__(16) TriRec { float v[9]; uint32_t geo, prim, pad; };
+struct __align__(16) TriRec { float v[9]; uint32_t geo, prim, flags; };   // flags: RT_GEOMETRY_* of its geometry (during the build: flags << 24 | BLAS id)
 static_assert(sizeof(TriRec) == 48, "TriRec must be 48 B");
 
 struct __align__(16) InstanceRec {
@@ -73,6 +73,7 @@ struct GeomDesc {
     uint32_t blas;              // which BLAS of the batch
     uint32_t geo_index;         // gl_GeometryIndexEXT inside that BLAS
     uint32_t has_xform;
+    uint32_t flags;             // RT_GEOMETRY_* (low 8 bits are kept with every triangle)
     float    xform[12];
 };
 
@@ -97,6 +98,7 @@ struct BuildScratch {           // all device pointers, sized for n primitives
     uint32_t* far_end;          // 2n: far end of the range of the child deposited at (split, side), border subtrees only
     uint32_t* arrived;          // n + 1: arrival counters of the splits resolved through global memory, then the border-job count
     float4*   jobs;             // 3 x float4 per border job, tree_job_capacity(n) of them
+    float4*   xchg;             // 4n: the two deposited child halves of the splits resolved through global memory (sparsely touched)
     void*     sort_scratch;
     int*      error_flag;       // 1 int
 };
@@ -146,6 +148,7 @@ struct TraceParams {
     uint32_t local_rows;                           // rows this launch covers (packed)
     float tmin, tmax;
     uint32_t cull_mask, sbt_offset, sbt_stride, bounce_seed;
+    uint32_t ray_flags;         // RT_RAY_FLAG_*; anything beyond OPAQUE/NO_OPAQUE selects the GENERAL kernel variant
     uint32_t bounces;
     const float* hit_records; uint32_t n_records;
     float miss[3];

@@ -27,8 +27,8 @@ struct rt_context {
     std::string err;
     // shader data
     float* d_hit_records = nullptr; uint32_t n_records = 0;
-    float miss[3] = {0.0f, 0.0f, 0.2f};                           // main.cpp:1065
-    rt_ray_params rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u};          // main.cpp:1047-1052
+    std::vector<float> miss = {0.0f, 0.0f, 0.2f};                 // miss records, 3 floats each; record 0 = main.cpp:1065
+    rt_ray_params rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, RT_RAY_FLAG_OPAQUE, 0u};   // main.cpp:1047-1052
     // grow-only device buffers
     void* scratch = nullptr; size_t scratch_cap = 0;
     void* fb = nullptr; size_t fb_cap = 0;
@@ -107,7 +107,7 @@ size_t build_scratch_bytes(uint32_t n, const SortPlan& sp, bool tris, uint32_t n
     size_t b = 0;
     auto add = [&](size_t bytes) { b = align_up(b, 256) + bytes; };
     add(8ull * n); add(8ull * n); add(4ull * n); add(4ull * n);          // keys a/b, vals a/b
-    add(8ull * n); add(4ull * n + 4); add(48ull * tree_job_capacity(n));    // far_end, arrived (+ job count), border jobs
+    add(8ull * n); add(4ull * n + 4); add(48ull * tree_job_capacity(n)); add(64ull * n);   // far_end, arrived (+ job count), border jobs, deposits
     add(sp.scratch_bytes);
     if (tris) { add(48ull * n); add(sizeof(GeomDesc) * (size_t)n_geoms); add(4ull * (n_geoms + 1)); add(24ull * n_blas); }
     else { add(96ull * n); add(24ull * n); add(64ull * n); add(64); add(64); }
@@ -119,6 +119,7 @@ void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
     s.vals_a = c.take<uint32_t>(n); s.vals_b = c.take<uint32_t>(n);
     s.far_end = c.take<uint32_t>(2 * (size_t)n); s.arrived = c.take<uint32_t>((size_t)n + 1);
     s.jobs = c.take<float4>(3 * (size_t)tree_job_capacity(n));
+    s.xchg = c.take<float4>(4 * (size_t)n);
     s.sort_scratch = c.take<uint8_t>(sp.scratch_bytes);
 }
 
@@ -220,6 +221,7 @@ static void storage_release(BlasStorage* st) {
 int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
                         uint32_t build_flags, rt_blas** out_array) {
     if (!ctx || !out_array || n_blas == 0 || !geom_counts) return RT_ERROR_INVALID_ARG;
+    if (n_blas > (1u << 24)) return fail(ctx, RT_ERROR_INVALID_ARG, "at most 2^24 BLASes per batch");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     for (uint32_t b = 0; b < n_blas; ++b) out_array[b] = nullptr;
     uint32_t n_geoms = 0;
@@ -249,7 +251,7 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
                 GeomDesc& D = descs[g];
                 memset(&D, 0, sizeof(D));
                 D.stride_f = G.vertex_stride_bytes / 4; D.tri_first = (uint32_t)total; D.tri_count = G.triangle_count;
-                D.blas = b; D.geo_index = k;
+                D.blas = b; D.geo_index = k; D.flags = G.flags & 0xFFu;
                 total += G.triangle_count; bt += G.triangle_count;
                 if (!(G.flags & RT_GEOMETRY_DEVICE_POINTERS)) {
                     stage_bytes = align_up(stage_bytes, 16) + (size_t)G.vertex_count * G.vertex_stride_bytes;
@@ -609,9 +611,15 @@ int rt_set_miss_color(rt_context* ctx, const float rgb[3]) {
     return RT_SUCCESS;
 }
 
+int rt_set_miss_records(rt_context* ctx, const float* rgb, uint32_t count) {
+    if (!ctx || !rgb || count == 0) return RT_ERROR_INVALID_ARG;
+    ctx->miss.assign(rgb, rgb + 3 * (size_t)count);
+    return RT_SUCCESS;
+}
+
 int rt_set_ray_params(rt_context* ctx, const rt_ray_params* params) {
     if (!ctx) return RT_ERROR_INVALID_ARG;
-    if (params) ctx->rp = *params; else ctx->rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u};
+    if (params) ctx->rp = *params; else ctx->rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, RT_RAY_FLAG_OPAQUE, 0u};
     return RT_SUCCESS;
 }
 
@@ -637,6 +645,8 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
                                    : (uint64_t)tlas->max_sbt + (uint64_t)tlas->max_geo * ctx->rp.sbt_record_stride + ctx->rp.sbt_record_offset;
         if (bound >= ctx->n_records) return fail(ctx, RT_ERROR_SBT_RANGE, "hit record %llu addressed but only %u set", (unsigned long long)bound, ctx->n_records);
     }
+    if ((size_t)ctx->rp.miss_index * 3 + 3 > ctx->miss.size())
+        return fail(ctx, RT_ERROR_SBT_RANGE, "miss record %u addressed but only %u set", ctx->rp.miss_index, (unsigned)(ctx->miss.size() / 3));
     const int stack_needed = (int)tlas->height + tlas->max_blas_height + 4;
     if (stack_needed > 160) return fail(ctx, RT_ERROR_STACK_DEPTH, "BVH depth %d exceeds the traversal stack", stack_needed);
 
@@ -645,14 +655,14 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     const bool dev_out = (flags & RT_TRACE_OUT_DEVICE) != 0;
     TraceParams P{};
     P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
-    for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[k]; }
+    for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[3 * (size_t)ctx->rp.miss_index + k]; }
     // raygen constants of main.cpp:1038-1039; tan is evaluated once on the host in fp32
     P.aspect_y = tanf((cam->yfov_deg * 0.017453292519943295f) * 0.5f);
     P.aspect_x = P.aspect_y * (float)width / (float)height;
     P.width = width; P.height = height; P.block_rows = block_rows; P.part_index = part_index; P.part_count = part_count;
     P.local_rows = (uint32_t)(pixels / width);
     P.tmin = ctx->rp.tmin; P.tmax = ctx->rp.tmax; P.cull_mask = ctx->rp.cull_mask; P.sbt_offset = ctx->rp.sbt_record_offset;
-    P.sbt_stride = ctx->rp.sbt_record_stride; P.bounce_seed = ctx->rp.bounce_seed; P.bounces = bounces;
+    P.sbt_stride = ctx->rp.sbt_record_stride; P.bounce_seed = ctx->rp.bounce_seed; P.bounces = bounces; P.ray_flags = ctx->rp.ray_flags;
     P.hit_records = ctx->d_hit_records; P.n_records = ctx->n_records;
     int rc;
     if (dev_out) { P.rgba = rgba_out; P.primary_hits = primary_hits_out; P.secondary_hits = secondary_hits_out; }

@@ -21,6 +21,10 @@
 //    the sample uses gl_RayFlagsOpaqueEXT only and TRIANGLE_FACING_CULL_DISABLE (main.cpp:852,1048).
 //  * Closest hit = smallest t in (tmin, tmax); equal t resolved by lowest (instance, geometry,
 //    primitive) so the result does not depend on BVH shape or traversal order.
+//  * GENERAL kernel variant (selected only when the ray flags ask for more than Opaque/NoOpaque, so the sample's
+//    path pays nothing): opacity resolution geometry -> instance FORCE_* -> ray flags with CULL_OPAQUE/CULL_NO_OPAQUE,
+//    front/back-face culling in object space with the instance FLIP_FACING / FACING_CULL_DISABLE flags,
+//    TERMINATE_ON_FIRST_HIT and SKIP_CLOSEST_HIT_SHADER (include/rtcore.h, RT_RAY_FLAG_*).
 #include <float.h>
 
 #include "rt_device.cuh"
@@ -227,7 +231,7 @@ __device__ __forceinline__ void flush_stats(const TraceParams& P, const Counters
 
 // ---- the shaders' epilogue: closest-hit (main.cpp:1080-1091, SBT rule main.cpp:1260-1262) / miss (main.cpp:1063-1066)
 // / imageStore (main.cpp:1054), plus the generation of the diffuse bounce ray (stage 0) or the blend (stage 1).
-template <int STAGE, bool STATS>
+template <int STAGE, bool STATS, bool GENERAL>
 __device__ __forceinline__ void shade(const TraceParams& P, const RayId id, const V3 o, const V3 d, float col0, float col1, float col2,
                                       float best_t, float best_u, float best_v, float best_w0, uint32_t best_slot, uint32_t best_tri,
                                       bool& enqueue, float4& e0, float4& e1, float4& e2, Counters& c) {
@@ -260,13 +264,14 @@ __device__ __forceinline__ void shade(const TraceParams& P, const RayId id, cons
         }
         rec.instance_id = inst_id; rec.geometry_index = geo; rec.primitive_id = prim; rec.custom_index = custom;
         rec.t = best_t; rec.u = best_u; rec.v = best_v;
+        if (GENERAL && (P.ray_flags & RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER)) sc0 = sc1 = sc2 = 0.0f;   // payload keeps its initial value (main.cpp:1045)
         if (STATS) { ++c.hits; if (STAGE == 0 && fminf(fminf(best_u, best_v), best_w0) < 9.5367431640625e-07f) ++c.edge; }
     } else {
         sc0 = P.miss[0]; sc1 = P.miss[1]; sc2 = P.miss[2];
     }
     if (STAGE == 0) {
         if (P.primary_hits) P.primary_hits[lidx] = rec;
-        if (hit && P.bounces > 0u) {
+        if (hit && P.bounces > 0u && !(GENERAL && (P.ray_flags & RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER))) {
             // ---- deterministic diffuse bounce (our definition; the reference's recursion depth is 1) ----
             const V3 p = {o.x + best_t * d.x, o.y + best_t * d.y, o.z + best_t * d.z};
             float w2o[12];
@@ -327,7 +332,7 @@ __device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueu
 // The shaders' epilogue runs inside this kernel for the lanes whose ray just finished. (Measured alternatives, both
 // slower on B200 - profiles/README.md r01h: a separate warp-convergent shading kernel with refill thresholds 16..28,
 // and speculative traversal with one postponed leaf.)
-template <int STAGE, bool STATS, int STACK>
+template <int STAGE, bool STATS, int STACK, bool GENERAL>
 __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -353,6 +358,8 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     sl.rdx = sl.rdy = sl.rdz = sl.cnx = sl.cny = sl.cnz = sl.cfx = sl.cfy = sl.cfz = 0.0f; sl.px = sl.py = sl.pz = false;
     wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
     uint32_t cur_slot = 0;
+    uint32_t cur_iflags = 0;                 // GENERAL: instance flags of the BLAS being traversed
+    V3 cur_od = {0.0f, 0.0f, 0.0f};          // GENERAL: object-space ray direction (facing test)
     float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
     uint32_t best_slot = NO_HIT, best_tri = 0;
     int32_t stack[STACK];
@@ -431,17 +438,37 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         woop_setup(wp, oo, od);
                         nodes = R->nodes; tris = R->tris;
                         cur_slot = first;
+                        if (GENERAL) { cur_iflags = __ldg(&R->sbt_flags) >> 24; cur_od = od; }
                         in_blas = true;
                         stack[sp++] = REF_POP_INSTANCE;
                         cur = root;
                     } else cur = stack[--sp];
                 } else {
+                    bool terminated = false;
                     for (uint32_t k = 0; k < count; ++k) {
                         const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
                         const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
                         if (STATS) ++c.tris;
                         float t, bu, bv, bw0;
                         if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
+                            if (GENERAL) {
+                                // opacity: geometry flag -> instance FORCE_* -> ray flags; then the opacity culls
+                                const uint32_t rf = P.ray_flags;
+                                bool opaque = (__float_as_uint(q2.w) & RT_GEOMETRY_OPAQUE) != 0u;
+                                if (cur_iflags & RT_INSTANCE_FORCE_OPAQUE) opaque = true;
+                                else if (cur_iflags & RT_INSTANCE_FORCE_NO_OPAQUE) opaque = false;
+                                if (rf & RT_RAY_FLAG_OPAQUE) opaque = true;
+                                else if (rf & RT_RAY_FLAG_NO_OPAQUE) opaque = false;
+                                if (opaque ? (rf & RT_RAY_FLAG_CULL_OPAQUE) : (rf & RT_RAY_FLAG_CULL_NO_OPAQUE)) continue;
+                                if ((rf & (RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES | RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES)) &&
+                                    !(cur_iflags & RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE)) {
+                                    // front = clockwise seen from the ray origin = ((v1-v0) x (v2-v0)) . d > 0, object space
+                                    const V3 ed1 = {q0.w - q0.x, q1.x - q0.y, q1.y - q0.z};
+                                    const V3 ed2 = {q1.z - q0.x, q1.w - q0.y, q2.x - q0.z};
+                                    const bool front = (dot3(cross3(ed1, ed2), cur_od) > 0.0f) != ((cur_iflags & RT_INSTANCE_TRIANGLE_FLIP_FACING) != 0u);
+                                    if (front ? (rf & RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES) : (rf & RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES)) continue;
+                                }
+                            }
                             bool better = t < best_t;
                             if (t == best_t && best_slot != NO_HIT) {
                                 // equal t: lowest (instance, geometry, primitive) wins; rare, so the ids of the
@@ -454,8 +481,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                                 better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
                             }
                             if (better) { best_t = t; best_u = bu; best_v = bv; best_w0 = bw0; best_slot = cur_slot; best_tri = first + k; }
+                            if (GENERAL && (P.ray_flags & RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT)) { terminated = true; break; }
                         }
                     }
+                    if (GENERAL && terminated) { cur = REF_DONE; break; }
                     cur = stack[--sp];
                 }
             } else if (cur == REF_POP_INSTANCE) {                                // back to world space
@@ -476,7 +505,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
         if (finish) {
             have_ray = false;
-            shade<STAGE, STATS>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+            shade<STAGE, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
         }
         if (STAGE == 0) enqueue_bounce(P, enqueue, e0, e1, e2, lane, lt_mask);
     }
@@ -493,11 +522,11 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ 
     out[(size_t)y * width + x] = packed_all[((size_t)part * rows_per_part + lr) * width + x];
 }
 
-template <int STAGE, bool STATS, int STACK>
+template <int STAGE, bool STATS, int STACK, bool GENERAL>
 int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
     static int blocks_per_sm = 0;       // same for every device of this process (one device per process)
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK>, TRACE_THREADS, 0) != cudaSuccess || blocks_per_sm < 1)
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK, GENERAL>, TRACE_THREADS, 0) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
     }
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
@@ -505,15 +534,23 @@ int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
     const uint32_t max_useful = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
     if (STAGE == 0 && blocks > max_useful) blocks = max_useful;
     if (blocks == 0) return 0;
-    k_trace<STAGE, STATS, STACK><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    k_trace<STAGE, STATS, STACK, GENERAL><<<blocks, TRACE_THREADS, 0, st>>>(p);
     return 1;
 }
 
-template <bool STATS, int STACK>
+template <bool STATS, int STACK, bool GENERAL>
 int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
-    int n = launch_stage<0, STATS, STACK>(p, sm_count, st);
-    if (p.bounces > 0) n += launch_stage<1, STATS, STACK>(p, sm_count, st);
+    int n = launch_stage<0, STATS, STACK, GENERAL>(p, sm_count, st);
+    if (p.bounces > 0) n += launch_stage<1, STATS, STACK, GENERAL>(p, sm_count, st);
     return n;
+}
+
+template <int STACK>
+int launch_stack(const TraceParams& p, bool stats, int sm_count, cudaStream_t st) {
+    // the sample's flags (Opaque) and NoOpaque change nothing without an any-hit stage: fast variant
+    const bool general = (p.ray_flags & ~(uint32_t)(RT_RAY_FLAG_OPAQUE | RT_RAY_FLAG_NO_OPAQUE)) != 0u;
+    if (general) return stats ? launch_both<true, STACK, true>(p, sm_count, st) : launch_both<false, STACK, true>(p, sm_count, st);
+    return stats ? launch_both<true, STACK, false>(p, sm_count, st) : launch_both<false, STACK, false>(p, sm_count, st);
 }
 
 }  // namespace
@@ -523,8 +560,8 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     if (tiles == 0) return 0;
     if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
     int n;
-    if (stack_needed <= 64) n = stats ? launch_both<true, 64>(p, sm_count, st) : launch_both<false, 64>(p, sm_count, st);
-    else if (stack_needed <= 160) n = stats ? launch_both<true, 160>(p, sm_count, st) : launch_both<false, 160>(p, sm_count, st);
+    if (stack_needed <= 64) n = launch_stack<64>(p, stats, sm_count, st);
+    else if (stack_needed <= 160) n = launch_stack<160>(p, stats, sm_count, st);
     else return -2;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return n;

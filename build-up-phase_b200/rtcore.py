@@ -37,7 +37,7 @@ EXPORTED_SYMBOLS = [
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
     "rt_update_tlas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
-    "rt_set_hit_records", "rt_set_miss_color", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
+    "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
     # include/rtcore_io.h
@@ -68,7 +68,14 @@ class RtCamera(C.Structure):
 
 class RtRayParams(C.Structure):
     _fields_ = [("tmin", C.c_float), ("tmax", C.c_float), ("cull_mask", C.c_uint32),
-                ("sbt_record_offset", C.c_uint32), ("sbt_record_stride", C.c_uint32), ("bounce_seed", C.c_uint32)]
+                ("sbt_record_offset", C.c_uint32), ("sbt_record_stride", C.c_uint32), ("bounce_seed", C.c_uint32),
+                ("ray_flags", C.c_uint32), ("miss_index", C.c_uint32)]
+
+
+# RT_RAY_FLAG_* / RT_INSTANCE_* (include/rtcore.h)
+RAY_FLAG_OPAQUE, RAY_FLAG_NO_OPAQUE, RAY_FLAG_TERMINATE_ON_FIRST_HIT, RAY_FLAG_SKIP_CLOSEST_HIT_SHADER = 0x01, 0x02, 0x04, 0x08
+RAY_FLAG_CULL_BACK_FACING, RAY_FLAG_CULL_FRONT_FACING, RAY_FLAG_CULL_OPAQUE, RAY_FLAG_CULL_NO_OPAQUE = 0x10, 0x20, 0x40, 0x80
+INSTANCE_FACING_CULL_DISABLE, INSTANCE_FLIP_FACING, INSTANCE_FORCE_OPAQUE, INSTANCE_FORCE_NO_OPAQUE = 0x1, 0x2, 0x4, 0x8
 
 
 class RtBuildSizes(C.Structure):
@@ -160,6 +167,7 @@ def load(build_if_missing: bool = True):
     L.rt_tlas_get_info.argtypes = [vp, vp, C.POINTER(RtTlasInfo)]
     L.rt_set_hit_records.argtypes = [vp, vp, u32]
     L.rt_set_miss_color.argtypes = [vp, C.POINTER(C.c_float)]
+    L.rt_set_miss_records.argtypes = [vp, vp, u32]
     L.rt_set_ray_params.argtypes = [vp, C.POINTER(RtRayParams)]
     L.rt_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, vp, vp, vp]
     L.rt_trace_rows.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
@@ -317,7 +325,7 @@ class Context:
                 arr[i].indices = _ptr(idx)
                 arr[i].triangle_count = int(idx.shape[0]) if idx is not None else int(v.shape[0]) // 3
                 arr[i].transform3x4 = _ptr(t)
-                arr[i].flags = RT_GEOMETRY_OPAQUE | RT_GEOMETRY_DEVICE_POINTERS
+                arr[i].flags = (getattr(g, "flags", RT_GEOMETRY_OPAQUE) & 0xFF) | RT_GEOMETRY_DEVICE_POINTERS
                 keep.extend([v, idx, t])
             else:
                 v = np.ascontiguousarray(g.vertices, dtype=np.float32)
@@ -333,7 +341,7 @@ class Context:
                     t = np.ascontiguousarray(g.transform, dtype=np.float32)
                     keep.append(t)
                     arr[i].transform3x4 = t.ctypes.data
-                arr[i].flags = RT_GEOMETRY_OPAQUE
+                arr[i].flags = getattr(g, "flags", RT_GEOMETRY_OPAQUE) & 0xFF
             arr[i].vertex_stride_bytes = 12
         return arr
 
@@ -413,8 +421,13 @@ class Context:
         arr = (C.c_float * 3)(*[float(x) for x in rgb])
         self._check(self.L.rt_set_miss_color(self.h, arr))
 
-    def set_ray_params(self, tmin=0.0, tmax=100.0, cull_mask=0xFF, sbt_record_offset=0, sbt_record_stride=1, bounce_seed=1):
-        p = RtRayParams(tmin, tmax, cull_mask, sbt_record_offset, sbt_record_stride, bounce_seed)
+    def set_miss_records(self, rgb: np.ndarray):
+        rgb = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
+        self._check(self.L.rt_set_miss_records(self.h, rgb.ctypes.data, rgb.shape[0]))
+
+    def set_ray_params(self, tmin=0.0, tmax=100.0, cull_mask=0xFF, sbt_record_offset=0, sbt_record_stride=1, bounce_seed=1,
+                       ray_flags=RAY_FLAG_OPAQUE, miss_index=0):
+        p = RtRayParams(tmin, tmax, cull_mask, sbt_record_offset, sbt_record_stride, bounce_seed, ray_flags, miss_index)
         self._check(self.L.rt_set_ray_params(self.h, C.byref(p)))
 
     # -- dispatch -----------------------------------------------------------------------------------------

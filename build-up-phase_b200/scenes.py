@@ -25,6 +25,7 @@ class Geometry:
     vertices: np.ndarray                     # float32 [nv, 3] (stride 12, R32G32B32_SFLOAT)
     indices: Optional[np.ndarray]            # uint32 [nt, 3] or None for a non-indexed list
     transform: Optional[np.ndarray] = None   # float32 [12], row-major 3x4 (VkTransformMatrixKHR)
+    flags: int = 1                           # VkGeometryFlagsKHR; 1 = OPAQUE (main.cpp:741)
 
     @property
     def triangle_count(self) -> int:

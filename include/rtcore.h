@@ -45,6 +45,7 @@ enum {
 
 /* ---- geometry flags (rt_geometry.flags) ------------------------------------------------ */
 #define RT_GEOMETRY_OPAQUE          0x1u  /* VK_GEOMETRY_OPAQUE_BIT_KHR, main.cpp:741 */
+#define RT_GEOMETRY_NO_DUPLICATE_ANY_HIT 0x2u /* VK_GEOMETRY_NO_DUPLICATE_ANY_HIT_INVOCATION_BIT_KHR: accepted; no any-hit stage exists in this ABI */
 #define RT_GEOMETRY_DEVICE_POINTERS 0x100u /* vertices/indices/transform are CUDA device pointers */
 
 /* ---- build flags ---------------------------------------------------------------------- */
@@ -54,6 +55,26 @@ enum {
 
 /* ---- instance flags (rt_instance.flags, low 8 bits like VkGeometryInstanceFlagsKHR) ---- */
 #define RT_INSTANCE_TRIANGLE_FACING_CULL_DISABLE 0x1u /* main.cpp:852 */
+#define RT_INSTANCE_TRIANGLE_FLIP_FACING         0x2u /* VK_GEOMETRY_INSTANCE_TRIANGLE_FLIP_FACING_BIT_KHR (= ..._FRONT_COUNTERCLOCKWISE) */
+#define RT_INSTANCE_FORCE_OPAQUE                 0x4u /* VK_GEOMETRY_INSTANCE_FORCE_OPAQUE_BIT_KHR */
+#define RT_INSTANCE_FORCE_NO_OPAQUE              0x8u /* VK_GEOMETRY_INSTANCE_FORCE_NO_OPAQUE_BIT_KHR */
+
+/* ---- ray flags (rt_ray_params.ray_flags): the gl_RayFlags*EXT argument of traceRayEXT (main.cpp:1048 passes Opaque) ----
+ * Opacity of a candidate: geometry RT_GEOMETRY_OPAQUE, overridden by the instance FORCE_* flags, overridden by the ray
+ * OPAQUE / NO_OPAQUE flags. No any-hit stage exists in this ABI (the sample registers none), so a non-opaque candidate
+ * is accepted like an opaque one; opacity only feeds CULL_OPAQUE / CULL_NO_OPAQUE.
+ * Facing (object space, so the baked geometry transform counts and the instance transform does not): a triangle is
+ * FRONT facing when its vertices appear clockwise from the ray origin, i.e. ((v1-v0) x (v2-v0)) . dir > 0, inverted by
+ * RT_INSTANCE_TRIANGLE_FLIP_FACING; facing culls are ignored for instances with TRIANGLE_FACING_CULL_DISABLE.
+ * TERMINATE_ON_FIRST_HIT accepts the first candidate the traversal meets: hit/miss is defined, WHICH hit is not. */
+#define RT_RAY_FLAG_OPAQUE                      0x01u
+#define RT_RAY_FLAG_NO_OPAQUE                   0x02u
+#define RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT      0x04u
+#define RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER     0x08u /* a hit leaves the payload at its initial value (0,0,0), main.cpp:1045 */
+#define RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES  0x10u
+#define RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES 0x20u
+#define RT_RAY_FLAG_CULL_OPAQUE                 0x40u
+#define RT_RAY_FLAG_CULL_NO_OPAQUE              0x80u
 
 /* ---- rt_trace output flags -------------------------------------------------------------- */
 #define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
@@ -102,6 +123,8 @@ typedef struct rt_ray_params {
     uint32_t sbt_record_offset; /* 0     */
     uint32_t sbt_record_stride; /* 1     */
     uint32_t bounce_seed;       /* seed of the deterministic diffuse bounce (ours; default 1) */
+    uint32_t ray_flags;         /* RT_RAY_FLAG_*; default RT_RAY_FLAG_OPAQUE (main.cpp:1048) */
+    uint32_t miss_index;        /* which miss record runs on a miss (main.cpp:1051 passes 0) */
 } rt_ray_params;
 
 /* Per-ray result: the built-ins the closest-hit shader sees (main.cpp:1080-1086).
@@ -208,7 +231,9 @@ RT_API int  rt_tlas_get_info(rt_context* ctx, const rt_tlas* tlas, rt_tlas_info*
 /* ---- shader data ------------------------------------------------------------------------ */
 /* Payloads of the hit-group records: count x {r,g,b} (main.cpp:1310-1317). */
 RT_API int  rt_set_hit_records(rt_context* ctx, const float* rgb, uint32_t count);
-RT_API int  rt_set_miss_color(rt_context* ctx, const float rgb[3]);          /* default (0,0,0.2), main.cpp:1065 */
+RT_API int  rt_set_miss_color(rt_context* ctx, const float rgb[3]);          /* miss record 0; default (0,0,0.2), main.cpp:1065 */
+/* Several miss shaders (each one, like the sample's, writes a constant colour): count x {r,g,b}; rt_ray_params.miss_index selects. */
+RT_API int  rt_set_miss_records(rt_context* ctx, const float* rgb, uint32_t count);
 RT_API int  rt_set_ray_params(rt_context* ctx, const rt_ray_params* params); /* NULL restores the defaults */
 
 /* ---- dispatch --------------------------------------------------------------------------- */

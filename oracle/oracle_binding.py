@@ -40,7 +40,8 @@ class OrcCamera(C.Structure):
 
 class OrcRayParams(C.Structure):
     _fields_ = [("tmin", C.c_float), ("tmax", C.c_float), ("cull_mask", C.c_uint32),
-                ("sbt_record_offset", C.c_uint32), ("sbt_record_stride", C.c_uint32), ("bounce_seed", C.c_uint32)]
+                ("sbt_record_offset", C.c_uint32), ("sbt_record_stride", C.c_uint32), ("bounce_seed", C.c_uint32),
+                ("ray_flags", C.c_uint32), ("miss_index", C.c_uint32)]
 
 
 class OrcStats(C.Structure):
@@ -52,7 +53,8 @@ class OrcStats(C.Structure):
 
 
 class OrcShaderData(C.Structure):
-    _fields_ = [("hit_records_rgb", C.c_void_p), ("hit_record_count", C.c_uint32), ("miss_rgb", C.c_float * 3)]
+    _fields_ = [("hit_records_rgb", C.c_void_p), ("hit_record_count", C.c_uint32), ("miss_rgb", C.c_float * 3),
+                ("miss_records_rgb", C.c_void_p), ("miss_record_count", C.c_uint32)]
 
 
 class OrcBlasInfo(C.Structure):
@@ -121,7 +123,7 @@ def _geom_array(geoms, keep: list):
             arr[i].transform3x4 = t.ctypes.data
         else:
             arr[i].transform3x4 = None
-        arr[i].flags = 1
+        arr[i].flags = getattr(g, "flags", 1) & 0xFF
     return arr
 
 
@@ -150,6 +152,13 @@ class OracleScene:
         self.sd.hit_record_count = self.records.shape[0]
         for k in range(3):
             self.sd.miss_rgb[k] = float(scene.miss_color[k])
+        self.sd.miss_records_rgb = None
+        self.sd.miss_record_count = 0
+
+    def set_miss_records(self, rgb):
+        self.miss_records = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
+        self.sd.miss_records_rgb = self.miss_records.ctypes.data
+        self.sd.miss_record_count = self.miss_records.shape[0]
 
     def trace(self, width: Optional[int] = None, height: Optional[int] = None, bounces: Optional[int] = None,
               mode: int = MODE_BVH, rows=(0, None, 1), ray_params: Optional[OrcRayParams] = None,
@@ -212,6 +221,11 @@ def time_blas_build(geoms) -> float:
     keep: list = []
     arr = _geom_array(geoms, keep)
     return float(lib().orc_time_blas_build(arr, len(geoms), 30))
+
+
+def ray_params(tmin=0.0, tmax=100.0, cull_mask=0xFF, sbt_record_offset=0, sbt_record_stride=1, bounce_seed=1,
+               ray_flags=0x1, miss_index=0) -> OrcRayParams:
+    return OrcRayParams(tmin, tmax, cull_mask, sbt_record_offset, sbt_record_stride, bounce_seed, ray_flags, miss_index)
 
 
 def num_threads() -> int:

@@ -81,7 +81,7 @@ static inline uint32_t pcg_hash(uint32_t v) {
 // ------------------------------------------------------------------------------------------
 // scene containers
 // ------------------------------------------------------------------------------------------
-struct Tri { V3 v0, v1, v2; uint32_t geo, prim; };
+struct Tri { V3 v0, v1, v2; uint32_t geo, prim, flags; };   // flags: VkGeometryFlagBitsKHR of its geometry
 
 constexpr int32_t REF_DONE = 0x7FFFFFFF;
 constexpr int32_t REF_EMPTY = 0x7FFFFFFD;
@@ -132,12 +132,11 @@ static inline uint32_t morton30(const Box& pb, const Box& scene) {
 }
 
 // Karras-2012 LBVH over N primitive boxes with keys; leaves collapsed to <= leaf_max primitives.
-// Node numbering: an internal node is stored at the slot of its SPLIT position gamma (its left child ends at
-// sorted primitive gamma, its right child starts at gamma + 1); every split position occurs exactly once, so
-// this is a permutation of Karras' own numbering. The ranges/splits are found top-down exactly as in the
-// paper; the GPU product finds the same tree bottom-up, which makes the comparison an independent check.
+// Node numbering is the paper's (node i covers a range that starts or ends at sorted primitive i; the children of a
+// node with split gamma are nodes gamma and gamma + 1). The ranges/splits are found top-down exactly as in the paper;
+// the GPU product finds the same tree bottom-up, which makes the bit-for-bit comparison an independent check.
 struct Lbvh {
-    std::vector<Node> nodes;        // N-1 slots (split-position numbering), unreachable ones are garbage
+    std::vector<Node> nodes;        // N-1 slots (Karras numbering), unreachable ones are garbage
     std::vector<uint64_t> keys;     // sorted
     std::vector<uint32_t> prims;    // sorted position -> original primitive
     int32_t root = REF_EMPTY;
@@ -182,7 +181,6 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
     std::vector<int32_t> other_end(NI);           // j of node i; range = [min(i,j), max(i,j)]
     std::vector<uint32_t> parent_of_node(NI, 0xFFFFFFFFu), parent_of_leaf(N);  // (parent << 1) | side
     std::vector<int32_t> left_child(NI), right_child(NI);                       // >=0 internal, ~idx leaf position
-    std::vector<int32_t> slot_of(NI);                                           // Karras node i -> storage slot (its split position)
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < NI; ++i) {
         int d = (delta(i, i + 1) - delta(i, i - 1)) >= 0 ? 1 : -1;
@@ -203,7 +201,6 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
         int64_t gamma = i + s * d + std::min(d, 0);
         int64_t first = std::min(i, j), last = std::max(i, j);
         other_end[i] = (int32_t)j;
-        slot_of[i] = (int32_t)gamma;
         if (first == gamma) { left_child[i] = ~(int32_t)gamma; parent_of_leaf[gamma] = ((uint32_t)i << 1) | 0u; }
         else { left_child[i] = (int32_t)gamma; parent_of_node[gamma] = ((uint32_t)i << 1) | 0u; }
         if (last == gamma + 1) { right_child[i] = ~(int32_t)(gamma + 1); parent_of_leaf[gamma + 1] = ((uint32_t)i << 1) | 1u; }
@@ -222,17 +219,17 @@ static void lbvh_build(Lbvh& bvh, const std::vector<Box>& pboxes, const std::vec
         uint32_t p = parent_of_leaf[leaf];
         for (;;) {
             uint32_t node = p >> 1, side = p & 1u;
-            NodeHalf& h = bvh.nodes[slot_of[node]].c[side];
+            NodeHalf& h = bvh.nodes[node].c[side];
             for (int k = 0; k < 3; ++k) { h.lo[k] = b.lo[k]; h.hi[k] = b.hi[k]; }
             h.ref = ref; h.height = height;
             if (arrived[node].fetch_add(1, std::memory_order_acq_rel) == 0) break;  // first: sibling will finish
-            const NodeHalf& o = bvh.nodes[slot_of[node]].c[side ^ 1u];
+            const NodeHalf& o = bvh.nodes[node].c[side ^ 1u];
             for (int k = 0; k < 3; ++k) { b.lo[k] = fminf(b.lo[k], o.lo[k]); b.hi[k] = fmaxf(b.hi[k], o.hi[k]); }
             int64_t j = other_end[node];
             int64_t first = std::min<int64_t>(node, j), last = std::max<int64_t>(node, j);
             uint32_t count = (uint32_t)(last - first + 1);
             if ((int)count <= leaf_max) { ref = leaf_ref((uint32_t)first, count); height = 0; }
-            else { ref = slot_of[node]; height = std::max(height, o.height) + 1; }
+            else { ref = (int32_t)node; height = std::max(height, o.height) + 1; }
             if (node == 0) { root_box = b; root_height = height; root_ref = ref; break; }
             p = parent_of_node[node];
         }
@@ -287,7 +284,7 @@ static void gather_tris(const orc_geometry* geoms, uint32_t n_geoms, std::vector
                 v[k] = {src[0], src[1], src[2]};
                 if (G.transform3x4) v[k] = xform_point(G.transform3x4, v[k]);   // baked at build time
             }
-            tris[offs[g] + p] = {v[0], v[1], v[2], g, (uint32_t)p};
+            tris[offs[g] + p] = {v[0], v[1], v[2], g, (uint32_t)p, G.flags & 0xFFu};
         }
     }
     Box b = empty_box();
@@ -368,15 +365,36 @@ static inline bool id_less(uint32_t i0, uint32_t g0, uint32_t p0, uint32_t i1, u
     if (g0 != g1) return g0 < g1;
     return p0 < p1;
 }
-static inline void consider(Best& best, const RayPre& r, const Tri& tr, uint32_t inst_id, const OInst* I,
-                            float tmin, float tmax) {
+// Ray flag semantics [spec: GL_EXT_ray_tracing / Vulkan "Ray Intersection Culling"], stated once for both sides:
+//  * opacity of a candidate = geometry OPAQUE bit, overridden by the instance FORCE_OPAQUE / FORCE_NO_OPAQUE flags,
+//    overridden by the ray Opaque / NoOpaque flags; CullOpaque / CullNoOpaque then drop it. There is no any-hit
+//    shader in the sample (main.cpp:1199-1216 builds raygen + miss + closest-hit only), so a surviving non-opaque
+//    candidate is accepted like an opaque one.
+//  * facing is decided in object space: front = vertices clockwise as seen from the ray origin, i.e.
+//    ((v1-v0) x (v2-v0)) . d > 0, inverted by the instance FLIP_FACING flag; CullBack/CullFront are ignored for
+//    instances with TRIANGLE_FACING_CULL_DISABLE (what the sample sets, main.cpp:852).
+// Returns true when a candidate was ACCEPTED (TerminateOnFirstHit ends the ray there).
+static inline bool consider(Best& best, const RayPre& r, const Tri& tr, uint32_t inst_id, const OInst* I,
+                            float tmin, float tmax, uint32_t ray_flags) {
     float t, u, v, w0;
-    if (!woop(r, tr, t, u, v, w0)) return;
-    if (!(t > tmin && t < tmax)) return;            // tmin < t < tmax, both exclusive
+    if (!woop(r, tr, t, u, v, w0)) return false;
+    if (!(t > tmin && t < tmax)) return false;      // tmin < t < tmax, both exclusive
+    bool opaque = (tr.flags & ORC_GEOM_OPAQUE) != 0u;
+    if (I->flags & ORC_INST_FORCE_OPAQUE) opaque = true;
+    else if (I->flags & ORC_INST_FORCE_NO_OPAQUE) opaque = false;
+    if (ray_flags & ORC_RAY_OPAQUE) opaque = true;
+    else if (ray_flags & ORC_RAY_NO_OPAQUE) opaque = false;
+    if (opaque ? (ray_flags & ORC_RAY_CULL_OPAQUE) : (ray_flags & ORC_RAY_CULL_NO_OPAQUE)) return false;
+    if ((ray_flags & (ORC_RAY_CULL_BACK | ORC_RAY_CULL_FRONT)) && !(I->flags & ORC_INST_FACING_CULL_DISABLE)) {
+        V3 n = cross3(sub(tr.v1, tr.v0), sub(tr.v2, tr.v0));
+        bool front = (dot3(n, r.d) > 0.0f) != ((I->flags & ORC_INST_FLIP_FACING) != 0u);
+        if (front ? (ray_flags & ORC_RAY_CULL_FRONT) : (ray_flags & ORC_RAY_CULL_BACK)) return false;
+    }
     bool better = t < best.t || (t == best.t && id_less(inst_id, tr.geo, tr.prim, best.inst, best.geo, best.prim));
-    if (!better) return;
+    if (!better) return true;
     best.t = t; best.inst = inst_id; best.geo = tr.geo; best.prim = tr.prim; best.u = u; best.v = v; best.w0 = w0;
     best.I = I; best.tri = &tr;
+    return true;
 }
 
 // conservative slab test state for one (ray, space)
@@ -415,17 +433,22 @@ static inline bool slab_hit(const Slab& s, const float* lo, const float* hi, flo
 
 struct Counters { uint64_t nodes = 0, tris = 0, insts = 0; };
 
-static void traverse_blas(const orc_blas* B, const RayPre& r, uint32_t inst_id, const OInst* I, float tmin, float tmax,
-                          Best& best, Counters& cnt) {
+// returns true when the ray was terminated (TerminateOnFirstHit and a candidate accepted)
+static bool traverse_blas(const orc_blas* B, const RayPre& r, uint32_t inst_id, const OInst* I, float tmin, float tmax,
+                          uint32_t ray_flags, Best& best, Counters& cnt) {
+    const bool first_hit = (ray_flags & ORC_RAY_TERMINATE_ON_FIRST_HIT) != 0u;
     const Lbvh& bvh = B->bvh;
-    if (bvh.root == REF_EMPTY) return;
+    if (bvh.root == REF_EMPTY) return false;
     Slab s = slab_pre(r.o, r.d, B->bounds);
     int32_t stack[192]; int sp = 0;
     int32_t cur = bvh.root;
     for (;;) {
         if (ref_is_leaf(cur)) {
             uint32_t f = leaf_first(cur), c = leaf_count(cur);
-            for (uint32_t i = 0; i < c; ++i) { consider(best, r, B->sorted_tris[f + i], inst_id, I, tmin, tmax); ++cnt.tris; }
+            for (uint32_t i = 0; i < c; ++i) {
+                ++cnt.tris;
+                if (consider(best, r, B->sorted_tris[f + i], inst_id, I, tmin, tmax, ray_flags) && first_hit) return true;
+            }
             if (sp == 0) break;
             cur = stack[--sp];
             continue;
@@ -442,24 +465,29 @@ static void traverse_blas(const orc_blas* B, const RayPre& r, uint32_t inst_id, 
         else if (h1) cur = n.c[1].ref;
         else { if (sp == 0) break; cur = stack[--sp]; }
     }
+    return false;
 }
 
 struct TraceCtx {
     const orc_tlas* T; orc_ray_params rp; const orc_shader_data* sd; int mode;
 };
 
-static inline void enter_instance(const TraceCtx& c, uint32_t i, V3 o, V3 d, float tmin, float tmax, Best& best, Counters& cnt) {
+static inline bool enter_instance(const TraceCtx& c, uint32_t i, V3 o, V3 d, float tmin, float tmax, Best& best, Counters& cnt) {
     const OInst& I = c.T->inst[i];
-    if (!I.active) return;
-    if ((I.mask & c.rp.cull_mask) == 0) return;
+    if (!I.active) return false;
+    if ((I.mask & c.rp.cull_mask) == 0) return false;
+    const bool first_hit = (c.rp.ray_flags & ORC_RAY_TERMINATE_ON_FIRST_HIT) != 0u;
     ++cnt.insts;
     V3 oo = xform_point(I.w2o, o), od = xform_vec(I.w2o, d);
     RayPre r = ray_pre(oo, od);
     if (c.mode == ORC_MODE_BRUTE || !I.blas->has_bvh) {
-        for (const Tri& tr : I.blas->tris) { consider(best, r, tr, i, &I, tmin, tmax); ++cnt.tris; }
-    } else {
-        traverse_blas(I.blas, r, i, &I, tmin, tmax, best, cnt);
+        for (const Tri& tr : I.blas->tris) {
+            ++cnt.tris;
+            if (consider(best, r, tr, i, &I, tmin, tmax, c.rp.ray_flags) && first_hit) return true;
+        }
+        return false;
     }
+    return traverse_blas(I.blas, r, i, &I, tmin, tmax, c.rp.ray_flags, best, cnt);
 }
 
 static Best trace_ray(const TraceCtx& c, V3 o, V3 d, float tmin, float tmax, Counters& cnt) {
@@ -467,7 +495,8 @@ static Best trace_ray(const TraceCtx& c, V3 o, V3 d, float tmin, float tmax, Cou
     best.I = nullptr; best.tri = nullptr;
     const orc_tlas* T = c.T;
     if (c.mode == ORC_MODE_BRUTE || !T->has_bvh) {
-        for (uint32_t i = 0; i < (uint32_t)T->inst.size(); ++i) enter_instance(c, i, o, d, tmin, tmax, best, cnt);
+        for (uint32_t i = 0; i < (uint32_t)T->inst.size(); ++i)
+            if (enter_instance(c, i, o, d, tmin, tmax, best, cnt)) break;
         return best;
     }
     const Lbvh& bvh = T->bvh;
@@ -478,8 +507,9 @@ static Best trace_ray(const TraceCtx& c, V3 o, V3 d, float tmin, float tmax, Cou
     for (;;) {
         if (ref_is_leaf(cur)) {
             uint32_t f = leaf_first(cur), n = leaf_count(cur);
-            for (uint32_t k = 0; k < n; ++k) enter_instance(c, bvh.prims[f + k], o, d, tmin, tmax, best, cnt);
-            if (sp == 0) break;
+            bool done = false;
+            for (uint32_t k = 0; k < n && !done; ++k) done = enter_instance(c, bvh.prims[f + k], o, d, tmin, tmax, best, cnt);
+            if (done || sp == 0) break;
             cur = stack[--sp];
             continue;
         }
@@ -627,7 +657,12 @@ int orc_trace(const orc_tlas* tlas, const orc_camera* cam, const orc_ray_params*
               uint8_t* rgba_out, orc_hit* primary_out, orc_hit* secondary_out, orc_stats* stats_out) {
     if (!tlas || !cam || !sd || width == 0 || height == 0 || row_step == 0) return -1;
     TraceCtx c; c.T = tlas; c.sd = sd; c.mode = mode;
-    if (rp_in) c.rp = *rp_in; else c.rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u};
+    if (rp_in) c.rp = *rp_in; else c.rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, ORC_RAY_OPAQUE, 0u};
+    // miss shader table: each miss shader, like the sample's (main.cpp:1063-1066), writes one constant colour
+    const float* miss_rgb = sd->miss_rgb;
+    if (sd->miss_records_rgb) { if (c.rp.miss_index >= sd->miss_record_count) return -5; miss_rgb = sd->miss_records_rgb + 3 * (size_t)c.rp.miss_index; }
+    else if (c.rp.miss_index != 0u) return -5;
+    const bool skip_chit = (c.rp.ray_flags & ORC_RAY_SKIP_CLOSEST_HIT) != 0u;   // payload stays (0,0,0) on a hit (main.cpp:1045)
     // SBT range pre-check (the product reports RT_ERROR_SBT_RANGE for the same condition)
     for (const OInst& I : tlas->inst) {
         if (!I.blas) continue;
@@ -662,19 +697,19 @@ int orc_trace(const orc_tlas* tlas, const orc_camera* cam, const orc_ray_params*
             if (b.I) {
                 ++s_ph;
                 if (fminf(fminf(b.u, b.v), b.w0) < 9.5367431640625e-07f) ++s_edge;
-                hit_value = closest_hit(c, b);
-                if (bounces > 0) {
+                if (!skip_chit) hit_value = closest_hit(c, b);
+                if (bounces > 0 && !skip_chit) {
                     V3 o2, d2;
                     bounce_ray(b, cam_o, d, pixel, c.rp.bounce_seed, o2, d2);
                     b2 = trace_ray(c, o2, d2, c.rp.tmin, c.rp.tmax, cnt);
                     ++s_sec;
                     V3 sc;
                     if (b2.I) { ++s_sh; sc = closest_hit(c, b2); }
-                    else sc = {sd->miss_rgb[0], sd->miss_rgb[1], sd->miss_rgb[2]};
+                    else sc = {miss_rgb[0], miss_rgb[1], miss_rgb[2]};
                     hit_value = {0.5f * hit_value.x + 0.5f * sc.x, 0.5f * hit_value.y + 0.5f * sc.y, 0.5f * hit_value.z + 0.5f * sc.z};
                 }
             } else {
-                hit_value = {sd->miss_rgb[0], sd->miss_rgb[1], sd->miss_rgb[2]};   // miss shader, main.cpp:1063-1066
+                hit_value = {miss_rgb[0], miss_rgb[1], miss_rgb[2]};   // miss shader, main.cpp:1063-1066
             }
             if (secondary_out) write_hit(secondary_out + pixel, b2, c.rp.tmax);
             if (rgba_out) {   // imageStore(image, xy, vec4(hitValue, 0.0)) into rgba8, main.cpp:1054

@@ -55,7 +55,17 @@ typedef struct orc_camera { float pos[3]; float yfov_deg; } orc_camera;
 
 typedef struct orc_ray_params {
     float tmin, tmax; uint32_t cull_mask, sbt_record_offset, sbt_record_stride, bounce_seed;
+    uint32_t ray_flags;    /* gl_RayFlags*EXT bits (GL_EXT_ray_tracing); the sample passes Opaque = 0x1 (main.cpp:1048) */
+    uint32_t miss_index;   /* missIndex argument of traceRayEXT (main.cpp:1051 passes 0) */
 } orc_ray_params;
+
+/* gl_RayFlags*EXT / VkGeometryInstanceFlagBitsKHR / VkGeometryFlagBitsKHR values [spec] */
+enum {
+    ORC_RAY_OPAQUE = 0x1, ORC_RAY_NO_OPAQUE = 0x2, ORC_RAY_TERMINATE_ON_FIRST_HIT = 0x4, ORC_RAY_SKIP_CLOSEST_HIT = 0x8,
+    ORC_RAY_CULL_BACK = 0x10, ORC_RAY_CULL_FRONT = 0x20, ORC_RAY_CULL_OPAQUE = 0x40, ORC_RAY_CULL_NO_OPAQUE = 0x80,
+    ORC_INST_FACING_CULL_DISABLE = 0x1, ORC_INST_FLIP_FACING = 0x2, ORC_INST_FORCE_OPAQUE = 0x4, ORC_INST_FORCE_NO_OPAQUE = 0x8,
+    ORC_GEOM_OPAQUE = 0x1
+};
 
 typedef struct orc_hit {
     uint32_t instance_id, geometry_index, primitive_id, custom_index;
@@ -69,6 +79,7 @@ typedef struct orc_stats {
 
 typedef struct orc_shader_data {
     const float* hit_records_rgb; uint32_t hit_record_count; float miss_rgb[3];
+    const float* miss_records_rgb; uint32_t miss_record_count;   /* optional table of constant-colour miss shaders; NULL = {miss_rgb} */
 } orc_shader_data;
 
 enum { ORC_MODE_BRUTE = 0, ORC_MODE_BVH = 1 };

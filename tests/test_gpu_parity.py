@@ -301,3 +301,79 @@ def test_obj_mesh_build_and_trace(rt, ctx, oracle, tmp_path):
     rp, rs, rc = assert_parity(g, r, what="obj")
     assert rp["hits"] > 5000 and set(np.unique(g[1]["geometry_index"][g[1]["instance_id"] != MISS])) == {0, 1}
     print("obj", rp, rs, rc)
+
+
+def _flag_scene(seed=9):
+    """Fuzz scene with every flag that feeds the GENERAL trace variant: non-opaque geometries, instances with
+    FLIP_FACING / FORCE_OPAQUE / FORCE_NO_OPAQUE, some with facing culls disabled."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=500, n_instances=10, seed=seed, width=320, height=200, bounces=1,
+                                shared_edges=True)
+    for b, geoms in enumerate(scene.blases):
+        for g, geo in enumerate(geoms):
+            geo.flags = 1 if (b + g) % 2 == 0 else 0
+    for i, I in enumerate(scene.instances):
+        I.flags = [0x0, 0x1, 0x2, 0x4, 0x8, 0x2 | 0x8, 0x0, 0x4 | 0x2, 0x1 | 0x8, 0x0][i % 10]
+        I.mask = 0xFF
+    return scene
+
+
+@pytest.mark.parametrize("ray_flags", [0x10, 0x20, 0x40, 0x80, 0x1 | 0x10, 0x2 | 0x20 | 0x80, 0x10 | 0x40, 0x1 | 0x8, 0x8 | 0x20, 0x0, 0x2],
+                         ids=lambda f: f"rayflags{f:#04x}")
+def test_ray_flags_vs_brute_force(rt, ctx, oracle, ray_flags):
+    """face culls, opacity culls, instance FORCE_*/FLIP flags, SkipClosestHitShader — ids, t, u, v
+    bit-exact and RGBA8 within +-1 LSB against the oracle's brute force under the same flags."""
+    scene = _flag_scene()
+    sh = rt.SceneHandles(ctx, scene)
+    try:
+        ctx.set_ray_params(ray_flags=ray_flags)
+        g = sh.trace(want_hits=True)
+        ctx.set_ray_params()
+        base = sh.trace(want_hits=True)
+    finally:
+        ctx.set_ray_params()
+        sh.free()
+    o = oracle.OracleScene(scene)
+    r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=ray_flags))
+    o.close()
+    rp, rs, rc = assert_parity(g, r, what=f"rayflags{ray_flags:#x}")
+    changed = int((g[1]["primitive_id"] != base[1]["primitive_id"]).sum())
+    if ray_flags & 0xF0:
+        assert changed > 200, "the culls must actually change the image of this scene"
+    elif not (ray_flags & 0x8):
+        assert changed == 0
+    print("rayflags", hex(ray_flags), rp, rs, rc, "changed", changed)
+
+
+def test_terminate_on_first_hit_and_miss_records(rt, ctx, oracle):
+    """TerminateOnFirstHit: which hit is undefined, so only the hit/miss mask (primary) is compared; with
+    SkipClosestHitShader it is the classic shadow ray. Miss records: rt_ray_params.miss_index selects the colour."""
+    scene = _flag_scene(seed=10)
+    scene.bounces = 0
+    sh = rt.SceneHandles(ctx, scene)
+    o = oracle.OracleScene(scene)
+    try:
+        for rf in (0x1 | 0x4, 0x4 | 0x8 | 0x10, 0x4 | 0x40):
+            ctx.set_ray_params(ray_flags=rf)
+            rgba, prim, _ = sh.trace(want_hits=True)
+            r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=rf))
+            mg, mr = prim["instance_id"] != MISS, r[1]["instance_id"] != MISS
+            assert np.array_equal(mg, mr) and mg.sum() > 1000
+            if rf & 0x8:
+                assert np.array_equal(rgba, r[0])                      # hit -> (0,0,0,0), miss -> miss colour: fully defined
+        miss = np.array([[0, 0, 0.2], [0.25, 0.5, 1.0]], dtype=np.float32)
+        ctx.set_miss_records(miss)
+        o.set_miss_records(miss)
+        ctx.set_ray_params(miss_index=1)
+        g = sh.trace(want_hits=True)
+        r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(miss_index=1))
+        assert_parity(g, r, what="miss1")
+        assert tuple(g[0][prim["instance_id"] == MISS][0]) == (64, 128, 255, 0)
+        ctx.set_ray_params(miss_index=2)
+        with pytest.raises(rt.RtError) as e:
+            sh.trace()
+        assert e.value.code == rt.RT_ERROR_SBT_RANGE
+    finally:
+        ctx.set_ray_params()
+        ctx.set_miss_records(np.array([[0, 0, 0.2]], dtype=np.float32))
+        o.close()
+        sh.free()

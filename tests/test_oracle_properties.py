@@ -86,3 +86,57 @@ def test_scene_generators_sizes():
     assert scenes.soup_scene(1000).triangle_count == 1000
     # the full-size definitions (not generated here): 1000x500 quads -> 1,000,000; 1024 x 9,800 -> 10,035,200
     assert 1000 * 500 * 2 == 1_000_000 and 32 * 32 * 2 * 70 * 70 == 10_035_200
+
+
+def test_ray_flag_semantics_known_answers(oracle):
+    """Pins the ray-flag conventions on the reference's own scene. The sample's quad triangles
+    (0,1,3) and (1,2,3) (main.cpp:689-695) have the normal (v1-v0)x(v2-v0) = +z, towards the camera at z = 10: they
+    appear counter-clockwise from the ray origin, i.e. BACK facing under the default "front = clockwise" rule."""
+    S = scenes
+    base = S.sample_scene(300, 200)
+
+    def hits(scene, **rp):
+        o = oracle.OracleScene(scene)
+        rgba, prim, _, st = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(**rp))
+        o.close()
+        return rgba, prim, st["primary_hits"]
+
+    _, p0, n0 = hits(base)
+    assert n0 > 4000
+    # the sample sets TRIANGLE_FACING_CULL_DISABLE (main.cpp:852): facing culls change nothing
+    assert hits(base, ray_flags=0x1 | 0x10)[2] == n0 and hits(base, ray_flags=0x1 | 0x20)[2] == n0
+    # without that flag: back-facing quads vanish under CullBack, stay under CullFront; FLIP_FACING swaps the two
+    for flags, back, front in ((0x0, 0, n0), (0x2, n0, 0)):
+        sc = S.sample_scene(300, 200)
+        for I in sc.instances:
+            I.flags = flags
+        assert hits(sc, ray_flags=0x1 | 0x10)[2] == back
+        assert hits(sc, ray_flags=0x1 | 0x20)[2] == front
+    # opacity: geometry OPAQUE (main.cpp:741) -> CullOpaque removes everything, CullNoOpaque nothing; the ray's NoOpaque
+    # flag overrides the geometry, the instance FORCE_NO_OPAQUE flag does too, and the ray flag beats the instance flag
+    assert hits(base, ray_flags=0x40)[2] == 0 and hits(base, ray_flags=0x80)[2] == n0
+    assert hits(base, ray_flags=0x2 | 0x80)[2] == 0 and hits(base, ray_flags=0x2 | 0x40)[2] == n0
+    sc = S.sample_scene(300, 200)
+    sc.instances[0].flags |= 0x8                      # FORCE_NO_OPAQUE on the upper instance only
+    _, p, n = hits(sc, ray_flags=0x80)
+    assert 0 < n < n0 and set(np.unique(p["instance_id"][p["instance_id"] != MISS])) == {1}
+    assert hits(sc, ray_flags=0x1 | 0x80)[2] == n0
+    sc.blases[0][1].flags = 0                         # geometry 1 not opaque
+    _, p, n = hits(sc, ray_flags=0x40)                # CullOpaque: instance 0 (forced non-opaque) keeps both, instance 1 keeps geometry 1
+    m = p["instance_id"] != MISS
+    assert set(zip(p["instance_id"][m].tolist(), p["geometry_index"][m].tolist())) == {(0, 0), (0, 1), (1, 1)}
+    # SkipClosestHitShader: hit pixels keep the payload's initial (0,0,0); misses still run the miss shader
+    rgba, p, n = hits(base, ray_flags=0x1 | 0x8)
+    m = p["instance_id"] != MISS
+    assert n == n0 and np.all(rgba[m] == 0) and np.all(rgba[~m] == np.array((0, 0, 51, 0), dtype=np.uint8))
+    # TerminateOnFirstHit: same hit/miss mask (which hit is undefined)
+    _, p, n = hits(base, ray_flags=0x1 | 0x4)
+    assert np.array_equal(p["instance_id"] != MISS, p0["instance_id"] != MISS)
+    # miss records
+    o = oracle.OracleScene(base)
+    o.set_miss_records(np.array([[0, 0, 0.2], [1.0, 0.5, 0.0]], dtype=np.float32))
+    rgba = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(miss_index=1))[0]
+    assert tuple(rgba[0, 0]) == (255, 128, 0, 0)
+    with pytest.raises(RuntimeError):
+        o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(miss_index=2))
+    o.close()
