@@ -218,12 +218,15 @@ static void storage_release(BlasStorage* st) {
     if (--st->refs <= 0) { cudaFree(st->dev); delete st; }
 }
 
-int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
-                        uint32_t build_flags, rt_blas** out_array) {
-    if (!ctx || !out_array || n_blas == 0 || !geom_counts) return RT_ERROR_INVALID_ARG;
+// update != nullptr: rebuild that (single, unshared) BLAS inside its existing device allocation, so that its handle
+// and the device address TLAS instances refer to stay valid (VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR semantics:
+// same geometry/primitive counts, new vertex data).
+static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
+                                 uint32_t build_flags, rt_blas** out_array, rt_blas* update) {
+    if (!ctx || (!out_array && !update) || n_blas == 0 || !geom_counts) return RT_ERROR_INVALID_ARG;
     if (n_blas > (1u << 24)) return fail(ctx, RT_ERROR_INVALID_ARG, "at most 2^24 BLASes per batch");
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    for (uint32_t b = 0; b < n_blas; ++b) out_array[b] = nullptr;
+    if (out_array) for (uint32_t b = 0; b < n_blas; ++b) out_array[b] = nullptr;
     uint32_t n_geoms = 0;
     for (uint32_t b = 0; b < n_blas; ++b) n_geoms += geom_counts[b];
     if (n_geoms && !geoms) return RT_ERROR_INVALID_ARG;
@@ -272,15 +275,25 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     choose_record_format(sp, N, MORTON_BITS + seg_bits, build_flags);
 
     // ---- output storage: nodes | tris | records ----
-    BlasStorage* st = new BlasStorage();
-    st->n_tris = N; st->n_blas = n_blas;
-    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
-    st->bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
-    cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
-    if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", st->bytes, cudaGetErrorString(ce)); }
-    st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
+    BlasStorage* st;
+    if (update) {
+        st = update->st;
+        if (st->n_blas != 1 || n_blas != 1) return fail(ctx, RT_ERROR_INVALID_ARG, "rt_update_blas needs a BLAS that was built on its own (not part of a batch)");
+        if (st->n_tris != N || update->rec.n_geoms != geom_counts[0])
+            return fail(ctx, RT_ERROR_INVALID_ARG, "rt_update_blas: geometry/triangle counts differ from the original build (%u/%u vs %u/%u)",
+                        geom_counts[0], N, update->rec.n_geoms, st->n_tris);
+        ++st->refs;    // the guard below drops it again
+    } else {
+        st = new BlasStorage();
+        st->n_tris = N; st->n_blas = n_blas;
+        const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+        st->bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
+        cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
+        if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", st->bytes, cudaGetErrorString(ce)); }
+        st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
+        st->refs = 1;   // held by this function until handles exist
+    }
     for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->nodes + recs[b].first; recs[b].tris = st->tris + recs[b].first; }
-    st->refs = 1;   // held by this function until handles exist
     struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{st};
 
     // ---- scratch ----
@@ -383,6 +396,7 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
     }
     ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N; ctx->dbg_vb = sp.packed_val_bits;
 
+    if (update) { update->rec = recs[0]; return RT_SUCCESS; }
     for (uint32_t b = 0; b < n_blas; ++b) {
         rt_blas* h = new rt_blas();
         h->st = st; h->index = b; h->rec = recs[b];
@@ -390,6 +404,18 @@ int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_
         out_array[b] = h;
     }
     return RT_SUCCESS;   // guard drops the construction reference
+}
+
+int rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts, uint32_t n_blas,
+                        uint32_t build_flags, rt_blas** out_array) {
+    if (!out_array) return RT_ERROR_INVALID_ARG;
+    return build_blas_batch_impl(ctx, geoms, geom_counts, n_blas, build_flags, out_array, nullptr);
+}
+
+int rt_update_blas(rt_context* ctx, rt_blas* blas, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags) {
+    if (!blas) return RT_ERROR_INVALID_ARG;
+    uint32_t counts[1] = {n_geoms};
+    return build_blas_batch_impl(ctx, geoms, counts, 1, build_flags, nullptr, blas);
 }
 
 int rt_build_blas(rt_context* ctx, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags, rt_blas** out) {

@@ -35,7 +35,7 @@ RT_REF_EMPTY = 0x7FFFFFFD
 EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync",
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
-    "rt_update_tlas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
+    "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
@@ -153,6 +153,7 @@ def load(build_if_missing: bool = True):
     L.rt_build_blas_batch.argtypes = [vp, C.POINTER(RtGeometry), C.POINTER(u32), u32, u32, C.POINTER(vp)]
     L.rt_build_tlas.argtypes = [vp, vp, u32, u32, C.POINTER(vp)]
     L.rt_update_tlas.argtypes = [vp, vp, vp, u32, u32]
+    L.rt_update_blas.argtypes = [vp, vp, C.POINTER(RtGeometry), u32, u32]
     L.rt_free_blas.argtypes = [vp, vp]
     L.rt_free_blas.restype = None
     L.rt_free_tlas.argtypes = [vp, vp]
@@ -362,6 +363,12 @@ class Context:
         h = C.c_void_p()
         self._check(self.L.rt_build_blas(self.h, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE | flags, C.byref(h)))
         return Blas(self, h.value)
+
+    def update_blas(self, blas: Blas, geoms, device: bool = False, flags: int = 0):
+        """rt_update_blas: same counts, new vertex data; the handle (and what TLAS instances point at) stays valid."""
+        keep: list = []
+        arr = self._geom_array(geoms, keep, device)
+        self._check(self.L.rt_update_blas(self.h, blas.handle, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE | flags))
 
     def build_blas_batch(self, blases, device: bool = False, flags: int = 0) -> List[Blas]:
         keep: list = []

@@ -189,6 +189,12 @@ RT_API int  rt_build_blas(rt_context* ctx, const rt_geometry* geoms, uint32_t n_
 RT_API int  rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const uint32_t* geom_counts,
                                 uint32_t n_blas, uint32_t build_flags, rt_blas** out_array);
 
+/* VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR for a BLAS built by rt_build_blas: same geometry and triangle counts,
+ * new vertex data / transforms (the per-frame loop of an animated mesh, main.cpp:1444-1448). The BLAS is re-built inside its
+ * existing device allocation (a full LBVH build costs ~0.16 ns per triangle, so no refit-only shortcut with its quality
+ * loss is offered); the handle stays valid. As in Vulkan, a TLAS that references it must be rebuilt or updated afterwards. */
+RT_API int  rt_update_blas(rt_context* ctx, rt_blas* blas, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags);
+
 RT_API int  rt_build_tlas(rt_context* ctx, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags, rt_tlas** out);
 /* Re-fit an existing TLAS to new instance transforms (same count, same BLASes): the per-frame path. */
 RT_API int  rt_update_tlas(rt_context* ctx, rt_tlas* tlas, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags);

@@ -377,3 +377,63 @@ def test_terminate_on_first_hit_and_miss_records(rt, ctx, oracle):
         ctx.set_miss_records(np.array([[0, 0, 0.2]], dtype=np.float32))
         o.close()
         sh.free()
+
+
+def test_blas_update_animated_mesh(rt, ctx, oracle):
+    """the per-frame loop of an animated mesh. rt_update_blas re-builds the BLAS in place (same handle,
+    same device address), rt_update_tlas re-reads it; every frame equals a from-scratch build of that frame's geometry."""
+    S = scenes
+    frames = [S.heightfield(30, 20, -3.0, 3.0, -2.0, 2.0, 0.3 + 0.25 * f, 40 + f) for f in range(3)]
+    inst = [S.Instance(S.rotation_3x4(np.array([0.2, 1.0, 0.0]), 0.3, np.array([0.0, 0.0, 0.0])), 3, 0xFF, 0, 1, 0),
+            S.Instance(S.translation(0.0, 0.0, -3.0), 4, 0xFF, 1, 1, 0)]
+    scene = S.Scene("anim", [[frames[0]]], inst, S.SAMPLE_HIT_RECORDS[:2].copy(), width=320, height=200, bounces=1)
+    sh = rt.SceneHandles(ctx, scene)
+    handle0, info0 = sh.blases[0].handle, sh.blases[0].info()
+    try:
+        for f in (1, 2):
+            ctx.update_blas(sh.blases[0], [frames[f]])
+            assert sh.blases[0].handle == handle0
+            assert sh.blases[0].info().device_storage == info0.device_storage
+            ctx.update_tlas(sh.tlas, inst, sh.blases)
+            g = sh.trace(want_hits=True)
+            sc = S.Scene("anim", [[frames[f]]], inst, scene.hit_records, width=320, height=200, bounces=1)
+            o = oracle.OracleScene(sc)
+            r = o.trace(mode=oracle.MODE_BRUTE)
+            o.close()
+            rp, rs, rc = assert_parity(g, r, what=f"anim{f}")
+            assert rp["hits"] > 5000
+        # counts must match the original build
+        with pytest.raises(rt.RtError):
+            ctx.update_blas(sh.blases[0], [S.heightfield(10, 10, -1, 1, -1, 1, 0.1, 1)])
+    finally:
+        sh.free()
+
+
+def test_cpp_host_program(rt, ctx, oracle, tmp_path):
+    """The C++ host program above the C ABI (host/sample_scene.cpp, the headless mirror of the reference's main()):
+    its PPM equals the oracle's frame of the sample scene; with --obj it builds from a Wavefront file."""
+    import subprocess
+    from build_up_phase_b200 import build as b
+    exe = b.build_host_sample()
+    out = tmp_path / "frame.ppm"
+    p = subprocess.run([exe, str(out), "600", "400"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    raw = out.read_bytes()
+    hdr = b"P6\n600 400\n255\n"
+    assert raw.startswith(hdr)
+    img = np.frombuffer(raw[len(hdr):], dtype=np.uint8).reshape(400, 600, 3)
+    o = oracle.OracleScene(scenes.sample_scene(600, 400))
+    ref = o.trace(mode=oracle.MODE_BRUTE)[0]
+    o.close()
+    assert np.abs(img.astype(np.int16) - ref[:, :, :3].astype(np.int16)).max() <= 1
+    # --obj: a unit quad made of two groups fills the middle of the frame with the first two hit-record colours
+    objf = tmp_path / "quad.obj"
+    objf.write_text("v -1 -1 0\nv 1 -1 0\nv 1 1 0\nv -1 1 0\ng a\nf 1 2 4\ng b\nf 2 3 4\n")
+    p = subprocess.run([exe, str(out), "300", "200", "--obj", str(objf), "--srgb"], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    assert "4 vertices, 2 triangles, 2 group(s)" in p.stdout
+    raw = out.read_bytes()
+    img = np.frombuffer(raw[len(b"P6\n300 200\n255\n"):], dtype=np.uint8).reshape(200, 300, 3)
+    lut = rt.srgb8_table()
+    cols = {tuple(c) for c in img.reshape(-1, 3).tolist()}
+    assert cols == {tuple(lut[[0, 0, 51]].tolist()), tuple(lut[[153, 26, 51]].tolist()), tuple(lut[[26, 204, 102]].tolist())}
