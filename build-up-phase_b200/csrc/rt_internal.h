@@ -157,9 +157,13 @@ struct TraceParams {
     rt_hit* secondary_hits;     // may be null
     unsigned long long* stats;  // 8 counters (rt_trace_stats order), may be null
     uint32_t* counters;         // [0] primary ray fetch counter, [1] secondary fetch counter, [2] bounce-queue length (zeroed per launch)
-    float4* queue;              // bounce queue: 3 x float4 per secondary ray {pixel, o.xyz | d.xyz, r | g, b, -, -}
+    float4* queue;              // bounce rays: 3 x float4 per secondary ray {pixel, o.xyz | d.xyz, r | g, b, -, -}, one slot per tile-major ray index
+    uint32_t* tile_mask;        // one word per 8x4-pixel tile: which of its pixels spawned a bounce ray; followed by the block sums of the index build
+    uint32_t* bounce_index;     // compact tile-ordered list of the occupied queue slots (stage 1 reads rays through it)
 };
 constexpr size_t TRACE_QUEUE_ENTRY_BYTES = 48;
+// per ray slot: the ray record + its index entry + its share of the tile mask / block sums (rounded up)
+constexpr size_t TRACE_BOUNCE_AUX_BYTES_PER_SLOT = 4 + 1;
 int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st);
 int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,
                        uint32_t part_count, uint8_t* out, cudaStream_t st);

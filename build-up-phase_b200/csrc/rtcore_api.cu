@@ -700,8 +700,13 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     }
     P.counters = ctx->d_counters;
     if (bounces > 0) {
-        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, pixels * TRACE_QUEUE_ENTRY_BYTES)) != RT_SUCCESS) return rc;
+        // ray slots are numbered tile-major over whole 8x4 tiles, so round the image up to tiles
+        const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((P.local_rows + 3u) >> 2), slots = tiles * 32u;
+        const size_t ray_bytes = align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256), idx_bytes = align_up(slots * 4, 256);
+        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, ray_bytes + idx_bytes + (tiles + tiles / 1024 + 16) * 4)) != RT_SUCCESS) return rc;
         P.queue = (float4*)ctx->queue;
+        P.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes);
+        P.tile_mask = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes + idx_bytes);
     }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }

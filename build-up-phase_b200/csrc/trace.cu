@@ -46,6 +46,13 @@ constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal
 #define RT_NODE_CAP 4
 #endif
 constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner node loop when fewer lanes are still in it (0 = never)
+#ifndef RT_BOUNCE_ORDERED
+#define RT_BOUNCE_ORDERED 1
+#endif
+// RT_BOUNCE_ORDERED=1: stage 0 stores the bounce ray of a pixel in that pixel's slot (tile-major numbering) and sets its
+// bit in a per-tile mask; two small kernels turn the masks into a compact, TILE-ORDERED index list for stage 1, so the
+// 32 secondary rays a warp fetches start on neighbouring surface points. (=0: the rays are appended to a queue in the
+// order the persistent warps finish them, which scatters them over the ~40 pixel rows that are in flight at a time.)
 #ifndef RT_LDG256
 #define RT_LDG256 0
 #endif
@@ -189,7 +196,7 @@ __device__ __forceinline__ rt_hit miss_record(float tmax) {
 }
 
 // ---- ray identity ---------------------------------------------------------------------------------------
-struct RayId { bool in_buffer, valid; uint32_t lidx, pixel; };
+struct RayId { bool in_buffer, valid; uint32_t lidx, pixel, tm; };   // tm: tile-major ray index of the launch
 
 // Primary ray `idx` (tile-major numbering: 8x4-pixel tiles, 32 consecutive ids per tile) -> raygen shader
 // (main.cpp:1033-1046); aspect_x/aspect_y are computed once on the host (tanf).
@@ -204,6 +211,7 @@ __device__ __forceinline__ RayId primary_ray(const TraceParams& P, uint32_t idx,
     id.valid = id.in_buffer && y < P.height;
     id.lidx = lr * P.width + x;
     id.pixel = y * P.width + x;
+    id.tm = idx;
     const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
     const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
     const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
 
     // ---- per-lane ray state ----
     bool have_ray = false, exhausted = false;
-    RayId id = {false, false, 0u, 0u};
+    RayId id = {false, false, 0u, 0u, 0u};
     V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
     float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
     int32_t cur = REF_DONE;
@@ -380,7 +388,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     if (STAGE == 0) {
                         id = primary_ray(P, idx, tiles_x, o, d);
                     } else {
+#if RT_BOUNCE_ORDERED
+                        const float4* q = P.queue + 3 * (size_t)__ldg(P.bounce_index + idx);
+#else
                         const float4* q = P.queue + 3 * (size_t)idx;
+#endif
                         const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
                         id.lidx = __float_as_uint(q0.x);
                         o = {q0.y, q0.z, q0.w};
@@ -507,9 +519,74 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
             have_ray = false;
             shade<STAGE, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
         }
+#if RT_BOUNCE_ORDERED
+        if (STAGE == 0 && enqueue) {
+            float4* q = P.queue + 3 * (size_t)id.tm;
+            __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
+            atomicOr(P.tile_mask + (id.tm >> 5), 1u << (id.tm & 31u));
+        }
+#else
         if (STAGE == 0) enqueue_bounce(P, enqueue, e0, e1, e2, lane, lt_mask);
+#endif
     }
     if (STATS) flush_stats<STAGE>(P, c, lane);
+}
+
+// ---- bounce index: per-tile hit masks -> compact tile-ordered list of ray slots -----------------------------
+constexpr int BIDX_THREADS = 256, BIDX_WORDS = 4, BIDX_CHUNK = BIDX_THREADS * BIDX_WORDS;   // mask words per block
+
+// block_sums[b] = number of bounce rays in the b-th chunk of mask words; counters[2] += it
+__global__ void __launch_bounds__(BIDX_THREADS) k_bounce_count(const uint32_t* __restrict__ tile_mask, uint32_t n_words,
+                                                               uint32_t* __restrict__ block_sums, uint32_t* __restrict__ counters) {
+    __shared__ uint32_t s_w[BIDX_THREADS / 32];
+    const uint32_t w0 = blockIdx.x * BIDX_CHUNK + threadIdx.x * BIDX_WORDS;
+    uint32_t c = 0;
+#pragma unroll
+    for (int k = 0; k < BIDX_WORDS; ++k) if (w0 + k < n_words) c += __popc(__ldg(tile_mask + w0 + k));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < BIDX_THREADS / 32; ++w) t += s_w[w];
+        block_sums[blockIdx.x] = t;
+        if (t) atomicAdd(counters + 2, t);
+    }
+}
+
+// index[prefix + rank] = 32 * word + bit, in word/bit order (= tile-major pixel order)
+__global__ void __launch_bounds__(BIDX_THREADS) k_bounce_index(const uint32_t* __restrict__ tile_mask, uint32_t n_words,
+                                                               const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ index) {
+    __shared__ uint32_t s_w[BIDX_THREADS / 32];
+    __shared__ uint32_t s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // exclusive prefix of the preceding blocks' sums (a few hundred values)
+    uint32_t pre = 0;
+    for (uint32_t b = threadIdx.x; b < blockIdx.x; b += BIDX_THREADS) pre += __ldg(block_sums + b);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, o);
+    if (lane == 0) s_w[warp] = pre;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < BIDX_THREADS / 32; ++w) t += s_w[w]; s_base = t; }
+    __syncthreads();
+    const uint32_t w0 = blockIdx.x * BIDX_CHUNK + threadIdx.x * BIDX_WORDS;
+    uint32_t m[BIDX_WORDS], c = 0;
+#pragma unroll
+    for (int k = 0; k < BIDX_WORDS; ++k) { m[k] = w0 + k < n_words ? __ldg(tile_mask + w0 + k) : 0u; c += __popc(m[k]); }
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    __syncthreads();
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t pos = s_base + inc - c;
+    for (int w = 0; w < warp; ++w) pos += s_w[w];
+#pragma unroll
+    for (int k = 0; k < BIDX_WORDS; ++k) {
+        uint32_t mm = m[k];
+        while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1u; index[pos++] = (w0 + k) * 32u + (uint32_t)b; }
+    }
 }
 
 __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ packed_all, uint32_t width, uint32_t height,
@@ -541,7 +618,17 @@ int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
 template <bool STATS, int STACK, bool GENERAL>
 int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
     int n = launch_stage<0, STATS, STACK, GENERAL>(p, sm_count, st);
-    if (p.bounces > 0) n += launch_stage<1, STATS, STACK, GENERAL>(p, sm_count, st);
+    if (p.bounces > 0) {
+#if RT_BOUNCE_ORDERED
+        const uint32_t n_words = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
+        const uint32_t blocks = (n_words + BIDX_CHUNK - 1) / BIDX_CHUNK;
+        uint32_t* block_sums = p.tile_mask + n_words;
+        k_bounce_count<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, block_sums, p.counters);
+        k_bounce_index<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, block_sums, p.bounce_index);
+        n += 2;
+#endif
+        n += launch_stage<1, STATS, STACK, GENERAL>(p, sm_count, st);
+    }
     return n;
 }
 
@@ -559,6 +646,9 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     if (tiles == 0) return 0;
     if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
+#if RT_BOUNCE_ORDERED
+    if (p.bounces > 0 && cudaMemsetAsync(p.tile_mask, 0, sizeof(uint32_t) * (size_t)tiles, st) != cudaSuccess) return -1;
+#endif
     int n;
     if (stack_needed <= 64) n = launch_stack<64>(p, stats, sm_count, st);
     else if (stack_needed <= 160) n = launch_stack<160>(p, stats, sm_count, st);
