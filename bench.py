@@ -169,14 +169,26 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "Mrays/s (primary+secondary rays per second)", "value": res["mrays_per_s"], "unit": "Mrays/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": res["ms_per_step"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(scene, args, 1),
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(scene, args, args.gpus),
         "cpu_baseline": {"value": res["mrays_per_s"], "unit": "Mrays/s", "cores": res["threads"], "kind": "port",
                          "sample": f"rows {res['rows'][0]}..{res['rows'][1]} step {res['rows'][2]} of the {scene.width}x{scene.height} frame "
                                    f"({res['rays_per_step']} rays/step), oracle LBVH traversal, OpenMP"},
         "e2e": {"value": res["mrays_per_s"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def ncu_traffic(kind: str, workload: str):
+    """Measured DRAM bytes per launch from the committed ncu summary (profiles/ncu_traffic.json, written by
+    tools/summarise_profile.py from one `ncu --set full` capture); None when there is no capture for this workload."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kind]
+        if t["workload"] != workload:
+            return None, None
+        return t.get("dram_bytes_per_frame", t.get("dram_bytes_per_build")), t["source"]
+    except Exception:
+        return None, None
 
 
 def workload_config(scene, args, n_gpus):
@@ -431,6 +443,8 @@ def run_gpu(args):
         n_tris = n_tris_total
         build_total_ms = bt["total_ms"] + bcast_ms
         build_gbs = n_tris * B_TRI_BUILD / (build_total_ms * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic("k_trace", args.workload) if world == 1 else (None, None)
+        btraffic, btraffic_src = ncu_traffic("build", args.workload)
         line = {
             "metric": "Mrays/s (primary+secondary rays per second)", "value": total_rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
@@ -442,8 +456,8 @@ def run_gpu(args):
                     "h2d_bytes_per_step": 16, "d2h_bytes_per_step": W * H * 4,
                     "note": "rt_trace with a pinned host framebuffer: camera struct in, RGBA8 frame out"},
             "gpu_launches": int(l1 - l0),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": None,
-                         "kernel": "k_trace", "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                         "traffic_source": traffic_src, "kernel": "k_trace (stage 0 + stage 1 of one frame)", "peak_source": peak_src,
                          "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass",
                          "algorithmic_bytes_per_launch": algo_bytes / world,
                          "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
@@ -452,7 +466,7 @@ def run_gpu(args):
                       "value": n_tris / (build_total_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms": build_total_ms, "phases_ms": bt,
                       "broadcast_ms": bcast_ms, "note": build_note, "tlas_ms": tlas_t["total_ms"],
                       "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
-                                   "bytes_per_triangle": B_TRI_BUILD}},
+                                   "bytes_per_triangle": B_TRI_BUILD, "traffic": btraffic, "traffic_source": btraffic_src}},
             "traversal": tot,
             "crc32": crc,
             "clocks": clocks,

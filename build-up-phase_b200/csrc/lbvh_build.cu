@@ -30,7 +30,11 @@ namespace rt {
 namespace {
 
 constexpr int SETUP_THREADS = 256;
+#ifndef RT_SETUP_BATCH
+#define RT_SETUP_BATCH 1
+#endif
 constexpr int SETUP_ITEMS = 8;                       // triangles per thread
+constexpr int SETUP_BATCH = RT_SETUP_BATCH;           // of which this many are in flight together
 constexpr int SETUP_WARP_SPAN = 32 * SETUP_ITEMS;    // contiguous triangles per warp
 constexpr int SETUP_CHUNK = SETUP_THREADS * SETUP_ITEMS;
 
@@ -64,34 +68,54 @@ __global__ void __launch_bounds__(SETUP_THREADS) k_tri_setup(const GeomDesc* __r
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     uint32_t g = g_first;
     uint32_t gbeg = __ldg(prefix + g), gend = __ldg(prefix + g + 1);
-#pragma unroll 2
-    for (int i = 0; i < SETUP_ITEMS; ++i) {
-        const uint32_t t = wfirst + i * 32 + lane;
-        if (t >= n_tris) break;
-        if (t < gbeg || t >= gend) { g = find_geom(prefix, n_geoms, t); gbeg = __ldg(prefix + g); gend = __ldg(prefix + g + 1); }
-        const GeomDesc& G = geoms[g];
-        const uint32_t p = t - gbeg;
-        uint32_t i0, i1, i2;
-        if (G.idx) { i0 = __ldg(G.idx + 3 * (size_t)p); i1 = __ldg(G.idx + 3 * (size_t)p + 1); i2 = __ldg(G.idx + 3 * (size_t)p + 2); }
-        else { i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2; }
-        const float* a = G.verts + (size_t)i0 * G.stride_f;
-        const float* b = G.verts + (size_t)i1 * G.stride_f;
-        const float* c = G.verts + (size_t)i2 * G.stride_f;
-        V3 v0 = {__ldg(a), __ldg(a + 1), __ldg(a + 2)};
-        V3 v1 = {__ldg(b), __ldg(b + 1), __ldg(b + 2)};
-        V3 v2 = {__ldg(c), __ldg(c + 1), __ldg(c + 2)};
-        if (G.has_xform) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
-        float4* dst = reinterpret_cast<float4*>(out + t);
-        dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
-        dst[1] = make_float4(v1.y, v1.z, v2.x, v2.y);
-        dst[2] = make_float4(v2.z, __uint_as_float(G.geo_index), __uint_as_float(p), __uint_as_float(G.blas | (G.flags << 24)));
-        float tlo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
-        float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
-        if (uniform) {
+    // Batches of SETUP_BATCH triangles per lane: all index loads of a batch are issued before its first vertex load, all
+    // vertex loads before the first use. Measured on B200 (inst10m, profiles/README.md r01q): 0.201 / 0.226 / 0.270 / 0.329 ms
+    // for batches of 1 / 2 / 4 / 8 — the kernel is bound by LSU transactions of the 4-byte gathers (lg_throttle), not by
+    // their latency, so wider batches only cost occupancy. Default 1.
+#pragma unroll 1
+    for (int i0 = 0; i0 < SETUP_ITEMS; i0 += SETUP_BATCH) {
+        uint32_t gi[SETUP_BATCH], pi[SETUP_BATCH], ix[SETUP_BATCH][3];
+        bool ok[SETUP_BATCH];
 #pragma unroll
-            for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], tlo[k]); hi[k] = fmaxf(hi[k], thi[k]); }
-        } else {
-            atomic_bounds(bounds + 6 * (size_t)G.blas, tlo, thi);
+        for (int k = 0; k < SETUP_BATCH; ++k) {
+            const uint32_t t = wfirst + (i0 + k) * 32 + lane;
+            ok[k] = t < n_tris;
+            if (ok[k] && (t < gbeg || t >= gend)) { g = find_geom(prefix, n_geoms, t); gbeg = __ldg(prefix + g); gend = __ldg(prefix + g + 1); }
+            gi[k] = g; pi[k] = t - gbeg;
+            const uint32_t* idx = geoms[g].idx;
+            if (ok[k] && idx) { ix[k][0] = __ldg(idx + 3 * (size_t)pi[k]); ix[k][1] = __ldg(idx + 3 * (size_t)pi[k] + 1); ix[k][2] = __ldg(idx + 3 * (size_t)pi[k] + 2); }
+            else { ix[k][0] = 3 * pi[k]; ix[k][1] = 3 * pi[k] + 1; ix[k][2] = 3 * pi[k] + 2; }
+        }
+        float vx[SETUP_BATCH][9];
+#pragma unroll
+        for (int k = 0; k < SETUP_BATCH; ++k) {
+            if (!ok[k]) continue;
+            const GeomDesc& G = geoms[gi[k]];
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const float* a = G.verts + (size_t)ix[k][c] * G.stride_f;
+                vx[k][3 * c] = __ldg(a); vx[k][3 * c + 1] = __ldg(a + 1); vx[k][3 * c + 2] = __ldg(a + 2);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SETUP_BATCH; ++k) {
+            if (!ok[k]) continue;
+            const uint32_t t = wfirst + (i0 + k) * 32 + lane;
+            const GeomDesc& G = geoms[gi[k]];
+            V3 v0 = {vx[k][0], vx[k][1], vx[k][2]}, v1 = {vx[k][3], vx[k][4], vx[k][5]}, v2 = {vx[k][6], vx[k][7], vx[k][8]};
+            if (G.has_xform) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
+            float4* dst = reinterpret_cast<float4*>(out + t);
+            dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+            dst[1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+            dst[2] = make_float4(v2.z, __uint_as_float(G.geo_index), __uint_as_float(pi[k]), __uint_as_float(G.blas | (G.flags << 24)));
+            float tlo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
+            float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+            if (uniform) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], tlo[c]); hi[c] = fmaxf(hi[c], thi[c]); }
+            } else {
+                atomic_bounds(bounds + 6 * (size_t)G.blas, tlo, thi);
+            }
         }
     }
     if (uniform) {

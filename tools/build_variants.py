@@ -10,6 +10,9 @@ def _split(t0, t1):
 VARIANTS = {
     "base": [],
     "tile128": ["RT_TREE_TILE=128"],
+    "setup1": ["RT_SETUP_BATCH=1"],
+    "setup2": ["RT_SETUP_BATCH=2"],
+    "setup8": ["RT_SETUP_BATCH=8"],
     "bounce_unordered": ["RT_BOUNCE_ORDERED=0"],
     "match": ["RT_SORT_USE_MATCH=1"],
     "ballot_5": ["RT_SORT_MIN_CTAS=5"],

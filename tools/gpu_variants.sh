@@ -8,7 +8,7 @@ for lib in build-up-phase_b200/build/librtcore_*.so; do
 import json
 try:
     d=json.loads(open("gpurun_out/var_$name.json").read().strip().splitlines()[-1])
-    print("$name", "Mrays/s=%.1f ms=%.3f build_Mtri/s=%.0f refit_ms=%.3f sort_ms=%.3f crc=%s" % (d["value"], d["ms_per_step"], d["build"]["value"], d["build"]["phases_ms"]["refit_ms"], d["build"]["phases_ms"]["sort_ms"], d.get("crc32")))
+    print("$name", "Mrays/s=%.1f ms=%.3f build_Mtri/s=%.0f setup_ms=%.3f refit_ms=%.3f sort_ms=%.3f crc=%s" % (d["value"], d["ms_per_step"], d["build"]["value"], d["build"]["phases_ms"]["setup_ms"], d["build"]["phases_ms"]["refit_ms"], d["build"]["phases_ms"]["sort_ms"], d.get("crc32")))
 except Exception as e:
     print("$name", "FAILED", e, open("gpurun_out/var_$name.err").read()[-500:])
 PY

@@ -70,9 +70,36 @@ def full(rep, tag):
     print(json.dumps(res, indent=1))
 
 
+def _bytes(v):
+    x, unit = v.split()[0].replace(",", ""), v.split()[1].lower()
+    return float(x) * {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[unit]
+
+
+def traffic(tag):
+    """profiles/ncu_traffic.json: measured DRAM bytes (read + write) per launch of the dominant kernels, taken from the full
+    captures of this tag; bench.py copies the matching entry into roofline.traffic."""
+    out = {"tag": tag, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one `ncu --set full` capture each (inst10m, N = 1)"}
+    tp = os.path.join(PR, f"prof_trace_{tag}.json")
+    if os.path.exists(tp):
+        ks = json.load(open(tp))
+        per = {("stage%d" % i): _bytes(k["dram__bytes_read.sum"]) + _bytes(k["dram__bytes_write.sum"]) for i, k in enumerate(ks)}
+        out["k_trace"] = {"workload": "inst10m", "dram_bytes_per_frame": sum(per.values()), "per_stage": per, "source": f"profiles/prof_trace_{tag}.json"}
+    bp = os.path.join(PR, f"prof_build_{tag}.json")
+    if os.path.exists(bp):
+        ks = json.load(open(bp))
+        per = collections.OrderedDict()
+        for k in ks:
+            name = k["Kernel Name"].split("(")[0].split("::")[-1]
+            per[name] = per.get(name, 0.0) + _bytes(k["dram__bytes_read.sum"]) + _bytes(k["dram__bytes_write.sum"])
+        out["build"] = {"workload": "inst10m", "dram_bytes_per_build": sum(per.values()), "per_kernel": per, "source": f"profiles/prof_build_{tag}.json"}
+    json.dump(out, open(os.path.join(PR, "ncu_traffic.json"), "w"), indent=1)
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
     os.makedirs(PR, exist_ok=True)
     tag = sys.argv[1]
     launches(tag)
     for rep in sys.argv[2:]:
         full(rep, tag)
+    traffic(tag)
