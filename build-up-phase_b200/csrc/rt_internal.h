@@ -146,6 +146,8 @@ struct TraceParams {
     uint32_t width, height;
     uint32_t block_rows, part_index, part_count;   // image-space partition (1 part = whole image)
     uint32_t local_rows;                           // rows this launch covers (packed)
+    uint32_t row0;                                 // first (packed) row of this launch: a frame may be traced in row chunks so that the
+                                                   // device->host copy of one chunk overlaps the trace of the next
     float tmin, tmax;
     uint32_t cull_mask, sbt_offset, sbt_stride, bounce_seed;
     uint32_t ray_flags;         // RT_RAY_FLAG_*; anything beyond OPAQUE/NO_OPAQUE selects the GENERAL kernel variant

@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -23,6 +24,11 @@ struct rt_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    cudaStream_t copy_stream = nullptr;                           // device->host copies of finished row chunks (overlaps the next chunk's trace)
+    cudaEvent_t chunk_ev[8]{};
+    int e2e_chunks = 1;                                            // row chunks of a host-output trace (RTCORE_E2E_CHUNKS). Measured on B200,
+                                                                   // inst10m 4K: 1/2/3/4/6/8 chunks -> 4.17/4.13/4.27/4.42/4.94/5.34 ms end to end:
+                                                                   // the extra launches and kernel tails cost what the overlapped PCIe copy saves
     cudaDeviceProp prop{};
     std::string err;
     // shader data
@@ -149,6 +155,9 @@ int rt_create(int device_ordinal, rt_context** out) {
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     ctx->own_stream = true;
     for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    for (auto& e : ctx->chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (const char* v = getenv("RTCORE_E2E_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->e2e_chunks = k; }
     if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess ||
         cudaMalloc(&ctx->d_counters, 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     cudaMemset(ctx->d_error, 0, 64);
@@ -163,6 +172,8 @@ void rt_destroy(rt_context* ctx) {
     cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -710,15 +721,35 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }
+    // Host output: the frame is traced in row chunks (multiples of 8 rows) and every finished chunk is copied device->host
+    // on a second stream while the next one is traced. Device output: one launch.
+    const uint32_t total_rows = P.local_rows;
+    uint32_t chunks = 1;
+    if (!dev_out && pixels >= (1u << 20)) chunks = (uint32_t)ctx->e2e_chunks;
+    uint32_t rows_per_chunk = (((total_rows + chunks - 1) / chunks) + 7u) & ~7u;
+    if (rows_per_chunk == 0) rows_per_chunk = 8;
+    chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    int l = launch_trace(P, stats, stack_needed, ctx->prop.multiProcessorCount, ctx->stream);
-    if (l < 0) return fail(ctx, RT_ERROR_CUDA, "trace launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    ctx->launches += (uint64_t)l;
+    for (uint32_t c = 0; c < chunks; ++c) {
+        TraceParams Pc = P;
+        Pc.row0 = c * rows_per_chunk;
+        Pc.local_rows = total_rows - Pc.row0 < rows_per_chunk ? total_rows - Pc.row0 : rows_per_chunk;
+        int l = launch_trace(Pc, stats, stack_needed, ctx->prop.multiProcessorCount, ctx->stream);
+        if (l < 0) return fail(ctx, RT_ERROR_CUDA, "trace launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        ctx->launches += (uint64_t)l;
+        if (!dev_out) RT_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+    }
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!dev_out) {
-        RT_CUDA(ctx, cudaMemcpyAsync(rgba_out, P.rgba, pixels * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out, P.primary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
-        if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out, P.secondary_hits, pixels * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->stream));
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const size_t p0 = (size_t)c * rows_per_chunk * width;
+            const size_t np = (size_t)((total_rows - c * rows_per_chunk < rows_per_chunk ? total_rows - c * rows_per_chunk : rows_per_chunk)) * width;
+            RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
+            RT_CUDA(ctx, cudaMemcpyAsync(rgba_out + 4 * p0, P.rgba + 4 * p0, np * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out + p0, P.primary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out + p0, P.secondary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        RT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }
     if ((flags & RT_TRACE_ASYNC) && dev_out && !stats) return RT_SUCCESS;
     if (stats) RT_CUDA(ctx, cudaMemcpyAsync(&ctx->last_stats, ctx->d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));

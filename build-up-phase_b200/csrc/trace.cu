@@ -204,10 +204,10 @@ __device__ __forceinline__ RayId primary_ray(const TraceParams& P, uint32_t idx,
     RayId id;
     const uint32_t tile = idx >> 5, within = idx & 31u;
     const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
-    const uint32_t lr = (tile / tiles_x) * 4u + (within >> 3);
+    const uint32_t lr = P.row0 + (tile / tiles_x) * 4u + (within >> 3);
     const uint32_t band = lr / P.block_rows;
     const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
-    id.in_buffer = x < P.width && lr < P.local_rows;
+    id.in_buffer = x < P.width && lr < P.row0 + P.local_rows;
     id.valid = id.in_buffer && y < P.height;
     id.lidx = lr * P.width + x;
     id.pixel = y * P.width + x;
