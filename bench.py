@@ -3,7 +3,8 @@
 
 A "step" is one vkCmdTraceRaysKHR-equivalent pass over the full frame of the workload (primary rays +
 one diffuse bounce), with the acceleration structures already resident in HBM. At N GPUs the frame is
-split into interleaved 8-scanline bands (scene replicated), gathered to rank 0 with NCCL and unpacked.
+split into interleaved 8-scanline bands (scene replicated); every rank's trace kernel stores its pixels straight into
+rank 0's framebuffer over NVLink (--gather p2p, default) or the packed bands are gathered with NCCL and unpacked.
 
   python bench.py                         # N=1, inst10m (BASELINE configs[3], the config the metric is quoted on)
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N
@@ -196,7 +197,10 @@ def workload_config(scene, args, n_gpus):
     return {"workload": f"{args.workload}: {scene.name}, {n_tris} triangles in {len(scene.blases)} BLAS, "
                         f"{len(scene.instances)} instances, {scene.width}x{scene.height} primary + {scene.bounces} diffuse bounce",
             "triangles": n_tris, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
-            "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated",
+            "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated"
+            + ("" if n_gpus == 1 else {"p2p": "; every rank stores its pixels straight into rank 0's framebuffer over NVLink (CUDA IPC), NCCL all-reduce as frame barrier",
+                                       "allgather": "; packed bands, NCCL all-gather, unpack on rank 0",
+                                       "gather": "; packed bands, NCCL gather to rank 0, unpack"}[args.gather]),
             "l2_policy": "inputs larger than L2 (BVH nodes + triangles >> 126 MB); no flush between iterations"
                          if n_tris * 112 > 2 * 126e6 else "scene fits in L2: numbers are L2-resident (parity config)"}
 
@@ -331,33 +335,65 @@ def run_gpu(args):
 
     # ---- buffers ----
     px_packed = ctx.rows_packed_pixels(W, H, BLOCK_ROWS, world)
+    mode = args.gather if world > 1 else "single"
+    shared, shared_ptrs, token = [], [], None
     if world > 1:
         packed = torch.zeros((px_packed, 4), dtype=torch.uint8, device=dev)
-        gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
-        gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
+        if mode == "gather":
+            gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+            gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
+        elif mode == "allgather":
+            gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev)
+        else:
+            # two framebuffers on rank 0 (double buffer: frame k may still be read while frame k + 1 is written), mapped by every rank
+            handles = [None, None]
+            if rank == 0:
+                for k in range(2):
+                    ptr, h = ctx.frame_share_create(W * H * 4)
+                    shared_ptrs.append(ptr); handles[k] = h
+            dist.broadcast_object_list(handles, src=0)
+            if rank != 0:
+                shared_ptrs = [ctx.frame_share_open(h) for h in handles]
+            if rank == 0:
+                shared = [rtcore.device_view(p, W * H * 4, dev).view(H, W, 4) for p in shared_ptrs]
+            token = torch.zeros(1, dtype=torch.int32, device=dev)
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
     host_np = host_frame.numpy()
+    step_no = [0]
+
+    def step_multi():
+        """One frame at N > 1; returns the tensor holding the finished frame on rank 0 (None elsewhere)."""
+        if mode == "p2p":
+            k = step_no[0] & 1
+            step_no[0] += 1
+            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
+            dist.all_reduce(token)          # frame-complete barrier on the stream: every rank's stores have landed
+            return shared[k] if rank == 0 else None
+        ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
+        if mode == "gather":
+            dist.gather(packed, gather_list, dst=0)
+        else:
+            dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+        if rank == 0:
+            ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
+            return frame
+        return None
 
     def step_device():
         if world == 1:
             ctx.trace_device(tlas, cam, W, H, bounces, frame, async_=True)
         else:
-            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
-            dist.gather(packed, gather_list, dst=0)
-            if rank == 0:
-                ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
+            step_multi()
 
     def step_e2e():
         # reference-facing call with HOST buffers: camera struct in (16 B), RGBA8 framebuffer out (pinned host memory)
         if world == 1:
             ctx.trace(tlas, cam, W, H, bounces, rgba_out=host_np)
         else:
-            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
-            dist.gather(packed, gather_list, dst=0)
+            done = step_multi()
             if rank == 0:
-                ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
-                host_frame.copy_(frame, non_blocking=True)
+                host_frame.copy_(done, non_blocking=True)
             torch.cuda.synchronize()
 
     def barrier():
@@ -434,6 +470,12 @@ def run_gpu(args):
         crc = {"rgba": zlib.crc32(frame.cpu().numpy().tobytes()), "primary_hits": zlib.crc32(prim_c.cpu().numpy().tobytes()),
                "secondary_hits": zlib.crc32(sec_c.cpu().numpy().tobytes())}
         del prim_c, sec_c
+    else:
+        import zlib
+        done = step_multi()                 # the assembled frame of the multi-GPU path must be the single-GPU frame, bit for bit
+        torch.cuda.synchronize()
+        if rank == 0:
+            crc = {"rgba": zlib.crc32(done.cpu().numpy().tobytes()), "gather": mode}
 
     if rank == 0:
         hbm, peak_src = peaks()
@@ -494,6 +536,16 @@ def run_gpu(args):
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
+        torch.cuda.synchronize()
+        if mode == "p2p":               # peers unmap first, then the owner frees
+            shared = []
+            if rank != 0:
+                for p_ in shared_ptrs:
+                    ctx.frame_share_close(p_)
+            dist.barrier()
+            if rank == 0:
+                for p_ in shared_ptrs:
+                    ctx.frame_share_free(p_)
         dist.destroy_process_group()
 
 
@@ -509,6 +561,10 @@ def main():
     ap.add_argument("--build-reps", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "allgather", "gather"],
+                    help="N > 1: how the bands reach rank 0. p2p = every rank's trace kernel stores its pixels straight into rank 0's "
+                         "framebuffer over NVLink (CUDA IPC mapping) + one tiny NCCL all-reduce as the frame-complete barrier; "
+                         "allgather / gather = packed bands + NCCL collective + unpack kernel on rank 0")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()

@@ -690,7 +690,10 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     // one part = the plain width x height image; several parts = equal-sized packed band buffers
     const uint64_t pixels = part_count == 1 ? (uint64_t)width * height : rt_rows_packed_pixels(width, height, block_rows, part_count);
     const bool dev_out = (flags & RT_TRACE_OUT_DEVICE) != 0;
+    const bool full_frame = (flags & RT_TRACE_OUT_FULL_FRAME) != 0;
+    if (full_frame && !dev_out) return fail(ctx, RT_ERROR_INVALID_ARG, "RT_TRACE_OUT_FULL_FRAME needs RT_TRACE_OUT_DEVICE");
     TraceParams P{};
+    P.full_frame = full_frame ? 1u : 0u;
     P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
     for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[3 * (size_t)ctx->rp.miss_index + k]; }
     // raygen constants of main.cpp:1038-1039; tan is evaluated once on the host in fp32
@@ -714,7 +717,7 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         // ray slots are numbered tile-major over whole 8x4 tiles, so round the image up to tiles
         const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((P.local_rows + 3u) >> 2), slots = tiles * 32u;
         const size_t ray_bytes = align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256), idx_bytes = align_up(slots * 4, 256);
-        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, ray_bytes + idx_bytes + (tiles + tiles / 1024 + 16) * 4)) != RT_SUCCESS) return rc;
+        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, ray_bytes + idx_bytes + (tiles + 9 * (tiles / 64 + 2) + 16) * 4)) != RT_SUCCESS) return rc;
         P.queue = (float4*)ctx->queue;
         P.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes);
         P.tile_mask = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes + idx_bytes);
@@ -777,6 +780,42 @@ int rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t width, u
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);
+    return RT_SUCCESS;
+}
+
+int rt_frame_share_create(rt_context* ctx, uint64_t bytes, void** device_ptr_out, uint8_t handle_out[64]) {
+    if (!ctx || !bytes || !device_ptr_out || !handle_out) return RT_ERROR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    void* p = nullptr;
+    RT_CUDA(ctx, cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) { cudaFree(p); return fail(ctx, RT_ERROR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e)); }
+    memcpy(handle_out, &h, 64);
+    RT_CUDA(ctx, cudaMemset(p, 0, bytes));
+    *device_ptr_out = p;
+    return RT_SUCCESS;
+}
+int rt_frame_share_open(rt_context* ctx, const uint8_t handle[64], void** device_ptr_out) {
+    if (!ctx || !handle || !device_ptr_out) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    RT_CUDA(ctx, cudaIpcOpenMemHandle(device_ptr_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_SUCCESS;
+}
+int rt_frame_share_close(rt_context* ctx, void* mapped_device_ptr) {
+    if (!ctx || !mapped_device_ptr) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    RT_CUDA(ctx, cudaIpcCloseMemHandle(mapped_device_ptr));
+    return RT_SUCCESS;
+}
+int rt_frame_share_free(rt_context* ctx, void* device_ptr) {
+    if (!ctx || !device_ptr) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaFree(device_ptr));
     return RT_SUCCESS;
 }
 

@@ -30,6 +30,7 @@ RT_BUILD_NO_PACKED_SORT = 0x200
 RT_TRACE_OUT_DEVICE = 0x1
 RT_TRACE_STATS = 0x2
 RT_TRACE_ASYNC = 0x4
+RT_TRACE_OUT_FULL_FRAME = 0x8
 RT_REF_EMPTY = 0x7FFFFFFD
 
 EXPORTED_SYMBOLS = [
@@ -38,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
-    "rt_rows_packed_pixels", "rt_unpack_rows", "rt_last_trace_stats", "rt_last_trace_ms",
+    "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
@@ -175,6 +176,10 @@ def load(build_if_missing: bool = True):
     L.rt_rows_packed_pixels.argtypes = [u32, u32, u32, u32]
     L.rt_rows_packed_pixels.restype = u64
     L.rt_unpack_rows.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+    L.rt_frame_share_create.argtypes = [vp, u64, C.POINTER(vp), vp]
+    L.rt_frame_share_open.argtypes = [vp, vp, C.POINTER(vp)]
+    L.rt_frame_share_close.argtypes = [vp, vp]
+    L.rt_frame_share_free.argtypes = [vp, vp]
     L.rt_last_trace_stats.argtypes = [vp, C.POINTER(RtTraceStats)]
     L.rt_last_trace_ms.argtypes = [vp]
     L.rt_last_trace_ms.restype = C.c_float
@@ -461,10 +466,30 @@ class Context:
         flags = RT_TRACE_OUT_DEVICE | (RT_TRACE_STATS if stats else 0) | (RT_TRACE_ASYNC if async_ else 0)
         self._check(self.L.rt_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, _ptr(rgba_dev), _ptr(prim_dev), _ptr(sec_dev)))
 
+    def frame_share_create(self, nbytes: int):
+        """-> (device pointer, 64-byte IPC handle as bytes) of a framebuffer other ranks can map (rt_frame_share_create)."""
+        p = C.c_void_p()
+        h = (C.c_uint8 * 64)()
+        self._check(self.L.rt_frame_share_create(self.h, nbytes, C.byref(p), h))
+        return p.value, bytes(h)
+
+    def frame_share_open(self, handle: bytes) -> int:
+        p = C.c_void_p()
+        h = (C.c_uint8 * 64).from_buffer_copy(handle)
+        self._check(self.L.rt_frame_share_open(self.h, h, C.byref(p)))
+        return p.value
+
+    def frame_share_close(self, ptr: int):
+        self._check(self.L.rt_frame_share_close(self.h, ptr))
+
+    def frame_share_free(self, ptr: int):
+        self._check(self.L.rt_frame_share_free(self.h, ptr))
+
     def trace_rows(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, block_rows: int, part_index: int,
                    part_count: int, rgba, prim=None, sec=None, device: bool = False, stats: bool = False,
-                   async_: bool = False):
-        flags = (RT_TRACE_OUT_DEVICE if device else 0) | (RT_TRACE_STATS if stats else 0) | (RT_TRACE_ASYNC if async_ else 0)
+                   async_: bool = False, full_frame: bool = False):
+        flags = (RT_TRACE_OUT_DEVICE if device else 0) | (RT_TRACE_STATS if stats else 0) | (RT_TRACE_ASYNC if async_ else 0) | \
+                (RT_TRACE_OUT_FULL_FRAME if full_frame else 0)
         self._check(self.L.rt_trace_rows(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, block_rows, part_index,
                                          part_count, _ptr(rgba), _ptr(prim), _ptr(sec)))
 

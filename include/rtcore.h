@@ -80,6 +80,10 @@ enum {
 #define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
 #define RT_TRACE_STATS      0x2u  /* also accumulate traversal counters (slower kernel variant) */
 #define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait) */
+#define RT_TRACE_OUT_FULL_FRAME 0x8u /* rt_trace_rows with RT_TRACE_OUT_DEVICE: rgba_out is the WHOLE width*height*4 frame and this part's
+                                        pixels are stored at their final position (no packing, no unpack step). The frame may be peer memory
+                                        of another GPU (rt_frame_share_open): the trace kernel then writes over NVLink straight into rank 0's
+                                        framebuffer and the gather disappears. */
 
 typedef struct rt_context rt_context;
 typedef struct rt_blas    rt_blas;
@@ -265,6 +269,14 @@ RT_API uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t 
  * rt_rows_packed_pixels()*4 bytes, device memory) into the final width*height*4 framebuffer (device). */
 RT_API int  rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t width, uint32_t height,
                            uint32_t block_rows, uint32_t part_count, uint8_t* rgba_out_device);
+
+/* A framebuffer that other processes (one per GPU) can map: cudaMalloc + cudaIpcGetMemHandle on the owner, cudaIpcOpenMemHandle on
+ * the peers (the 64-byte handle travels through any host channel, e.g. a torch.distributed broadcast). Peers pass the mapped pointer
+ * to rt_trace_rows(..., RT_TRACE_OUT_DEVICE | RT_TRACE_OUT_FULL_FRAME, ...). Completion is the caller's job (a barrier after the trace). */
+RT_API int  rt_frame_share_create(rt_context* ctx, uint64_t bytes, void** device_ptr_out, uint8_t handle_out[64]);
+RT_API int  rt_frame_share_open(rt_context* ctx, const uint8_t handle[64], void** device_ptr_out);
+RT_API int  rt_frame_share_close(rt_context* ctx, void* mapped_device_ptr);     /* a pointer from rt_frame_share_open */
+RT_API int  rt_frame_share_free(rt_context* ctx, void* device_ptr);             /* a pointer from rt_frame_share_create */
 
 RT_API int  rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out);
 /* CUDA-event milliseconds of the kernels of the most recent rt_trace / rt_trace_rows / rt_unpack_rows call (no copies). */

@@ -241,6 +241,21 @@ def test_row_partition_and_unpack(rt, ctx, oracle):
         ctx.unpack_rows(packed, scene.width, scene.height, 8, parts, out)
         torch.cuda.synchronize()
         assert np.array_equal(out.cpu().numpy(), full), f"parts={parts}"
+        # RT_TRACE_OUT_FULL_FRAME: every part stores its pixels at their final position of ONE frame (what the ranks do with
+        # rank 0's shared framebuffer over NVLink): no packing, no unpack
+        direct = torch.zeros((scene.height, scene.width, 4), dtype=torch.uint8, device="cuda:0")
+        for p in range(parts):
+            ctx.trace_rows(sh.tlas, sh.cam, scene.width, scene.height, 1, 8, p, parts, direct, device=True, full_frame=True)
+        torch.cuda.synchronize()
+        assert np.array_equal(direct.cpu().numpy(), full), f"full-frame parts={parts}"
+    # a shareable framebuffer (cudaMalloc + IPC handle) works as an output like any device buffer
+    ptr, handle = ctx.frame_share_create(scene.width * scene.height * 4)
+    assert len(handle) == 64 and any(handle)
+    ctx.trace_rows(sh.tlas, sh.cam, scene.width, scene.height, 1, 8, 0, 1, ptr, device=True, full_frame=True)
+    view = rt.device_view(ptr, scene.width * scene.height * 4, "cuda:0").view(scene.height, scene.width, 4)
+    assert np.array_equal(view.cpu().numpy(), full)
+    del view
+    ctx.frame_share_free(ptr)
     sh.free()
 
 
