@@ -179,12 +179,6 @@ static_assert(TREE_TILE <= 512 && (TREE_TILE & (TREE_TILE - 1)) == 0, "tile");
 // CTA-scope acquire/release fence (cheaper than the sequentially consistent one __threadfence_block() emits)
 __device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
 
-__device__ __forceinline__ void store_half(BvhNode* nodes, uint32_t node, uint32_t side, const Box3& b, int32_t ref, uint32_t height) {
-    float4* dst = reinterpret_cast<float4*>(&nodes[node].c[side]);
-    dst[0] = make_float4(b.lo[0], b.lo[1], b.lo[2], b.hi[0]);
-    dst[1] = make_float4(b.hi[1], b.hi[2], __int_as_float(ref), __uint_as_float(height));
-}
-
 // common-prefix length of the augmented strings (key_i, i) and (key_{i+1}, i+1)
 __device__ __forceinline__ int delta_adjacent(uint64_t ka, uint64_t kb, uint32_t i) {
     return ka == kb ? 64 + __clz((int)(i ^ (i + 1u))) : __clzll((long long)(ka ^ kb));

@@ -53,6 +53,8 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 // bit in a per-tile mask; two small kernels turn the masks into a compact, TILE-ORDERED index list for stage 1, so the
 // 32 secondary rays a warp fetches start on neighbouring surface points. (=0: the rays are appended to a queue in the
 // order the persistent warps finish them, which scatters them over the ~40 pixel rows that are in flight at a time.)
+// Measured and removed (profiles/README.md r01t): listing the rays of every 64-tile group by direction octant first
+// (three index kernels, directions re-read) made the frame 3 % SLOWER (3019 vs 3108 Mrays/s).
 #ifndef RT_LDG256
 #define RT_LDG256 0
 #endif
@@ -321,6 +323,7 @@ __device__ __forceinline__ void shade(const TraceParams& P, const RayId id, cons
     }
 }
 
+#if !RT_BOUNCE_ORDERED
 // warp-aggregated append to the bounce queue (all 32 lanes must call)
 __device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueue, const float4& e0, const float4& e1, const float4& e2,
                                                int lane, uint32_t lt_mask) {
@@ -336,6 +339,7 @@ __device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueu
         }
     }
 }
+#endif
 
 // STAGE 0: primary rays generated from pixel ids. STAGE 1: secondary rays read from the bounce queue.
 // The shaders' epilogue runs inside this kernel for the lanes whose ray just finished. (Measured alternatives, both
@@ -535,10 +539,6 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
 }
 
 // ---- bounce index: per-tile hit masks -> compact tile-ordered list of ray slots -----------------------------
-#ifndef RT_BOUNCE_OCTANT
-#define RT_BOUNCE_OCTANT 0
-#endif
-#if !RT_BOUNCE_OCTANT
 constexpr int BIDX_THREADS = 256, BIDX_WORDS = 4, BIDX_CHUNK = BIDX_THREADS * BIDX_WORDS;   // mask words per block
 
 // block_sums[b] = number of bounce rays in the b-th chunk of mask words; counters[2] += it
@@ -594,109 +594,6 @@ __global__ void __launch_bounds__(BIDX_THREADS) k_bounce_index(const uint32_t* _
         while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1u; index[pos++] = (w0 + k) * 32u + (uint32_t)b; }
     }
 }
-constexpr int BIDX_SUMS_PER_BLOCK = 1;
-#else
-// RT_BOUNCE_OCTANT=1 (experiment): inside every group of 64 tiles the rays are listed by direction octant first, tile order
-// second, so that a warp of stage 1 holds rays that start close together AND agree on the order they visit a node's children.
-constexpr int BIDX_THREADS = 64, BIDX_CHUNK = 64;      // one mask word per thread
-constexpr int BIDX_SUMS_PER_BLOCK = 9;                 // 8 octant counts + the block's exclusive base (filled by k_bounce_scan)
-
-__device__ __forceinline__ uint32_t ray_octant(const float4* __restrict__ queue, uint32_t slot) {
-    const float4 e1 = __ldcg(queue + 3 * (size_t)slot + 1);
-    return (e1.x < 0.0f ? 1u : 0u) | (e1.y < 0.0f ? 2u : 0u) | (e1.z < 0.0f ? 4u : 0u);
-}
-
-__global__ void __launch_bounds__(BIDX_THREADS) k_bounce_count(const uint32_t* __restrict__ tile_mask, uint32_t n_words, const float4* __restrict__ queue,
-                                                               uint32_t* __restrict__ block_sums, uint32_t* __restrict__ counters) {
-    __shared__ uint32_t s_sum[8];
-    if (threadIdx.x < 8) s_sum[threadIdx.x] = 0;
-    __syncthreads();
-    const uint32_t w = blockIdx.x * BIDX_CHUNK + threadIdx.x;
-    uint32_t mm = w < n_words ? __ldg(tile_mask + w) : 0u;
-    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    while (mm) {
-        const int b = __ffs(mm) - 1; mm &= mm - 1u;
-        const uint32_t o = ray_octant(queue, w * 32u + (uint32_t)b);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] += o == (uint32_t)k ? 1u : 0u;
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t v = c[k];
-#pragma unroll
-        for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_xor_sync(0xffffffffu, v, ofs);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s_sum[k], v);
-    }
-    __syncthreads();
-    if (threadIdx.x < 8) block_sums[(size_t)blockIdx.x * BIDX_SUMS_PER_BLOCK + threadIdx.x] = s_sum[threadIdx.x];
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int k = 0; k < 8; ++k) t += s_sum[k];
-        if (t) atomicAdd(counters + 2, t);
-    }
-}
-
-// block_sums[b][8] = exclusive prefix over the blocks of their totals; one block, sequential over chunks of 1024 blocks
-__global__ void __launch_bounds__(1024) k_bounce_scan(uint32_t* __restrict__ block_sums, uint32_t n_blocks) {
-    __shared__ uint32_t s_w[32];
-    __shared__ uint32_t s_carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_carry = 0;
-    __syncthreads();
-    for (uint32_t b0 = 0; b0 < n_blocks; b0 += 1024) {
-        const uint32_t b = b0 + threadIdx.x;
-        uint32_t t = 0;
-        if (b < n_blocks) for (int k = 0; k < 8; ++k) t += block_sums[(size_t)b * BIDX_SUMS_PER_BLOCK + k];
-        uint32_t inc = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-        if (lane == 31) s_w[warp] = inc;
-        __syncthreads();
-        uint32_t pre = s_carry;
-        for (int w = 0; w < warp; ++w) pre += s_w[w];
-        if (b < n_blocks) block_sums[(size_t)b * BIDX_SUMS_PER_BLOCK + 8] = pre + inc - t;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry = pre + inc;
-        __syncthreads();
-    }
-}
-
-__global__ void __launch_bounds__(BIDX_THREADS) k_bounce_index(const uint32_t* __restrict__ tile_mask, uint32_t n_words, const float4* __restrict__ queue,
-                                                               const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ index) {
-    __shared__ uint32_t s_pos[8][BIDX_THREADS];        // next write position of (octant, thread)
-    __shared__ uint32_t s_wtot[8];                     // per octant: total of warp 0
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t w = blockIdx.x * BIDX_CHUNK + threadIdx.x;
-    const uint32_t m = w < n_words ? __ldg(tile_mask + w) : 0u;
-    uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (uint32_t mm = m; mm; mm &= mm - 1u) {
-        const uint32_t o = ray_octant(queue, w * 32u + (uint32_t)(__ffs(mm) - 1));
-#pragma unroll
-        for (int k = 0; k < 8; ++k) c[k] += o == (uint32_t)k ? 1u : 0u;
-    }
-    const uint32_t* bs = block_sums + (size_t)blockIdx.x * BIDX_SUMS_PER_BLOCK;
-    uint32_t region = __ldg(bs + 8);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        uint32_t inc = c[k];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
-        if (warp == 0 && lane == 31) s_wtot[k] = inc;
-        s_pos[k][threadIdx.x] = inc - c[k];              // exclusive within the warp for now
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-        s_pos[k][threadIdx.x] += region + (warp == 1 ? s_wtot[k] : 0u);
-        region += __ldg(bs + k);
-    }
-    for (uint32_t mm = m; mm; mm &= mm - 1u) {
-        const uint32_t slot = w * 32u + (uint32_t)(__ffs(mm) - 1);
-        index[s_pos[ray_octant(queue, slot)][threadIdx.x]++] = slot;      // the direction was just read above: L1 hit
-    }
-}
-#endif
-
 __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ packed_all, uint32_t width, uint32_t height,
                                                     uint32_t block_rows, uint32_t part_count, uint32_t rows_per_part, uchar4* __restrict__ out) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -731,16 +628,9 @@ int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
         const uint32_t n_words = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
         const uint32_t blocks = (n_words + BIDX_CHUNK - 1) / BIDX_CHUNK;
         uint32_t* block_sums = p.tile_mask + n_words;
-#if RT_BOUNCE_OCTANT
-        k_bounce_count<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, p.queue, block_sums, p.counters);
-        k_bounce_scan<<<1, 1024, 0, st>>>(block_sums, blocks);
-        k_bounce_index<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, p.queue, block_sums, p.bounce_index);
-        n += 3;
-#else
         k_bounce_count<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, block_sums, p.counters);
         k_bounce_index<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, block_sums, p.bounce_index);
         n += 2;
-#endif
 #endif
         n += launch_stage<1, STATS, STACK, GENERAL>(p, sm_count, st);
     }

@@ -14,7 +14,6 @@ VARIANTS = {
     "setup2": ["RT_SETUP_BATCH=2"],
     "setup8": ["RT_SETUP_BATCH=8"],
     "bounce_unordered": ["RT_BOUNCE_ORDERED=0"],
-    "bounce_octant": ["RT_BOUNCE_OCTANT=1"],
     "match": ["RT_SORT_USE_MATCH=1"],
     "ballot_5": ["RT_SORT_MIN_CTAS=5"],
     "ballot_6": ["RT_SORT_MIN_CTAS=6"],
