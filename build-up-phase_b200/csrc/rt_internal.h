@@ -163,6 +163,10 @@ struct TraceParams {
     float4* queue;              // bounce rays: 3 x float4 per secondary ray {pixel, o.xyz | d.xyz, r | g, b, -, -}, one slot per tile-major ray index
     uint32_t* tile_mask;        // one word per 8x4-pixel tile: which of its pixels spawned a bounce ray; followed by the block sums of the index build
     uint32_t* bounce_index;     // compact tile-ordered list of the occupied queue slots (stage 1 reads rays through it)
+    // fused launch (both stages in one persistent kernel): the queue is an append queue again, entry i is published by
+    // queue_flags[i] = epoch (a per-launch number, so the flags never need clearing); counters[3] counts finished primary rays
+    uint32_t* queue_flags; uint32_t epoch; uint32_t queue_capacity;
+    int* error_flag;            // device int: set to 2 by the fused kernel's watchdog (a claim that is never published)
 };
 constexpr size_t TRACE_QUEUE_ENTRY_BYTES = 48;
 // per ray slot: the ray record + its index entry + its share of the tile mask / block sums (rounded up)

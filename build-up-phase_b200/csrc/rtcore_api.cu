@@ -41,6 +41,8 @@ struct rt_context {
     void* hits1 = nullptr; size_t hits1_cap = 0;
     void* hits2 = nullptr; size_t hits2_cap = 0;
     void* queue = nullptr; size_t queue_cap = 0;       // bounce queue of the two-stage wavefront
+    uint32_t* qflags = nullptr; size_t qflags_cap = 0; // per-entry publication flags of the fused launch (hold the epoch of the launch that wrote the entry)
+    uint32_t trace_epoch = 0;
     uint32_t* d_counters = nullptr;                    // ray-fetch / queue counters of the persistent trace kernels
     unsigned long long* d_stats = nullptr;
     int* d_error = nullptr;
@@ -170,7 +172,7 @@ void rt_destroy(rt_context* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
-    cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->d_counters);
+    cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->qflags); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
@@ -721,6 +723,15 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         P.queue = (float4*)ctx->queue;
         P.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes);
         P.tile_mask = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes + idx_bytes);
+        if (ctx->qflags_cap < slots) {                  // grown: new flags start at 0, an epoch no launch ever uses
+            if (ctx->qflags) { RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->qflags); ctx->qflags = nullptr; ctx->qflags_cap = 0; }
+            RT_CUDA(ctx, cudaMalloc((void**)&ctx->qflags, (slots + slots / 8) * 4));
+            ctx->qflags_cap = slots + slots / 8;
+            RT_CUDA(ctx, cudaMemsetAsync(ctx->qflags, 0, ctx->qflags_cap * 4, ctx->stream));
+        }
+        P.queue_flags = ctx->qflags;
+        P.error_flag = ctx->d_error;
+        P.queue_capacity = (uint32_t)slots;
     }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }
@@ -735,6 +746,8 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     for (uint32_t c = 0; c < chunks; ++c) {
         TraceParams Pc = P;
+        if (++ctx->trace_epoch == 0u) ctx->trace_epoch = 1u;
+        Pc.epoch = ctx->trace_epoch;
         Pc.row0 = c * rows_per_chunk;
         Pc.local_rows = total_rows - Pc.row0 < rows_per_chunk ? total_rows - Pc.row0 : rows_per_chunk;
         int l = launch_trace(Pc, stats, stack_needed, ctx->prop.multiProcessorCount, ctx->stream);
@@ -756,7 +769,10 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     }
     if ((flags & RT_TRACE_ASYNC) && dev_out && !stats) return RT_SUCCESS;
     if (stats) RT_CUDA(ctx, cudaMemcpyAsync(&ctx->last_stats, ctx->d_stats, 64, cudaMemcpyDeviceToHost, ctx->stream));
+    int h_err = 0;
+    if (bounces > 0) RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_err) { cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream); return fail(ctx, RT_ERROR_INTERNAL, "trace watchdog fired (bounce-queue entry never published)"); }
     cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);
     if (!stats) memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
     return RT_SUCCESS;

@@ -55,6 +55,19 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 // order the persistent warps finish them, which scatters them over the ~40 pixel rows that are in flight at a time.)
 // Measured and removed (profiles/README.md r01t): listing the rays of every 64-tile group by direction octant first
 // (three index kernels, directions re-read) made the frame 3 % SLOWER (3019 vs 3108 Mrays/s).
+#ifndef RT_FUSED_STAGES
+#define RT_FUSED_STAGES 1
+#endif
+// RT_FUSED_STAGES=1: a SMALL launch with a bounce is ONE persistent kernel. Warps take primary rays while there are any,
+// then bounce rays from an append queue that the finishing primary rays fill, so the tail of the primary stage (its
+// longest rays running alone) overlaps the bulk of the secondary stage and the dependent launches in between disappear.
+// That fixed cost (~0.35 ms per frame) is what limits multi-GPU scaling. Measured on B200 (profiles/README.md r01u), fused
+// vs stage 0 + index kernels + stage 1: 0.49 vs 0.58 ms at 0.5 M pixels, 0.78 vs 0.83 at 1.0 M, 1.29 vs 1.27 at 2.1 M,
+// 3.92 vs 3.60 at 8.3 M (the fused kernel carries more live state through the traversal loop and pays ~18 % per ray), so
+// launches of up to RT_FUSED_MAX_PIXELS pixels are fused and larger ones are not. (=0: never fuse.)
+#ifndef RT_FUSED_MAX_PIXELS
+#define RT_FUSED_MAX_PIXELS 1500000u
+#endif
 #ifndef RT_LDG256
 #define RT_LDG256 0
 #endif
@@ -76,6 +89,20 @@ __device__ __forceinline__ F8 ldg256(const void* p) {
     return r;
 }
 constexpr uint32_t NO_HIT = 0xFFFFFFFFu;
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 struct Slab {
     float rdx, rdy, rdz;     // 1/d (zero components replaced by +-1e-20)
@@ -351,14 +378,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tiles_x = (P.width + 7u) >> 3;
     const uint32_t tiles_y = (P.local_rows + 3u) >> 2;
-    const uint32_t total = STAGE == 0 ? tiles_x * tiles_y * 32u : P.counters[2];
-    uint32_t* fetch_counter = P.counters + STAGE;
+    constexpr bool FUSED = STAGE == 2;       // both stages in one launch: a lane holds a primary OR a secondary ray (`sec`)
+    const uint32_t total = STAGE == 1 ? P.counters[2] : tiles_x * tiles_y * 32u;
+    uint32_t* fetch_counter = P.counters + (STAGE == 1 ? 1 : 0);
     constexpr int THRESHOLD = REFILL_THRESHOLD;
 
-    Counters c;
+    Counters c, c1;                          // c1: FUSED only, the secondary rays' ray/hit counts
 
     // ---- per-lane ray state ----
     bool have_ray = false, exhausted = false;
+    bool sec = STAGE == 1;                   // FUSED: this lane's ray is a bounce ray
+    bool pending = false;                    // FUSED: holds a claim on bounce-queue entry pend_idx that is not written yet
+    bool prim_empty = false;                 // FUSED, warp-uniform: the primary pool is exhausted
+    uint32_t pend_idx = 0;
+    uint32_t idle_polls = 0;
+    uint32_t fin_local = 0;                  // FUSED, warp-uniform: primary rays this warp finished but has not reported yet
     RayId id = {false, false, 0u, 0u, 0u, 0u};
     V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
     float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
@@ -379,18 +413,20 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
-        const unsigned need = __ballot_sync(0xffffffffu, !have_ray && !exhausted);
-        if (need) {
+        const unsigned need = __ballot_sync(0xffffffffu, !have_ray && !exhausted && !pending);
+        if (need && !(FUSED && prim_empty)) {
             const int leader = __ffs(need) - 1;
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(need));
             base = __shfl_sync(0xffffffffu, base, leader);
-            if (!have_ray && !exhausted) {
+            if (FUSED && base + (uint32_t)__popc(need) >= total) prim_empty = true;
+            if (!have_ray && !exhausted && !pending) {
                 const uint32_t idx = base + __popc(need & lt_mask);
-                if (idx >= total) exhausted = true;
+                if (idx >= total) { if (!FUSED) exhausted = true; }
                 else {
                     have_ray = true;
-                    if (STAGE == 0) {
+                    if (STAGE != 1) {
+                        sec = false;
                         id = primary_ray(P, idx, tiles_x, o, d);
                     } else {
 #if RT_BOUNCE_ORDERED
@@ -418,8 +454,65 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 }
             }
         }
-        if (__ballot_sync(0xffffffffu, have_ray) == 0u) break;
-        const bool warp_exhausted = __ballot_sync(0xffffffffu, exhausted) != 0u;
+        if (FUSED) {
+            if (prim_empty && fin_local) {            // report this warp's finished primary rays (after everything they published)
+                __threadfence();
+                if (lane == 0) atomicAdd(P.counters + 3, fin_local);
+                fin_local = 0;
+            }
+            // Primary pool empty: idle lanes CLAIM bounce-queue entries (possibly ahead of the producers) ...
+            const unsigned need2 = __ballot_sync(0xffffffffu, !have_ray && !exhausted && !pending);
+            if (need2 && prim_empty) {
+                const int leader = __ffs(need2) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(P.counters + 1, (uint32_t)__popc(need2));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (!have_ray && !exhausted && !pending) { pend_idx = base + __popc(need2 & lt_mask); pending = true; }
+            }
+            // ... and start the ray as soon as its entry has been published (flag == this launch's epoch). A claim beyond the
+            // final queue length can only be recognised once every primary ray has finished (counters[3] == total).
+            if (pending) {
+                bool ready = false;
+                if (pend_idx < P.queue_capacity && ld_acquire_u32(P.queue_flags + pend_idx) == P.epoch) ready = true;
+                else if (ld_acquire_u32(P.counters + 3) == total) {
+                    if (pend_idx >= ld_volatile_u32(P.counters + 2)) { pending = false; exhausted = true; }
+                    else if (ld_acquire_u32(P.queue_flags + pend_idx) == P.epoch) ready = true;
+                }
+                if (ready) {
+                    const float4* q = P.queue + 3 * (size_t)pend_idx;
+                    const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
+                    id.lidx = __float_as_uint(q0.x);
+                    id.out = __float_as_uint(q2.z);
+                    o = {q0.y, q0.z, q0.w};
+                    d = {q1.x, q1.y, q1.z};
+                    col0 = q1.w; col1 = q2.x; col2 = q2.y;
+                    id.in_buffer = id.valid = true;
+                    pending = false; have_ray = true; sec = true;
+                    best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
+                    sp = 0;
+                    stack[sp++] = REF_DONE;
+                    in_blas = false;
+                    nodes = P.tlas_nodes;
+                    cur = P.tlas_root;
+                    if (cur == REF_EMPTY) cur = REF_DONE;
+                    slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
+                }
+            }
+            if (__ballot_sync(0xffffffffu, have_ray) == 0u) {
+                if (__ballot_sync(0xffffffffu, !exhausted) == 0u) break;      // every lane is done
+                if (__ballot_sync(0xffffffffu, pending) != 0u) {                  // only unpublished claims left: poll again
+                    __nanosleep(200);
+                    if (++idle_polls > (1u << 23)) {                              // ~2 s: protocol violated -> error flag instead of a hung GPU
+                        if (lane == 0 && P.error_flag) atomicExch(P.error_flag, 2);
+                        break;
+                    }
+                }
+                continue;
+            }
+        }
+        if (!FUSED && __ballot_sync(0xffffffffu, have_ray) == 0u) break;
+        // nobody is waiting for work any more -> no reason to leave the traversal loops early
+        const bool warp_exhausted = FUSED ? __ballot_sync(0xffffffffu, !have_ray && !exhausted) == 0u : __ballot_sync(0xffffffffu, exhausted) != 0u;
 
         // ================= two-level while-while traversal =================
         while (cur != REF_DONE) {
@@ -523,8 +616,34 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         float4 e0 = make_float4(0.f, 0.f, 0.f, 0.f), e1 = e0, e2 = e0;
         if (finish) {
             have_ray = false;
-            shade<STAGE, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+            if (FUSED) {
+                if (sec) shade<1, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c1);
+                else shade<0, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+            } else {
+                shade<STAGE == 2 ? 0 : STAGE, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+            }
         }
+        if (FUSED) {
+            // append the bounce rays (warp-aggregated slot allocation): entries, ONE fence for the warp, then the per-entry
+            // publication flags (= this launch's epoch). Finished primary rays are counted per warp and added to counters[3]
+            // only once the primary pool is empty (that is when consumers start to care); the count is released after the
+            // slot allocations it covers, so "counters[3] == total" implies counters[2] is final.
+            const unsigned em = __ballot_sync(0xffffffffu, enqueue);
+            if (em) {
+                const int leader = __ffs(em) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(P.counters + 2, (uint32_t)__popc(em));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                const uint32_t pos = base + __popc(em & lt_mask);
+                if (enqueue) {
+                    float4* q = P.queue + 3 * (size_t)pos;
+                    __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
+                }
+                __threadfence();
+                if (enqueue) st_volatile_u32(P.queue_flags + pos, P.epoch);
+            }
+            fin_local += (uint32_t)__popc(__ballot_sync(0xffffffffu, finish && !sec));    // reported at the top of the loop
+        } else {
 #if RT_BOUNCE_ORDERED
         if (STAGE == 0 && enqueue) {
             float4* q = P.queue + 3 * (size_t)id.tm;
@@ -534,8 +653,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
 #else
         if (STAGE == 0) enqueue_bounce(P, enqueue, e0, e1, e2, lane, lt_mask);
 #endif
+        }
     }
-    if (STATS) flush_stats<STAGE>(P, c, lane);
+    if (STATS) { flush_stats<STAGE == 2 ? 0 : STAGE>(P, c, lane); if (FUSED) flush_stats<1>(P, c1, lane); }
 }
 
 // ---- bounce index: per-tile hit masks -> compact tile-ordered list of ray slots -----------------------------
@@ -614,7 +734,7 @@ int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     uint32_t blocks = (uint32_t)(sm_count * blocks_per_sm);            // persistent: a multiple of the SM count
     const uint32_t max_useful = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
-    if (STAGE == 0 && blocks > max_useful) blocks = max_useful;
+    if (STAGE != 1 && blocks > max_useful) blocks = max_useful;
     if (blocks == 0) return 0;
     k_trace<STAGE, STATS, STACK, GENERAL><<<blocks, TRACE_THREADS, 0, st>>>(p);
     return 1;
@@ -622,6 +742,9 @@ int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
 
 template <bool STATS, int STACK, bool GENERAL>
 int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
+#if RT_FUSED_STAGES
+    if (p.bounces > 0 && (uint64_t)p.width * p.local_rows <= (uint64_t)RT_FUSED_MAX_PIXELS) return launch_stage<2, STATS, STACK, GENERAL>(p, sm_count, st);
+#endif
     int n = launch_stage<0, STATS, STACK, GENERAL>(p, sm_count, st);
     if (p.bounces > 0) {
 #if RT_BOUNCE_ORDERED
@@ -652,7 +775,8 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     if (tiles == 0) return 0;
     if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
 #if RT_BOUNCE_ORDERED
-    if (p.bounces > 0 && cudaMemsetAsync(p.tile_mask, 0, sizeof(uint32_t) * (size_t)tiles, st) != cudaSuccess) return -1;
+    const bool fused = RT_FUSED_STAGES && (uint64_t)p.width * p.local_rows <= (uint64_t)RT_FUSED_MAX_PIXELS;
+    if (p.bounces > 0 && !fused && cudaMemsetAsync(p.tile_mask, 0, sizeof(uint32_t) * (size_t)tiles, st) != cudaSuccess) return -1;
 #endif
     int n;
     if (stack_needed <= 64) n = launch_stack<64>(p, stats, sm_count, st);

@@ -13,7 +13,9 @@ VARIANTS = {
     "setup1": ["RT_SETUP_BATCH=1"],
     "setup2": ["RT_SETUP_BATCH=2"],
     "setup8": ["RT_SETUP_BATCH=8"],
-    "bounce_unordered": ["RT_BOUNCE_ORDERED=0"],
+    "bounce_unordered": ["RT_BOUNCE_ORDERED=0", "RT_FUSED_STAGES=0"],
+    "two_launches": ["RT_FUSED_STAGES=0"],
+    "always_fused": ["RT_FUSED_MAX_PIXELS=4000000000u"],
     "match": ["RT_SORT_USE_MATCH=1"],
     "ballot_5": ["RT_SORT_MIN_CTAS=5"],
     "ballot_6": ["RT_SORT_MIN_CTAS=6"],
