@@ -227,28 +227,34 @@ __device__ __forceinline__ rt_hit miss_record(float tmax) {
 // ---- ray identity ---------------------------------------------------------------------------------------
 struct RayId { bool in_buffer, valid; uint32_t lidx, pixel, tm, out; };   // tm: tile-major ray index of the launch; out: where the RGBA8 pixel goes
 
-// Primary ray `idx` (tile-major numbering: 8x4-pixel tiles, 32 consecutive ids per tile) -> raygen shader
-// (main.cpp:1033-1046); aspect_x/aspect_y are computed once on the host (tanf).
-__device__ __forceinline__ RayId primary_ray(const TraceParams& P, uint32_t idx, uint32_t tiles_x, V3& o, V3& d) {
+// Primary ray `idx` (tile-major numbering: 8x4-pixel tiles, 32 consecutive ids per tile). A lane keeps only `idx` while it
+// traverses; the pixel identity is recomputed for the epilogue (a dozen integer instructions instead of five live registers).
+__device__ __forceinline__ RayId primary_id(const TraceParams& P, uint32_t idx, uint32_t tiles_x, uint32_t& x, uint32_t& y) {
     RayId id;
     const uint32_t tile = idx >> 5, within = idx & 31u;
-    const uint32_t x = (tile % tiles_x) * 8u + (within & 7u);
+    x = (tile % tiles_x) * 8u + (within & 7u);
     const uint32_t lr = P.row0 + (tile / tiles_x) * 4u + (within >> 3);
     const uint32_t band = lr / P.block_rows;
-    const uint32_t y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
+    y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
     id.in_buffer = x < P.width && lr < P.row0 + P.local_rows;
     id.valid = id.in_buffer && y < P.height;
     id.lidx = lr * P.width + x;
     id.pixel = y * P.width + x;
     id.tm = idx;
     id.out = P.full_frame ? id.pixel : id.lidx;
+    return id;
+}
+// raygen shader (main.cpp:1033-1046); aspect_x/aspect_y are computed once on the host (tanf). Returns id.valid.
+__device__ __forceinline__ bool primary_ray(const TraceParams& P, uint32_t idx, uint32_t tiles_x, V3& o, V3& d) {
+    uint32_t x, y;
+    const RayId id = primary_id(P, idx, tiles_x, x, y);
     const float scx = (float)x + 0.5f, scy = (float)y + 0.5f;
     const float ndcx = scx / (float)P.width * 2.0f - 1.0f;
     const float ndcy = scy / (float)P.height * 2.0f - 1.0f;
     const float ax = ndcx * P.aspect_x, ay = ndcy * P.aspect_y;
     o = {P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]};
     d = {(ax * 1.0f + ay * 0.0f) + 0.0f, (ax * 0.0f + ay * -1.0f) + 0.0f, (ax * 0.0f + ay * 0.0f) + -1.0f};
-    return id;
+    return id.valid;
 }
 
 struct Counters { unsigned long long nodes = 0, tris = 0, insts = 0, hits = 0, rays = 0, edge = 0; };
@@ -270,9 +276,21 @@ __device__ __forceinline__ void flush_stats(const TraceParams& P, const Counters
 // ---- the shaders' epilogue: closest-hit (main.cpp:1080-1091, SBT rule main.cpp:1260-1262) / miss (main.cpp:1063-1066)
 // / imageStore (main.cpp:1054), plus the generation of the diffuse bounce ray (stage 0) or the blend (stage 1).
 template <int STAGE, bool STATS, bool GENERAL>
-__device__ __forceinline__ void shade(const TraceParams& P, const RayId id, const V3 o, const V3 d, float col0, float col1, float col2,
+__device__ __forceinline__ void shade(const TraceParams& P, const uint32_t rid, const uint32_t tiles_x, const V3 o, const V3 d,
                                       float best_t, float best_u, float best_v, float best_w0, uint32_t best_slot, uint32_t best_tri,
                                       bool& enqueue, float4& e0, float4& e1, float4& e2, Counters& c) {
+    // rid: tile-major ray index (stage 0) or ray-slot index of the bounce ray (stage 1: pixel ids and the primary colour are
+    // re-read from the slot {o.xyz lidx | d.xyz out | r g b -})
+    RayId id;
+    float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
+    if (STAGE == 0) { uint32_t x, y; id = primary_id(P, rid, tiles_x, x, y); }
+    else {
+        const float4* q = P.queue + 3 * (size_t)rid;
+        const float4 q2 = __ldcg(q + 2);
+        id.lidx = __float_as_uint(__ldcg(&q[0].w)); id.out = __float_as_uint(__ldcg(&q[1].w));
+        id.pixel = 0u; id.tm = rid; id.in_buffer = id.valid = true;
+        col0 = q2.x; col1 = q2.y; col2 = q2.z;
+    }
     const uint32_t lidx = id.lidx;
     if (!id.valid) {
         if (id.in_buffer) {
@@ -336,9 +354,9 @@ __device__ __forceinline__ void shade(const TraceParams& P, const RayId id, cons
             else { const float dl = sqrtf(dl2); dir = {dir.x / dl, dir.y / dl, dir.z / dl}; }
             const float eps = 0.0009765625f;
             enqueue = true;
-            e0 = make_float4(__uint_as_float(lidx), p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps);
-            e1 = make_float4(dir.x, dir.y, dir.z, sc0);
-            e2 = make_float4(sc1, sc2, __uint_as_float(id.out), 0.0f);
+            e0 = make_float4(p.x + n.x * eps, p.y + n.y * eps, p.z + n.z * eps, __uint_as_float(lidx));
+            e1 = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id.out));
+            e2 = make_float4(sc0, sc1, sc2, 0.0f);
         } else {
             reinterpret_cast<uchar4*>(P.rgba)[id.out] = make_uchar4(unorm8(sc0), unorm8(sc1), unorm8(sc2), 0);   // imageStore, main.cpp:1054
             if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
@@ -388,14 +406,12 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     // ---- per-lane ray state ----
     bool have_ray = false, exhausted = false;
     bool sec = STAGE == 1;                   // FUSED: this lane's ray is a bounce ray
-    bool pending = false;                    // FUSED: holds a claim on bounce-queue entry pend_idx that is not written yet
+    bool pending = false;                    // FUSED: holds a claim on bounce-queue entry rid that is not written yet
     bool prim_empty = false;                 // FUSED, warp-uniform: the primary pool is exhausted
-    uint32_t pend_idx = 0;
     uint32_t idle_polls = 0;
     uint32_t fin_local = 0;                  // FUSED, warp-uniform: primary rays this warp finished but has not reported yet
-    RayId id = {false, false, 0u, 0u, 0u, 0u};
+    uint32_t rid = 0;                        // tile-major index of the primary ray / slot of the bounce ray this lane traces
     V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
-    float col0 = 0.0f, col1 = 0.0f, col2 = 0.0f;
     int32_t cur = REF_DONE;
     int sp = 0;
     bool in_blas = false;
@@ -425,22 +441,21 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 if (idx >= total) { if (!FUSED) exhausted = true; }
                 else {
                     have_ray = true;
+                    bool valid = true;
                     if (STAGE != 1) {
                         sec = false;
-                        id = primary_ray(P, idx, tiles_x, o, d);
+                        rid = idx;
+                        valid = primary_ray(P, idx, tiles_x, o, d);
                     } else {
 #if RT_BOUNCE_ORDERED
-                        const float4* q = P.queue + 3 * (size_t)__ldg(P.bounce_index + idx);
+                        rid = __ldg(P.bounce_index + idx);
 #else
-                        const float4* q = P.queue + 3 * (size_t)idx;
+                        rid = idx;
 #endif
-                        const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
-                        id.lidx = __float_as_uint(q0.x);
-                        id.out = __float_as_uint(q2.z);
-                        o = {q0.y, q0.z, q0.w};
+                        const float4* q = P.queue + 3 * (size_t)rid;
+                        const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1);
+                        o = {q0.x, q0.y, q0.z};
                         d = {q1.x, q1.y, q1.z};
-                        col0 = q1.w; col1 = q2.x; col2 = q2.y;
-                        id.in_buffer = id.valid = true;
                     }
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
@@ -448,7 +463,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     stack[sp++] = REF_DONE;
                     in_blas = false;
                     nodes = P.tlas_nodes;
-                    cur = id.valid ? P.tlas_root : REF_DONE;
+                    cur = valid ? P.tlas_root : REF_DONE;
                     if (cur == REF_EMPTY) cur = REF_DONE;
                     slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
                 }
@@ -467,26 +482,22 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 uint32_t base = 0;
                 if (lane == leader) base = atomicAdd(P.counters + 1, (uint32_t)__popc(need2));
                 base = __shfl_sync(0xffffffffu, base, leader);
-                if (!have_ray && !exhausted && !pending) { pend_idx = base + __popc(need2 & lt_mask); pending = true; }
+                if (!have_ray && !exhausted && !pending) { rid = base + __popc(need2 & lt_mask); pending = true; }
             }
             // ... and start the ray as soon as its entry has been published (flag == this launch's epoch). A claim beyond the
             // final queue length can only be recognised once every primary ray has finished (counters[3] == total).
             if (pending) {
                 bool ready = false;
-                if (pend_idx < P.queue_capacity && ld_acquire_u32(P.queue_flags + pend_idx) == P.epoch) ready = true;
+                if (rid < P.queue_capacity && ld_acquire_u32(P.queue_flags + rid) == P.epoch) ready = true;
                 else if (ld_acquire_u32(P.counters + 3) == total) {
-                    if (pend_idx >= ld_volatile_u32(P.counters + 2)) { pending = false; exhausted = true; }
-                    else if (ld_acquire_u32(P.queue_flags + pend_idx) == P.epoch) ready = true;
+                    if (rid >= ld_volatile_u32(P.counters + 2)) { pending = false; exhausted = true; }
+                    else if (ld_acquire_u32(P.queue_flags + rid) == P.epoch) ready = true;
                 }
                 if (ready) {
-                    const float4* q = P.queue + 3 * (size_t)pend_idx;
-                    const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1), q2 = __ldcg(q + 2);
-                    id.lidx = __float_as_uint(q0.x);
-                    id.out = __float_as_uint(q2.z);
-                    o = {q0.y, q0.z, q0.w};
+                    const float4* q = P.queue + 3 * (size_t)rid;
+                    const float4 q0 = __ldcg(q), q1 = __ldcg(q + 1);
+                    o = {q0.x, q0.y, q0.z};
                     d = {q1.x, q1.y, q1.z};
-                    col0 = q1.w; col1 = q2.x; col2 = q2.y;
-                    id.in_buffer = id.valid = true;
                     pending = false; have_ray = true; sec = true;
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
@@ -617,10 +628,10 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         if (finish) {
             have_ray = false;
             if (FUSED) {
-                if (sec) shade<1, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c1);
-                else shade<0, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+                if (sec) shade<1, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c1);
+                else shade<0, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
             } else {
-                shade<STAGE == 2 ? 0 : STAGE, STATS, GENERAL>(P, id, o, d, col0, col1, col2, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+                shade<STAGE == 2 ? 0 : STAGE, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
             }
         }
         if (FUSED) {
@@ -646,9 +657,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         } else {
 #if RT_BOUNCE_ORDERED
         if (STAGE == 0 && enqueue) {
-            float4* q = P.queue + 3 * (size_t)id.tm;
+            float4* q = P.queue + 3 * (size_t)rid;
             __stcg(q, e0); __stcg(q + 1, e1); __stcg(q + 2, e2);
-            atomicOr(P.tile_mask + (id.tm >> 5), 1u << (id.tm & 31u));
+            atomicOr(P.tile_mask + (rid >> 5), 1u << (rid & 31u));
         }
 #else
         if (STAGE == 0) enqueue_bounce(P, enqueue, e0, e1, e2, lane, lt_mask);
