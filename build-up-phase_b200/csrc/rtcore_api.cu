@@ -25,10 +25,15 @@ struct rt_context {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     cudaStream_t copy_stream = nullptr;                           // device->host copies of finished row chunks (overlaps the next chunk's trace)
+    cudaStream_t aux_stream = nullptr;                            // second compute stream: odd row chunks of a frame (their CTAs fill the even chunks' kernel tails)
+    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
+    int trace_chunks = 1;                                         // row chunks of a DEVICE-output trace (RTCORE_TRACE_CHUNKS); measured 3.56/3.55/3.67/3.67/4.02/4.07 ms for
+                                                                  // 1/2/3/4/6/8 chunks: tail filling only pays back the extra launches, so the default is one launch
     cudaEvent_t chunk_ev[8]{};
-    int e2e_chunks = 1;                                            // row chunks of a host-output trace (RTCORE_E2E_CHUNKS). Measured on B200,
-                                                                   // inst10m 4K: 1/2/3/4/6/8 chunks -> 4.17/4.13/4.27/4.42/4.94/5.34 ms end to end:
-                                                                   // the extra launches and kernel tails cost what the overlapped PCIe copy saves
+    int e2e_chunks = 4;                                            // row chunks of a HOST-output trace (RTCORE_E2E_CHUNKS): chunk c is copied device->host
+                                                                   // while chunk c + 1 is traced; the chunks alternate over two compute streams so that the
+                                                                   // next chunk's CTAs fill the previous chunk's kernel tails. Measured on B200, inst10m 4K,
+                                                                   // 1/2/3/4/6/8 chunks: 4.19/3.88/3.90/3.85/4.15/4.17 ms end to end (one stream: 4.17/4.13/4.27/4.42)
     cudaDeviceProp prop{};
     std::string err;
     // shader data
@@ -160,8 +165,11 @@ int rt_create(int device_ordinal, rt_context** out) {
     if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     for (auto& e : ctx->chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     if (const char* v = getenv("RTCORE_E2E_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->e2e_chunks = k; }
+    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    if (const char* v = getenv("RTCORE_TRACE_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->trace_chunks = k; }
     if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+        cudaMalloc(&ctx->d_counters, 8 * 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     cudaMemset(ctx->d_error, 0, 64);
     *out = ctx;
     return RT_SUCCESS;
@@ -176,6 +184,9 @@ void rt_destroy(rt_context* ctx) {
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -714,46 +725,69 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         if (primary_hits_out) { if ((rc = ensure(ctx, &ctx->hits1, &ctx->hits1_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.primary_hits = (rt_hit*)ctx->hits1; }
         if (secondary_hits_out) { if ((rc = ensure(ctx, &ctx->hits2, &ctx->hits2_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.secondary_hits = (rt_hit*)ctx->hits2; }
     }
-    P.counters = ctx->d_counters;
-    if (bounces > 0) {
-        // ray slots are numbered tile-major over whole 8x4 tiles, so round the image up to tiles
-        const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((P.local_rows + 3u) >> 2), slots = tiles * 32u;
-        const size_t ray_bytes = align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256), idx_bytes = align_up(slots * 4, 256);
-        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, ray_bytes + idx_bytes + (tiles + 9 * (tiles / 64 + 2) + 16) * 4)) != RT_SUCCESS) return rc;
-        P.queue = (float4*)ctx->queue;
-        P.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes);
-        P.tile_mask = (uint32_t*)((uint8_t*)ctx->queue + ray_bytes + idx_bytes);
-        if (ctx->qflags_cap < slots) {                  // grown: new flags start at 0, an epoch no launch ever uses
-            if (ctx->qflags) { RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->qflags); ctx->qflags = nullptr; ctx->qflags_cap = 0; }
-            RT_CUDA(ctx, cudaMalloc((void**)&ctx->qflags, (slots + slots / 8) * 4));
-            ctx->qflags_cap = slots + slots / 8;
-            RT_CUDA(ctx, cudaMemsetAsync(ctx->qflags, 0, ctx->qflags_cap * 4, ctx->stream));
-        }
-        P.queue_flags = ctx->qflags;
-        P.error_flag = ctx->d_error;
-        P.queue_capacity = (uint32_t)slots;
-    }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }
-    // Host output: the frame is traced in row chunks (multiples of 8 rows) and every finished chunk is copied device->host
-    // on a second stream while the next one is traced. Device output: one launch.
+    // Row chunks (multiples of 8 rows). Host output: every finished chunk is copied device->host on the copy stream while the next
+    // one is traced. Several chunks alternate over TWO compute streams: the persistent kernels of chunk c + 1 are queued behind
+    // those of chunk c on the block scheduler, so their CTAs start as the CTAs of c retire and fill its kernel tails.
     const uint32_t total_rows = P.local_rows;
     uint32_t chunks = 1;
-    if (!dev_out && pixels >= (1u << 20)) chunks = (uint32_t)ctx->e2e_chunks;
+    if (pixels >= (1u << 20)) chunks = (uint32_t)(dev_out ? ctx->trace_chunks : ctx->e2e_chunks);
     uint32_t rows_per_chunk = (((total_rows + chunks - 1) / chunks) + 7u) & ~7u;
     if (rows_per_chunk == 0) rows_per_chunk = 8;
     chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
+    if (chunks > 8) return fail(ctx, RT_ERROR_INTERNAL, "too many row chunks");
+    const bool two_streams = chunks > 1;
+    // per-chunk scratch: ray slots (tile-major over whole 8x4 tiles), index list, tile masks + block sums, publication flags
+    size_t ray_off[9] = {0}, idx_off[9] = {0}, mask_off[9] = {0}, slot_off[9] = {0};
+    if (bounces > 0) {
+        size_t bytes = 0, slots_total = 0;
+        for (uint32_t c = 0; c < chunks; ++c) {
+            const uint32_t rows = total_rows - c * rows_per_chunk < rows_per_chunk ? total_rows - c * rows_per_chunk : rows_per_chunk;
+            const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((rows + 3u) >> 2), slots = tiles * 32u;
+            ray_off[c] = bytes; bytes += align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256);
+            idx_off[c] = bytes; bytes += align_up(slots * 4, 256);
+            mask_off[c] = bytes; bytes += align_up((tiles + tiles / 1024 + 16) * 4, 256);
+            slot_off[c] = slots_total; slots_total += slots;
+        }
+        slot_off[chunks] = slots_total;
+        if ((rc = ensure(ctx, &ctx->queue, &ctx->queue_cap, bytes)) != RT_SUCCESS) return rc;
+        if (ctx->qflags_cap < slots_total) {               // grown: new flags start at 0, an epoch no launch ever uses
+            if (ctx->qflags) { RT_CUDA(ctx, cudaDeviceSynchronize()); cudaFree(ctx->qflags); ctx->qflags = nullptr; ctx->qflags_cap = 0; }
+            RT_CUDA(ctx, cudaMalloc((void**)&ctx->qflags, (slots_total + slots_total / 8) * 4));
+            ctx->qflags_cap = slots_total + slots_total / 8;
+            RT_CUDA(ctx, cudaMemsetAsync(ctx->qflags, 0, ctx->qflags_cap * 4, ctx->stream));
+        }
+        P.error_flag = ctx->d_error;
+    }
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if (two_streams) {
+        RT_CUDA(ctx, cudaEventRecord(ctx->fork_ev, ctx->stream));
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->fork_ev, 0));
+    }
     for (uint32_t c = 0; c < chunks; ++c) {
         TraceParams Pc = P;
         if (++ctx->trace_epoch == 0u) ctx->trace_epoch = 1u;
         Pc.epoch = ctx->trace_epoch;
         Pc.row0 = c * rows_per_chunk;
         Pc.local_rows = total_rows - Pc.row0 < rows_per_chunk ? total_rows - Pc.row0 : rows_per_chunk;
-        int l = launch_trace(Pc, stats, stack_needed, ctx->prop.multiProcessorCount, ctx->stream);
+        Pc.counters = ctx->d_counters + 16 * c;
+        if (bounces > 0) {
+            Pc.queue = (float4*)((uint8_t*)ctx->queue + ray_off[c]);
+            Pc.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + idx_off[c]);
+            Pc.tile_mask = (uint32_t*)((uint8_t*)ctx->queue + mask_off[c]);
+            Pc.queue_flags = ctx->qflags + slot_off[c];
+            Pc.queue_capacity = (uint32_t)(slot_off[c + 1] - slot_off[c]);
+        }
+        cudaStream_t cs = (two_streams && (c & 1u)) ? ctx->aux_stream : ctx->stream;
+        int l = launch_trace(Pc, stats, stack_needed, ctx->prop.multiProcessorCount, cs);
         if (l < 0) return fail(ctx, RT_ERROR_CUDA, "trace launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         ctx->launches += (uint64_t)l;
-        if (!dev_out) RT_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], ctx->stream));
+        if (!dev_out) RT_CUDA(ctx, cudaEventRecord(ctx->chunk_ev[c], cs));
+    }
+    if (two_streams) {
+        RT_CUDA(ctx, cudaEventRecord(ctx->join_ev, ctx->aux_stream));
+        RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->join_ev, 0));
     }
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!dev_out) {
