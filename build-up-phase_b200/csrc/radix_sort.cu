@@ -246,6 +246,73 @@ __global__ void __launch_bounds__(SORT_THREADS, RT_SORT_MIN_CTAS) k_onesweep_pas
     }
 }
 
+// ---- segmented sort: one CTA sorts one whole segment (a BLAS of a batch) in shared memory -----------------------------
+// The build input is already grouped by BLAS, so sorting every segment by its Morton bits gives exactly what the global
+// sort by (BLAS id, Morton) gives — with one global read and one global write of the records instead of one per 8-bit
+// pass, no look-back chain between tiles and no scattered global stores. LSD passes of 8 bits over shared memory, same
+// warp-level match_any ranking as the onesweep pass (stable: ties keep the input order).
+constexpr int SEG_THREADS = 1024, SEG_WARPS = SEG_THREADS / 32, SEG_ITEMS = 12;
+static_assert(SEG_THREADS * SEG_ITEMS == (int)SEG_SORT_CAPACITY, "segment capacity");
+constexpr size_t SEG_SMEM_BYTES = sizeof(uint64_t) * SEG_SORT_CAPACITY + sizeof(uint32_t) * (SEG_WARPS * RADIX + RADIX + 32);
+
+__global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_sort(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
+                                                            const BlasRecord* __restrict__ recs, int shift0, int key_bits) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_keys + SEG_SORT_CAPACITY);   // [warp][digit]
+    uint32_t* s_loff = s_cnt + SEG_WARPS * RADIX;                                 // start of digit d in the segment-local order
+    uint32_t* s_wtot = s_loff + RADIX;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t first = recs[blockIdx.x].first, n = recs[blockIdx.x].tri_count;
+    if (n == 0) return;
+    const uint32_t wbase = warp * (32 * SEG_ITEMS) + lane;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint64_t key[SEG_ITEMS];
+#pragma unroll
+    for (int i = 0; i < SEG_ITEMS; ++i) { const uint32_t li = wbase + i * 32; key[i] = li < n ? in[first + li] : ~0ull; }   // padding sorts last, stays last
+    for (int shift = shift0; shift < shift0 + key_bits; shift += 8) {
+        for (int j = tid; j < SEG_WARPS * RADIX; j += SEG_THREADS) s_cnt[j] = 0;
+        __syncthreads();
+        uint32_t rank[SEG_ITEMS];
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+            const uint32_t m = __match_any_sync(0xffffffffu, d);
+            uint32_t prev = 0;
+            if (lane == __ffs(m) - 1) prev = atomicAdd(&s_cnt[warp * RADIX + d], (uint32_t)__popc(m));
+            rank[i] = __shfl_sync(0xffffffffu, prev, __ffs(m) - 1) + __popc(m & lt_mask);
+        }
+        __syncthreads();
+        uint32_t run = 0, inc = 0;
+        if (tid < RADIX) {            // thread d: exclusive scan over the warps' counts of digit d, then over the digits
+#pragma unroll 8
+            for (int w = 0; w < SEG_WARPS; ++w) { const uint32_t c = s_cnt[w * RADIX + tid]; s_cnt[w * RADIX + tid] = run; run += c; }
+            inc = run;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) s_wtot[warp] = inc;
+        }
+        __syncthreads();
+        if (tid < RADIX) {
+            uint32_t wb = 0;
+            for (int w = 0; w < warp; ++w) wb += s_wtot[w];
+            s_loff[tid] = wb + inc - run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) {
+            const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+            s_keys[s_loff[d] + s_cnt[warp * RADIX + d] + rank[i]] = key[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) key[i] = s_keys[wbase + i * 32];
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < SEG_ITEMS; ++i) { const uint32_t li = wbase + i * 32; if (li < n) out[first + li] = key[i]; }
+}
+
 }  // namespace
 
 SortPlan sort_plan(uint32_t n, int key_bits) {
@@ -265,6 +332,17 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
     const int base_shift = has_vals ? 0 : plan.packed_val_bits;
     *result_in_b = false;
     if (plan.n == 0) return 0;
+    if (plan.seg_records && !has_vals) {                 // segmented path: one kernel, result in keys_b
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG_SMEM_BYTES) != cudaSuccess) return -1;
+            attr_set = true;
+        }
+        k_seg_sort<<<plan.n_segments, SEG_THREADS, SEG_SMEM_BYTES, stream>>>(keys_a, keys_b, plan.seg_records, base_shift, plan.seg_key_bits);
+        *result_in_b = true;
+        if (cudaGetLastError() != cudaSuccess) return -1;
+        return 1;
+    }
     uint32_t* hist = (uint32_t*)scratch;
     uint32_t* counters = hist + MAX_PASSES * RADIX;
     uint32_t* states = counters + 16;

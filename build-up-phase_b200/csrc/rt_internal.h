@@ -78,14 +78,19 @@ struct GeomDesc {
 };
 
 // ---- radix sort (csrc/radix_sort.cu) ---------------------------------------------------------
+struct BlasRecord;
 struct SortPlan {
     uint32_t n = 0;
     int passes = 0;             // 8-bit digits
     uint32_t tiles = 0;
     size_t scratch_bytes = 0;   // histogram + look-back state
     int packed_val_bits = 0;    // > 0: records are 64-bit words `key << packed_val_bits | value` (vals arrays unused)
+    // segmented path (batches of small BLASes, packed records): the input is already grouped by segment, every segment
+    // fits one CTA's shared memory and is sorted there by its low seg_key_bits key bits in one kernel (no global passes)
+    const struct BlasRecord* seg_records = nullptr; uint32_t n_segments = 0; int seg_key_bits = 0;
 };
 SortPlan sort_plan(uint32_t n, int key_bits);
+constexpr uint32_t SEG_SORT_CAPACITY = 12288;   // records one CTA sorts in shared memory (1024 threads x 12)
 // Sorts (keys, vals) by the low key_bits of the key, stable. vals_a == nullptr selects the packed format. Result ends in keys_a/vals_a or keys_b/vals_b;
 // *result_in_b tells which. Returns the number of kernels launched, or <0 on a launch error.
 int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,

@@ -391,6 +391,14 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
     }
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
 
+    // batches of BLASes that each fit one CTA's shared memory: segmented sort (one kernel) instead of 5 global passes
+    {
+        uint32_t max_seg = 0;
+        for (uint32_t b = 0; b < n_blas; ++b) max_seg = recs[b].tri_count > max_seg ? recs[b].tri_count : max_seg;
+        if (sp.packed_val_bits > 0 && max_seg <= SEG_SORT_CAPACITY && !(build_flags & RT_BUILD_NO_SEGMENTED_SORT)) {
+            sp.seg_records = st->records; sp.n_segments = n_blas; sp.seg_key_bits = (int)MORTON_BITS;
+        }
+    }
     // ---- device build ----
     a.geoms = d_descs; a.n_geoms = n_geoms; a.geom_tri_first = d_prefix; a.n_tris = N; a.n_blas = n_blas; a.seg_bits = seg_bits;
     a.tris_sorted = st->tris; a.nodes = st->nodes; a.records = st->records; a.bounds_ordered = d_bounds; a.sort = sp;

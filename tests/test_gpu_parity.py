@@ -92,16 +92,21 @@ def test_instanced_batched_scene(rt, ctx, oracle):
 
 
 @pytest.mark.parametrize("flags", [0, 0x200], ids=["packed-sort", "pair-sort"])
-@pytest.mark.parametrize("kind", ["tess", "dupkeys", "tiny"])
+@pytest.mark.parametrize("kind", ["tess", "dupkeys", "tiny", "seg", "dupseg"])
 def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
     """Integer/byte work must be bit-exact: sorted Morton keys, primitive order, tree topology and
     every node box of the GPU LBVH equal the CPU restatement's (both sort record formats). The CPU side finds the
     radix tree top-down (Karras), the GPU bottom-up in shared-memory tiles: "dupkeys" exercises the index-augmented
-    prefix rule on long runs of equal keys, "tiny" a tree smaller than one tile."""
+    prefix rule on long runs of equal keys, "tiny" a tree smaller than one tile. "seg" / "dupseg" / "tiny" fit one CTA's
+    shared memory and take the segmented sort (dupseg: exactly its capacity), the others the global onesweep sort."""
     if kind == "tess":
         scene = scenes.tess_scene(nx=120, ny=70, width=64, height=64, bounces=0)
     elif kind == "dupkeys":
         scene = scenes.duplicate_key_scene(20_000)
+    elif kind == "seg":
+        scene = scenes.tess_scene(nx=80, ny=70, width=64, height=64, bounces=0)
+    elif kind == "dupseg":
+        scene = scenes.duplicate_key_scene(12288)
     else:
         scene = scenes.tess_scene(nx=9, ny=7, width=64, height=64, bounces=0)
     blas = ctx.build_blas(scene.blases[0], flags=flags)
@@ -112,8 +117,15 @@ def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
     o = oracle.OracleScene(scene)
     oinfo, onodes, otris, okeys, oprims = o.blas_export(0)
     assert info.triangle_count == oinfo.triangle_count == scene.triangle_count
-    if kind == "dupkeys":
+    if kind in ("dupkeys", "dupseg"):
         assert np.count_nonzero(keys[1:] == keys[:-1]) > info.triangle_count // 2
+    if kind in ("seg", "tiny") and flags == 0:
+        # the segmented and the global sort are interchangeable, bit for bit
+        blas2 = ctx.build_blas(scene.blases[0], flags=0x400)
+        keys2, prims2 = ctx.last_sorted_keys()
+        nodes2, tris2 = blas2.export()
+        blas2.free()
+        assert np.array_equal(keys, keys2) and np.array_equal(prims, prims2) and np.array_equal(nodes, nodes2) and np.array_equal(tris, tris2)
     assert np.array_equal(keys, okeys), "sorted Morton keys differ"
     assert np.array_equal(prims, oprims), "sorted primitive order differs (sort not stable?)"
     assert np.array_equal(tris[:, :11], otris[:, :11]), "sorted triangle records differ"
