@@ -90,7 +90,7 @@ struct SortPlan {
     const struct BlasRecord* seg_records = nullptr; uint32_t n_segments = 0; int seg_key_bits = 0;
 };
 SortPlan sort_plan(uint32_t n, int key_bits);
-constexpr uint32_t SEG_SORT_CAPACITY = 12288;   // records one CTA sorts in shared memory (1024 threads x 12)
+constexpr uint32_t SEG_SORT_CAPACITY = 11264;   // records one CTA sorts in shared memory (1024 threads x 11)
 // Sorts (keys, vals) by the low key_bits of the key, stable. vals_a == nullptr selects the packed format. Result ends in keys_a/vals_a or keys_b/vals_b;
 // *result_in_b tells which. Returns the number of kernels launched, or <0 on a launch error.
 int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a, uint32_t* vals_b,

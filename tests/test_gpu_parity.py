@@ -106,7 +106,7 @@ def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
     elif kind == "seg":
         scene = scenes.tess_scene(nx=80, ny=70, width=64, height=64, bounces=0)
     elif kind == "dupseg":
-        scene = scenes.duplicate_key_scene(12288)
+        scene = scenes.duplicate_key_scene(11264)
     else:
         scene = scenes.tess_scene(nx=9, ny=7, width=64, height=64, bounces=0)
     blas = ctx.build_blas(scene.blases[0], flags=flags)
