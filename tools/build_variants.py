@@ -30,6 +30,8 @@ VARIANTS = {
     "sort16_4": ["RT_SORT_ITEMS=16", "RT_SORT_MIN_CTAS=4"],
     "sort16_3": ["RT_SORT_ITEMS=16", "RT_SORT_MIN_CTAS=3"],
     "tile256": ["RT_TREE_TILE=256"],
+    "tile512": ["RT_TREE_TILE=512"],
+    "tile64": ["RT_TREE_TILE=64"],
     "tile256_4": ["RT_TREE_TILE=256", "RT_TREE_MIN_CTAS=4"],
     "tile512_2": ["RT_TREE_TILE=512", "RT_TREE_MIN_CTAS=2"],
     "split_16_16": _split(16, 16),
