@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtcore.so")
 SOURCES = ["rtcore_api.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu",
            os.path.join("..", "host", "rtcore_io.cpp")]     # host-side .obj / image I/O (include/rtcore_io.h), no device code
-HEADERS = ["rt_internal.h", "rt_device.cuh", os.path.join("..", "..", "include", "rtcore.h"),
+HEADERS = ["rt_internal.h", "rt_device.cuh", "seg_sort.cuh", os.path.join("..", "..", "include", "rtcore.h"),
            os.path.join("..", "..", "include", "rtcore_io.h")]
 
 NVCC_FLAGS = [

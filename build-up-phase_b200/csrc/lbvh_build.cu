@@ -24,6 +24,7 @@
 #include <float.h>
 
 #include "rt_device.cuh"
+#include "seg_sort.cuh"
 
 namespace rt {
 
@@ -147,6 +148,91 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
     const uint64_t key = ((uint64_t)blas << MORTON_BITS) | (uint64_t)morton30(plo, phi, slo, shi);
     if (vb) keys[t] = (key << vb) | (uint64_t)t;
     else { keys[t] = key; vals[t] = t; }
+}
+
+// ---- batches of small BLASes: setup + Morton + sort of one whole BLAS in ONE CTA ---------------------------------------
+// When every BLAS of the batch fits one CTA's shared memory (SEG_SORT_CAPACITY triangles), CTA b does for BLAS b what
+// k_tri_setup, k_tri_morton and the sort do for the general case: fetch + bake its triangles (48-B records out), reduce
+// ITS bounds in the block (no global atomics), compute the Morton keys (each thread re-reads its own records: cache hits),
+// and sort the packed records in shared memory (seg_sort.cuh). One launch, the records
+// written once, the keys written once, already sorted.
+__global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ prefix, uint32_t n_geoms,
+                                                                  const BlasRecord* __restrict__ recs, TriRec* __restrict__ out,
+                                                                  uint64_t* __restrict__ keys_out, int vb) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);
+    __shared__ float s_red[6][SEG_WARPS];
+    __shared__ float s_bounds[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t blas = blockIdx.x, first = recs[blas].first, n = recs[blas].tri_count;
+    if (n == 0) return;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    uint32_t g = 0, gbeg = 1, gend = 0;                  // empty range: the first triangle looks its geometry up
+#pragma unroll 1
+    for (int i = 0; i < SEG_ITEMS; ++i) {
+        const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG_THREADS;
+        if (t >= n) continue;
+        const uint32_t T = first + t;
+        if (T < gbeg || T >= gend) { g = find_geom(prefix, n_geoms, T); gbeg = __ldg(prefix + g); gend = __ldg(prefix + g + 1); }
+        const GeomDesc& G = geoms[g];
+        const uint32_t p = T - gbeg;
+        uint32_t i0, i1, i2;
+        if (G.idx) { i0 = __ldg(G.idx + 3 * (size_t)p); i1 = __ldg(G.idx + 3 * (size_t)p + 1); i2 = __ldg(G.idx + 3 * (size_t)p + 2); }
+        else { i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2; }
+        const float* a = G.verts + (size_t)i0 * G.stride_f;
+        const float* b = G.verts + (size_t)i1 * G.stride_f;
+        const float* c = G.verts + (size_t)i2 * G.stride_f;
+        V3 v0 = {__ldg(a), __ldg(a + 1), __ldg(a + 2)};
+        V3 v1 = {__ldg(b), __ldg(b + 1), __ldg(b + 2)};
+        V3 v2 = {__ldg(c), __ldg(c + 1), __ldg(c + 2)};
+        if (G.has_xform) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
+        float4* dst = reinterpret_cast<float4*>(out + T);
+        dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+        dst[1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+        dst[2] = make_float4(v2.z, __uint_as_float(G.geo_index), __uint_as_float(p), __uint_as_float(G.blas | (G.flags << 24)));
+        const float tlo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
+        const float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], tlo[k]); hi[k] = fmaxf(hi[k], thi[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if (lane == 0) { s_red[k][warp] = lo[k]; s_red[3 + k][warp] = hi[k]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float v = s_red[k][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = k < 3 ? fminf(v, w) : fmaxf(v, w); }
+            if (lane == 0) s_bounds[k] = v;
+        }
+    }
+    __syncthreads();
+    const float slo[3] = {s_bounds[0], s_bounds[1], s_bounds[2]}, shi[3] = {s_bounds[3], s_bounds[4], s_bounds[5]};
+#pragma unroll
+    for (int i = 0; i < SEG_ITEMS; ++i) {
+        const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG_THREADS;
+        uint64_t rec = ~0ull;                              // padding sorts last and stays last
+        if (t < n) {
+            // this thread's own record, written a moment ago (L1/L2 hit): cheaper than keeping 33 centre floats live across the reduction
+            const float4* src = reinterpret_cast<const float4*>(out + first + t);
+            const float4 q0 = src[0], q1 = src[1], q2 = src[2];
+            const float plo[3] = {fminf(fminf(q0.x, q0.w), q1.z), fminf(fminf(q0.y, q1.x), q1.w), fminf(fminf(q0.z, q1.y), q2.x)};
+            const float phi[3] = {fmaxf(fmaxf(q0.x, q0.w), q1.z), fmaxf(fmaxf(q0.y, q1.x), q1.w), fmaxf(fmaxf(q0.z, q1.y), q2.x)};
+            rec = ((((uint64_t)blas << MORTON_BITS) | (uint64_t)morton30(plo, phi, slo, shi)) << vb) | (uint64_t)(first + t);
+        }
+        s_keys[t] = rec;
+    }
+    __syncthreads();
+    seg_sort_passes(seg_smem, vb, (int)MORTON_BITS);
+    for (uint32_t i = tid; i < n; i += SEG_THREADS) keys_out[first + i] = s_keys[i];
 }
 
 // ---- hierarchy emission + refit, one bottom-up pass ---------------------------------------------------
@@ -483,16 +569,29 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
     *sorted_in_b = false;
     if (a.n_tris == 0) return 0;
     if (ev) cudaEventRecord(ev->e[0], st);
-    k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
-    ++launches;
-    if (ev) cudaEventRecord(ev->e[1], st);
     const int vb = a.sort.packed_val_bits;
-    k_tri_morton<<<div_up(a.n_tris, 256), 256, 0, st>>>(a.tris_unsorted, a.n_tris, a.bounds_ordered, a.s.keys_a, a.s.vals_a, vb);
-    ++launches;
-    if (ev) cudaEventRecord(ev->e[2], st);
-    int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, vb ? nullptr : a.s.vals_a, vb ? nullptr : a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, sorted_in_b);
-    if (sl < 0) return -1;
-    launches += sl;
+    if (a.sort.seg_records && vb > 0 && a.sort.seg_fused) {
+        // every BLAS fits one CTA: setup + Morton + sort fused, one launch (its time is reported as sort_ms)
+        static bool attr_set = false;
+        if (!attr_set) {
+            if (cudaFuncSetAttribute(k_seg_setup_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG_SMEM_BYTES) != cudaSuccess) return -1;
+            attr_set = true;
+        }
+        if (ev) { cudaEventRecord(ev->e[1], st); cudaEventRecord(ev->e[2], st); }
+        k_seg_setup_sort<<<a.sort.n_segments, SEG_THREADS, SEG_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb);
+        ++launches;
+        *sorted_in_b = true;
+    } else {
+        k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
+        ++launches;
+        if (ev) cudaEventRecord(ev->e[1], st);
+        k_tri_morton<<<div_up(a.n_tris, 256), 256, 0, st>>>(a.tris_unsorted, a.n_tris, a.bounds_ordered, a.s.keys_a, a.s.vals_a, vb);
+        ++launches;
+        if (ev) cudaEventRecord(ev->e[2], st);
+        int sl = sort_pairs(a.sort, a.s.keys_a, a.s.keys_b, vb ? nullptr : a.s.vals_a, vb ? nullptr : a.s.vals_b, a.s.sort_scratch, a.s.error_flag, st, sorted_in_b);
+        if (sl < 0) return -1;
+        launches += sl;
+    }
     const uint64_t* keys = *sorted_in_b ? a.s.keys_b : a.s.keys_a;
     const uint32_t* vals = *sorted_in_b ? a.s.vals_b : a.s.vals_a;
     if (ev) cudaEventRecord(ev->e[3], st);

@@ -97,6 +97,13 @@ __device__ __forceinline__ uint32_t quant10(float c, float lo, float hi) {
     if (!(q >= 0.0f)) q = 0.0f;
     return (uint32_t)q;
 }
+// 30-bit Morton code of a box centre inside scene box [slo,shi]
+__device__ __forceinline__ uint32_t morton30_centre(float cx, float cy, float cz, const float* slo, const float* shi) {
+    uint32_t x = quant10(cx, slo[0], shi[0]);
+    uint32_t y = quant10(cy, slo[1], shi[1]);
+    uint32_t z = quant10(cz, slo[2], shi[2]);
+    return (expand10(x) << 2) | (expand10(y) << 1) | expand10(z);
+}
 // 30-bit Morton code of the centre of primitive box [plo,phi] inside scene box [slo,shi]
 __device__ __forceinline__ uint32_t morton30(const float* plo, const float* phi, const float* slo, const float* shi) {
     float cx = (plo[0] + phi[0]) * 0.5f, cy = (plo[1] + phi[1]) * 0.5f, cz = (plo[2] + phi[2]) * 0.5f;

@@ -397,6 +397,7 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
         for (uint32_t b = 0; b < n_blas; ++b) max_seg = recs[b].tri_count > max_seg ? recs[b].tri_count : max_seg;
         if (sp.packed_val_bits > 0 && max_seg <= SEG_SORT_CAPACITY && !(build_flags & RT_BUILD_NO_SEGMENTED_SORT)) {
             sp.seg_records = st->records; sp.n_segments = n_blas; sp.seg_key_bits = (int)MORTON_BITS;
+            sp.seg_fused = !(build_flags & RT_BUILD_NO_FUSED_SETUP);
         }
     }
     // ---- device build ----

@@ -1,0 +1,91 @@
+// seg_sort.cuh — one CTA sorts one whole segment (a BLAS of a batch) in shared memory; shared by the stand-alone
+// k_seg_sort (radix_sort.cu) and the fused setup + Morton + sort kernel of the batched build (lbvh_build.cu).
+#pragma once
+#include "rt_internal.h"
+
+namespace rt {
+
+// The build input is already grouped by BLAS, so sorting every segment by its Morton bits gives exactly what the global
+// sort by (BLAS id, Morton) gives — with one global read and one global write of the records instead of one per 8-bit
+// pass, no look-back chain between tiles and no scattered global stores.
+// LSD passes of FOUR bits with a match-free ranking: a thread owns SEG_ITEMS consecutive records (blocked order), counts
+// its 16 digits in one 64-bit register of 4-bit fields (which also yields each record's rank among the thread's own
+// records), and a block-wide exclusive scan of the per-thread counts (4 registers of 4 x 16-bit fields: warp shuffles,
+// then one warp over the 32 warp totals) gives every (thread, digit) its start in the sorted order. Stable by
+// construction. (The first version ranked 8-bit digits with MATCH.ANY like the onesweep pass: 0.33 ms for 10 M records,
+// bound by the rate of MATCH.ANY itself, ~60 cycles per warp instruction and SM; profiles/README.md r01x/r01y.)
+constexpr int SEG_THREADS = 1024, SEG_WARPS = SEG_THREADS / 32, SEG_ITEMS = 11;     // 11: odd stride -> blocked shared-memory access without bank pile-ups
+static_assert(SEG_THREADS * SEG_ITEMS == (int)SEG_SORT_CAPACITY, "segment capacity");
+constexpr size_t SEG_SMEM_BYTES = sizeof(uint64_t) * SEG_SORT_CAPACITY + sizeof(uint16_t) * 16 * SEG_THREADS + sizeof(uint64_t) * (4 * SEG_WARPS + 4) + 64;
+
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int o) {
+    const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), o);
+    return ((uint64_t)hi << 32) | lo;
+}
+// digits 4q .. 4q+3 of a register of 4-bit fields -> 16-bit fields
+__device__ __forceinline__ uint64_t expand4(uint64_t cnt, int q) {
+    const uint32_t f = (uint32_t)(cnt >> (16 * q)) & 0xFFFFu;
+    return (uint64_t)(f & 15u) | ((uint64_t)((f >> 4) & 15u) << 16) | ((uint64_t)((f >> 8) & 15u) << 32) | ((uint64_t)((f >> 12) & 15u) << 48);
+}
+
+// Sorts the SEG_SORT_CAPACITY records in s_keys (padding = ~0 sorts last) by bits [shift0, shift0 + key_bits). All threads of
+// the 1024-thread CTA call it after a __syncthreads(); the records are sorted and visible to all threads on return.
+__device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shift0, int key_bits) {
+    uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);                         // the segment, sorted by the passes so far
+    uint64_t* s_wsum = s_keys + SEG_SORT_CAPACITY;                                     // [4][SEG_WARPS] packed warp totals -> exclusive warp bases
+    uint64_t* s_tot = s_wsum + 4 * SEG_WARPS;                                          // [4] packed digit totals
+    uint16_t* s_off = reinterpret_cast<uint16_t*>(s_tot + 4);                          // [16][SEG_THREADS] start of (digit, thread)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint64_t key[SEG_ITEMS];
+    for (int shift = shift0; shift < shift0 + key_bits; shift += 4) {
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) key[i] = s_keys[tid * SEG_ITEMS + i];
+        uint64_t cnt = 0, rk = 0;                                                      // 16 x 4-bit digit counts; 4-bit rank of record i among this thread's records of its digit
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) {
+            const int d4 = 4 * ((int)(key[i] >> shift) & 15);
+            rk |= ((cnt >> d4) & 15ull) << (4 * i);
+            cnt += 1ull << d4;
+        }
+        uint64_t ex[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const uint64_t own = expand4(cnt, q);
+            uint64_t inc = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint64_t t = shfl_up_u64(inc, o); if (lane >= o) inc += t; }
+            if (lane == 31) s_wsum[q * SEG_WARPS + warp] = inc;
+            ex[q] = inc - own;                                                         // exclusive within the warp
+        }
+        __syncthreads();                                                               // also: every thread has read its records
+        if (warp < 4) {                                                                // warp q: exclusive scan of the 32 warp totals of digits 4q .. 4q+3
+            const uint64_t own = s_wsum[warp * SEG_WARPS + lane];
+            uint64_t inc = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint64_t t = shfl_up_u64(inc, o); if (lane >= o) inc += t; }
+            s_wsum[warp * SEG_WARPS + lane] = inc - own;
+            if (lane == 31) s_tot[warp] = inc;
+        }
+        __syncthreads();
+        {
+            uint32_t dbase = 0;                                                        // start of the digit in the sorted order
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint64_t tot = s_tot[q], e = ex[q] + s_wsum[q * SEG_WARPS + warp];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    s_off[(4 * q + k) * SEG_THREADS + tid] = (uint16_t)(dbase + (uint32_t)((e >> (16 * k)) & 0xFFFFu));
+                    dbase += (uint32_t)((tot >> (16 * k)) & 0xFFFFu);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < SEG_ITEMS; ++i) {
+            const int d = (int)(key[i] >> shift) & 15;
+            s_keys[(uint32_t)s_off[d * SEG_THREADS + tid] + (uint32_t)((rk >> (4 * i)) & 15ull)] = key[i];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace rt

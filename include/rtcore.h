@@ -52,6 +52,7 @@ enum {
 #define RT_BUILD_PREFER_FAST_TRACE  0x4u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, main.cpp:751 */
 #define RT_BUILD_INSTANCES_ON_DEVICE 0x100u /* rt_build_tlas: the rt_instance array is device memory */
 #define RT_BUILD_NO_PACKED_SORT     0x200u /* keep (key, id) pairs in separate arrays during the sort (the general path; test hook) */
+#define RT_BUILD_NO_FUSED_SETUP     0x800u /* segmented sort, but triangle setup and Morton keys as separate kernels (test hook) */
 #define RT_BUILD_NO_SEGMENTED_SORT  0x400u /* always use the global onesweep sort, also for BLASes that fit one CTA's shared memory (test hook) */
 
 /* ---- instance flags (rt_instance.flags, low 8 bits like VkGeometryInstanceFlagsKHR) ---- */

@@ -121,11 +121,12 @@ def test_lbvh_build_matches_oracle_bit_for_bit(rt, ctx, oracle, flags, kind):
         assert np.count_nonzero(keys[1:] == keys[:-1]) > info.triangle_count // 2
     if kind in ("seg", "tiny") and flags == 0:
         # the segmented and the global sort are interchangeable, bit for bit
-        blas2 = ctx.build_blas(scene.blases[0], flags=0x400)
-        keys2, prims2 = ctx.last_sorted_keys()
-        nodes2, tris2 = blas2.export()
-        blas2.free()
-        assert np.array_equal(keys, keys2) and np.array_equal(prims, prims2) and np.array_equal(nodes, nodes2) and np.array_equal(tris, tris2)
+        for other in (0x400, 0x800):       # global sort; segmented sort with separate setup / Morton kernels
+            blas2 = ctx.build_blas(scene.blases[0], flags=other)
+            keys2, prims2 = ctx.last_sorted_keys()
+            nodes2, tris2 = blas2.export()
+            blas2.free()
+            assert np.array_equal(keys, keys2) and np.array_equal(prims, prims2) and np.array_equal(nodes, nodes2) and np.array_equal(tris, tris2), hex(other)
     assert np.array_equal(keys, okeys), "sorted Morton keys differ"
     assert np.array_equal(prims, oprims), "sorted primitive order differs (sort not stable?)"
     assert np.array_equal(tris[:, :11], otris[:, :11]), "sorted triangle records differ"
