@@ -14,7 +14,7 @@
 //                 the second child to arrive at a split unions the boxes and continues. Splits inside
 //                 a CTA's 128-leaf tile meet in shared memory, only the tile-border subtrees use global
 //                 arrival counters. Because the BLAS id is the key prefix, every BLAS of a batch is
-//                 exactly one subtree of the global radix tree; subtrees of <= 4 triangles collapse
+//                 exactly one subtree of the global radix tree; subtrees of <= 2 triangles collapse
 //                 into a leaf; the thread that completes a BLAS publishes its root/bounds/height.
 // TLAS: same machinery over instance world boxes (k_inst_setup computes world->object in fp64).
 //

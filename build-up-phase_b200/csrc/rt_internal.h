@@ -24,7 +24,10 @@ constexpr int32_t REF_DONE  = 0x7FFFFFFF;
 constexpr int32_t REF_POP_INSTANCE = 0x7FFFFFFE;
 constexpr int32_t REF_EMPTY = RT_REF_EMPTY;      // 0x7FFFFFFD
 constexpr int32_t REF_SENTINEL_MIN = 0x7FFFFFF0;
-constexpr int BLAS_LEAF_MAX = 4;
+#ifndef RT_BLAS_LEAF_MAX
+#define RT_BLAS_LEAF_MAX 2
+#endif
+constexpr int BLAS_LEAF_MAX = RT_BLAS_LEAF_MAX;   // <= 8 (leaf refs pack count - 1 into 3 bits); the oracle's LEAF_MAX must match for the bit-for-bit build test
 constexpr int TLAS_LEAF_MAX = 1;
 constexpr uint32_t MORTON_BITS = 30;
 constexpr uint32_t MAX_PRIMS = 1u << 28;         // leaf ref packs (first << 3) into 31 bits

@@ -85,7 +85,7 @@ struct Tri { V3 v0, v1, v2; uint32_t geo, prim, flags; };   // flags: VkGeometry
 
 constexpr int32_t REF_DONE = 0x7FFFFFFF;
 constexpr int32_t REF_EMPTY = 0x7FFFFFFD;
-constexpr int LEAF_MAX = 4;
+constexpr int LEAF_MAX = 2;      // triangles per BLAS leaf (the product's BLAS_LEAF_MAX; measured on B200: 1/2/3/4/6/8 -> 3124/3236/3198/3145/2981/2823 Mrays/s)
 static inline int32_t leaf_ref(uint32_t first, uint32_t count) { return ~(int32_t)((first << 3) | (count - 1)); }
 static inline bool ref_is_leaf(int32_t r) { return r < 0; }
 static inline uint32_t leaf_first(int32_t r) { return ((uint32_t)~r) >> 3; }

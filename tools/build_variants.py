@@ -10,6 +10,11 @@ def _split(t0, t1):
 VARIANTS = {
     "base": [],
     "tile128": ["RT_TREE_TILE=128"],
+    "leaf1": ["RT_BLAS_LEAF_MAX=1"],
+    "leaf2": ["RT_BLAS_LEAF_MAX=2"],
+    "leaf3": ["RT_BLAS_LEAF_MAX=3"],
+    "leaf6": ["RT_BLAS_LEAF_MAX=6"],
+    "leaf8": ["RT_BLAS_LEAF_MAX=8"],
     "setup1": ["RT_SETUP_BATCH=1"],
     "setup2": ["RT_SETUP_BATCH=2"],
     "setup8": ["RT_SETUP_BATCH=8"],
