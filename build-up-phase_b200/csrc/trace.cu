@@ -43,9 +43,10 @@ constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
 constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
 #ifndef RT_NODE_CAP
-#define RT_NODE_CAP 4
+#define RT_NODE_CAP 6
 #endif
-constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner node loop when fewer lanes are still in it (0 = never)
+constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner node loop when fewer lanes are still in it (0 = never);
+                                                          // measured 0/2/4/6/8 -> 3028/3138/3247/3273/3265 Mrays/s (profiles r02b)
 #ifndef RT_BOUNCE_ORDERED
 #define RT_BOUNCE_ORDERED 1
 #endif
@@ -72,7 +73,7 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 #define RT_LDG256 0
 #endif
 #ifndef RT_FAST_SLAB
-#define RT_FAST_SLAB 0
+#define RT_FAST_SLAB 1
 #endif
 
 // Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128

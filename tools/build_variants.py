@@ -10,6 +10,10 @@ def _split(t0, t1):
 VARIANTS = {
     "base": [],
     "tile128": ["RT_TREE_TILE=128"],
+    "thr8": ["RT_REFILL_THRESHOLD=8"], "thr10": ["RT_REFILL_THRESHOLD=10"], "thr14": ["RT_REFILL_THRESHOLD=14"], "thr16": ["RT_REFILL_THRESHOLD=16"],
+    "cap0": ["RT_NODE_CAP=0"], "cap2": ["RT_NODE_CAP=2"], "cap6": ["RT_NODE_CAP=6"], "cap8": ["RT_NODE_CAP=8"],
+    "blk7": ["RT_TRACE_MIN_BLOCKS=7"], "blk6": ["RT_TRACE_MIN_BLOCKS=6"], "blk10": ["RT_TRACE_MIN_BLOCKS=10"],
+    "fastslab": ["RT_FAST_SLAB=1"],
     "leaf1": ["RT_BLAS_LEAF_MAX=1"],
     "leaf2": ["RT_BLAS_LEAF_MAX=2"],
     "leaf3": ["RT_BLAS_LEAF_MAX=3"],
