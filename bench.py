@@ -192,6 +192,18 @@ def ncu_traffic(kind: str, workload: str):
         return None, None
 
 
+def ncu_issue(workload: str):
+    """The bound that actually limits the trace kernels (they are latency/issue bound, not HBM bound): issue-slot utilisation, lanes
+    per instruction and cache hit rates of both stages from the committed ncu capture; None without one."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_trace"]
+        if t["workload"] != workload:
+            return None
+        return {k: t[k] for k in ("issue_slot_utilisation_pct", "lanes_per_instruction", "l1_hit_pct", "l2_hit_pct", "source") if k in t}
+    except Exception:
+        return None
+
+
 def workload_config(scene, args, n_gpus):
     n_tris = SOUP_SIZES[args.workload][0] if args.workload in SOUP_SIZES else scene.triangle_count
     return {"workload": f"{args.workload}: {scene.name}, {n_tris} triangles in {len(scene.blases)} BLAS, "
@@ -500,6 +512,9 @@ def run_gpu(args):
             "gpu_launches": int(l1 - l0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": "k_trace (stage 0 + stage 1 of one frame)", "peak_source": peak_src,
+                         "note": "achieved = ALGORITHMIC bytes (served mostly by L1/L2) over HBM peak, as SURVEY 8(d) defines it; the kernels are bound by "
+                                 "issue slots x SIMD divergence and L1/L2 latency: see `sm_issue`",
+                         "sm_issue": ncu_issue(args.workload),
                          "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass",
                          "algorithmic_bytes_per_launch": algo_bytes / world,
                          "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,

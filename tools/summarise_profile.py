@@ -83,7 +83,16 @@ def traffic(tag):
     if os.path.exists(tp):
         ks = json.load(open(tp))
         per = {("stage%d" % i): _bytes(k["dram__bytes_read.sum"]) + _bytes(k["dram__bytes_write.sum"]) for i, k in enumerate(ks)}
-        out["k_trace"] = {"workload": "inst10m", "dram_bytes_per_frame": sum(per.values()), "per_stage": per, "source": f"profiles/prof_trace_{tag}.json"}
+        def _f(k, key):
+            try:
+                return float(str(k.get(key, "nan")).split()[0].replace(",", ""))
+            except ValueError:
+                return None
+        out["k_trace"] = {"workload": "inst10m", "dram_bytes_per_frame": sum(per.values()), "per_stage": per, "source": f"profiles/prof_trace_{tag}.json",
+                          "issue_slot_utilisation_pct": {("stage%d" % i): _f(k, "derived.issue_slot_utilisation_pct") for i, k in enumerate(ks)},
+                          "lanes_per_instruction": {("stage%d" % i): _f(k, "smsp__thread_inst_executed_per_inst_executed.ratio") for i, k in enumerate(ks)},
+                          "l1_hit_pct": {("stage%d" % i): _f(k, "l1tex__t_sector_hit_rate.pct") for i, k in enumerate(ks)},
+                          "l2_hit_pct": {("stage%d" % i): _f(k, "lts__t_sector_hit_rate.pct") for i, k in enumerate(ks)}}
     bp = os.path.join(PR, f"prof_build_{tag}.json")
     if os.path.exists(bp):
         ks = json.load(open(bp))
