@@ -210,7 +210,7 @@ def workload_config(scene, args, n_gpus):
                         f"{len(scene.instances)} instances, {scene.width}x{scene.height} primary + {scene.bounces} diffuse bounce",
             "triangles": n_tris, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
             "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated"
-            + ("" if n_gpus == 1 else {"p2p": "; every rank stores its pixels straight into rank 0's framebuffer over NVLink (CUDA IPC), NCCL all-reduce as frame barrier",
+            + ("" if n_gpus == 1 else {"p2p": "; every rank stores its pixels straight into rank 0's framebuffer over NVLink (CUDA IPC), frame barrier: " + ("stream-ordered counters in that buffer" if args.barrier == "flags" else "NCCL all-reduce"),
                                        "allgather": "; packed bands, NCCL all-gather, unpack on rank 0",
                                        "gather": "; packed bands, NCCL gather to rank 0, unpack"}[args.gather]),
             "l2_policy": "inputs larger than L2 (BVH nodes + triangles >> 126 MB); no flush between iterations"
@@ -361,7 +361,7 @@ def run_gpu(args):
             handles = [None, None]
             if rank == 0:
                 for k in range(2):
-                    ptr, h = ctx.frame_share_create(W * H * 4)
+                    ptr, h = ctx.frame_share_create(W * H * 4 + 256)      # + the frame's "done" and "free" counters
                     shared_ptrs.append(ptr); handles[k] = h
             dist.broadcast_object_list(handles, src=0)
             if rank != 0:
@@ -374,13 +374,27 @@ def run_gpu(args):
     host_np = host_frame.numpy()
     step_no = [0]
 
-    def step_multi():
-        """One frame at N > 1; returns the tensor holding the finished frame on rank 0 (None elsewhere)."""
+    def step_multi(consume=None):
+        """One frame at N > 1; on rank 0 `consume(frame)` is enqueued once the frame is complete. Returns the frame tensor on rank 0."""
         if mode == "p2p":
-            k = step_no[0] & 1
+            k, use = step_no[0] & 1, step_no[0] >> 1
             step_no[0] += 1
+            if args.barrier == "flags":
+                done_ctr, free_ctr = shared_ptrs[k] + W * H * 4, shared_ptrs[k] + W * H * 4 + 4
+                ctx.flag_wait_ge(free_ctr, use)                 # rank 0 has handed buffer k back `use` times: safe to overwrite it
+                ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
+                ctx.flag_add(done_ctr)                          # this rank's pixels of frame k have landed in rank 0's memory
+                if rank == 0:
+                    ctx.flag_wait_ge(done_ctr, world * (use + 1))   # ... and so have everybody else's: the frame is complete
+                    if consume:
+                        consume(shared[k])
+                    ctx.flag_add(free_ctr)
+                    return shared[k]
+                return None
             ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
             dist.all_reduce(token)          # frame-complete barrier on the stream: every rank's stores have landed
+            if rank == 0 and consume:
+                consume(shared[k])
             return shared[k] if rank == 0 else None
         ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
         if mode == "gather":
@@ -389,6 +403,8 @@ def run_gpu(args):
             dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
         if rank == 0:
             ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
+            if consume:
+                consume(frame)
             return frame
         return None
 
@@ -403,9 +419,7 @@ def run_gpu(args):
         if world == 1:
             ctx.trace(tlas, cam, W, H, bounces, rgba_out=host_np)
         else:
-            done = step_multi()
-            if rank == 0:
-                host_frame.copy_(done, non_blocking=True)
+            step_multi(consume=lambda f: host_frame.copy_(f, non_blocking=True))
             torch.cuda.synchronize()
 
     def barrier():
@@ -484,10 +498,12 @@ def run_gpu(args):
         del prim_c, sec_c
     else:
         import zlib
-        done = step_multi()                 # the assembled frame of the multi-GPU path must be the single-GPU frame, bit for bit
+        # the assembled frame of the multi-GPU path must be the single-GPU frame, bit for bit
+        step_multi(consume=lambda f: host_frame.copy_(f, non_blocking=True))
         torch.cuda.synchronize()
+        ctx.sync()                          # also surfaces a device watchdog (flag wait timed out) as an error
         if rank == 0:
-            crc = {"rgba": zlib.crc32(done.cpu().numpy().tobytes()), "gather": mode}
+            crc = {"rgba": zlib.crc32(host_frame.numpy().tobytes()), "gather": mode, "barrier": args.barrier if mode == "p2p" else "nccl"}
 
     if rank == 0:
         hbm, peak_src = peaks()
@@ -580,6 +596,10 @@ def main():
                     help="N > 1: how the bands reach rank 0. p2p = every rank's trace kernel stores its pixels straight into rank 0's "
                          "framebuffer over NVLink (CUDA IPC mapping) + one tiny NCCL all-reduce as the frame-complete barrier; "
                          "allgather / gather = packed bands + NCCL collective + unpack kernel on rank 0")
+    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],
+                    help="--gather p2p: how a frame is declared complete. flags = stream-ordered counters in rank 0's shared frame "
+                         "(every rank adds 1 after its trace, rank 0 waits for N; a second counter hands the buffer back): no collective "
+                         "on the step; nccl = a 4-byte all-reduce per frame")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()

@@ -181,6 +181,8 @@ constexpr size_t TRACE_QUEUE_ENTRY_BYTES = 48;
 // per ray slot: the ray record + its index entry + its share of the tile mask / block sums (rounded up)
 constexpr size_t TRACE_BOUNCE_AUX_BYTES_PER_SLOT = 4 + 1;
 int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st);
+int launch_flag_add(uint32_t* counter, cudaStream_t st);
+int launch_flag_wait_ge(const uint32_t* counter, uint32_t target, int* error_flag, cudaStream_t st);
 int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,
                        uint32_t part_count, uint8_t* out, cudaStream_t st);
 

@@ -214,7 +214,10 @@ int rt_set_stream(rt_context* ctx, void* cuda_stream) {
 
 int rt_sync(rt_context* ctx) {
     if (!ctx) return RT_ERROR_INVALID_ARG;
+    int h_err = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (h_err) { cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream); return fail(ctx, RT_ERROR_INTERNAL, "device watchdog fired (code %d: 2 = bounce queue, 3 = flag wait timed out)", h_err); }
     return RT_SUCCESS;
 }
 
@@ -875,6 +878,21 @@ int rt_frame_share_free(rt_context* ctx, void* device_ptr) {
     if (!ctx || !device_ptr) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaFree(device_ptr));
+    return RT_SUCCESS;
+}
+
+int rt_flag_add(rt_context* ctx, uint32_t* counter) {
+    if (!ctx || !counter) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (launch_flag_add(counter, ctx->stream) < 0) return fail(ctx, RT_ERROR_CUDA, "flag launch failed");
+    ctx->launches += 1;
+    return RT_SUCCESS;
+}
+int rt_flag_wait_ge(rt_context* ctx, const uint32_t* counter, uint32_t target) {
+    if (!ctx || !counter) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (launch_flag_wait_ge(counter, target, ctx->d_error, ctx->stream) < 0) return fail(ctx, RT_ERROR_CUDA, "flag launch failed");
+    ctx->launches += 1;
     return RT_SUCCESS;
 }
 

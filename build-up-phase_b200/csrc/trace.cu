@@ -726,6 +726,22 @@ __global__ void __launch_bounds__(BIDX_THREADS) k_bounce_index(const uint32_t* _
         while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1u; index[pos++] = (w0 + k) * 32u + (uint32_t)b; }
     }
 }
+// ---- stream-ordered flags in (peer) device memory: the multi-GPU frame handshake without a collective ----------------------
+__global__ void k_flag_add(uint32_t* counter) {
+    __threadfence_system();
+    atomicAdd_system(counter, 1u);
+}
+__global__ void k_flag_wait_ge(const uint32_t* counter, uint32_t target, int* error_flag) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if ((int32_t)(v - target) >= 0) break;
+        __nanosleep(spins < 64 ? 100 : 1000);
+        if (++spins > (1u << 22)) { if (error_flag) atomicExch(error_flag, 3); break; }   // ~4 s: give up instead of hanging the GPU
+    }
+}
+
 __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ packed_all, uint32_t width, uint32_t height,
                                                     uint32_t block_rows, uint32_t part_count, uint32_t rows_per_part, uchar4* __restrict__ out) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -796,6 +812,15 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     else return -2;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return n;
+}
+
+int launch_flag_add(uint32_t* counter, cudaStream_t st) {
+    k_flag_add<<<1, 1, 0, st>>>(counter);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+int launch_flag_wait_ge(const uint32_t* counter, uint32_t target, int* error_flag, cudaStream_t st) {
+    k_flag_wait_ge<<<1, 1, 0, st>>>(counter, target, error_flag);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
 
 int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,

@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
-    "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_last_trace_stats", "rt_last_trace_ms",
+    "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
@@ -180,6 +180,8 @@ def load(build_if_missing: bool = True):
     L.rt_frame_share_open.argtypes = [vp, vp, C.POINTER(vp)]
     L.rt_frame_share_close.argtypes = [vp, vp]
     L.rt_frame_share_free.argtypes = [vp, vp]
+    L.rt_flag_add.argtypes = [vp, vp]
+    L.rt_flag_wait_ge.argtypes = [vp, vp, u32]
     L.rt_last_trace_stats.argtypes = [vp, C.POINTER(RtTraceStats)]
     L.rt_last_trace_ms.argtypes = [vp]
     L.rt_last_trace_ms.restype = C.c_float
@@ -484,6 +486,12 @@ class Context:
 
     def frame_share_free(self, ptr: int):
         self._check(self.L.rt_frame_share_free(self.h, ptr))
+
+    def flag_add(self, counter_ptr: int):
+        self._check(self.L.rt_flag_add(self.h, counter_ptr))
+
+    def flag_wait_ge(self, counter_ptr: int, target: int):
+        self._check(self.L.rt_flag_wait_ge(self.h, counter_ptr, target & 0xFFFFFFFF))
 
     def trace_rows(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, block_rows: int, part_index: int,
                    part_count: int, rgba, prim=None, sec=None, device: bool = False, stats: bool = False,

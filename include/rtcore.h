@@ -278,6 +278,13 @@ RT_API int  rt_unpack_rows(rt_context* ctx, const uint8_t* packed_all, uint32_t 
 RT_API int  rt_frame_share_create(rt_context* ctx, uint64_t bytes, void** device_ptr_out, uint8_t handle_out[64]);
 RT_API int  rt_frame_share_open(rt_context* ctx, const uint8_t handle[64], void** device_ptr_out);
 RT_API int  rt_frame_share_close(rt_context* ctx, void* mapped_device_ptr);     /* a pointer from rt_frame_share_open */
+/* Stream-ordered 32-bit flags in (peer-)device memory, e.g. in the tail of a shared frame: the frame-complete / buffer-free
+ * handshake between the ranks without a collective. rt_flag_add enqueues "counter += 1" (system scope, after everything enqueued
+ * before it on the context stream, including stores to peer memory); rt_flag_wait_ge makes the context stream wait until
+ * *counter >= target (a one-thread kernel polling with back-off; after ~4 s it gives up, sets the context's error state —
+ * reported by the next synchronising call as RT_ERROR_INTERNAL — and lets the stream continue rather than hanging the GPU). */
+RT_API int  rt_flag_add(rt_context* ctx, uint32_t* counter_device_ptr);
+RT_API int  rt_flag_wait_ge(rt_context* ctx, const uint32_t* counter_device_ptr, uint32_t target);
 RT_API int  rt_frame_share_free(rt_context* ctx, void* device_ptr);             /* a pointer from rt_frame_share_create */
 
 RT_API int  rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out);

@@ -269,6 +269,21 @@ def test_row_partition_and_unpack(rt, ctx, oracle):
     assert np.array_equal(view.cpu().numpy(), full)
     del view
     ctx.frame_share_free(ptr)
+    # stream-ordered flags (the multi-GPU frame handshake): add / wait on a counter in the tail of a shared frame
+    ptr, _ = ctx.frame_share_create(scene.width * scene.height * 4 + 256)
+    ctr = ptr + scene.width * scene.height * 4
+    ctx.flag_wait_ge(ctr, 0)
+    ctx.flag_add(ctr)
+    ctx.flag_add(ctr)
+    ctx.flag_wait_ge(ctr, 2)
+    ctx.sync()
+    assert int(rt.device_view(ctr, 4, "cuda:0").view(torch.int32).cpu()[0]) == 2
+    ctx.flag_wait_ge(ctr, 3)              # nobody will ever add the third: the wait gives up after ~4 s and reports instead of hanging
+    with pytest.raises(rt.RtError) as e:
+        ctx.sync()
+    assert e.value.code == rt.RT_ERROR_INTERNAL
+    ctx.sync()                            # the error state is cleared
+    ctx.frame_share_free(ptr)
     sh.free()
 
 
