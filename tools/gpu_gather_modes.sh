@@ -2,7 +2,7 @@
 # N-GPU bench in the three gather modes. Usage: gpu_gather_modes.sh TAG N [steps]
 mkdir -p gpurun_out
 TAG=${1:-x}; N=${2:-2}; STEPS=${3:-20}
-for mode in p2p p2p:nccl gather; do
+for mode in ${MODES:-p2p p2p:nccl gather}; do
   timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29540+N)) bench.py --gpus $N --steps $STEPS --warmup 3 --no-cpu-baseline --build-reps 1 --gather ${mode%%:*} --barrier $( [ "${mode##*:}" = "nccl" ] && echo nccl || echo flags ) \
       > gpurun_out/gather_${TAG}_${mode}_n$N.json 2> gpurun_out/gather_${TAG}_${mode}_n$N.err
   echo "$mode N=$N rc=$?"
