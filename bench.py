@@ -359,16 +359,43 @@ def run_gpu(args):
         else:
             # two framebuffers on rank 0 (double buffer: frame k may still be read while frame k + 1 is written), mapped by every rank
             handles = [None, None]
-            if rank == 0:
-                for k in range(2):
-                    ptr, h = ctx.frame_share_create(W * H * 4 + 256)      # + the frame's "done" and "free" counters
-                    shared_ptrs.append(ptr); handles[k] = h
+            ok = 1
+            try:
+                if os.environ.get("RTCORE_BENCH_NO_IPC"):
+                    raise RuntimeError("disabled by RTCORE_BENCH_NO_IPC (test hook of the fallback)")
+                if rank == 0:
+                    for k in range(2):
+                        ptr, h = ctx.frame_share_create(W * H * 4 + 256)      # + the frame's "done" and "free" counters
+                        shared_ptrs.append(ptr); handles[k] = h
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write(f"[bench] shared framebuffer unavailable on rank 0 ({e}); falling back to the NCCL gather\n")
+                ok = 0
             dist.broadcast_object_list(handles, src=0)
-            if rank != 0:
-                shared_ptrs = [ctx.frame_share_open(h) for h in handles]
-            if rank == 0:
-                shared = [rtcore.device_view(p, W * H * 4, dev).view(H, W, 4) for p in shared_ptrs]
-            token = torch.zeros(1, dtype=torch.int32, device=dev)
+            try:
+                if rank != 0 and ok and handles[0] is not None:
+                    shared_ptrs = [ctx.frame_share_open(h) for h in handles]
+                elif rank != 0:
+                    ok = 0
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write(f"[bench] rank {rank} cannot map rank 0's framebuffer ({e}); falling back to the NCCL gather\n")
+                ok = 0
+            agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+            if int(agree.item()) == 0:          # CUDA IPC not usable here: every rank takes the packed-bands + NCCL path instead
+                for p_ in shared_ptrs:
+                    try:
+                        (ctx.frame_share_free if rank == 0 else ctx.frame_share_close)(p_)
+                    except Exception:   # noqa: BLE001
+                        pass
+                shared_ptrs = []
+                mode = "gather"
+                args.gather = "gather"
+                gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
+                gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
+            else:
+                if rank == 0:
+                    shared = [rtcore.device_view(p, W * H * 4, dev).view(H, W, 4) for p in shared_ptrs]
+                token = torch.zeros(1, dtype=torch.int32, device=dev)
     frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
     host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
     host_np = host_frame.numpy()
