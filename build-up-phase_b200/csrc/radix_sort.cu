@@ -282,10 +282,13 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
     *result_in_b = false;
     if (plan.n == 0) return 0;
     if (plan.seg_records && !has_vals) {                 // segmented path: one kernel, result in keys_b
-        static bool attr_set = false;
-        if (!attr_set) {
+        // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it once per device
+        static bool attr_set[64] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev]) {
             if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG_SMEM_BYTES) != cudaSuccess) return -1;
-            attr_set = true;
+            if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         k_seg_sort<<<plan.n_segments, SEG_THREADS, SEG_SMEM_BYTES, stream>>>(keys_a, keys_b, plan.seg_records, base_shift, plan.seg_key_bits);
         *result_in_b = true;
