@@ -30,10 +30,11 @@ struct rt_context {
     int trace_chunks = 1;                                         // row chunks of a DEVICE-output trace (RTCORE_TRACE_CHUNKS); measured 3.56/3.55/3.67/3.67/4.02/4.07 ms for
                                                                   // 1/2/3/4/6/8 chunks: tail filling only pays back the extra launches, so the default is one launch
     cudaEvent_t chunk_ev[8]{};
-    int e2e_chunks = 4;                                            // row chunks of a HOST-output trace (RTCORE_E2E_CHUNKS): chunk c is copied device->host
-                                                                   // while chunk c + 1 is traced; the chunks alternate over two compute streams so that the
-                                                                   // next chunk's CTAs fill the previous chunk's kernel tails. Measured on B200, inst10m 4K,
-                                                                   // 1/2/3/4/6/8 chunks: 4.19/3.88/3.90/3.85/4.15/4.17 ms end to end (one stream: 4.17/4.13/4.27/4.42)
+    int e2e_chunks = 3;                                            // row chunks of a HOST-output trace (RTCORE_E2E_CHUNKS): chunk c is copied device->host
+                                                                   // while chunk c + 1 is traced; the chunks alternate over two compute streams (the next
+                                                                   // chunk's CTAs fill the previous chunk's kernel tails) and shrink towards the end of the
+                                                                   // frame (3 : 2 : 1), since only the last copy is exposed. Measured on B200, inst10m 4K:
+                                                                   // 1 chunk 4.19 ms; equal chunks 2/3/4: 3.88/3.90/3.85; shrinking 3/4/5/6: 3.59/3.72/3.81/3.85
     cudaDeviceProp prop{};
     std::string err;
     // shader data
@@ -745,17 +746,29 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     const uint32_t total_rows = P.local_rows;
     uint32_t chunks = 1;
     if (pixels >= (1u << 20)) chunks = (uint32_t)(dev_out ? ctx->trace_chunks : ctx->e2e_chunks);
-    uint32_t rows_per_chunk = (((total_rows + chunks - 1) / chunks) + 7u) & ~7u;
-    if (rows_per_chunk == 0) rows_per_chunk = 8;
-    chunks = (total_rows + rows_per_chunk - 1) / rows_per_chunk;
-    if (chunks > 8) return fail(ctx, RT_ERROR_INTERNAL, "too many row chunks");
+    // chunk c covers rows [row_begin[c], row_begin[c + 1]), multiples of 8. Host output: the chunks SHRINK towards the end of the frame
+    // (weights 4 : 3 : 2 : 1 for four chunks), because only the copy of the last chunk is not hidden behind a trace
+    uint32_t row_begin[10] = {0};
+    {
+        if (chunks > 8) chunks = 8;
+        const uint32_t wsum = dev_out ? chunks : chunks * (chunks + 1) / 2;
+        uint32_t acc = 0, n = 0;
+        for (uint32_t c = 0; c < chunks; ++c) {
+            acc += dev_out ? 1u : chunks - c;
+            uint32_t end = (uint32_t)(((uint64_t)total_rows * acc / wsum + 7u) & ~7ull);
+            if (end > total_rows || c + 1 == chunks) end = total_rows;
+            if (end > row_begin[n]) row_begin[++n] = end;
+        }
+        chunks = n ? n : 1;
+        row_begin[chunks] = total_rows;
+    }
     const bool two_streams = chunks > 1;
     // per-chunk scratch: ray slots (tile-major over whole 8x4 tiles), index list, tile masks + block sums, publication flags
     size_t ray_off[9] = {0}, idx_off[9] = {0}, mask_off[9] = {0}, slot_off[9] = {0};
     if (bounces > 0) {
         size_t bytes = 0, slots_total = 0;
         for (uint32_t c = 0; c < chunks; ++c) {
-            const uint32_t rows = total_rows - c * rows_per_chunk < rows_per_chunk ? total_rows - c * rows_per_chunk : rows_per_chunk;
+            const uint32_t rows = row_begin[c + 1] - row_begin[c];
             const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((rows + 3u) >> 2), slots = tiles * 32u;
             ray_off[c] = bytes; bytes += align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256);
             idx_off[c] = bytes; bytes += align_up(slots * 4, 256);
@@ -781,8 +794,8 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         TraceParams Pc = P;
         if (++ctx->trace_epoch == 0u) ctx->trace_epoch = 1u;
         Pc.epoch = ctx->trace_epoch;
-        Pc.row0 = c * rows_per_chunk;
-        Pc.local_rows = total_rows - Pc.row0 < rows_per_chunk ? total_rows - Pc.row0 : rows_per_chunk;
+        Pc.row0 = row_begin[c];
+        Pc.local_rows = row_begin[c + 1] - row_begin[c];
         Pc.counters = ctx->d_counters + 16 * c;
         if (bounces > 0) {
             Pc.queue = (float4*)((uint8_t*)ctx->queue + ray_off[c]);
@@ -804,8 +817,8 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     RT_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     if (!dev_out) {
         for (uint32_t c = 0; c < chunks; ++c) {
-            const size_t p0 = (size_t)c * rows_per_chunk * width;
-            const size_t np = (size_t)((total_rows - c * rows_per_chunk < rows_per_chunk ? total_rows - c * rows_per_chunk : rows_per_chunk)) * width;
+            const size_t p0 = (size_t)row_begin[c] * width;
+            const size_t np = (size_t)(row_begin[c + 1] - row_begin[c]) * width;
             RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
             RT_CUDA(ctx, cudaMemcpyAsync(rgba_out + 4 * p0, P.rgba + 4 * p0, np * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out + p0, P.primary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));

@@ -1,7 +1,7 @@
 #!/bin/bash
 # e2e (host-buffer rt_trace) as a function of the number of row chunks whose D2H copy overlaps the next chunk's trace
 mkdir -p gpurun_out
-for k in 1 2 3 4 6 8; do
+for k in ${CHUNK_LIST:-1 2 3 4 6 8}; do
   RTCORE_E2E_CHUNKS=$k timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --build-reps 1 > gpurun_out/e2e_chunks_$k.json 2> gpurun_out/e2e_chunks_$k.err
   python - <<PY
 import json
