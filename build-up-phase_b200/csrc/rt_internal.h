@@ -164,6 +164,7 @@ struct TraceParams {
     const float* hit_records; uint32_t n_records;
     float miss[3];
     uint8_t* rgba;              // packed local_rows x width x 4, or (full_frame) the whole height x width x 4 image, possibly peer memory
+    uint32_t bgra;              // 1: store B,G,R,A byte order (the sample's swapchain format) instead of R,G,B,A
     uint32_t full_frame;        // 1: pixels are stored at their final position y * width + x (multi-GPU: straight into rank 0's frame over NVLink)
     rt_hit* primary_hits;       // may be null
     rt_hit* secondary_hits;     // may be null

@@ -720,6 +720,7 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     if (full_frame && !dev_out) return fail(ctx, RT_ERROR_INVALID_ARG, "RT_TRACE_OUT_FULL_FRAME needs RT_TRACE_OUT_DEVICE");
     TraceParams P{};
     P.full_frame = full_frame ? 1u : 0u;
+    P.bgra = (flags & RT_TRACE_OUT_BGRA) ? 1u : 0u;
     P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
     for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[3 * (size_t)ctx->rp.miss_index + k]; }
     // raygen constants of main.cpp:1038-1039; tan is evaluated once on the host in fp32

@@ -210,6 +210,12 @@ __device__ __forceinline__ unsigned char unorm8(float c) {
     return (unsigned char)__float2int_rn(v * 255.0f);
 }
 
+// rgba8 imageStore of vec4(hitValue, 0.0) (main.cpp:1054); bgra: the byte order of the sample's B8G8R8A8 swapchain (main.cpp:50)
+__device__ __forceinline__ uchar4 store_pixel(const TraceParams& P, float r, float g, float b) {
+    const unsigned char cr = unorm8(r), cg = unorm8(g), cb = unorm8(b);
+    return P.bgra ? make_uchar4(cb, cg, cr, 0) : make_uchar4(cr, cg, cb, 0);
+}
+
 __device__ __forceinline__ void load_w2o(const InstanceRec* R, float* w2o) {
     const float4* m4 = reinterpret_cast<const float4*>(R);
     const float4 m0 = __ldg(m4), m1 = __ldg(m4 + 1), m2 = __ldg(m4 + 2);
@@ -359,13 +365,13 @@ __device__ __forceinline__ void shade(const TraceParams& P, const uint32_t rid, 
             e1 = make_float4(dir.x, dir.y, dir.z, __uint_as_float(id.out));
             e2 = make_float4(sc0, sc1, sc2, 0.0f);
         } else {
-            reinterpret_cast<uchar4*>(P.rgba)[id.out] = make_uchar4(unorm8(sc0), unorm8(sc1), unorm8(sc2), 0);   // imageStore, main.cpp:1054
+            reinterpret_cast<uchar4*>(P.rgba)[id.out] = store_pixel(P, sc0, sc1, sc2);   // imageStore, main.cpp:1054
             if (P.secondary_hits) P.secondary_hits[lidx] = miss_record(P.tmax);
         }
     } else {
         if (P.secondary_hits) P.secondary_hits[lidx] = rec;
         const float f0 = 0.5f * col0 + 0.5f * sc0, f1 = 0.5f * col1 + 0.5f * sc1, f2 = 0.5f * col2 + 0.5f * sc2;
-        reinterpret_cast<uchar4*>(P.rgba)[id.out] = make_uchar4(unorm8(f0), unorm8(f1), unorm8(f2), 0);
+        reinterpret_cast<uchar4*>(P.rgba)[id.out] = store_pixel(P, f0, f1, f2);
     }
 }
 

@@ -31,6 +31,7 @@ RT_TRACE_OUT_DEVICE = 0x1
 RT_TRACE_STATS = 0x2
 RT_TRACE_ASYNC = 0x4
 RT_TRACE_OUT_FULL_FRAME = 0x8
+RT_TRACE_OUT_BGRA = 0x10
 RT_REF_EMPTY = 0x7FFFFFFD
 
 EXPORTED_SYMBOLS = [
@@ -454,12 +455,12 @@ class Context:
         return cam
 
     def trace(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int = 0, want_hits: bool = False,
-              stats: bool = False, rgba_out: Optional[np.ndarray] = None):
+              stats: bool = False, rgba_out: Optional[np.ndarray] = None, bgra: bool = False):
         """Host-buffer trace (the reference-facing call): returns (rgba[h,w,4], primary hits, secondary hits)."""
         rgba = rgba_out if rgba_out is not None else np.empty((height, width, 4), dtype=np.uint8)
         prim = np.empty((height, width), dtype=HIT_DTYPE) if want_hits else None
         sec = np.empty((height, width), dtype=HIT_DTYPE) if want_hits else None
-        flags = RT_TRACE_STATS if stats else 0
+        flags = (RT_TRACE_STATS if stats else 0) | (RT_TRACE_OUT_BGRA if bgra else 0)
         self._check(self.L.rt_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, _ptr(rgba), _ptr(prim), _ptr(sec)))
         return rgba, prim, sec
 

@@ -82,6 +82,8 @@ enum {
 #define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
 #define RT_TRACE_STATS      0x2u  /* also accumulate traversal counters (slower kernel variant) */
 #define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait) */
+#define RT_TRACE_OUT_BGRA   0x10u /* store B,G,R,A byte order — the sample copies its image raw into a B8G8R8A8 swapchain (main.cpp:50,971-974,1371-1375);
+                                    the default is the logical R,G,B,A of imageStore(vec4(hitValue, 0.0)) */
 #define RT_TRACE_OUT_FULL_FRAME 0x8u /* rt_trace_rows with RT_TRACE_OUT_DEVICE: rgba_out is the WHOLE width*height*4 frame and this part's
                                         pixels are stored at their final position (no packing, no unpack step). The frame may be peer memory
                                         of another GPU (rt_frame_share_open): the trace kernel then writes over NVLink straight into rank 0's

@@ -41,6 +41,11 @@ def test_sample_scene(rt, ctx, oracle, wh):
         assert (xs.min(), xs.max(), ys.min(), ys.max()) == (392, 530, 192, 330)
         assert np.all(rgba[m] == np.array((153, 26, 51, 0), dtype=np.uint8))
     assert gs["rays_primary"] == wh[0] * wh[1] and gs["primary_hits"] == hit.sum()
+    if wh == (1200, 800):    # swapchain byte order on request (main.cpp:50): the same image with R and B exchanged
+        sh = rt.SceneHandles(ctx, scene)
+        bgra, _, _ = ctx.trace(sh.tlas, sh.cam, wh[0], wh[1], 0, bgra=True)
+        sh.free()
+        assert np.array_equal(bgra[..., [2, 1, 0, 3]], rgba)
     assert gs["near_edge_hits"] == r[3]["near_edge_hits"]
     print("sample", wh, rp, rc)
 
