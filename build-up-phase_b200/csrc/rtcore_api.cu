@@ -151,6 +151,8 @@ extern "C" {
 
 const char* rt_version(void) { return "rtcore-b200 0.1 (sm_100a)"; }
 
+void rt_destroy(rt_context* ctx);
+
 int rt_create(int device_ordinal, rt_context** out) {
     if (!out) return RT_ERROR_INVALID_ARG;
     *out = nullptr;
@@ -159,19 +161,22 @@ int rt_create(int device_ordinal, rt_context** out) {
     if (cudaSetDevice(device_ordinal) != cudaSuccess) return RT_ERROR_CUDA;
     rt_context* ctx = new rt_context();
     ctx->device = device_ordinal;
-    if (cudaGetDeviceProperties(&ctx->prop, device_ordinal) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    ctx->own_stream = true;
-    for (auto& e : ctx->ev) if (cudaEventCreate(&e) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    for (auto& e : ctx->chunk_ev) if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
+    bool ok = cudaGetDeviceProperties(&ctx->prop, device_ordinal) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) == cudaSuccess;
+    ctx->own_stream = ok;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (auto& e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
+    for (auto& e : ctx->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_error, 64) == cudaSuccess;
+    ok = ok && cudaMalloc(&ctx->d_counters, 8 * 64) == cudaSuccess;
+    ok = ok && cudaMemset(ctx->d_error, 0, 64) == cudaSuccess;
+    if (!ok) { rt_destroy(ctx); return RT_ERROR_CUDA; }          // releases whatever was created so far
     if (const char* v = getenv("RTCORE_E2E_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->e2e_chunks = k; }
-    if (cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    if (cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
     if (const char* v = getenv("RTCORE_TRACE_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->trace_chunks = k; }
-    if (cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) != cudaSuccess || cudaMalloc(&ctx->d_error, 64) != cudaSuccess ||
-        cudaMalloc(&ctx->d_counters, 8 * 64) != cudaSuccess) { delete ctx; return RT_ERROR_CUDA; }
-    cudaMemset(ctx->d_error, 0, 64);
     *out = ctx;
     return RT_SUCCESS;
 }
@@ -179,7 +184,7 @@ int rt_create(int device_ordinal, rt_context** out) {
 void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->qflags); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
