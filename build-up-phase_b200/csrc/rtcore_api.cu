@@ -197,6 +197,20 @@ void rt_destroy(rt_context* ctx) {
     delete ctx;
 }
 
+int rt_release_scratch(rt_context* ctx) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->scratch); ctx->scratch = nullptr; ctx->scratch_cap = 0;
+    cudaFree(ctx->fb); ctx->fb = nullptr; ctx->fb_cap = 0;
+    cudaFree(ctx->hits1); ctx->hits1 = nullptr; ctx->hits1_cap = 0;
+    cudaFree(ctx->hits2); ctx->hits2 = nullptr; ctx->hits2_cap = 0;
+    cudaFree(ctx->queue); ctx->queue = nullptr; ctx->queue_cap = 0;
+    cudaFree(ctx->qflags); ctx->qflags = nullptr; ctx->qflags_cap = 0;
+    ctx->dbg_keys = nullptr; ctx->dbg_vals = nullptr; ctx->dbg_n = 0;     // the debug view of the last sort lived in the scratch
+    return RT_SUCCESS;
+}
+
 const char* rt_last_error(const rt_context* ctx) { return ctx ? ctx->err.c_str() : "no context (CUDA device unavailable?)"; }
 
 int rt_device_info(const rt_context* ctx, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {

@@ -35,7 +35,7 @@ RT_TRACE_OUT_BGRA = 0x10
 RT_REF_EMPTY = 0x7FFFFFFD
 
 EXPORTED_SYMBOLS = [
-    "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync",
+    "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync", "rt_release_scratch",
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
@@ -149,6 +149,7 @@ def load(build_if_missing: bool = True):
     L.rt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(C.c_size_t)]
     L.rt_set_stream.argtypes = [vp, vp]
     L.rt_sync.argtypes = [vp]
+    L.rt_release_scratch.argtypes = [vp]
     L.rt_blas_build_sizes.argtypes = [vp, C.POINTER(u32), u32, C.POINTER(RtBuildSizes)]
     L.rt_tlas_build_sizes.argtypes = [vp, u32, C.POINTER(RtBuildSizes)]
     L.rt_build_blas.argtypes = [vp, C.POINTER(RtGeometry), u32, u32, C.POINTER(vp)]
@@ -319,6 +320,9 @@ class Context:
 
     def sync(self):
         self._check(self.L.rt_sync(self.h))
+
+    def release_scratch(self):
+        self._check(self.L.rt_release_scratch(self.h))
 
     def launch_count(self) -> int:
         return int(self.L.rt_kernel_launch_count(self.h))

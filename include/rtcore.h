@@ -183,6 +183,9 @@ RT_API int  rt_device_info(const rt_context* ctx, int* sm_count, int* cc_major, 
 /* Run subsequent work of this context on an existing CUDA stream (cudaStream_t as void*), e.g. torch's. */
 RT_API int  rt_set_stream(rt_context* ctx, void* cuda_stream);
 RT_API int  rt_sync(rt_context* ctx);
+/* The context keeps its build scratch, framebuffer staging and bounce-ray buffers between calls (they only grow: ~250 B per triangle
+ * of the largest build, ~60 B per pixel of the largest frame). rt_release_scratch frees them; the next call re-allocates. */
+RT_API int  rt_release_scratch(rt_context* ctx);
 
 /* ---- acceleration structures ------------------------------------------------------------ */
 RT_API int  rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, uint32_t n_geoms, rt_build_sizes* out);

@@ -236,6 +236,10 @@ def test_edge_cases(rt, ctx, oracle):
     ctx.set_ray_params()
     _, p, _ = sh.trace(want_hits=True)
     assert (p["instance_id"] != MISS).sum() > 1000
+    # releasing the cached scratch / staging buffers changes nothing but the memory footprint
+    ctx.release_scratch()
+    _, p2, _ = sh.trace(want_hits=True)
+    assert p2.tobytes() == p.tobytes()
     # SBT range: fewer records than addressed -> refused, never silently wrong
     ctx.set_hit_records(S.SAMPLE_HIT_RECORDS[:3])
     with pytest.raises(rt.RtError) as e:
