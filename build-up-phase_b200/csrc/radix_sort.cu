@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(SORT_THREADS, RT_SORT_MIN_CTAS) k_onesweep_pas
 
 // ---- segmented sort (seg_sort.cuh): the stand-alone kernel ---------------------------------------------------------
 __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_sort(const uint64_t* __restrict__ in, uint64_t* __restrict__ out,
-                                                            const BlasRecord* __restrict__ recs, int shift0, int key_bits) {
+                                                            const BlasRecord* __restrict__ recs, int shift0, int key_bits, uint32_t single_n) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);
     const int tid = threadIdx.x;
-    const uint32_t first = recs[blockIdx.x].first, n = recs[blockIdx.x].tri_count;
+    const uint32_t first = recs ? recs[blockIdx.x].first : 0u, n = recs ? recs[blockIdx.x].tri_count : single_n;   // recs == nullptr: the whole input is one segment
     if (n == 0) return;
     // coalesced load; padding (~0) sorts last and stays last
     for (uint32_t i = tid; i < SEG_SORT_CAPACITY; i += SEG_THREADS) s_keys[i] = i < n ? in[first + i] : ~0ull;
@@ -281,7 +281,7 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
     const int base_shift = has_vals ? 0 : plan.packed_val_bits;
     *result_in_b = false;
     if (plan.n == 0) return 0;
-    if (plan.seg_records && !has_vals) {                 // segmented path: one kernel, result in keys_b
+    if ((plan.seg_records || plan.seg_single) && !has_vals) {    // segmented path: one kernel, result in keys_b
         // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it once per device
         static bool attr_set[64] = {};
         int dev = 0;
@@ -290,7 +290,8 @@ int sort_pairs(const SortPlan& plan, uint64_t* keys_a, uint64_t* keys_b, uint32_
             if (cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG_SMEM_BYTES) != cudaSuccess) return -1;
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
-        k_seg_sort<<<plan.n_segments, SEG_THREADS, SEG_SMEM_BYTES, stream>>>(keys_a, keys_b, plan.seg_records, base_shift, plan.seg_key_bits);
+        k_seg_sort<<<plan.seg_single ? 1u : plan.n_segments, SEG_THREADS, SEG_SMEM_BYTES, stream>>>(keys_a, keys_b, plan.seg_single ? nullptr : plan.seg_records, base_shift,
+                                                                                              plan.seg_key_bits, plan.n);
         *result_in_b = true;
         if (cudaGetLastError() != cudaSuccess) return -1;
         return 1;

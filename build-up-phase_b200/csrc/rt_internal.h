@@ -92,6 +92,7 @@ struct SortPlan {
     // fits one CTA's shared memory and is sorted there by its low seg_key_bits key bits in one kernel (no global passes)
     const struct BlasRecord* seg_records = nullptr; uint32_t n_segments = 0; int seg_key_bits = 0;
     bool seg_fused = false;     // also fuse triangle setup + Morton into the segment's CTA (k_seg_setup_sort)
+    bool seg_single = false;    // no records: the whole input (n <= SEG_SORT_CAPACITY) is one segment (the TLAS build)
 };
 SortPlan sort_plan(uint32_t n, int key_bits);
 constexpr uint32_t SEG_SORT_CAPACITY = 11264;   // records one CTA sorts in shared memory (1024 threads x 11)

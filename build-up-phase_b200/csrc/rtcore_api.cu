@@ -572,6 +572,9 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     SortPlan sp = sort_plan(n, MORTON_BITS);
     choose_record_format(sp, n, MORTON_BITS, build_flags);
+    if (sp.packed_val_bits > 0 && n <= SEG_SORT_CAPACITY && !(build_flags & RT_BUILD_NO_SEGMENTED_SORT)) {
+        sp.seg_single = true; sp.seg_key_bits = (int)MORTON_BITS;     // a TLAS of up to 11,264 instances: one shared-memory sort kernel instead of six launches
+    }
     const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256);
     const size_t bytes = inst_b + nodes_b + 256;
     if (T->bytes < bytes) {
