@@ -199,4 +199,67 @@ int rt_write_ppm(const char* path, const uint8_t* rgba, uint32_t width, uint32_t
     return RT_SUCCESS;
 }
 
+namespace {
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 255u] ^ (crc >> 8);
+    return crc;
+}
+void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+bool write_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    std::vector<uint8_t> head;
+    put_be32(head, (uint32_t)data.size());
+    head.insert(head.end(), type, type + 4);
+    uint32_t crc = crc32_update(0xFFFFFFFFu, (const uint8_t*)type, 4);
+    if (!data.empty()) crc = crc32_update(crc, data.data(), data.size());
+    std::vector<uint8_t> tail;
+    put_be32(tail, crc ^ 0xFFFFFFFFu);
+    return fwrite(head.data(), 1, head.size(), f) == head.size() && (data.empty() || fwrite(data.data(), 1, data.size(), f) == data.size()) &&
+           fwrite(tail.data(), 1, 4, f) == 4;
+}
+}  // namespace
+
+int rt_write_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height, uint32_t flags) {
+    if (!path || !rgba || !width || !height) return RT_ERROR_INVALID_ARG;
+    uint8_t lut[256];
+    if (flags & RT_IMAGE_SRGB_ENCODE) rt_srgb8_table(lut);
+    else for (int i = 0; i < 256; ++i) lut[i] = (uint8_t)i;
+    // raw scanlines: filter byte 0 + RGB
+    const size_t stride = 1 + 3 * (size_t)width;
+    std::vector<uint8_t> raw(stride * height);
+    for (uint32_t y = 0; y < height; ++y) {
+        const uint8_t* src = rgba + 4 * (size_t)width * ((flags & RT_IMAGE_FLIP_Y) ? height - 1 - y : y);
+        uint8_t* dst = raw.data() + stride * y;
+        dst[0] = 0;
+        for (uint32_t x = 0; x < width; ++x) { dst[1 + 3 * x] = lut[src[4 * x]]; dst[2 + 3 * x] = lut[src[4 * x + 1]]; dst[3 + 3 * x] = lut[src[4 * x + 2]]; }
+    }
+    // zlib stream: header, stored blocks of <= 65535 bytes, Adler-32
+    std::vector<uint8_t> z;
+    z.reserve(raw.size() + raw.size() / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);
+    uint32_t a = 1, b = 0;
+    for (size_t off = 0; off < raw.size(); off += 65535) {
+        const size_t n = raw.size() - off < 65535 ? raw.size() - off : 65535;
+        z.push_back(off + n == raw.size() ? 1 : 0);
+        z.push_back((uint8_t)(n & 255)); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)(~n & 255)); z.push_back((uint8_t)((~n >> 8) & 255));
+        z.insert(z.end(), raw.begin() + off, raw.begin() + off + n);
+        for (size_t i = 0; i < n; ++i) { a = (a + raw[off + i]) % 65521u; b = (b + a) % 65521u; }
+    }
+    put_be32(z, (b << 16) | a);
+    FILE* f = fopen(path, "wb");
+    if (!f) return fail(RT_ERROR_IO, "cannot create (errno %ld): %s", (long)errno, path);
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0D, 0x0A, 0x1A, 0x0A};
+    std::vector<uint8_t> ihdr;
+    put_be32(ihdr, width); put_be32(ihdr, height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);     // 8-bit, RGB, deflate, adaptive filtering, no interlace
+    const bool ok = fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr) && write_chunk(f, "IDAT", z) && write_chunk(f, "IEND", {});
+    if (fclose(f) != 0 || !ok) return fail(RT_ERROR_IO, "write error (errno %ld): %s", (long)errno, path);
+    return RT_SUCCESS;
+}
+
 }  // extern "C"

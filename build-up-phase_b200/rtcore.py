@@ -45,7 +45,7 @@ EXPORTED_SYMBOLS = [
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
     "rt_obj_group_count", "rt_obj_vertices", "rt_obj_indices", "rt_obj_group_name", "rt_obj_group_first_triangle",
-    "rt_obj_group_triangle_count", "rt_obj_geometry", "rt_write_ppm", "rt_srgb8_table",
+    "rt_obj_group_triangle_count", "rt_obj_geometry", "rt_write_ppm", "rt_write_png", "rt_srgb8_table",
 ]
 
 
@@ -211,6 +211,7 @@ def load(build_if_missing: bool = True):
     L.rt_obj_group_triangle_count.restype = u32
     L.rt_obj_geometry.argtypes = [vp, u32, C.POINTER(RtGeometry)]
     L.rt_write_ppm.argtypes = [C.c_char_p, vp, u32, u32, u32]
+    L.rt_write_png.argtypes = [C.c_char_p, vp, u32, u32, u32]
     L.rt_srgb8_table.argtypes = [vp]
     L.rt_srgb8_table.restype = None
     _lib = L
@@ -605,6 +606,14 @@ def write_ppm(path: str, rgba: np.ndarray, flags: int = 0) -> None:
     a = np.ascontiguousarray(rgba, dtype=np.uint8)
     h, w = a.shape[0], a.shape[1]
     rc = load().rt_write_ppm(os.fsencode(path), a.ctypes.data, w, h, flags)
+    if rc != 0:
+        raise RtError(rc, load().rt_obj_last_error().decode())
+
+
+def write_png(path: str, rgba: np.ndarray, flags: int = 0) -> None:
+    a = np.ascontiguousarray(rgba, dtype=np.uint8)
+    h, w = a.shape[0], a.shape[1]
+    rc = load().rt_write_png(os.fsencode(path), a.ctypes.data, w, h, flags)
     if rc != 0:
         raise RtError(rc, load().rt_obj_last_error().decode())
 

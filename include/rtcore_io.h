@@ -55,6 +55,9 @@ RT_API int  rt_obj_geometry(const rt_obj_mesh* mesh, uint32_t group, rt_geometry
 #define RT_IMAGE_FLIP_Y      0x2u
 /* Binary PPM (P6, maxval 255) of the R,G,B channels of a host RGBA8 image (alpha is dropped: the sample stores 0). */
 RT_API int  rt_write_ppm(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height, uint32_t flags);
+/* PNG (8-bit RGB, colour type 2, filter 0, zlib stream of STORED deflate blocks: no compression library needed, any decoder reads
+ * it). Same flags as rt_write_ppm. */
+RT_API int  rt_write_png(const char* path, const uint8_t* rgba, uint32_t width, uint32_t height, uint32_t flags);
 /* The 8-bit sRGB encode table used by RT_IMAGE_SRGB_ENCODE: out[i] = round(255 * oetf(i / 255)). */
 RT_API void rt_srgb8_table(uint8_t out[256]);
 

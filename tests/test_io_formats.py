@@ -140,3 +140,28 @@ def test_ppm_and_srgb(rt, tmp_path):
     rt.write_ppm(str(p), img, rt.IMAGE_SRGB_ENCODE | rt.IMAGE_FLIP_Y)
     body = np.frombuffer(p.read_bytes()[len(b"P6\n13 7\n255\n"):], dtype=np.uint8).reshape(7, 13, 3)
     assert np.array_equal(body, lut[img[::-1, :, :3]])
+
+
+def test_png(rt, tmp_path):
+    """rt_write_png against a minimal independent decoder (chunk walk, CRCs, zlib inflate, filter 0)."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(4)
+    for (h, w) in ((5, 9), (300, 401)):          # the second one needs several stored deflate blocks (> 65535 bytes of scanlines)
+        img = rng.integers(0, 256, size=(h, w, 4), dtype=np.uint8)
+        p = tmp_path / "a.png"
+        rt.write_png(str(p), img, rt.IMAGE_FLIP_Y)
+        raw = p.read_bytes()
+        assert raw[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(raw):
+            n, typ = struct.unpack(">I4s", raw[pos:pos + 8])
+            data = raw[pos + 8:pos + 8 + n]
+            assert struct.unpack(">I", raw[pos + 8 + n:pos + 12 + n])[0] == zlib.crc32(typ + data)
+            chunks.append((typ, data))
+            pos += 12 + n
+        assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        assert struct.unpack(">IIBBBBB", chunks[0][1]) == (w, h, 8, 2, 0, 0, 0)
+        lines = np.frombuffer(zlib.decompress(chunks[1][1]), dtype=np.uint8).reshape(h, 1 + 3 * w)
+        assert np.all(lines[:, 0] == 0)
+        assert np.array_equal(lines[:, 1:].reshape(h, w, 3), img[::-1, :, :3])
