@@ -11,7 +11,7 @@
 // librtcore's trace kernel. The frame is written as a binary PPM instead of being presented.
 //
 // Build: g++ -std=c++17 sample_scene.cpp -I../../include -L.. -lrtcore -Wl,-rpath,'$ORIGIN/..' -o sample_scene
-// Usage: sample_scene [out.ppm] [width height] [--obj mesh.obj] [--srgb]
+// Usage: sample_scene [out.ppm | out.png] [width height] [--obj mesh.obj] [--srgb]
 //   --obj: the reference's next assignment (vulkan-raytracing-basic/README.md:225-226): "load an obj file -> build the
 //          acceleration structure" — the mesh replaces the two quads (one geometry per o/g group, one instance, fitted
 //          into the view); everything else is the sample's pipeline.
@@ -180,7 +180,10 @@ int main(int argc, char** argv) {
         size_t hits = 0;
         for (size_t p = 0; p < (size_t)width * height; ++p)
             if (!(frame[4 * p] == 0 && frame[4 * p + 1] == 0 && frame[4 * p + 2] == 51)) ++hits;
-        if (rt_write_ppm(out, frame.data(), width, height, image_flags) != RT_SUCCESS) throw std::runtime_error(std::string("rt_write_ppm: ") + rt_obj_last_error());
+        const std::string outs = out;
+        const bool png = outs.size() > 4 && outs.compare(outs.size() - 4, 4, ".png") == 0;
+        if ((png ? rt_write_png(out, frame.data(), width, height, image_flags) : rt_write_ppm(out, frame.data(), width, height, image_flags)) != RT_SUCCESS)
+            throw std::runtime_error(std::string("writing the frame failed: ") + rt_obj_last_error());
         printf("%s: %ux%u, %zu non-miss pixels, trace kernel %.3f ms, build %.3f ms, %llu kernel launches\n", out, width, height, hits,
                rt_last_trace_ms(vk.ctx), rt_last_build_ms(vk.ctx), (unsigned long long)rt_kernel_launch_count(vk.ctx));
     } catch (const std::exception& e) {
