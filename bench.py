@@ -400,6 +400,7 @@ def run_gpu(args):
     host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
     host_np = host_frame.numpy()
     step_no = [0]
+    frame_uses = [0, 0]
 
     def step_multi(consume=None):
         """One frame at N > 1; on rank 0 `consume(frame)` is enqueued once the frame is complete. Returns the frame tensor on rank 0."""
@@ -407,12 +408,14 @@ def run_gpu(args):
             k, use = step_no[0] & 1, step_no[0] >> 1
             step_no[0] += 1
             if args.barrier == "flags":
+                fu = frame_uses[k]                              # how often THIS path (whole-frame `done` counter) has used buffer k
+                frame_uses[k] += 1
                 done_ctr, free_ctr = shared_ptrs[k] + W * H * 4, shared_ptrs[k] + W * H * 4 + 4
                 ctx.flag_wait_ge(free_ctr, use)                 # rank 0 has handed buffer k back `use` times: safe to overwrite it
                 ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
                 ctx.flag_add(done_ctr)                          # this rank's pixels of frame k have landed in rank 0's memory
                 if rank == 0:
-                    ctx.flag_wait_ge(done_ctr, world * (use + 1))   # ... and so have everybody else's: the frame is complete
+                    ctx.flag_wait_ge(done_ctr, world * (fu + 1))    # ... and so have everybody else's: the frame is complete
                     if consume:
                         consume(shared[k])
                     ctx.flag_add(free_ctr)
@@ -435,6 +438,41 @@ def run_gpu(args):
             return frame
         return None
 
+    # ---- e2e at N > 1 (p2p + counters): row-chunk pipeline. Packed rows [a, b) of every rank together are image rows [a*N, b*N).
+    chunk_bounds, chunk_uses, ctx2, copy_stream = None, [0, 0], None, None
+    if mode == "p2p" and args.barrier == "flags" and args.e2e_chunks > 1:
+        local_rows = px_packed // W
+        nc, wsum, acc, chunk_bounds = args.e2e_chunks, args.e2e_chunks * (args.e2e_chunks + 1) // 2, 0, [0]
+        for c in range(nc):
+            acc += nc - c
+            end = local_rows if c == nc - 1 else min(local_rows, (local_rows * acc // wsum + 7) // 8 * 8)
+            if end > chunk_bounds[-1]:
+                chunk_bounds.append(end)
+        if rank == 0:
+            copy_stream = torch.cuda.Stream(device=dev)
+            ctx2 = rtcore.Context(local_rank)           # only enqueues flag waits / adds on the copy stream
+            ctx2.set_stream(copy_stream.cuda_stream)
+
+    def step_e2e_chunked():
+        k, use = step_no[0] & 1, step_no[0] >> 1
+        step_no[0] += 1
+        cu = chunk_uses[k]
+        chunk_uses[k] += 1
+        tail = shared_ptrs[k] + W * H * 4
+        ctx.flag_wait_ge(tail + 4, use)
+        for c in range(len(chunk_bounds) - 1):
+            a, b = chunk_bounds[c], chunk_bounds[c + 1]
+            ctx.trace_rows_range(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, a, b - a, shared_ptrs[k], full_frame=True)
+            ctx.flag_add(tail + 8 + 4 * c)
+            if rank == 0:
+                ctx2.flag_wait_ge(tail + 8 + 4 * c, world * (cu + 1))      # on the copy stream: every rank's rows of this chunk have landed
+                g0, g1 = a * world, min(b * world, H)
+                with torch.cuda.stream(copy_stream):
+                    host_frame[g0:g1].copy_(shared[k][g0:g1], non_blocking=True)
+        if rank == 0:
+            ctx2.flag_add(tail + 4)                     # buffer handed back once its last rows are on the host
+        torch.cuda.synchronize()
+
     def step_device():
         if world == 1:
             ctx.trace_device(tlas, cam, W, H, bounces, frame, async_=True)
@@ -445,6 +483,8 @@ def run_gpu(args):
         # reference-facing call with HOST buffers: camera struct in (16 B), RGBA8 framebuffer out (pinned host memory)
         if world == 1:
             ctx.trace(tlas, cam, W, H, bounces, rgba_out=host_np)
+        elif chunk_bounds is not None:
+            step_e2e_chunked()
         else:
             step_multi(consume=lambda f: host_frame.copy_(f, non_blocking=True))
             torch.cuda.synchronize()
@@ -551,7 +591,10 @@ def run_gpu(args):
             "trace_kernel_ms": kernel_ms,
             "e2e": {"value": total_rays / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_ms.item()),
                     "h2d_bytes_per_step": 16, "d2h_bytes_per_step": W * H * 4,
-                    "note": "rt_trace with a pinned host framebuffer: camera struct in, RGBA8 frame out"},
+                    "note": "rt_trace with a pinned host framebuffer: camera struct in, RGBA8 frame out" if world == 1 else
+                            ("every rank traces its share in %d shrinking row chunks straight into rank 0's frame; rank 0 copies the finished image rows "
+                             "to pinned host memory while the next chunk is traced" % (len(chunk_bounds) - 1) if chunk_bounds is not None else
+                             "frame assembled on rank 0, then copied to pinned host memory")},
             "gpu_launches": int(l1 - l0),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                          "traffic_source": traffic_src, "kernel": "k_trace (stage 0 + stage 1 of one frame)", "peak_source": peak_src,
@@ -595,6 +638,8 @@ def run_gpu(args):
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
+        if ctx2 is not None:
+            ctx2.close()
         if mode == "p2p":               # peers unmap first, then the owner frees
             shared = []
             if rank != 0:
@@ -627,6 +672,9 @@ def main():
                     help="--gather p2p: how a frame is declared complete. flags = stream-ordered counters in rank 0's shared frame "
                          "(every rank adds 1 after its trace, rank 0 waits for N; a second counter hands the buffer back): no collective "
                          "on the step; nccl = a 4-byte all-reduce per frame")
+    ap.add_argument("--e2e-chunks", type=int, default=3,
+                    help="N > 1, p2p + flags: the e2e step traces every rank's share in this many shrinking row chunks with one 'done' counter "
+                         "each, and rank 0 copies the finished image rows of ALL ranks to the host while the next chunk is traced (1 = one chunk)")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()

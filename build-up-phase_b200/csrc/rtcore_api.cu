@@ -715,9 +715,10 @@ uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_r
     return ((bands + part_count - 1) / part_count) * block_rows * (uint64_t)width;
 }
 
-int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
-                  uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count,
-                  uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
+// range_rows == 0: all packed rows of this part; else only the packed rows [range_first, range_first + range_rows) (device output)
+static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+                           uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t range_first, uint32_t range_rows,
+                           uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
     if (!ctx || !tlas || !cam || !width || !height || !rgba_out) return RT_ERROR_INVALID_ARG;
     if (!block_rows || (block_rows & 3u) || !part_count || part_index >= part_count) return fail(ctx, RT_ERROR_INVALID_ARG, "block_rows must be a positive multiple of 4 and part_index < part_count");
     if ((uint64_t)width * height > 0xFFFFFFFFull) return RT_ERROR_INVALID_ARG;
@@ -784,6 +785,13 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
         }
         chunks = n ? n : 1;
         row_begin[chunks] = total_rows;
+    }
+    if (range_rows) {                                  // an explicit row range: exactly that, one launch
+        if (!dev_out || (range_first & 7u) || range_first >= total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: device output, first row a multiple of 8 inside the part");
+        chunks = 1;
+        row_begin[0] = range_first;
+        row_begin[1] = range_first + range_rows < total_rows ? range_first + range_rows : total_rows;
+        if ((row_begin[1] & 7u) && row_begin[1] != total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: row count must be a multiple of 8 unless it ends the part");
     }
     const bool two_streams = chunks > 1;
     // per-chunk scratch: ray slots (tile-major over whole 8x4 tiles), index list, tile masks + block sums, publication flags
@@ -858,6 +866,19 @@ int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, ui
     cudaEventElapsedTime(&ctx->last_trace_ms, ctx->ev[0], ctx->ev[1]);
     if (!stats) memset(&ctx->last_stats, 0, sizeof(ctx->last_stats));
     return RT_SUCCESS;
+}
+
+int rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+                  uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count,
+                  uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
+    return trace_rows_impl(ctx, tlas, cam, width, height, bounces, flags, block_rows, part_index, part_count, 0, 0, rgba_out, primary_hits_out, secondary_hits_out);
+}
+
+int rt_trace_rows_range(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+                        uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t first_row, uint32_t n_rows,
+                        uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out) {
+    if (!n_rows) return RT_ERROR_INVALID_ARG;
+    return trace_rows_impl(ctx, tlas, cam, width, height, bounces, flags, block_rows, part_index, part_count, first_row, n_rows, rgba_out, primary_hits_out, secondary_hits_out);
 }
 
 int rt_trace(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,

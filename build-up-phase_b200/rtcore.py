@@ -39,7 +39,7 @@ EXPORTED_SYMBOLS = [
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
-    "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows",
+    "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version",
     # include/rtcore_io.h
@@ -175,6 +175,7 @@ def load(build_if_missing: bool = True):
     L.rt_set_ray_params.argtypes = [vp, C.POINTER(RtRayParams)]
     L.rt_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, vp, vp, vp]
     L.rt_trace_rows.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
+    L.rt_trace_rows_range.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
     L.rt_rows_packed_pixels.argtypes = [u32, u32, u32, u32]
     L.rt_rows_packed_pixels.restype = u64
     L.rt_unpack_rows.argtypes = [vp, vp, u32, u32, u32, u32, vp]
@@ -506,6 +507,13 @@ class Context:
                 (RT_TRACE_OUT_FULL_FRAME if full_frame else 0)
         self._check(self.L.rt_trace_rows(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, block_rows, part_index,
                                          part_count, _ptr(rgba), _ptr(prim), _ptr(sec)))
+
+    def trace_rows_range(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, block_rows: int, part_index: int,
+                         part_count: int, first_row: int, n_rows: int, rgba, full_frame: bool = False, async_: bool = True):
+        """rt_trace_rows_range: only the packed rows [first_row, first_row + n_rows) of this part (device output)."""
+        flags = RT_TRACE_OUT_DEVICE | (RT_TRACE_ASYNC if async_ else 0) | (RT_TRACE_OUT_FULL_FRAME if full_frame else 0)
+        self._check(self.L.rt_trace_rows_range(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, block_rows, part_index,
+                                               part_count, first_row, n_rows, _ptr(rgba), None, None))
 
     def rows_packed_pixels(self, width: int, height: int, block_rows: int, part_count: int) -> int:
         return int(self.L.rt_rows_packed_pixels(width, height, block_rows, part_count))

@@ -271,6 +271,13 @@ RT_API int  rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera*
                           uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
                           uint32_t block_rows, uint32_t part_index, uint32_t part_count,
                           uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
+/* The same for only the packed rows [first_row, first_row + n_rows) of this part (multiples of 8 rows; device output): lets a caller
+ * pipeline a frame in row chunks, e.g. rank 0 copying the finished rows of all ranks to the host while the next chunk is traced.
+ * With interleaved bands, packed rows [a, b) of every part together are the image rows [a * part_count, b * part_count). */
+RT_API int  rt_trace_rows_range(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam,
+                                uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
+                                uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t first_row, uint32_t n_rows,
+                                uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
 RT_API uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_rows, uint32_t part_count);
 /* Rank 0 after the gather: scatter part_count packed buffers (contiguous, each
  * rt_rows_packed_pixels()*4 bytes, device memory) into the final width*height*4 framebuffer (device). */

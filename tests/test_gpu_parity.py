@@ -270,6 +270,13 @@ def test_row_partition_and_unpack(rt, ctx, oracle):
             ctx.trace_rows(sh.tlas, sh.cam, scene.width, scene.height, 1, 8, p, parts, direct, device=True, full_frame=True)
         torch.cuda.synchronize()
         assert np.array_equal(direct.cpu().numpy(), full), f"full-frame parts={parts}"
+    # rt_trace_rows_range: the same frame in three row ranges of two parts (what the chunk-pipelined multi-GPU e2e path does)
+    direct = torch.zeros((scene.height, scene.width, 4), dtype=torch.uint8, device="cuda:0")
+    for p in range(2):
+        for a, b in ((0, 64), (64, 104), (104, 128)):       # 250 rows / 2 parts -> 128 packed rows per part
+            ctx.trace_rows_range(sh.tlas, sh.cam, scene.width, scene.height, 1, 8, p, 2, a, b - a, direct, full_frame=True)
+    ctx.sync()
+    assert np.array_equal(direct.cpu().numpy(), full)
     # a shareable framebuffer (cudaMalloc + IPC handle) works as an output like any device buffer
     ptr, handle = ctx.frame_share_create(scene.width * scene.height * 4)
     assert len(handle) == 64 and any(handle)
