@@ -672,9 +672,11 @@ def main():
                     help="--gather p2p: how a frame is declared complete. flags = stream-ordered counters in rank 0's shared frame "
                          "(every rank adds 1 after its trace, rank 0 waits for N; a second counter hands the buffer back): no collective "
                          "on the step; nccl = a 4-byte all-reduce per frame")
-    ap.add_argument("--e2e-chunks", type=int, default=3,
+    ap.add_argument("--e2e-chunks", type=int, default=1,
                     help="N > 1, p2p + flags: the e2e step traces every rank's share in this many shrinking row chunks with one 'done' counter "
-                         "each, and rank 0 copies the finished image rows of ALL ranks to the host while the next chunk is traced (1 = one chunk)")
+                         "each, and rank 0 copies the finished image rows of ALL ranks to the host while the next chunk is traced. Measured "
+                         "with 3 chunks (profiles/README.md r02k): N = 2 e2e 4475 vs 4398 Mrays/s, N = 8 8293 vs 8979 (the per-rank chunks get "
+                         "too small) -> default 1 = one chunk, frame copied after the frame barrier")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()
