@@ -107,3 +107,96 @@ def test_single_triangle(oracle):
     assert abs(hit.sum() - 2.0 / px ** 2) < 100      # boundary pixels: ~perimeter/2
     assert np.all(prim["custom_index"][hit] == 7)
     assert np.all(rgba[hit] == np.array((153, 26, 51, 0), dtype=np.uint8))
+
+
+def _exact_plane_hits(width, height, tris, cam=(0.0, 0.0, 10.0), fov=60.0, oracle=None):
+    """Independent evaluation of the raygen shader (main.cpp:1033-1046, fp32 exactly as written) followed by an EXACT z = 0 plane
+    intersection and 2-D edge functions in float64 (all inputs are fp32 values with few significant bits: the products and sums below
+    are exact or far inside double precision). tris: list of 3x2 arrays in the z = 0 plane. Returns, per triangle, the smallest
+    oriented edge function of every pixel (> 0 strictly inside, < 0 outside, 0 exactly on the boundary), and t."""
+    f32 = np.float32
+    aspect_y = f32(oracle.lib().orc_aspect_y(f32(fov)))
+    aspect_x = f32(aspect_y * f32(width) / f32(height))
+    px = (np.arange(width, dtype=np.float32) + f32(0.5))
+    py = (np.arange(height, dtype=np.float32) + f32(0.5))
+    ndcx = (px / f32(width) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = (py / f32(height) * f32(2.0) - f32(1.0)).astype(np.float32)
+    dx = (ndcx * aspect_x).astype(np.float32)                       # direction = (ax, -ay, -1)
+    dy = (-(ndcy * aspect_y)).astype(np.float32)
+    t = 10.0                                                        # o.z + t * (-1) = 0
+    X = cam[0] + t * dx.astype(np.float64)[None, :] + np.zeros((height, 1))
+    Y = cam[1] + t * dy.astype(np.float64)[:, None] + np.zeros((1, width))
+    smin = []
+    for T in tris:
+        T = np.asarray(T, dtype=np.float64)
+        e = []
+        for a, b in ((0, 1), (1, 2), (2, 0)):
+            e.append((T[b, 0] - T[a, 0]) * (Y - T[a, 1]) - (T[b, 1] - T[a, 1]) * (X - T[a, 0]))
+        orient = np.sign((T[1, 0] - T[0, 0]) * (T[2, 1] - T[0, 1]) - (T[1, 1] - T[0, 1]) * (T[2, 0] - T[0, 0]))
+        smin.append((np.stack(e) * orient).min(axis=0))
+    return smin, t
+
+
+EDGE_BAND = 1e-5      # pixels whose exact edge function is smaller than this are "on the edge" for an fp32 implementation
+
+
+def test_single_triangle_exact_mask(oracle):
+    """The literal single-triangle config against an exact, independent evaluation: every pixel's hit/miss decision and t."""
+    s = scenes.single_triangle_scene(600, 400)
+    o = oracle.OracleScene(s)
+    rgba, prim, _, st = o.trace(mode=oracle.MODE_BRUTE)
+    (smin,), t = _exact_plane_hits(600, 400, [[(-1, -1), (1, -1), (0, 1)]], oracle=oracle)
+    assert np.abs(smin).min() > EDGE_BAND, "a pixel centre lies on an edge: the exact mask would be ambiguous"
+    inside = smin > 0
+    hit = prim["instance_id"] != MISS
+    assert np.array_equal(hit, inside)
+    assert np.abs(prim["t"][hit].astype(np.float64) - t).max() <= 2e-6      # t = T * (1/det) in fp32: within 2 ulp of the exact 10
+    assert st["primary_hits"] == int(inside.sum())
+
+
+def test_sample_scene_exact_masks_and_diagonal(traced, oracle):
+    """The sample scene's eight triangles (main.cpp:676-695,835-858 composed) against the exact evaluation: which pixel belongs to
+    which (instance, geometry, primitive) — including the split along each quad's diagonal, which SURVEY 8(c) left to 'compare, don't
+    hard-code' — and u, v of the barycentric triangle within 1e-6 of the exact values."""
+    _, _, out = traced
+    rgba, prim, _, st = out[oracle.MODE_BRUTE]
+    h, w = prim.shape
+    tris, ids = [], []
+    for inst, oy in ((0, 2.0), (1, -2.0)):
+        for geo, ox in ((0, -2.0), (1, 2.0)):
+            q = [(-1 + ox, -1 + oy), (1 + ox, -1 + oy), (1 + ox, 1 + oy), (-1 + ox, 1 + oy)]
+            tris.append([q[0], q[1], q[3]]); ids.append((inst, geo, 0))        # indices {0,1,3, 1,2,3}
+            tris.append([q[1], q[2], q[3]]); ids.append((inst, geo, 1))
+    smins, t = _exact_plane_hits(w, h, tris, oracle=oracle)
+    masks, total, on_edge, diagonal_pixels = [], np.zeros((h, w), dtype=bool), 0, 0
+    for k, (sm, (inst, geo, p)) in enumerate(zip(smins, ids)):
+        sel = (prim["instance_id"] == inst) & (prim["geometry_index"] == geo) & (prim["primitive_id"] == p)
+        assert np.all(sel[sm > EDGE_BAND]), (inst, geo, p, "a pixel strictly inside is not attributed to its triangle")
+        assert not np.any(sel[sm < -EDGE_BAND]), (inst, geo, p, "a pixel strictly outside is attributed to the triangle")
+        band = np.abs(sm) <= EDGE_BAND
+        on_edge += int(band.sum())
+        if p == 0:
+            # the quad's diagonal passes through the pixel centres with x - y = 200 (exactly in real arithmetic, within ~1e-7 in the
+            # shader's fp32): watertightness means each of these pixels belongs to exactly ONE of the two triangles — never a hole,
+            # never both (which one is decided by the fp32 ray; an exact tie goes to primitive 0)
+            shared = band & (np.abs(smins[k + 1]) <= EDGE_BAND)
+            nxt = (prim["instance_id"] == inst) & (prim["geometry_index"] == geo) & (prim["primitive_id"] == 1)
+            assert int(shared.sum()) in (0, 139) and np.all((sel ^ nxt)[shared])     # the two quads with ox + oy = 0 have it
+            diagonal_pixels += int(shared.sum())
+        masks.append(sm > 0)
+        assert not np.any(total & sel)
+        total |= sel
+    assert np.array_equal(total, prim["instance_id"] != MISS) and int(total.sum()) == 77284 and diagonal_pixels == 2 * 139
+    # barycentrics of the special-cased triangle (instance 1, geometry 1, primitive 1): u -> vertex 1, v -> vertex 2
+    m = masks[ids.index((1, 1, 1))]
+    T = np.asarray(tris[ids.index((1, 1, 1))], dtype=np.float64)
+    f32 = np.float32
+    aspect_y = f32(oracle.lib().orc_aspect_y(f32(60.0)))
+    aspect_x = f32(aspect_y * f32(w) / f32(h))
+    ys, xs = np.nonzero(m)
+    X = 10.0 * ((((xs.astype(np.float32) + f32(0.5)) / f32(w) * f32(2.0) - f32(1.0)).astype(np.float32)) * aspect_x).astype(np.float64)
+    Y = -10.0 * ((((ys.astype(np.float32) + f32(0.5)) / f32(h) * f32(2.0) - f32(1.0)).astype(np.float32)) * aspect_y).astype(np.float64)
+    det = (T[1, 0] - T[0, 0]) * (T[2, 1] - T[0, 1]) - (T[1, 1] - T[0, 1]) * (T[2, 0] - T[0, 0])
+    u = ((X - T[0, 0]) * (T[2, 1] - T[0, 1]) - (Y - T[0, 1]) * (T[2, 0] - T[0, 0])) / det
+    v = ((T[1, 0] - T[0, 0]) * (Y - T[0, 1]) - (T[1, 1] - T[0, 1]) * (X - T[0, 0])) / det
+    assert np.abs(prim["u"][ys, xs] - u).max() < 1e-6 and np.abs(prim["v"][ys, xs] - v).max() < 1e-6
