@@ -140,3 +140,96 @@ def test_ray_flag_semantics_known_answers(oracle):
     with pytest.raises(RuntimeError):
         o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(miss_index=2))
     o.close()
+
+
+def _world_triangles(scene):
+    """All instanced triangles in WORLD space, float64: geometry transform (baked at BLAS build) then instance transform; plus ids."""
+    P, ids = [], []
+    for ii, I in enumerate(scene.instances):
+        if I.mask == 0:
+            continue
+        M = np.asarray(I.transform, dtype=np.float64).reshape(3, 4)
+        for gi, g in enumerate(scene.blases[I.blas]):
+            v = np.asarray(g.vertices, dtype=np.float64)
+            idx = np.asarray(g.indices, dtype=np.int64) if g.indices is not None else np.arange(v.shape[0]).reshape(-1, 3)
+            tri = v[idx]                                                     # [nt, 3, 3]
+            if g.transform is not None:
+                G = np.asarray(g.transform, dtype=np.float64).reshape(3, 4)
+                tri = tri @ G[:, :3].T + G[:, 3]
+            tri = tri @ M[:, :3].T + M[:, 3]
+            P.append(tri)
+            n = tri.shape[0]
+            ids.append(np.stack([np.full(n, ii), np.full(n, gi), np.arange(n), np.full(n, I.custom_index), np.full(n, I.sbt_offset)], axis=1))
+    return np.concatenate(P), np.concatenate(ids)
+
+
+def test_oracle_vs_float64_world_space_intersection(oracle):
+    """An INDEPENDENT statement of the whole primary-ray path for a fuzz scene: fp32 raygen as written in the shader, then everything
+    else in float64 in world space (geometry transform, instance transform, Moeller-Trumbore instead of the watertight test, no
+    world->object matrices at all), SBT rule rec = instanceSbtOffset + geometryIndex. Every ray whose float64 answer is unambiguous
+    (closest hit separated from the runner-up, not within 1e-4 of an edge) must get the same instance / geometry / primitive /
+    customIndex, t within 1e-4 and the same hit-record colour from the oracle."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=300, n_instances=8, seed=5, width=160, height=100, bounces=0, shared_edges=True)
+    o = oracle.OracleScene(scene)
+    rgba, prim, _, st = o.trace(mode=oracle.MODE_BRUTE)
+    o.close()
+    W, H = scene.width, scene.height
+    f32 = np.float32
+    ay = f32(oracle.lib().orc_aspect_y(f32(scene.yfov_deg)))
+    ax = f32(ay * f32(W) / f32(H))
+    ndcx = ((np.arange(W, dtype=np.float32) + f32(0.5)) / f32(W) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = ((np.arange(H, dtype=np.float32) + f32(0.5)) / f32(H) * f32(2.0) - f32(1.0)).astype(np.float32)
+    D = np.empty((H, W, 3))
+    D[..., 0] = (ndcx * ax).astype(np.float64)[None, :]
+    D[..., 1] = (-(ndcy * ay)).astype(np.float64)[:, None]
+    D[..., 2] = -1.0
+    D = D.reshape(-1, 3)
+    O = np.asarray(scene.camera_pos, dtype=np.float64)
+    tri, ids = _world_triangles(scene)
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    best_t = np.full(D.shape[0], np.inf); second_t = np.full(D.shape[0], np.inf)
+    best_k = np.full(D.shape[0], -1); best_margin = np.zeros(D.shape[0])
+    for k0 in range(0, tri.shape[0], 256):                                    # chunks of triangles against all rays
+        E1, E2, V0 = e1[k0:k0 + 256], e2[k0:k0 + 256], tri[k0:k0 + 256, 0]
+        pvec = np.cross(D[:, None, :], E2[None, :, :])
+        det = np.einsum("rkc,kc->rk", pvec, E1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tvec = O[None, None, :] - V0[None, :, :]
+            u = np.einsum("rkc,rkc->rk", np.broadcast_to(tvec, pvec.shape), pvec) * inv
+            qvec = np.cross(np.broadcast_to(tvec, pvec.shape), E1[None, :, :])
+            v = np.einsum("rc,rkc->rk", D, qvec) * inv
+            t = np.einsum("kc,rkc->rk", E2, qvec) * inv
+        margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
+        ok = (np.abs(det) > 1e-12) & (margin > 0) & (t > 0.0) & (t < 100.0)
+        t = np.where(ok, t, np.inf)
+        kk = np.argmin(t, axis=1)
+        tt = t[np.arange(t.shape[0]), kk]
+        t2 = np.partition(t, 1, axis=1)[:, 1] if t.shape[1] > 1 else np.full(t.shape[0], np.inf)
+        better = tt < best_t
+        second_t = np.where(better, np.minimum(best_t, t2), np.minimum(second_t, tt))
+        best_margin = np.where(better, margin[np.arange(t.shape[0]), kk], best_margin)
+        best_k = np.where(better, k0 + kk, best_k)
+        best_t = np.where(better, tt, best_t)
+        # near-edge candidates that fail narrowly make the ray ambiguous too
+        near = (np.abs(margin) < 1e-4) & (np.abs(det) > 1e-12) & np.isfinite(u * v)
+        second_t = np.where(near.any(axis=1), np.minimum(second_t, best_t), second_t)
+    hit64 = np.isfinite(best_t)
+    with np.errstate(invalid="ignore"):
+        clear = np.where(hit64, (best_margin > 1e-4) & (second_t - best_t > 1e-4 * np.maximum(1.0, best_t)), second_t == np.inf)
+    p = prim.reshape(-1)
+    ohit = p["instance_id"] != MISS
+    n_clear = int(clear.sum())
+    assert n_clear > 0.9 * D.shape[0] and int((clear & hit64).sum()) > 1500
+    assert np.array_equal(ohit[clear], hit64[clear])
+    c = clear & hit64
+    want = ids[best_k[c]]
+    assert np.array_equal(p["instance_id"][c], want[:, 0]) and np.array_equal(p["geometry_index"][c], want[:, 1])
+    assert np.array_equal(p["primitive_id"][c], want[:, 2]) and np.array_equal(p["custom_index"][c], want[:, 3])
+    assert np.abs(p["t"][c] - best_t[c]).max() < 1e-4 * best_t[c].max()
+    # closest-hit colour: hit record instanceSbtOffset + geometryIndex (main.cpp:1260-1262), except the shader's barycentric special case
+    rec = want[:, 4] + want[:, 1]
+    special = (want[:, 2] == 1) & (want[:, 0] == 1) & (want[:, 3] == 100) & (want[:, 1] == 1)
+    col = np.clip(np.asarray(scene.hit_records, dtype=np.float32)[rec], 0, 1) * np.float32(255)
+    got = rgba.reshape(-1, 4)[c][:, :3].astype(np.float64)
+    assert np.abs(got - np.rint(col))[~special].max() <= 1.0
