@@ -163,6 +163,44 @@ def _world_triangles(scene):
     return np.concatenate(P), np.concatenate(ids)
 
 
+def _closest_hits_f64(O, D, tri, tmin=0.0, tmax=100.0):
+    """Moeller-Trumbore of rays (O, D) against all triangles in float64. Returns (t, triangle index, clear) where clear marks the
+    rays whose answer is unambiguous: the closest hit is separated from the runner-up and no candidate lies within 1e-4 of an edge."""
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    n = D.shape[0]
+    best_t = np.full(n, np.inf); second_t = np.full(n, np.inf)
+    best_k = np.full(n, -1); best_margin = np.zeros(n)
+    rows = np.arange(n)
+    for k0 in range(0, tri.shape[0], 256):                                    # chunks of triangles against all rays
+        E1, E2, V0 = e1[k0:k0 + 256], e2[k0:k0 + 256], tri[k0:k0 + 256, 0]
+        pvec = np.cross(D[:, None, :], E2[None, :, :])
+        det = np.einsum("rkc,kc->rk", pvec, E1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tvec = O[:, None, :] - V0[None, :, :]
+            u = np.einsum("rkc,rkc->rk", tvec, pvec) * inv
+            qvec = np.cross(tvec, E1[None, :, :])
+            v = np.einsum("rc,rkc->rk", D, qvec) * inv
+            t = np.einsum("kc,rkc->rk", E2, qvec) * inv
+            margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
+            ok = (np.abs(det) > 1e-12) & (margin > 0) & (t > tmin) & (t < tmax)
+            near = (np.abs(margin) < 1e-4) & (np.abs(det) > 1e-12) & (t > tmin - 1e-3) & (t < tmax + 1e-3)
+        t = np.where(ok, t, np.inf)
+        kk = np.argmin(t, axis=1)
+        tt = t[rows, kk]
+        t2 = np.partition(t, 1, axis=1)[:, 1] if t.shape[1] > 1 else np.full(n, np.inf)
+        better = tt < best_t
+        second_t = np.where(better, np.minimum(best_t, t2), np.minimum(second_t, tt))
+        best_margin = np.where(better, margin[rows, kk], best_margin)
+        best_k = np.where(better, k0 + kk, best_k)
+        best_t = np.where(better, tt, best_t)
+        second_t = np.where(near.any(axis=1), -np.inf, second_t)              # a near-edge candidate anywhere: ambiguous ray
+    hit = np.isfinite(best_t)
+    with np.errstate(invalid="ignore"):
+        clear = np.where(hit, (best_margin > 1e-4) & (second_t - best_t > 1e-4 * np.maximum(1.0, best_t)), second_t == np.inf)
+    return best_t, best_k, clear
+
+
 def test_oracle_vs_float64_world_space_intersection(oracle):
     """An INDEPENDENT statement of the whole primary-ray path for a fuzz scene: fp32 raygen as written in the shader, then everything
     else in float64 in world space (geometry transform, instance transform, Moeller-Trumbore instead of the watertight test, no
@@ -186,37 +224,8 @@ def test_oracle_vs_float64_world_space_intersection(oracle):
     D = D.reshape(-1, 3)
     O = np.asarray(scene.camera_pos, dtype=np.float64)
     tri, ids = _world_triangles(scene)
-    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
-    best_t = np.full(D.shape[0], np.inf); second_t = np.full(D.shape[0], np.inf)
-    best_k = np.full(D.shape[0], -1); best_margin = np.zeros(D.shape[0])
-    for k0 in range(0, tri.shape[0], 256):                                    # chunks of triangles against all rays
-        E1, E2, V0 = e1[k0:k0 + 256], e2[k0:k0 + 256], tri[k0:k0 + 256, 0]
-        pvec = np.cross(D[:, None, :], E2[None, :, :])
-        det = np.einsum("rkc,kc->rk", pvec, E1)
-        with np.errstate(divide="ignore", invalid="ignore"):
-            inv = 1.0 / det
-            tvec = O[None, None, :] - V0[None, :, :]
-            u = np.einsum("rkc,rkc->rk", np.broadcast_to(tvec, pvec.shape), pvec) * inv
-            qvec = np.cross(np.broadcast_to(tvec, pvec.shape), E1[None, :, :])
-            v = np.einsum("rc,rkc->rk", D, qvec) * inv
-            t = np.einsum("kc,rkc->rk", E2, qvec) * inv
-        margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
-        ok = (np.abs(det) > 1e-12) & (margin > 0) & (t > 0.0) & (t < 100.0)
-        t = np.where(ok, t, np.inf)
-        kk = np.argmin(t, axis=1)
-        tt = t[np.arange(t.shape[0]), kk]
-        t2 = np.partition(t, 1, axis=1)[:, 1] if t.shape[1] > 1 else np.full(t.shape[0], np.inf)
-        better = tt < best_t
-        second_t = np.where(better, np.minimum(best_t, t2), np.minimum(second_t, tt))
-        best_margin = np.where(better, margin[np.arange(t.shape[0]), kk], best_margin)
-        best_k = np.where(better, k0 + kk, best_k)
-        best_t = np.where(better, tt, best_t)
-        # near-edge candidates that fail narrowly make the ray ambiguous too
-        near = (np.abs(margin) < 1e-4) & (np.abs(det) > 1e-12) & np.isfinite(u * v)
-        second_t = np.where(near.any(axis=1), np.minimum(second_t, best_t), second_t)
+    best_t, best_k, clear = _closest_hits_f64(np.broadcast_to(O, D.shape), D, tri)
     hit64 = np.isfinite(best_t)
-    with np.errstate(invalid="ignore"):
-        clear = np.where(hit64, (best_margin > 1e-4) & (second_t - best_t > 1e-4 * np.maximum(1.0, best_t)), second_t == np.inf)
     p = prim.reshape(-1)
     ohit = p["instance_id"] != MISS
     n_clear = int(clear.sum())
@@ -233,3 +242,91 @@ def test_oracle_vs_float64_world_space_intersection(oracle):
     col = np.clip(np.asarray(scene.hit_records, dtype=np.float32)[rec], 0, 1) * np.float32(255)
     got = rgba.reshape(-1, 4)[c][:, :3].astype(np.float64)
     assert np.abs(got - np.rint(col))[~special].max() <= 1.0
+
+
+def _pcg(v):
+    v = np.asarray(v, dtype=np.uint32)
+    with np.errstate(over="ignore"):
+        state = v * np.uint32(747796405) + np.uint32(2891336453)
+        word = ((state >> ((state >> np.uint32(28)) + np.uint32(4))) ^ state) * np.uint32(277803737)
+    return ((word >> np.uint32(22)) ^ word).astype(np.uint32)
+
+
+def test_bounce_definition_restated(oracle):
+    """The diffuse bounce is OUR definition (the reference's recursion depth is 1): restated here from that text in numpy —
+    hit point, geometric normal through the instance transform, flip against the ray, first of <= 8 cube-rejection samples from
+    pcg_hash(pixel + pcg_hash(seed + 0x9E3779B9)), normalize(n + s), origin p + n * 2^-10 — and traced in float64 world space. On every
+    unambiguous secondary ray the oracle must report the same hit / miss, ids and t, and the 0.5 / 0.5 blend of the two colours."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=300, n_instances=8, seed=5, width=160, height=100, bounces=1, shared_edges=True)
+    o = oracle.OracleScene(scene)
+    rgba, prim, sec, st = o.trace(mode=oracle.MODE_BRUTE)
+    o.close()
+    W, H = scene.width, scene.height
+    f32 = np.float32
+    ay = f32(oracle.lib().orc_aspect_y(f32(scene.yfov_deg)))
+    ax = f32(ay * f32(W) / f32(H))
+    ndcx = ((np.arange(W, dtype=np.float32) + f32(0.5)) / f32(W) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = ((np.arange(H, dtype=np.float32) + f32(0.5)) / f32(H) * f32(2.0) - f32(1.0)).astype(np.float32)
+    D = np.empty((H, W, 3), dtype=np.float32)
+    D[..., 0] = (ndcx * ax)[None, :]; D[..., 1] = (-(ndcy * ay))[:, None]; D[..., 2] = f32(-1.0)
+    D = D.reshape(-1, 3)
+    O = np.asarray(scene.camera_pos, dtype=np.float32)
+    tri, ids = _world_triangles(scene)
+    p = prim.reshape(-1); s2 = sec.reshape(-1)
+    hit = p["instance_id"] != MISS
+    rays = np.nonzero(hit)[0]
+    # world-space triangle of every primary hit (looked up by ids), its geometric normal; the oracle derives the same normal from the
+    # object-space triangle and the transposed world->object matrix: n_world ~ M^-T (e1 x e2), which is parallel to the world-space
+    # cross product up to the sign of det(M) — restated here through the float64 inverse transpose
+    key = {tuple(r[:3]): k for k, r in enumerate(ids)}
+    k_hit = np.array([key[(int(a), int(b), int(c))] for a, b, c in zip(p["instance_id"][rays], p["geometry_index"][rays], p["primitive_id"][rays])])
+    n = np.empty((rays.size, 3))
+    for ii, I in enumerate(scene.instances):
+        sel = p["instance_id"][rays] == ii
+        if not sel.any():
+            continue
+        M = np.asarray(I.transform, dtype=np.float64).reshape(3, 4)[:, :3]
+        Minv = np.linalg.inv(M)
+        T = tri[k_hit[sel]]
+        obj = (T - np.asarray(I.transform, dtype=np.float64).reshape(3, 4)[:, 3]) @ Minv.T          # back to object space
+        n_obj = np.cross(obj[:, 1] - obj[:, 0], obj[:, 2] - obj[:, 0])
+        n[sel] = n_obj @ Minv                                                                       # (w2o)^T n
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    d = D[rays].astype(np.float64)
+    n = np.where((np.einsum("rc,rc->r", n, d) > 0)[:, None], -n, n)
+    P = O.astype(np.float64) + p["t"][rays].astype(np.float64)[:, None] * d
+    # cube rejection, hashes exactly as specified (integer arithmetic), samples in fp32 like the product
+    h = _pcg(rays.astype(np.uint32) + _pcg(np.uint32(1) + np.uint32(0x9E3779B9)))
+    s = np.zeros((rays.size, 3)); found = np.zeros(rays.size, dtype=bool)
+    for _ in range(8):
+        ha = _pcg(h); hb = _pcg(ha); hc = _pcg(hb); h = hc
+        q = np.stack([(x >> np.uint32(8)).astype(np.float32) * f32(2.0 ** -24) * f32(2.0) - f32(1.0) for x in (ha, hb, hc)], axis=1)
+        qq = (q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]) + q[:, 2] * q[:, 2]
+        take = ~found & (qq <= f32(1.0)) & (qq > f32(1e-8))
+        s[take] = (q[take] / np.sqrt(qq[take])[:, None]).astype(np.float64)
+        found |= take
+    dirv = n + s
+    dl = np.linalg.norm(dirv, axis=1)
+    dirv = np.where((dl * dl < 1e-12)[:, None], n, dirv / np.maximum(dl, 1e-30)[:, None])
+    O2 = P + n * (2.0 ** -10)
+    t2, k2, clear = _closest_hits_f64(O2, dirv, tri)
+    hit2 = np.isfinite(t2)
+    assert int(clear.sum()) > 0.85 * rays.size and int((clear & hit2).sum()) > 100
+    ohit2 = s2["instance_id"][rays] != MISS
+    assert np.array_equal(ohit2[clear], hit2[clear])
+    c = clear & hit2
+    want = ids[k2[c]]
+    got = s2[rays][c]
+    assert np.array_equal(got["instance_id"], want[:, 0]) and np.array_equal(got["geometry_index"], want[:, 1]) and np.array_equal(got["primitive_id"], want[:, 2])
+    assert np.abs(got["t"] - t2[c]).max() < 2e-3          # the ray itself is rebuilt from fp32 t and a float64 normal: looser than the primary check
+    # shading: 0.5 * primary colour + 0.5 * (secondary hit colour | miss colour), special barycentric case excluded
+    rec1 = ids[k_hit][:, 4] + ids[k_hit][:, 1]
+    spec1 = (ids[k_hit][:, 2] == 1) & (ids[k_hit][:, 0] == 1) & (ids[k_hit][:, 3] == 100) & (ids[k_hit][:, 1] == 1)
+    col1 = np.asarray(scene.hit_records, dtype=np.float64)[rec1]
+    col2 = np.tile(np.asarray(scene.miss_color, dtype=np.float64), (rays.size, 1))
+    rec2 = ids[np.maximum(k2, 0)][:, 4] + ids[np.maximum(k2, 0)][:, 1]
+    spec2 = hit2 & (ids[np.maximum(k2, 0)][:, 2] == 1) & (ids[np.maximum(k2, 0)][:, 0] == 1) & (ids[np.maximum(k2, 0)][:, 3] == 100) & (ids[np.maximum(k2, 0)][:, 1] == 1)
+    col2[hit2] = np.asarray(scene.hit_records, dtype=np.float64)[rec2[hit2]]
+    ok = clear & ~spec1 & ~spec2
+    expect = np.clip(0.5 * col1 + 0.5 * col2, 0, 1) * 255.0
+    assert np.abs(rgba.reshape(-1, 4)[rays][ok][:, :3].astype(np.float64) - expect[ok]).max() <= 1.0
