@@ -168,3 +168,41 @@ def test_coarsened_equals_karras(kind, K):
                 random.Random(seed).shuffle(o)
                 return o
             assert coarsened(keys, K, order) == ref, (kind, K, n, seed)
+
+
+def test_oracle_lbvh_is_karras_tree(oracle):
+    """The oracle's C++ LBVH (what the GPU build is compared with bit for bit) against the Python statement of the paper above: walking
+    the exported tree from the root, every live node sits in Karras' slot and splits its range exactly where the paper says; leaves hold
+    at most two primitives and together cover every sorted primitive once."""
+    from build_up_phase_b200 import scenes
+    for scene in (scenes.tess_scene(nx=23, ny=17, width=32, height=32, bounces=0), scenes.duplicate_key_scene(700)):
+        o = oracle.OracleScene(scene)
+        info, nodes, tris, keys, prims = o.blas_export(0)
+        o.close()
+        n = info.triangle_count
+        ref = karras_top_down(keys)
+        covered = np.zeros(n, dtype=np.int32)
+
+        def span(ref_, slot_range):
+            r = int(np.int32(ref_))
+            if r < 0:
+                first, count = (~r) >> 3, ((~r) & 7) + 1
+                assert count <= 2
+                covered[first:first + count] += 1
+                return first, first + count - 1
+            return ref[r][0], ref[r][1]
+
+        stack = [int(info.root_ref)]
+        live = 0
+        while stack:
+            slot = stack.pop()
+            first, last, gamma = ref[slot]
+            lref, rref = nodes[slot][6], nodes[slot][14]
+            assert span(lref, None) == (first, gamma), (slot, "left child range")
+            assert span(rref, None) == (gamma + 1, last), (slot, "right child range")
+            for r in (lref, rref):
+                if int(np.int32(r)) >= 0:
+                    assert int(np.int32(r)) in (gamma, gamma + 1)          # Karras numbering: children of split gamma
+                    stack.append(int(np.int32(r)))
+            live += 1
+        assert np.all(covered == 1) and live >= n // 4
