@@ -74,3 +74,59 @@ def test_host_cpp_mirror_equals_reference_literals():
     assert [h[i:i + 3] for i in range(0, 12, 3)] == LIT["hit_records"]
     assert f"WIDTH = {LIT['width']};" in src and f"HEIGHT = {LIT['height']};" in src
     assert "instance0.custom_index = 100;" in src and "instanceData[1].sbt_offset = 2;" in src and "vk.camera = {{0, 0, 10}, 60};" in src
+
+
+def test_raygen_restatement_equals_shader_text_evaluated():
+    """The reference's raygen shader body (read from /root/reference at test time, never copied) is translated line by line into numpy
+    float32 expressions and EVALUATED for every pixel; the ray directions must equal, bit for bit, the restatement the oracle and the
+    CUDA kernel use (ndc = (p + 0.5) / size * 2 - 1; dir = ndc.x*aspect_x*X + ndc.y*aspect_y*Y + Z, evaluated left to right)."""
+    path = "/root/reference/vulkan-raytracing-basic/main.cpp"
+    if not os.path.exists(path):
+        return
+    src = open(path).read()
+    body = src[src.index("const char* raygen_src"):]
+    body = body[body.index("void main()"):body.index("hitValue = vec3(0.0);")]
+    stmts = [ln.strip().rstrip(";") for ln in body.splitlines() if "=" in ln]
+    assert len(stmts) == 8 and stmts[-1].startswith("vec3 rayDir")
+
+    class V:                                     # just enough GLSL vector semantics, float32 throughout
+        __array_priority__ = 1000                # numpy scalars / arrays defer to V.__rmul__
+        def __init__(self, *c):
+            self.c = [np.asarray(x, dtype=np.float32) for x in c]
+        x = property(lambda s: s.c[0]); y = property(lambda s: s.c[1]); z = property(lambda s: s.c[2])
+        xy = property(lambda s: V(s.c[0], s.c[1]))
+
+        def _bin(self, o, f):
+            oc = o.c if isinstance(o, V) else [np.float32(o)] * len(self.c)
+            return V(*[f(a, b).astype(np.float32) for a, b in zip(self.c, oc)])
+        __add__ = lambda s, o: s._bin(o, np.add); __sub__ = lambda s, o: s._bin(o, np.subtract)
+        __mul__ = lambda s, o: s._bin(o, np.multiply); __truediv__ = lambda s, o: s._bin(o, np.divide)
+        __rmul__ = lambda s, o: s._bin(o, np.multiply)
+
+    W, H = LIT["width"], LIT["height"]
+    X, Y = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_binding as ob
+    tan_half = np.float32(ob.lib().orc_aspect_y(np.float32(LIT["yfov_deg"])))      # tan(radians(fov) * 0.5), evaluated once on the host
+    env = {"vec2": lambda *a: V(*(a if len(a) == 2 else (a[0].c if isinstance(a[0], V) else (a[0], a[0])))),
+           "vec3": lambda *a: V(*a), "float": lambda v: np.float32(v), "tan": lambda v: tan_half, "radians": lambda v: v,
+           "g": type("G", (), {"yFov_degree": np.float32(LIT["yfov_deg"])})(),
+           "gl_LaunchSizeEXT": V(np.float32(W), np.float32(H), np.float32(1)), "gl_LaunchIDEXT": V(X, Y, np.float32(0))}
+    for st in stmts:
+        name, expr = st.split("=", 1)
+        name = name.replace("const", "").split()[-1]
+        expr = re.sub(r"(\d+\.\d+|\b\d+\b)", lambda m: f"np.float32({m.group(1)})", expr)   # GLSL float literals / int-to-float conversions
+        env[name] = eval(expr, {"np": np}, env)
+    d = env["rayDir"]
+    # the restatement (rt_oracle.cpp / trace.cu): literally as written there
+    f32 = np.float32
+    ndcx = ((X + f32(0.5)) / f32(W) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = ((Y + f32(0.5)) / f32(H) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ay = tan_half
+    ax = f32(ay * f32(W) / f32(H))
+    axv, ayv = (ndcx * ax).astype(np.float32), (ndcy * ay).astype(np.float32)
+    rx = ((axv * f32(1.0) + ayv * f32(0.0)) + f32(0.0)).astype(np.float32)
+    ry = ((axv * f32(0.0) + ayv * f32(-1.0)) + f32(0.0)).astype(np.float32)
+    rz = ((axv * f32(0.0) + ayv * f32(0.0)) + f32(-1.0)).astype(np.float32)
+    for got, want in ((d.x, rx), (d.y, ry), (d.z, rz)):
+        assert np.array_equal(np.broadcast_to(got, want.shape).view(np.uint32), want.view(np.uint32))
