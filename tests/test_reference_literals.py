@@ -55,6 +55,15 @@ def test_abi_defaults_and_shader_constants_equal_reference_literals(rt):
         m = re.search(r"prim == (\d+)u && (?:inst_id|b\.inst) == (\d+)u && (?:custom|b\.I->custom) == (\d+)u && (?:geo|b\.geo) == (\d+)u", src.replace("b.prim", "prim"))
         assert m, path
         assert tuple(int(x) for x in m.groups()) == (bc["primitive"], bc["instance"], bc["custom_index"], bc["geometry"])
+    # ... and its value (1 - u - v, u, v), evaluated left to right, on all three sides
+    assert "1.0f - best_u - best_v; sc1 = best_u; sc2 = best_v" in open(os.path.join(ROOT, "build-up-phase_b200", "csrc", "trace.cu")).read()
+    assert "{1.0f - b.u - b.v, b.u, b.v}" in open(os.path.join(ROOT, "oracle", "rt_oracle.cpp")).read()
+    ref = "/root/reference/vulkan-raytracing-basic/main.cpp"
+    if os.path.exists(ref):
+        rsrc = open(ref).read()
+        assert "hitValue = vec3(1.0f - attribs.x - attribs.y, attribs.x, attribs.y);" in rsrc
+        assert "imageStore(image, ivec2(gl_LaunchIDEXT.xy), vec4(hitValue, 0.0));" in rsrc          # alpha 0, rgba8 image
+        assert "0, 1, 0,                            // sbtRecordOffset, sbtRecordStride, missIndex" in rsrc
 
 
 def test_host_cpp_mirror_equals_reference_literals():
