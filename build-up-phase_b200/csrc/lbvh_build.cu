@@ -501,7 +501,7 @@ __global__ void __launch_bounds__(128) k_inst_setup(const rt_instance* __restric
             const int ng = B->n_geoms ? (int)B->n_geoms : 1;
             sbt = (int)(sbt_flags & 0xFFFFFFu); geo = ng - 1; sbt_plus_geo = sbt + geo; bheight = (int)B->height;
         } else ok = false;
-        R.active = ok ? 1u : 0u;
+        R.active = (ok ? 1u : 0u) | ((uint32_t)geo << 1);      // bit 0: traversable; bits 1..: geometry count - 1 of its BLAS (exact SBT range check)
         if (!ok) R.root = REF_EMPTY;
         out[i] = R;
         float* bx = boxes + 6 * (size_t)i;
@@ -533,7 +533,7 @@ __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restri
     float plo[3] = {bx[0], bx[1], bx[2]}, phi[3] = {bx[3], bx[4], bx[5]};
     float slo[3] = {ordered_to_float(bounds[0]), ordered_to_float(bounds[1]), ordered_to_float(bounds[2])};
     float shi[3] = {ordered_to_float(bounds[3]), ordered_to_float(bounds[4]), ordered_to_float(bounds[5])};
-    const uint64_t key = inst[i].active ? (uint64_t)morton30(plo, phi, slo, shi) : 0x3FFFFFFFull;
+    const uint64_t key = (inst[i].active & 1u) ? (uint64_t)morton30(plo, phi, slo, shi) : 0x3FFFFFFFull;
     if (vb) keys[i] = (key << vb) | (uint64_t)i;
     else { keys[i] = key; vals[i] = i; }
 }

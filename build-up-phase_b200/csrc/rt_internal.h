@@ -48,7 +48,7 @@ struct __align__(16) InstanceRec {
     uint32_t sbt_flags;         // 76   sbt_offset:24 | flags:8
     uint32_t instance_id;       // 80   slot in the caller's rt_instance array (gl_InstanceID)
     float    absmax[3];         // 92   max(|blas.lo|, |blas.hi|) per axis
-    uint32_t active;            // 96
+    uint32_t active;            // 96   bit 0: traversable; bits 1..31: (geometry count of the BLAS) - 1
 };
 static_assert(sizeof(InstanceRec) == 96, "InstanceRec must be 96 B");
 
@@ -183,6 +183,9 @@ constexpr size_t TRACE_QUEUE_ENTRY_BYTES = 48;
 // per ray slot: the ray record + its index entry + its share of the tile mask / block sums (rounded up)
 constexpr size_t TRACE_BOUNCE_AUX_BYTES_PER_SLOT = 4 + 1;
 int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st);
+// max over the instances of sbt_offset + (n_geoms - 1) * stride: the highest hit record a trace with this stride can address (before
+// sbtRecordOffset); atomicMax into *out (device, pre-zeroed)
+int launch_sbt_bound(const InstanceRec* inst, uint32_t n, uint32_t stride, unsigned long long* out, cudaStream_t st);
 int launch_flag_add(uint32_t* counter, cudaStream_t st);
 int launch_flag_wait_ge(const uint32_t* counter, uint32_t target, int* error_flag, cudaStream_t st);
 int launch_unpack_rows(const uint8_t* packed_all, uint32_t width, uint32_t height, uint32_t block_rows,

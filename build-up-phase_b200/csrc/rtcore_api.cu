@@ -54,6 +54,7 @@ struct rt_context {
     int* d_error = nullptr;
     cudaEvent_t ev[8]{};
     rt_build_timing timing{};
+    size_t last_scratch_need = 0;                      // scratch bytes the most recent build asked for (rt_last_build_scratch_bytes)
     float last_trace_ms = 0.0f;
     rt_trace_stats last_stats{};
     uint64_t launches = 0;
@@ -80,6 +81,7 @@ struct rt_tlas {
     int32_t root = REF_EMPTY; uint32_t height = 0;
     float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
     int32_t max_sbt_plus_geo = 0, max_sbt = 0, max_geo = 0, max_blas_height = 0;
+    uint32_t bound_stride = 1; uint64_t bound = 0;     // cached max_i(sbt_i + (n_geoms_i - 1) * bound_stride); stride 1 comes with the build
 };
 
 namespace {
@@ -136,6 +138,19 @@ void carve_common(Carver& c, uint32_t n, const SortPlan& sp, BuildScratch& s) {
     s.xchg = c.take<float4>(4 * (size_t)n);
     s.sort_scratch = c.take<uint8_t>(sp.scratch_bytes);
 }
+
+// What the builds allocate; rt_blas_build_sizes / rt_tlas_build_sizes (vkGetAccelerationStructureBuildSizesKHR, main.cpp:756-762,892-898)
+// report these very numbers, so they are upper bounds by construction.
+size_t blas_storage_bytes(uint32_t n_tris, uint32_t n_blas) {
+    return align_up(sizeof(BvhNode) * (size_t)n_tris, 256) + align_up(sizeof(TriRec) * (size_t)n_tris, 256) + sizeof(BlasRecord) * (size_t)n_blas + 256;
+}
+size_t blas_scratch_bytes(uint32_t n_tris, const SortPlan& sp, uint32_t n_geoms, uint32_t n_blas, size_t stage_bytes) {
+    return build_scratch_bytes(n_tris ? n_tris : 1, sp, true, n_geoms, n_blas) + align_up(stage_bytes, 256) + 4096;
+}
+size_t tlas_storage_bytes(uint32_t n) {
+    return align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256) + align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256) + 256;
+}
+size_t tlas_scratch_bytes(uint32_t n, const SortPlan& sp) { return build_scratch_bytes(n ? n : 1, sp, false, 0, 0) + 64ull * (n ? n : 1) + 4096; }
 
 uint32_t ceil_log2(uint32_t v) { uint32_t b = 0; while ((1ull << b) < v) ++b; return b; }
 
@@ -224,9 +239,9 @@ int rt_device_info(const rt_context* ctx, int* sm_count, int* cc_major, int* cc_
 
 int rt_set_stream(rt_context* ctx, void* cuda_stream) {
     if (!ctx) return RT_ERROR_INVALID_ARG;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream && ctx->stream) RT_CUDA(ctx, cudaStreamDestroy(ctx->stream));
     ctx->stream = (cudaStream_t)cuda_stream;
     ctx->own_stream = false;
     return RT_SUCCESS;
@@ -247,16 +262,19 @@ int rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, ui
     for (uint32_t g = 0; g < n_geoms; ++g) n += max_triangle_counts[g];
     if (n > MAX_PRIMS) return fail(ctx, RT_ERROR_INVALID_ARG, "too many triangles (%llu > %u)", (unsigned long long)n, MAX_PRIMS);
     SortPlan sp = sort_plan((uint32_t)n, MORTON_BITS);
-    out->acceleration_structure_size = n * (sizeof(BvhNode) + sizeof(TriRec)) + sizeof(BlasRecord) + 512;
-    out->build_scratch_size = build_scratch_bytes((uint32_t)n, sp, true, n_geoms, 1);
+    out->acceleration_structure_size = blas_storage_bytes((uint32_t)n, 1);
+    // staging of HOST inputs: an upper bound for 12-byte vertices with at most 3 vertices per triangle (non-indexed lists are exactly
+    // that) plus 12 B of indices per triangle and the 16-byte alignment of every array; device-pointer inputs are not staged
+    const size_t stage = (size_t)n * 48 + 32ull * n_geoms;
+    out->build_scratch_size = blas_scratch_bytes((uint32_t)n, sp, n_geoms, 1, stage);
     return RT_SUCCESS;
 }
 
 int rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes* out) {
     if (!ctx || !out) return RT_ERROR_INVALID_ARG;
     SortPlan sp = sort_plan(max_instances, MORTON_BITS);
-    out->acceleration_structure_size = (uint64_t)max_instances * (sizeof(BvhNode) + sizeof(InstanceRec)) + 512;
-    out->build_scratch_size = build_scratch_bytes(max_instances, sp, false, 0, 0);
+    out->acceleration_structure_size = tlas_storage_bytes(max_instances);
+    out->build_scratch_size = tlas_scratch_bytes(max_instances, sp);
     return RT_SUCCESS;
 }
 
@@ -334,9 +352,9 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
         st = new BlasStorage();
         st->n_tris = N; st->n_blas = n_blas;
         const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
-        st->bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
+        st->bytes = blas_storage_bytes(N, n_blas);
         cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
-        if (ce != cudaSuccess) { delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", st->bytes, cudaGetErrorString(ce)); }
+        if (ce != cudaSuccess) { const size_t want = st->bytes; delete st; return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for BLAS storage failed: %s", want, cudaGetErrorString(ce)); }
         st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
         st->refs = 1;   // held by this function until handles exist
     }
@@ -344,7 +362,8 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
     struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{st};
 
     // ---- scratch ----
-    const size_t need = build_scratch_bytes(N ? N : 1, sp, true, n_geoms, n_blas) + align_up(stage_bytes, 256) + 4096;
+    const size_t need = blas_scratch_bytes(N, sp, n_geoms, n_blas, stage_bytes);
+    ctx->last_scratch_need = need;
     int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
     if (rc != RT_SUCCESS) return rc;
     Carver c(ctx->scratch);
@@ -493,6 +512,13 @@ int rt_last_build_timing(const rt_context* ctx, rt_build_timing* out) {
     return RT_SUCCESS;
 }
 float rt_last_build_ms(const rt_context* ctx) { return ctx ? ctx->timing.total_ms : 0.0f; }
+uint64_t rt_last_build_scratch_bytes(const rt_context* ctx) { return ctx ? (uint64_t)ctx->last_scratch_need : 0; }
+
+uint64_t rt_blas_device_reference(const rt_context* ctx, const rt_blas* blas) {
+    if (!ctx || !blas || !blas->st) return 0;
+    return (uint64_t)(uintptr_t)(blas->st->records + blas->index);
+}
+uint64_t rt_tlas_storage_bytes(const rt_context* ctx, const rt_tlas* tlas) { return (ctx && tlas) ? (uint64_t)tlas->bytes : 0; }
 
 int rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out) {
     if (!ctx || !blas || !out) return RT_ERROR_INVALID_ARG;
@@ -576,7 +602,7 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
         sp.seg_single = true; sp.seg_key_bits = (int)MORTON_BITS;     // a TLAS of up to 11,264 instances: one shared-memory sort kernel instead of six launches
     }
     const size_t inst_b = align_up(sizeof(InstanceRec) * (size_t)(n ? n : 1), 256), nodes_b = align_up(sizeof(BvhNode) * (size_t)(n ? n : 1), 256);
-    const size_t bytes = inst_b + nodes_b + 256;
+    const size_t bytes = tlas_storage_bytes(n);
     if (T->bytes < bytes) {
         if (T->dev) cudaFree(T->dev);
         T->dev = nullptr; T->bytes = 0;
@@ -587,9 +613,11 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
     T->n = n; T->root = REF_EMPTY; T->height = 0;
     for (int k = 0; k < 3; ++k) { T->lo[k] = FLT_MAX; T->hi[k] = -FLT_MAX; }
     T->max_sbt_plus_geo = T->max_sbt = T->max_geo = T->max_blas_height = 0;
+    T->bound_stride = 1; T->bound = 0;
     if (n == 0) return RT_SUCCESS;
 
-    const size_t need = build_scratch_bytes(n, sp, false, 0, 0) + 64ull * n + 4096;
+    const size_t need = tlas_scratch_bytes(n, sp);
+    ctx->last_scratch_need = need;
     int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
     if (rc != RT_SUCCESS) return rc;
     Carver c(ctx->scratch);
@@ -637,6 +665,7 @@ static int tlas_build_into(rt_context* ctx, rt_tlas* T, const rt_instance* insta
     if (h_err) return fail(ctx, RT_ERROR_INTERNAL, "radix-sort look-back watchdog fired");
     T->root = hmeta[0]; T->height = (uint32_t)hmeta[1];
     T->max_sbt_plus_geo = hmeta[2]; T->max_sbt = hmeta[3]; T->max_geo = hmeta[4]; T->max_blas_height = hmeta[5];
+    T->bound_stride = 1; T->bound = (uint64_t)hmeta[2];
     for (int k = 0; k < 3; ++k) { T->lo[k] = hbo[k]; T->hi[k] = hbo[3 + k]; }
     memset(&ctx->timing, 0, sizeof(ctx->timing));
     ctx->timing.primitives = n;
@@ -725,10 +754,20 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (bounces > 1) bounces = 1;
     // static SBT range check (Vulkan leaves out-of-range records undefined; we refuse)
-    if (tlas->n) {
-        const uint64_t bound = ctx->rp.sbt_record_stride == 1
-                                   ? (uint64_t)tlas->max_sbt_plus_geo + ctx->rp.sbt_record_offset
-                                   : (uint64_t)tlas->max_sbt + (uint64_t)tlas->max_geo * ctx->rp.sbt_record_stride + ctx->rp.sbt_record_offset;
+    // (exact: max over the instances of sbt_offset + (geometryCount - 1) * stride, + offset; no hit record is read at all when the
+    // closest-hit shader is skipped)
+    if (tlas->n && !(ctx->rp.ray_flags & RT_RAY_FLAG_SKIP_CLOSEST_HIT_SHADER)) {
+        rt_tlas* T = const_cast<rt_tlas*>(tlas);
+        if (T->bound_stride != ctx->rp.sbt_record_stride) {
+            unsigned long long h = 0ull;
+            RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 8, ctx->stream));
+            if (launch_sbt_bound(T->inst, T->n, ctx->rp.sbt_record_stride, ctx->d_stats, ctx->stream) < 0) return fail(ctx, RT_ERROR_CUDA, "SBT bound launch failed");
+            ctx->launches += 1;
+            RT_CUDA(ctx, cudaMemcpyAsync(&h, ctx->d_stats, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            T->bound_stride = ctx->rp.sbt_record_stride; T->bound = h;
+        }
+        const uint64_t bound = T->bound + ctx->rp.sbt_record_offset;
         if (bound >= ctx->n_records) return fail(ctx, RT_ERROR_SBT_RANGE, "hit record %llu addressed but only %u set", (unsigned long long)bound, ctx->n_records);
     }
     if ((size_t)ctx->rp.miss_index * 3 + 3 > ctx->miss.size())
@@ -787,11 +826,13 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
         row_begin[chunks] = total_rows;
     }
     if (range_rows) {                                  // an explicit row range: exactly that, one launch
-        if (!dev_out || (range_first & 7u) || range_first >= total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: device output, first row a multiple of 8 inside the part");
+        // whole bands only: packed rows [a, b) of all parts together are the image rows [a * part_count, b * part_count) only then
+        const uint32_t unit = part_count == 1 ? 8u : block_rows;
+        if (!dev_out || (range_first % unit) || range_first >= total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: device output, first row a multiple of block_rows inside the part");
         chunks = 1;
         row_begin[0] = range_first;
         row_begin[1] = range_first + range_rows < total_rows ? range_first + range_rows : total_rows;
-        if ((row_begin[1] & 7u) && row_begin[1] != total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: row count must be a multiple of 8 unless it ends the part");
+        if ((row_begin[1] % unit) && row_begin[1] != total_rows) return fail(ctx, RT_ERROR_INVALID_ARG, "row range: row count must be a multiple of block_rows unless it ends the part");
     }
     const bool two_streams = chunks > 1;
     // per-chunk scratch: ray slots (tile-major over whole 8x4 tiles), index list, tile masks + block sums, publication flags

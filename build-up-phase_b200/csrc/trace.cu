@@ -732,6 +732,15 @@ __global__ void __launch_bounds__(BIDX_THREADS) k_bounce_index(const uint32_t* _
         while (mm) { const int b = __ffs(mm) - 1; mm &= mm - 1u; index[pos++] = (w0 + k) * 32u + (uint32_t)b; }
     }
 }
+// ---- exact static SBT range: max_i (instanceSbtOffset_i + (geometryCount_i - 1) * sbtRecordStride), rule main.cpp:1260-1262 ----
+__global__ void __launch_bounds__(256) k_sbt_bound(const InstanceRec* __restrict__ inst, uint32_t n, uint32_t stride, unsigned long long* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned long long v = 0ull;
+    if (i < n) v = (unsigned long long)(__ldg(&inst[i].sbt_flags) & 0xFFFFFFu) + (unsigned long long)(__ldg(&inst[i].active) >> 1) * stride;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
+}
 // ---- stream-ordered flags in (peer) device memory: the multi-GPU frame handshake without a collective ----------------------
 __global__ void k_flag_add(uint32_t* counter) {
     __threadfence_system();
@@ -760,10 +769,14 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ 
 
 template <int STAGE, bool STATS, int STACK, bool GENERAL>
 int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
-    static int blocks_per_sm = 0;       // same for every device of this process (one device per process)
+    static int per_device[64] = {};     // occupancy of this instantiation, cached per device ordinal
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int blocks_per_sm = dev >= 0 && dev < 64 ? per_device[dev] : 0;
     if (blocks_per_sm == 0) {
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK, GENERAL>, TRACE_THREADS, 0) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
+        if (dev >= 0 && dev < 64) per_device[dev] = blocks_per_sm;
     }
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     uint32_t blocks = (uint32_t)(sm_count * blocks_per_sm);            // persistent: a multiple of the SM count
@@ -820,6 +833,11 @@ int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_coun
     return n;
 }
 
+int launch_sbt_bound(const InstanceRec* inst, uint32_t n, uint32_t stride, unsigned long long* out, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_sbt_bound<<<(n + 255) / 256, 256, 0, st>>>(inst, n, stride, out);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
 int launch_flag_add(uint32_t* counter, cudaStream_t st) {
     k_flag_add<<<1, 1, 0, st>>>(counter);
     return cudaGetLastError() == cudaSuccess ? 1 : -1;

@@ -38,6 +38,7 @@ EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync", "rt_release_scratch",
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
+    "rt_last_build_scratch_bytes", "rt_tlas_storage_bytes", "rt_blas_device_reference",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
@@ -164,6 +165,12 @@ def load(build_if_missing: bool = True):
     L.rt_last_build_timing.argtypes = [vp, C.POINTER(RtBuildTiming)]
     L.rt_last_build_ms.argtypes = [vp]
     L.rt_last_build_ms.restype = C.c_float
+    L.rt_last_build_scratch_bytes.argtypes = [vp]
+    L.rt_last_build_scratch_bytes.restype = u64
+    L.rt_tlas_storage_bytes.argtypes = [vp, vp]
+    L.rt_tlas_storage_bytes.restype = u64
+    L.rt_blas_device_reference.argtypes = [vp, vp]
+    L.rt_blas_device_reference.restype = u64
     L.rt_blas_get_info.argtypes = [vp, vp, C.POINTER(RtBlasInfo)]
     L.rt_blas_export.argtypes = [vp, vp, vp, vp]
     L.rt_debug_last_sorted_keys.argtypes = [vp, vp, vp, u32, C.POINTER(u32)]
@@ -254,6 +261,10 @@ class Blas:
         self.ctx._check(self.ctx.L.rt_blas_get_info(self.ctx.h, self.handle, C.byref(info)))
         return info
 
+    def device_reference(self) -> int:
+        """accelerationStructureReference: what a device-resident rt_instance array carries in its blas field."""
+        return int(self.ctx.L.rt_blas_device_reference(self.ctx.h, self.handle))
+
     def export(self):
         """(nodes uint32[n,16], tris uint32[n,12]) raw 64-B nodes and 48-B triangles."""
         info = self.info()
@@ -276,6 +287,9 @@ class Tlas:
         info = RtTlasInfo()
         self.ctx._check(self.ctx.L.rt_tlas_get_info(self.ctx.h, self.handle, C.byref(info)))
         return info
+
+    def storage_bytes(self) -> int:
+        return int(self.ctx.L.rt_tlas_storage_bytes(self.ctx.h, self.handle))
 
     def free(self):
         if self.handle:
@@ -415,6 +429,17 @@ class Context:
         h = C.c_void_p()
         self._check(self.L.rt_build_tlas(self.h, C.addressof(arr), len(instances), RT_BUILD_PREFER_FAST_TRACE, C.byref(h)))
         return Tlas(self, h.value)
+
+    def build_tlas_device(self, instance_records_dev, n_instances: int) -> Tlas:
+        """rt_build_tlas with RT_BUILD_INSTANCES_ON_DEVICE: `instance_records_dev` is a device buffer of n 64-byte rt_instance
+        records whose blas fields hold Blas.device_reference() values (the reference's instance buffer, main.cpp:860-868)."""
+        h = C.c_void_p()
+        self._check(self.L.rt_build_tlas(self.h, _ptr(instance_records_dev), n_instances,
+                                         RT_BUILD_PREFER_FAST_TRACE | RT_BUILD_INSTANCES_ON_DEVICE, C.byref(h)))
+        return Tlas(self, h.value)
+
+    def build_scratch_bytes(self) -> int:
+        return int(self.L.rt_last_build_scratch_bytes(self.h))
 
     def update_tlas(self, tlas: Tlas, instances, blas_handles: Sequence[Blas]):
         arr = self.instance_array(instances, blas_handles)

@@ -50,7 +50,8 @@ enum {
 
 /* ---- build flags ---------------------------------------------------------------------- */
 #define RT_BUILD_PREFER_FAST_TRACE  0x4u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, main.cpp:751 */
-#define RT_BUILD_INSTANCES_ON_DEVICE 0x100u /* rt_build_tlas: the rt_instance array is device memory */
+#define RT_BUILD_INSTANCES_ON_DEVICE 0x100u /* rt_build_tlas: the rt_instance array is DEVICE memory (what the reference's instance buffer is, main.cpp:860-868);
+                                              its `blas` fields must then hold rt_blas_device_reference() values, not host handles */
 #define RT_BUILD_NO_PACKED_SORT     0x200u /* keep (key, id) pairs in separate arrays during the sort (the general path; test hook) */
 #define RT_BUILD_NO_FUSED_SETUP     0x800u /* segmented sort, but triangle setup and Morton keys as separate kernels (test hook) */
 #define RT_BUILD_NO_SEGMENTED_SORT  0x400u /* always use the global onesweep sort, also for BLASes that fit one CTA's shared memory (test hook) */
@@ -188,8 +189,15 @@ RT_API int  rt_sync(rt_context* ctx);
 RT_API int  rt_release_scratch(rt_context* ctx);
 
 /* ---- acceleration structures ------------------------------------------------------------ */
+/* vkGetAccelerationStructureBuildSizesKHR (main.cpp:756-762, 892-898): upper bounds of what a build of these primitive counts
+ * allocates, computed by the helpers the builds themselves use. acceleration_structure_size == rt_blas_get_info().storage_bytes
+ * (resp. rt_tlas_storage_bytes) of the built structure; build_scratch_size >= rt_last_build_scratch_bytes() for host inputs of
+ * 12-byte vertices with at most 3 vertices per triangle (device-pointer inputs need less: they are not staged). */
 RT_API int  rt_blas_build_sizes(rt_context* ctx, const uint32_t* max_triangle_counts, uint32_t n_geoms, rt_build_sizes* out);
 RT_API int  rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes* out);
+/* Scratch bytes the most recent build on this context needed (the context's grow-only scratch buffer is at least that large). */
+RT_API uint64_t rt_last_build_scratch_bytes(const rt_context* ctx);
+RT_API uint64_t rt_tlas_storage_bytes(const rt_context* ctx, const rt_tlas* tlas);
 
 /* Builds one BLAS over n_geoms geometries. Inputs are copied/consumed before return: the caller
  * may free them immediately (the reference does, main.cpp:823-830). */
@@ -207,8 +215,13 @@ RT_API int  rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const
 RT_API int  rt_update_blas(rt_context* ctx, rt_blas* blas, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags);
 
 RT_API int  rt_build_tlas(rt_context* ctx, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags, rt_tlas** out);
-/* Re-fit an existing TLAS to new instance transforms (same count, same BLASes): the per-frame path. */
+/* The per-frame path: re-BUILDS the TLAS over new instance records inside the existing handle (and, when the count does not grow,
+ * inside its existing device allocation). A full rebuild of 1024 instances costs ~0.07 ms, so no refit-only shortcut is taken. */
 RT_API int  rt_update_tlas(rt_context* ctx, rt_tlas* tlas, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags);
+
+/* accelerationStructureReference of a BLAS (vkGetAccelerationStructureDeviceAddressKHR, main.cpp:785 `vk.blasAddress`): the 64-bit device
+ * address a DEVICE-resident rt_instance array (RT_BUILD_INSTANCES_ON_DEVICE) must carry in its `blas` field. 0 on error. */
+RT_API uint64_t rt_blas_device_reference(const rt_context* ctx, const rt_blas* blas);
 
 RT_API void rt_free_blas(rt_context* ctx, rt_blas* blas);
 RT_API void rt_free_tlas(rt_context* ctx, rt_tlas* tlas);
@@ -271,9 +284,10 @@ RT_API int  rt_trace_rows(rt_context* ctx, const rt_tlas* tlas, const rt_camera*
                           uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
                           uint32_t block_rows, uint32_t part_index, uint32_t part_count,
                           uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
-/* The same for only the packed rows [first_row, first_row + n_rows) of this part (multiples of 8 rows; device output): lets a caller
- * pipeline a frame in row chunks, e.g. rank 0 copying the finished rows of all ranks to the host while the next chunk is traced.
- * With interleaved bands, packed rows [a, b) of every part together are the image rows [a * part_count, b * part_count). */
+/* The same for only the packed rows [first_row, first_row + n_rows) of this part (device output; first_row and n_rows multiples of
+ * block_rows, i.e. whole bands, unless the range ends the part): lets a caller pipeline a frame in row chunks, e.g. rank 0 copying
+ * the finished rows of all ranks to the host while the next chunk is traced.
+ * With interleaved bands, packed rows [a, b) of every part together are then the image rows [a * part_count, b * part_count). */
 RT_API int  rt_trace_rows_range(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam,
                                 uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
                                 uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t first_row, uint32_t n_rows,

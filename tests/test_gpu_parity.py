@@ -522,3 +522,199 @@ def test_batched_build_paths_agree(rt, ctx, oracle):
     g, r, _ = _run(rt, ctx, oracle, scene, oracle.MODE_BRUTE, batch=True)
     rp, rs, rc = assert_parity(g, r, what="mixed-batch")
     assert rp["hits"] > 5000
+
+
+# ---- round 2: the surfaces VERDICT r01 listed as implemented but untested ----------------------------------------------
+def _sbt_scene(seed=21, n_geoms=3):
+    """Several geometries per BLAS and distinct instance SBT offsets, so that sbtRecordStride / sbtRecordOffset
+    (main.cpp:1260-1262) select visibly different hit records."""
+    scene = scenes.random_scene(n_blas=2, tris_per_blas=360, n_instances=6, seed=seed, width=320, height=200, bounces=1,
+                                n_geoms=n_geoms, shared_edges=True)
+    for i, I in enumerate(scene.instances):
+        I.mask = 0xFF
+        I.sbt_offset = [0, 3, 1, 5, 2, 4][i % 6]
+    rng = np.random.default_rng(seed)
+    scene.hit_records = rng.uniform(0.05, 0.95, size=(32, 3)).astype(np.float32)
+    return scene
+
+
+@pytest.mark.parametrize("stride,offset", [(2, 0), (3, 0), (1, 5), (2, 3), (3, 7), (0, 2)])
+def test_sbt_stride_and_offset_vs_brute_force(rt, ctx, oracle, stride, offset):
+    """record = instanceSbtOffset + geometryIndex * sbtRecordStride + sbtRecordOffset (main.cpp:1260-1262) for strides and
+    offsets other than the sample's (1, 0): ids/t/u/v bit-exact, RGBA8 within +-1 LSB of the oracle's brute force, and the
+    image must really differ from the default-parameter image (the records are all distinct)."""
+    scene = _sbt_scene()
+    sh = rt.SceneHandles(ctx, scene)
+    try:
+        base = sh.trace(want_hits=True)
+        ctx.set_ray_params(sbt_record_stride=stride, sbt_record_offset=offset)
+        g = sh.trace(want_hits=True)
+    finally:
+        ctx.set_ray_params()
+        sh.free()
+    o = oracle.OracleScene(scene)
+    r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(sbt_record_stride=stride, sbt_record_offset=offset))
+    o.close()
+    rp, rs, rc = assert_parity(g, r, what=f"sbt stride {stride} offset {offset}")
+    assert rp["hits"] > 3000 and rs["hits"] > 50
+    assert g[1].tobytes() == base[1].tobytes()                       # the SBT rule selects shading, never geometry
+    hit = g[1]["instance_id"] != MISS
+    assert (np.abs(g[0].astype(np.int16) - base[0].astype(np.int16)).max(axis=-1)[hit] > 0).mean() > 0.5
+    # spot-check the rule itself on the GPU output: pixels whose secondary ray missed show 0.5 * record + 0.5 * miss
+    sec_miss = hit & (g[2]["instance_id"] == MISS)
+    inst_sbt = np.array([I.sbt_offset for I in scene.instances], dtype=np.int64)
+    rec = inst_sbt[g[1]["instance_id"][sec_miss]] + g[1]["geometry_index"][sec_miss].astype(np.int64) * stride + offset
+    special = (g[1]["primitive_id"][sec_miss] == 1) & (g[1]["instance_id"][sec_miss] == 1) & (g[1]["custom_index"][sec_miss] == 100) & \
+              (g[1]["geometry_index"][sec_miss] == 1)
+    want = 0.5 * scene.hit_records[rec] + 0.5 * scene.miss_color[None, :]
+    got = g[0][sec_miss][:, :3].astype(np.float64) / 255.0
+    assert np.abs(got - want)[~special].max() < 1.01 / 255.0
+
+
+def test_sbt_range_check_is_exact(rt, ctx):
+    """the static range check must reduce max_i(sbt_i + (n_geoms_i - 1) * stride) per instance, not combine maxima
+    of different instances: instance A (sbt 0, 3 geometries) and B (sbt 5, 1 geometry) with stride 2 address records 0..5."""
+    S = scenes
+    quad_v = np.array([[-1, -1, 0], [1, -1, 0], [1, 1, 0], [-1, 1, 0]], dtype=np.float32)
+    quad_i = np.array([[0, 1, 3], [1, 2, 3]], dtype=np.uint32)
+    three = [S.Geometry(quad_v, quad_i, S.translation(-3 + 3 * k, 1.5, 0)) for k in range(3)]
+    one = [S.Geometry(quad_v, quad_i, S.translation(0, -1.5, 0))]
+    inst = [S.Instance(S.IDENTITY_3X4.copy(), 1, 0xFF, 0, 1, 0), S.Instance(S.IDENTITY_3X4.copy(), 2, 0xFF, 5, 1, 1)]
+    rec = np.linspace(0.1, 0.9, 18, dtype=np.float32).reshape(6, 3)
+    scene = S.Scene("sbt-exact", [three, one], inst, rec, width=200, height=120, bounces=0)
+    sh = rt.SceneHandles(ctx, scene)
+    try:
+        ctx.set_ray_params(sbt_record_stride=2)
+        rgba, prim, _ = sh.trace(want_hits=True)                    # six records are enough (the r01 bound said nine)
+        hit = prim["instance_id"] != MISS
+        got = {(int(i), int(g)): tuple(c) for i, g, c in zip(prim["instance_id"][hit], prim["geometry_index"][hit], rgba[hit][:, :3].tolist())}
+        for (i, g), c in got.items():
+            r = [0, 5][i] + 2 * g
+            assert np.abs(np.array(c) / 255.0 - rec[r]).max() < 1.01 / 255.0
+        assert set(got) == {(0, 0), (0, 1), (0, 2), (1, 0)}
+        ctx.set_hit_records(rec[:5])
+        with pytest.raises(rt.RtError) as e:
+            sh.trace()
+        assert e.value.code == rt.RT_ERROR_SBT_RANGE
+        ctx.set_ray_params(sbt_record_stride=2, ray_flags=0x1 | 0x8)   # SkipClosestHitShader: no hit record is read, nothing to refuse
+        rgba2, _, _ = sh.trace(want_hits=True)
+        assert np.all(rgba2[hit][:, :3] == 0)
+        ctx.set_ray_params(sbt_record_stride=3)                       # 0 + 2*3 = 6 > 5 records even with all six set
+        ctx.set_hit_records(rec)
+        with pytest.raises(rt.RtError):
+            sh.trace()
+    finally:
+        ctx.set_ray_params()
+        sh.free()
+
+
+@pytest.mark.parametrize("kind", ["sample", "tess1m"])
+def test_build_sizes_bound_real_allocations(rt, ctx, kind):
+    """vkGetAccelerationStructureBuildSizesKHR (main.cpp:756-762, 892-898): the reported sizes bound what the builds really
+    allocate — for the sample's {2, 2} triangle counts / 2 instances and for a 1 M-triangle mesh."""
+    if kind == "sample":
+        scene = scenes.sample_scene(64, 64)
+    else:
+        scene = scenes.tess_scene(nx=1000, ny=500, width=64, height=64, bounces=0)
+    geoms = scene.blases[0]
+    sizes = ctx.blas_build_sizes([g.triangle_count for g in geoms])
+    blas = ctx.build_blas(geoms)
+    info = blas.info()
+    assert info.storage_bytes > 0 and sizes.acceleration_structure_size >= info.storage_bytes
+    assert sizes.build_scratch_size >= ctx.build_scratch_bytes() > 0
+    assert sizes.acceleration_structure_size < 2 * info.storage_bytes + 4096      # a bound, not a wild guess
+    assert sizes.build_scratch_size < 2 * ctx.build_scratch_bytes() + 65536
+    tsizes = ctx.tlas_build_sizes(len(scene.instances))
+    tlas = ctx.build_tlas(scene.instances, [blas])
+    assert tsizes.acceleration_structure_size >= tlas.storage_bytes() > 0
+    assert tsizes.build_scratch_size >= ctx.build_scratch_bytes() > 0
+    tlas.free(); blas.free()
+    t1k = ctx.tlas_build_sizes(1024)
+    assert t1k.acceleration_structure_size >= 1024 * (64 + 96)
+
+
+def test_blas_import_roundtrip_traces_identically(rt, ctx, oracle):
+    """rt_blas_get_info().device_storage -> (copy, as an NCCL broadcast would deliver it) -> rt_blas_import on ANOTHER context:
+    the adopted BLAS has the same root/bounds/depth, exports the same nodes and triangles and traces to the same frame and hits
+    (the cfg5 per-GPU build + broadcast path)."""
+    import torch
+    S = scenes
+    geoms = [S.heightfield(50, 40, -2.5, 2.5, -2.0, 2.0, 0.7, 31), S.heightfield(20, 20, -1.0, 1.0, -1.0, 1.0, 0.3, 32)]
+    geoms[1].transform = S.translation(0.0, 0.0, 1.5)
+    inst = [S.Instance(S.rotation_3x4(np.array([0.3, 1.0, 0.2]), 0.5, np.array([0.5, 0.0, 0.0])), 9, 0xFF, 1, 1, 0),
+            S.Instance(S.translation(-1.0, 0.5, -2.0), 10, 0xFF, 0, 1, 0)]
+    scene = S.Scene("import", [geoms], inst, S.SAMPLE_HIT_RECORDS.copy(), width=320, height=200, bounces=1)
+    sh = rt.SceneHandles(ctx, scene)
+    g1 = sh.trace(want_hits=True)
+    src = sh.blases[0]
+    info = src.info()
+    blob = rt.device_view(info.device_storage, int(info.storage_bytes), "cuda:0").clone()      # the broadcast's receive buffer
+    torch.cuda.synchronize()
+    n1, t1 = src.export()
+    with rt.Context(0) as ctx2:
+        b2 = ctx2.import_blas(info, blob)
+        del blob
+        i2 = b2.info()
+        assert (i2.root_ref, i2.max_depth, i2.triangle_count) == (info.root_ref, info.max_depth, info.triangle_count)
+        assert list(i2.bounds_lo) == list(info.bounds_lo) and list(i2.bounds_hi) == list(info.bounds_hi)
+        assert i2.device_storage != info.device_storage
+        n2, t2 = b2.export()
+        assert np.array_equal(n1, n2) and np.array_equal(t1, t2)
+        tl2 = ctx2.build_tlas(scene.instances, [b2])
+        ctx2.set_hit_records(scene.hit_records); ctx2.set_miss_color(scene.miss_color)
+        g2 = ctx2.trace(tl2, ctx2.camera(scene.camera_pos, scene.yfov_deg), scene.width, scene.height, 1, want_hits=True)
+        tl2.free(); b2.free()
+    sh.free()
+    assert np.array_equal(g1[0], g2[0]) and g1[1].tobytes() == g2[1].tobytes() and g1[2].tobytes() == g2[2].tobytes()
+    o = oracle.OracleScene(scene)
+    r = o.trace(mode=oracle.MODE_BRUTE)
+    o.close()
+    rp, rs, _ = assert_parity(g2, r, what="imported blas")
+    assert rp["hits"] > 5000
+
+
+def test_tlas_from_device_resident_instances(rt, ctx, oracle):
+    """RT_BUILD_INSTANCES_ON_DEVICE: the 64-byte instance records live in device memory, like the reference's instance buffer
+    (main.cpp:860-868), and carry rt_blas_device_reference() values (its vk.blasAddress, main.cpp:785,853)."""
+    import ctypes as C
+    import torch
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=300, n_instances=7, seed=5, width=320, height=200, bounces=1)
+    sh = rt.SceneHandles(ctx, scene)
+    g_host = sh.trace(want_hits=True)
+    arr = ctx.instance_array(scene.instances, sh.blases)
+    for i, I in enumerate(scene.instances):
+        ref = sh.blases[I.blas].device_reference()
+        assert ref != 0 and ref != sh.blases[I.blas].handle
+        arr[i].blas = ref
+    raw = np.frombuffer(C.string_at(C.addressof(arr), 64 * len(scene.instances)), dtype=np.uint8).copy()
+    dev = torch.from_numpy(raw).cuda()
+    tl = ctx.build_tlas_device(dev, len(scene.instances))
+    g_dev = ctx.trace(tl, sh.cam, scene.width, scene.height, 1, want_hits=True)
+    tl.free(); sh.free()
+    assert np.array_equal(g_host[0], g_dev[0]) and g_host[1].tobytes() == g_dev[1].tobytes() and g_host[2].tobytes() == g_dev[2].tobytes()
+    o = oracle.OracleScene(scene)
+    r = o.trace(mode=oracle.MODE_BRUTE)
+    o.close()
+    assert_parity(g_dev, r, what="device instances")
+
+
+def test_rows_range_needs_whole_bands(rt, ctx):
+    """with block_rows = 16 a chunk of 8 packed rows is half a band; the header's promise (packed rows [a, b) of all
+    parts = image rows [a * parts, b * parts)) holds for whole bands only, so the call is refused."""
+    import torch
+    scene = scenes.sample_scene(160, 128)
+    sh = rt.SceneHandles(ctx, scene)
+    out = torch.zeros((128, 160, 4), dtype=torch.uint8, device="cuda:0")
+    try:
+        with pytest.raises(rt.RtError):
+            ctx.trace_rows_range(sh.tlas, sh.cam, 160, 128, 0, 16, 0, 2, 8, 16, out, full_frame=True)
+        with pytest.raises(rt.RtError):
+            ctx.trace_rows_range(sh.tlas, sh.cam, 160, 128, 0, 16, 0, 2, 0, 24, out, full_frame=True)
+        full, _, _ = sh.trace(want_hits=False)
+        for p in range(2):
+            for a, b in ((0, 32), (32, 64)):
+                ctx.trace_rows_range(sh.tlas, sh.cam, 160, 128, 0, 16, p, 2, a, b - a, out, full_frame=True)
+        ctx.sync()
+        assert np.array_equal(out.cpu().numpy(), full)
+    finally:
+        sh.free()
