@@ -12,9 +12,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librtcore.so")
-SOURCES = ["rtcore_api.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu",
+SOURCES = ["rtcore_api.cu", "rt_group.cu", "lbvh_build.cu", "radix_sort.cu", "trace.cu",
            os.path.join("..", "host", "rtcore_io.cpp")]     # host-side .obj / image I/O (include/rtcore_io.h), no device code
-HEADERS = ["rt_internal.h", "rt_device.cuh", "seg_sort.cuh", os.path.join("..", "..", "include", "rtcore.h"),
+HEADERS = ["rt_internal.h", "rt_host.h", "rt_device.cuh", "seg_sort.cuh", os.path.join("..", "..", "include", "rtcore.h"),
            os.path.join("..", "..", "include", "rtcore_io.h")]
 
 NVCC_FLAGS = [
@@ -48,7 +48,7 @@ def build_variant(name: str, defines) -> str:
     ccbin = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
     flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
     cmd = [_nvcc(), "-ccbin", ccbin, *flags, *[f"-D{d}" for d in defines], "-shared", "-o", out,
-           *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+           *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart", "-lrt"]
     subprocess.check_call(cmd)
     return out
 
@@ -73,7 +73,7 @@ def build_rtcore(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write("\n".join(log))
             raise RuntimeError(f"nvcc failed on {s}")
-    cmd = [_nvcc(), "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-ccbin", ccbin, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-lrt"]
     subprocess.check_call(cmd)
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
@@ -82,10 +82,11 @@ def build_rtcore(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
-def build_host_sample() -> str:
-    """Compiles the headless C++ host program (host/sample_scene.cpp) against librtcore.so."""
-    src = os.path.join(HERE, "host", "sample_scene.cpp")
-    out = os.path.join(HERE, "host", "sample_scene")
+def build_host_sample(name: str = "sample_scene") -> str:
+    """Compiles a headless C++ host program (host/sample_scene.cpp: the reference's main(); host/sample_scene_mgpu.cpp: the same on
+    the GPUs of one box, one process per GPU) against librtcore.so."""
+    src = os.path.join(HERE, "host", name + ".cpp")
+    out = os.path.join(HERE, "host", name)
     if os.path.exists(out) and os.path.getmtime(out) > max(os.path.getmtime(src), os.path.getmtime(LIB)):
         return out
     cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
@@ -97,3 +98,4 @@ def build_host_sample() -> str:
 if __name__ == "__main__":
     print(build_rtcore(force="--force" in sys.argv, verbose=True))
     print(build_host_sample())
+    print(build_host_sample("sample_scene_mgpu"))

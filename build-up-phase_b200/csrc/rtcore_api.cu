@@ -17,101 +17,14 @@
 #include <vector>
 
 #include "rt_device.cuh"
+#include "rt_host.h"
 
 using namespace rt;
 
-struct rt_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    cudaStream_t copy_stream = nullptr;                           // device->host copies of finished row chunks (overlaps the next chunk's trace)
-    cudaStream_t aux_stream = nullptr;                            // second compute stream: odd row chunks of a frame (their CTAs fill the even chunks' kernel tails)
-    cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
-    int trace_chunks = 1;                                         // row chunks of a DEVICE-output trace (RTCORE_TRACE_CHUNKS); measured 3.56/3.55/3.67/3.67/4.02/4.07 ms for
-                                                                  // 1/2/3/4/6/8 chunks: tail filling only pays back the extra launches, so the default is one launch
-    cudaEvent_t chunk_ev[8]{};
-    int e2e_chunks = 3;                                            // row chunks of a HOST-output trace (RTCORE_E2E_CHUNKS): chunk c is copied device->host
-                                                                   // while chunk c + 1 is traced; the chunks alternate over two compute streams (the next
-                                                                   // chunk's CTAs fill the previous chunk's kernel tails) and shrink towards the end of the
-                                                                   // frame (3 : 2 : 1), since only the last copy is exposed. Measured on B200, inst10m 4K:
-                                                                   // 1 chunk 4.19 ms; equal chunks 2/3/4: 3.88/3.90/3.85; shrinking 3/4/5/6: 3.59/3.72/3.81/3.85
-    cudaDeviceProp prop{};
-    std::string err;
-    // shader data
-    float* d_hit_records = nullptr; uint32_t n_records = 0;
-    std::vector<float> miss = {0.0f, 0.0f, 0.2f};                 // miss records, 3 floats each; record 0 = main.cpp:1065
-    rt_ray_params rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, RT_RAY_FLAG_OPAQUE, 0u};   // main.cpp:1047-1052
-    // grow-only device buffers
-    void* scratch = nullptr; size_t scratch_cap = 0;
-    void* fb = nullptr; size_t fb_cap = 0;
-    void* hits1 = nullptr; size_t hits1_cap = 0;
-    void* hits2 = nullptr; size_t hits2_cap = 0;
-    void* queue = nullptr; size_t queue_cap = 0;       // bounce queue of the two-stage wavefront
-    uint32_t* qflags = nullptr; size_t qflags_cap = 0; // per-entry publication flags of the fused launch (hold the epoch of the launch that wrote the entry)
-    uint32_t trace_epoch = 0;
-    uint32_t* d_counters = nullptr;                    // ray-fetch / queue counters of the persistent trace kernels
-    unsigned long long* d_stats = nullptr;
-    int* d_error = nullptr;
-    cudaEvent_t ev[8]{};
-    rt_build_timing timing{};
-    size_t last_scratch_need = 0;                      // scratch bytes the most recent build asked for (rt_last_build_scratch_bytes)
-    float last_trace_ms = 0.0f;
-    rt_trace_stats last_stats{};
-    uint64_t launches = 0;
-    // debug view of the last BLAS build's sorted keys (lives in scratch until the next build)
-    const uint64_t* dbg_keys = nullptr; const uint32_t* dbg_vals = nullptr; uint32_t dbg_n = 0; int dbg_vb = 0;
-};
-
-struct BlasStorage {
-    int refs = 0;
-    void* dev = nullptr;            // nodes[N] | tris[N] | records[n_blas]
-    size_t bytes = 0;
-    BvhNode* nodes = nullptr; TriRec* tris = nullptr; BlasRecord* records = nullptr;
-    uint32_t n_tris = 0, n_blas = 0;
-};
-struct rt_blas {
-    BlasStorage* st = nullptr;
-    uint32_t index = 0;
-    BlasRecord rec{};               // host copy
-};
-struct rt_tlas {
-    void* dev = nullptr; size_t bytes = 0;
-    InstanceRec* inst = nullptr; BvhNode* nodes = nullptr;
-    uint32_t n = 0;
-    int32_t root = REF_EMPTY; uint32_t height = 0;
-    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
-    int32_t max_sbt_plus_geo = 0, max_sbt = 0, max_geo = 0, max_blas_height = 0;
-    uint32_t bound_stride = 1; uint64_t bound = 0;     // cached max_i(sbt_i + (n_geoms_i - 1) * bound_stride); stride 1 comes with the build
-};
-
 namespace {
 
-int fail(rt_context* ctx, int code, const char* fmt, ...) {
-    if (ctx) {
-        char buf[512];
-        va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
-        ctx->err = buf;
-    }
-    return code;
-}
-#define RT_CUDA(ctx, call)                                                                                     \
-    do {                                                                                                       \
-        cudaError_t e__ = (call);                                                                              \
-        if (e__ != cudaSuccess)                                                                                \
-            return fail(ctx, e__ == cudaErrorMemoryAllocation ? RT_ERROR_OUT_OF_MEMORY : RT_ERROR_CUDA,        \
-                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__);         \
-    } while (0)
-
-int ensure(rt_context* ctx, void** p, size_t* cap, size_t need) {
-    if (*cap >= need && *p) return RT_SUCCESS;
-    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
-    size_t want = need + need / 8 + 256;
-    RT_CUDA(ctx, cudaMalloc(p, want));
-    *cap = want;
-    return RT_SUCCESS;
-}
-
-inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+#define fail rt_fail
+#define ensure rt_ensure
 
 struct Carver {
     uint8_t* base; size_t off = 0;
@@ -200,7 +113,8 @@ void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_hit_records); cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
+    if (ctx->own_hit_records) cudaFree(ctx->d_hit_records);
+    cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->qflags); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
     for (auto& e : ctx->chunk_ev) if (e) cudaEventDestroy(e);
@@ -737,6 +651,16 @@ int rt_set_ray_params(rt_context* ctx, const rt_ray_params* params) {
     return RT_SUCCESS;
 }
 
+}  // extern "C"
+// the render group's second context (odd frames of a pipelined sequence) follows the user's context
+int rt_context_mirror_shader_state(rt_context* dst, const rt_context* src) {
+    if (!dst || !src || dst->own_hit_records) return RT_ERROR_INVALID_ARG;
+    dst->d_hit_records = src->d_hit_records; dst->n_records = src->n_records;
+    dst->miss = src->miss; dst->rp = src->rp;
+    return RT_SUCCESS;
+}
+extern "C" {
+
 // ---- dispatch ------------------------------------------------------------------------------------------
 uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_rows, uint32_t part_count) {
     if (!block_rows || !part_count) return 0;
@@ -779,9 +703,13 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     const uint64_t pixels = part_count == 1 ? (uint64_t)width * height : rt_rows_packed_pixels(width, height, block_rows, part_count);
     const bool dev_out = (flags & RT_TRACE_OUT_DEVICE) != 0;
     const bool full_frame = (flags & RT_TRACE_OUT_FULL_FRAME) != 0;
-    if (full_frame && !dev_out) return fail(ctx, RT_ERROR_INVALID_ARG, "RT_TRACE_OUT_FULL_FRAME needs RT_TRACE_OUT_DEVICE");
+    // host output + FULL_FRAME: the kernels write this part's packed bands into the context's staging buffer and every finished row
+    // chunk is scattered band by band (one 2-D copy) to its final rows of the caller's whole-frame HOST buffer — with one process
+    // per GPU and a frame in shared pinned host memory, every GPU moves its share over its own PCIe link
+    const bool host_scatter = full_frame && !dev_out && part_count > 1;
+    if (host_scatter && (primary_hits_out || secondary_hits_out)) return fail(ctx, RT_ERROR_INVALID_ARG, "hit buffers are not scattered: use packed output for them");
     TraceParams P{};
-    P.full_frame = full_frame ? 1u : 0u;
+    P.full_frame = (full_frame && dev_out) ? 1u : 0u;
     P.bgra = (flags & RT_TRACE_OUT_BGRA) ? 1u : 0u;
     P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
     for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[3 * (size_t)ctx->rp.miss_index + k]; }
@@ -823,6 +751,16 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
             if (end > row_begin[n]) row_begin[++n] = end;
         }
         chunks = n ? n : 1;
+        row_begin[chunks] = total_rows;
+    }
+    if (host_scatter && chunks > 1) {                   // chunk boundaries on whole bands (and multiples of 8 rows)
+        const uint32_t unit = (block_rows % 8u == 0u) ? block_rows : 2u * block_rows;
+        uint32_t n = 0;
+        for (uint32_t c = 1; c < chunks; ++c) {
+            const uint32_t e = row_begin[c] / unit * unit;
+            if (e > row_begin[n] && e < total_rows) row_begin[++n] = e;
+        }
+        chunks = n + 1;
         row_begin[chunks] = total_rows;
     }
     if (range_rows) {                                  // an explicit row range: exactly that, one launch
@@ -892,6 +830,22 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
             const size_t p0 = (size_t)row_begin[c] * width;
             const size_t np = (size_t)(row_begin[c + 1] - row_begin[c]) * width;
             RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->chunk_ev[c], 0));
+            if (host_scatter) {
+                // packed band lb of this part = image rows [(lb * part_count + part_index) * block_rows, + block_rows), clipped to the image
+                const uint32_t lb0 = row_begin[c] / block_rows, lb1 = (row_begin[c + 1] + block_rows - 1) / block_rows;
+                const size_t band_bytes = (size_t)block_rows * width * 4;
+                uint32_t full = 0, tail_rows = 0;
+                for (uint32_t lb = lb0; lb < lb1; ++lb) {
+                    const uint64_t y0 = ((uint64_t)lb * part_count + part_index) * block_rows;
+                    if (y0 + block_rows <= height) ++full; else { if (y0 < height) tail_rows = (uint32_t)(height - y0); break; }
+                }
+                const uint8_t* src = P.rgba + (size_t)lb0 * band_bytes;
+                uint8_t* dst = rgba_out + ((size_t)lb0 * part_count + part_index) * band_bytes;
+                if (full) RT_CUDA(ctx, cudaMemcpy2DAsync(dst, band_bytes * part_count, src, band_bytes, band_bytes, full, cudaMemcpyDeviceToHost, ctx->copy_stream));
+                if (tail_rows) RT_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)full * band_bytes * part_count, src + (size_t)full * band_bytes, (size_t)tail_rows * width * 4,
+                                                            cudaMemcpyDeviceToHost, ctx->copy_stream));
+                continue;
+            }
             RT_CUDA(ctx, cudaMemcpyAsync(rgba_out + 4 * p0, P.rgba + 4 * p0, np * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out + p0, P.primary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out + p0, P.secondary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
@@ -991,6 +945,14 @@ int rt_flag_wait_ge(rt_context* ctx, const uint32_t* counter, uint32_t target) {
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     if (launch_flag_wait_ge(counter, target, ctx->d_error, ctx->stream) < 0) return fail(ctx, RT_ERROR_CUDA, "flag launch failed");
     ctx->launches += 1;
+    return RT_SUCCESS;
+}
+
+int rt_copy_to_host(rt_context* ctx, void* dst_host, const void* src_device, uint64_t bytes) {
+    if (!ctx || (bytes && (!dst_host || !src_device))) return RT_ERROR_INVALID_ARG;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (bytes) RT_CUDA(ctx, cudaMemcpyAsync(dst_host, src_device, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return RT_SUCCESS;
 }
 

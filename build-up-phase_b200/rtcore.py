@@ -42,7 +42,9 @@ EXPORTED_SYMBOLS = [
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
-    "rt_kernel_launch_count", "rt_version",
+    "rt_kernel_launch_count", "rt_version", "rt_copy_to_host",
+    "rt_group_create", "rt_group_destroy", "rt_group_trace", "rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world",
+    "rt_group_share_blas", "rt_group_share_finish", "rt_group_last_share_ms", "rt_group_host_frame_begin", "rt_group_host_frame_end", "rt_group_last_error",
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
     "rt_obj_group_count", "rt_obj_vertices", "rt_obj_indices", "rt_obj_group_name", "rt_obj_group_first_triangle",
@@ -198,6 +200,20 @@ def load(build_if_missing: bool = True):
     L.rt_kernel_launch_count.argtypes = [vp]
     L.rt_kernel_launch_count.restype = u64
     L.rt_version.restype = C.c_char_p
+    L.rt_copy_to_host.argtypes = [vp, vp, vp, u64]
+    L.rt_group_create.argtypes = [vp, C.c_char_p, i32, i32, u32, u32, C.POINTER(vp)]
+    L.rt_group_destroy.argtypes = [vp]
+    L.rt_group_destroy.restype = None
+    L.rt_group_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, C.POINTER(vp)]
+    for name in ("rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world", "rt_group_share_finish"):
+        getattr(L, name).argtypes = [vp]
+    L.rt_group_share_blas.argtypes = [vp, u32, i32, vp, C.POINTER(vp)]
+    L.rt_group_last_share_ms.argtypes = [vp]
+    L.rt_group_last_share_ms.restype = C.c_float
+    L.rt_group_host_frame_begin.argtypes = [vp, C.POINTER(vp)]
+    L.rt_group_host_frame_end.argtypes = [vp, C.POINTER(vp)]
+    L.rt_group_last_error.argtypes = [vp]
+    L.rt_group_last_error.restype = C.c_char_p
     # include/rtcore_io.h
     L.rt_obj_load.argtypes = [C.c_char_p, C.POINTER(vp)]
     L.rt_obj_parse.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(vp)]
@@ -553,6 +569,75 @@ class Context:
 
     def trace_ms(self) -> float:
         return float(self.L.rt_last_trace_ms(self.h))
+
+
+GROUP_OUT_DEVICE, GROUP_OUT_HOST, GROUP_ASYNC, GROUP_PIPELINE = 0x1, 0x2, 0x4, 0x8
+
+
+class Group:
+    """rt_group: `world` processes (one per GPU of one box, scene replicated) rendering one frame together. The ranks meet in a
+    POSIX shared-memory block named after `name`; no torch.distributed / NCCL is involved. ctx=None gives a host-only group
+    (barrier + shared host frame), which is what the CPU tests of the handshake use."""
+
+    def __init__(self, ctx: Optional["Context"], name: str, rank: int, world: int, max_width: int, max_height: int):
+        self.L = load()
+        self.ctx = ctx
+        h = C.c_void_p()
+        rc = self.L.rt_group_create(ctx.h if ctx is not None else None, name.encode(), rank, world, max_width, max_height, C.byref(h))
+        if rc != RT_SUCCESS:
+            raise RtError(rc, self.L.rt_last_error(ctx.h).decode() if ctx is not None else "rt_group_create failed")
+        self.h, self.rank, self.world = h, rank, world
+        self.max_width, self.max_height = max_width, max_height
+
+    def _check(self, rc: int):
+        if rc != RT_SUCCESS:
+            raise RtError(rc, self.L.rt_group_last_error(self.h).decode())
+
+    def trace(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, flags: int) -> Optional[int]:
+        """One group frame; returns the frame pointer on rank 0 (device or host, by flags), None elsewhere."""
+        p = C.c_void_p()
+        self._check(self.L.rt_group_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, C.byref(p)))
+        return p.value
+
+    def trace_host(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int) -> Optional[np.ndarray]:
+        """RT_GROUP_OUT_HOST: every rank copies its bands over its own PCIe link; rank 0 gets a numpy VIEW of the shared pinned frame."""
+        p = self.trace(tlas, cam, width, height, bounces, GROUP_OUT_HOST)
+        if not p:
+            return None
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(height, width, 4))
+
+    def host_frame_begin(self) -> int:
+        p = C.c_void_p()
+        self._check(self.L.rt_group_host_frame_begin(self.h, C.byref(p)))
+        return p.value
+
+    def host_frame_end(self) -> Optional[int]:
+        p = C.c_void_p()
+        self._check(self.L.rt_group_host_frame_end(self.h, C.byref(p)))
+        return p.value
+
+    def sync(self):
+        self._check(self.L.rt_group_sync(self.h))
+
+    def join(self):
+        self._check(self.L.rt_group_join(self.h))
+
+    def barrier(self):
+        self._check(self.L.rt_group_barrier(self.h))
+
+    def share_blas(self, slot: int, owner_rank: int, mine: Optional[Blas]) -> Blas:
+        h = C.c_void_p()
+        self._check(self.L.rt_group_share_blas(self.h, slot, owner_rank, mine.handle if mine is not None else None, C.byref(h)))
+        return mine if (mine is not None and self.rank == owner_rank) else Blas(self.ctx, h.value)
+
+    def share_finish(self) -> float:
+        self._check(self.L.rt_group_share_finish(self.h))
+        return float(self.L.rt_group_last_share_ms(self.h))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.rt_group_destroy(self.h)
+            self.h = None
 
 
 class SceneHandles:

@@ -334,3 +334,31 @@ def random_scene(n_blas: int, tris_per_blas: int, n_instances: int, seed: int, w
         mask = 0xFF if i % 7 != 6 else 0x00          # every 7th instance is invisible to cullMask 0xff
         instances.append(Instance(m, 100 if i == 1 else i, mask, int(rng.integers(0, 4)), 1, int(rng.integers(0, n_blas))))
     return Scene(f"random{seed}", blases, instances, records, width=width, height=height, bounces=bounces)
+
+
+def save_scene(scene: Scene, path: str) -> None:
+    """Writes the scene's host arrays as an "RTSCENE1" file, the input format of the C++ multi-GPU host program
+    (host/sample_scene_mgpu.cpp --scene): header {n_blas, n_instances, n_records, width, height, bounces} (uint32),
+    {camera xyz, fov, miss rgb} (float32); per BLAS: n_geoms, then per geometry {n_verts, n_indexed_tris, has_xform, flags}, the
+    vertices (float32 x 3), the indices (uint32 x 3, absent for a non-indexed list), the 3x4 transform (if any); the 64-byte
+    instance records (VkAccelerationStructureInstanceKHR layout, main.cpp:848-858, BLAS index in the reference field); hit records."""
+    import struct
+    with open(path, "wb") as f:
+        f.write(b"RTSCENE1")
+        f.write(struct.pack("<6I", len(scene.blases), len(scene.instances), int(scene.hit_records.shape[0]), scene.width, scene.height, scene.bounces))
+        f.write(struct.pack("<7f", *[float(x) for x in scene.camera_pos], float(scene.yfov_deg), *[float(x) for x in scene.miss_color]))
+        for geoms in scene.blases:
+            f.write(struct.pack("<I", len(geoms)))
+            for g in geoms:
+                v = np.ascontiguousarray(g.vertices, dtype=np.float32).reshape(-1, 3)
+                nt = 0 if g.indices is None else int(g.indices.shape[0])
+                f.write(struct.pack("<4I", v.shape[0], nt, 0 if g.transform is None else 1, int(getattr(g, "flags", 1)) & 0xFF))
+                f.write(v.tobytes())
+                if g.indices is not None:
+                    f.write(np.ascontiguousarray(g.indices, dtype=np.uint32).tobytes())
+                if g.transform is not None:
+                    f.write(np.ascontiguousarray(g.transform, dtype=np.float32).tobytes())
+        for I in scene.instances:
+            f.write(np.ascontiguousarray(I.transform, dtype=np.float32).tobytes())
+            f.write(struct.pack("<IIQ", (I.custom_index & 0xFFFFFF) | ((I.mask & 0xFF) << 24), (I.sbt_offset & 0xFFFFFF) | ((I.flags & 0xFF) << 24), int(I.blas)))
+        f.write(np.ascontiguousarray(scene.hit_records, dtype=np.float32).tobytes())

@@ -85,10 +85,13 @@ enum {
 #define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait) */
 #define RT_TRACE_OUT_BGRA   0x10u /* store B,G,R,A byte order — the sample copies its image raw into a B8G8R8A8 swapchain (main.cpp:50,971-974,1371-1375);
                                     the default is the logical R,G,B,A of imageStore(vec4(hitValue, 0.0)) */
-#define RT_TRACE_OUT_FULL_FRAME 0x8u /* rt_trace_rows with RT_TRACE_OUT_DEVICE: rgba_out is the WHOLE width*height*4 frame and this part's
-                                        pixels are stored at their final position (no packing, no unpack step). The frame may be peer memory
-                                        of another GPU (rt_frame_share_open): the trace kernel then writes over NVLink straight into rank 0's
-                                        framebuffer and the gather disappears. */
+#define RT_TRACE_OUT_FULL_FRAME 0x8u /* rt_trace_rows: rgba_out is the WHOLE width*height*4 frame and this part's pixels land at their final
+                                        position (no packed buffer to gather, no unpack step).
+                                        With RT_TRACE_OUT_DEVICE the trace kernel stores them there itself; the frame may be peer memory of
+                                        another GPU (rt_frame_share_open): the kernel then writes over NVLink straight into rank 0's framebuffer.
+                                        With a HOST rgba_out (e.g. a frame in shared pinned host memory that every rank's process maps) the
+                                        part's bands are copied to their final rows, chunk by chunk while the next chunk is traced: every GPU
+                                        moves its share of the image over its own PCIe link. */
 
 typedef struct rt_context rt_context;
 typedef struct rt_blas    rt_blas;
@@ -312,6 +315,54 @@ RT_API int  rt_frame_share_close(rt_context* ctx, void* mapped_device_ptr);     
 RT_API int  rt_flag_add(rt_context* ctx, uint32_t* counter_device_ptr);
 RT_API int  rt_flag_wait_ge(rt_context* ctx, const uint32_t* counter_device_ptr, uint32_t target);
 RT_API int  rt_frame_share_free(rt_context* ctx, void* device_ptr);             /* a pointer from rt_frame_share_create */
+
+/* ---- render group: the 8 GPUs of one box, one process per GPU (SURVEY 8(b) "rt_create_group", 8(e)) ------------------------------
+ * The reference is single-GPU (one device, one queue: main.cpp:294-388); a group makes `world` processes — each with its own
+ * rt_context on its own GPU and the scene replicated — render ONE frame: the image is cut into 8-scanline bands, band b belongs to
+ * rank b % world. No MPI / NCCL / torch is needed: the ranks meet in a POSIX shared-memory object named after `name`
+ * (every rank passes the same name, e.g. derived from the job id; rank 0 creates it, the others attach; 60-s timeouts everywhere).
+ *   RT_GROUP_OUT_DEVICE: every rank's trace kernel stores its pixels straight into rank 0's device frame over NVLink / NVSwitch
+ *     (CUDA-IPC mapping, two alternating frames, stream-ordered completion counters in the frame's tail: no collective, no host
+ *     round trip). On rank 0 *frame_out is the device pointer of the finished frame, valid until the second-next group trace.
+ *   RT_GROUP_OUT_HOST: every rank copies its bands over its OWN PCIe link into the group's pinned host frame (shared memory that
+ *     all ranks registered with CUDA); on rank 0 *frame_out is the host pointer of the finished frame (valid until the second-next
+ *     group trace). The call returns on rank 0 when the whole frame is there, on the other ranks when their share is.
+ *   RT_GROUP_ASYNC (device output): enqueue and return; rt_group_sync() waits for everything enqueued so far.
+ *   RT_GROUP_PIPELINE (device output, implies ASYNC): consecutive frames alternate over two internal streams, so frame k + 1's
+ *     first rays fill the tail of frame k's persistent kernels (the per-frame fixed cost that limits scaling at 8 GPUs).
+ * Every rank must make the same sequence of group calls. A group of world = 1 is valid (no peer traffic). */
+typedef struct rt_group rt_group;
+#define RT_GROUP_OUT_DEVICE 0x1u
+#define RT_GROUP_OUT_HOST   0x2u
+#define RT_GROUP_ASYNC      0x4u
+#define RT_GROUP_PIPELINE   0x8u
+RT_API int  rt_group_create(rt_context* ctx, const char* name, int rank, int world, uint32_t max_width, uint32_t max_height, rt_group** out);
+RT_API void rt_group_destroy(rt_group* group);
+RT_API int  rt_group_trace(rt_group* group, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
+                           uint32_t flags, const uint8_t** frame_out);
+RT_API int  rt_group_sync(rt_group* group);       /* all frames enqueued by this rank are complete (and, on rank 0, assembled) */
+RT_API int  rt_group_join(rt_group* group);       /* stream-ordered: the context stream waits for the group's internal streams (no host wait) */
+RT_API int  rt_group_barrier(rt_group* group);    /* host barrier of all ranks */
+/* The host-frame handshake on its own (rt_group_trace with RT_GROUP_OUT_HOST = begin + rt_trace_rows into the frame + end): begin gives
+ * every rank the shared pinned host frame of this turn once rank 0's caller has let go of its previous content; end publishes this rank's
+ * share and, on rank 0, returns when all `world` shares are there. Works without CUDA too (ctx == NULL at rt_group_create). */
+RT_API int  rt_group_host_frame_begin(rt_group* group, uint8_t** frame_out);
+RT_API int  rt_group_host_frame_end(rt_group* group, const uint8_t** frame_out_rank0);
+RT_API const char* rt_group_last_error(const rt_group* group);
+RT_API int  rt_group_rank(const rt_group* group);
+RT_API int  rt_group_world(const rt_group* group);
+/* cfg5: "BLASes are built per GPU and broadcast". Collective over the group: rank `owner_rank` passes its BLAS (built on
+ * its own, rt_build_blas), the others NULL; on return *out is that BLAS on the owner and, on every other rank, a handle to a local copy
+ * that is being PULLED from the owner's memory over NVLink on a copy stream (CUDA-IPC mapping + cudaMemcpyAsync: the copy overlaps
+ * whatever the rank builds next). `slot` < 64 names the exchange; rt_group_share_finish() waits for this rank's pulls and is a barrier:
+ * after it every handle is usable and owners may free or update their BLASes. */
+RT_API int  rt_group_share_blas(rt_group* group, uint32_t slot, int owner_rank, const rt_blas* mine, rt_blas** out);
+RT_API int  rt_group_share_finish(rt_group* group);
+RT_API float rt_group_last_share_ms(const rt_group* group);   /* device time of this rank's pulls between the first share and share_finish */
+
+/* Copies device memory of this context's GPU (e.g. the frame rt_group_trace returned with RT_GROUP_OUT_DEVICE) to host memory, ordered
+ * after the work enqueued on the context stream; returns when the bytes are there. For callers that do not link the CUDA runtime. */
+RT_API int  rt_copy_to_host(rt_context* ctx, void* dst_host, const void* src_device, uint64_t bytes);
 
 RT_API int  rt_last_trace_stats(const rt_context* ctx, rt_trace_stats* out);
 /* CUDA-event milliseconds of the kernels of the most recent rt_trace / rt_trace_rows / rt_unpack_rows call (no copies). */
