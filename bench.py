@@ -49,7 +49,7 @@ def make_workload(name: str, width: int | None, height: int | None, only_parts=N
         s = scenes.sample_scene(1920, 1080)
     elif name in SOUP_SIZES:
         n, w, h = SOUP_SIZES[name]
-        s = scenes.soup_scene(n, w, h, 0, only_parts=only_parts, split=soup_split)
+        s = scenes.soup_scene(n, w, h, 1, only_parts=only_parts, split=soup_split)
     else:
         raise SystemExit(f"unknown workload {name}")
     if width:
@@ -193,32 +193,77 @@ def ncu_traffic(kind: str, workload: str):
 
 
 def ncu_issue(workload: str):
-    """The bound that actually limits the trace kernels (they are latency/issue bound, not HBM bound): issue-slot utilisation, lanes
-    per instruction and cache hit rates of both stages from the committed ncu capture; None without one."""
+    """Fallback for the issue-slot roofline when the live counter pass (count_instructions) is unavailable: the committed capture."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["k_trace"]
         if t["workload"] != workload:
             return None
-        return {k: t[k] for k in ("issue_slot_utilisation_pct", "lanes_per_instruction", "l1_hit_pct", "l2_hit_pct", "source") if k in t}
+        return {k: t[k] for k in ("issue_slot_utilisation_pct", "lanes_per_instruction", "l1_hit_pct", "l2_hit_pct", "warp_instructions_per_frame", "source") if k in t}
     except Exception:
+        return None
+
+
+def count_instructions(args):
+    """Live counters for the bound that really limits the trace kernels (issue slots): one frame of THIS workload with THIS library under
+    `ncu --metrics smsp__inst_executed.sum,smsp__thread_inst_executed.sum` (counts only — no time measured under the profiler is
+    used anywhere). Returns {"warp_inst": .., "thread_inst": .., "kernels": ..} per frame, or None when ncu cannot run here."""
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu) or os.environ.get("RTCORE_BENCH_NO_NCU"):
+        return None
+    cmd = [ncu, "--metrics", "smsp__inst_executed.sum,smsp__thread_inst_executed.sum", "--clock-control", "none", "-k", "regex:k_trace",
+           "--csv", sys.executable, os.path.join(ROOT, "tools", "frame_once.py"), "--workload", args.workload]
+    if args.width:
+        cmd += ["--width", str(args.width)]
+    if args.height:
+        cmd += ["--height", str(args.height)]
+    try:
+        env = dict(os.environ)
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+        if p.returncode != 0:
+            return None
+        import csv
+        import io
+        rows = [r for r in csv.reader(io.StringIO(p.stdout)) if len(r) > 6]
+        hdr = next(r for r in rows if "Metric Name" in r)
+        ni, vi, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
+        out = {"warp_inst": 0.0, "thread_inst": 0.0, "kernels": set()}
+        for r in rows:
+            if r is hdr or len(r) <= max(ni, vi, ki):
+                continue
+            v = float(r[vi].replace(",", ""))
+            if r[ni] == "smsp__inst_executed.sum":
+                out["warp_inst"] += v
+                out["kernels"].add(r[ki][:40])
+            elif r[ni] == "smsp__thread_inst_executed.sum":
+                out["thread_inst"] += v
+        out["kernels"] = len(out["kernels"])
+        return out if out["warp_inst"] > 0 else None
+    except Exception:       # noqa: BLE001
         return None
 
 
 def workload_config(scene, args, n_gpus):
     n_tris = SOUP_SIZES[args.workload][0] if args.workload in SOUP_SIZES else scene.triangle_count
+    how = {"p2p": "; every rank's trace kernel stores its pixels straight into rank 0's frame over NVLink (rt_group_*: CUDA IPC + stream-ordered "
+                  "counters, no collective)" + (", consecutive frames alternate over two streams" if getattr(args, "pipeline", True) else ""),
+           "allgather": "; packed bands, NCCL all-gather, unpack on rank 0",
+           "gather": "; packed bands, NCCL gather to rank 0, unpack"}
     return {"workload": f"{args.workload}: {scene.name}, {n_tris} triangles in {len(scene.blases)} BLAS, "
                         f"{len(scene.instances)} instances, {scene.width}x{scene.height} primary + {scene.bounces} diffuse bounce",
             "triangles": n_tris, "instances": len(scene.instances), "width": scene.width, "height": scene.height,
             "bounces": scene.bounces, "partition": f"{BLOCK_ROWS}-scanline bands interleaved over {n_gpus} GPU(s), scene replicated"
-            + ("" if n_gpus == 1 else {"p2p": "; every rank stores its pixels straight into rank 0's framebuffer over NVLink (CUDA IPC), frame barrier: " + ("stream-ordered counters in that buffer" if args.barrier == "flags" else "NCCL all-reduce"),
-                                       "allgather": "; packed bands, NCCL all-gather, unpack on rank 0",
-                                       "gather": "; packed bands, NCCL gather to rank 0, unpack"}[args.gather]),
+            + ("" if n_gpus == 1 else how[args.gather]),
             "l2_policy": "inputs larger than L2 (BVH nodes + triangles >> 126 MB); no flush between iterations"
                          if n_tris * 112 > 2 * 126e6 else "scene fits in L2: numbers are L2-resident (parity config)"}
 
 
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    import zlib
+
     import torch
     import torch.distributed as dist
     from build_up_phase_b200 import rtcore
@@ -233,18 +278,45 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        dist.init_process_group("nccl", device_id=dev)       # plumbing only: timing reductions, scene-wide counters, the NCCL comparison modes
     steps = args.steps if args.steps else 20
     warmup = args.warmup if args.warmup is not None else 3
     if warmup < 3:
         warmup = 3
 
+    def rmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def rall(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world == 1:
+            return [float(x)]
+        out = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
+
     is_soup = args.workload in SOUP_SIZES
+    want_cpu = not args.no_cpu_baseline
+    # cfg5: the soup is 8 BLASes. Which parts a rank needs on the HOST: its own for the split build; all of them for the replicated
+    # build (measured beside it) and, on rank 0, for the CPU arm / parity.
+    soup_modes = ("split", "replicated") if (is_soup and args.soup_build == "both") else ((args.soup_build,) if is_soup else ())
+    if world == 1 and is_soup:
+        soup_modes = ("replicated",)
     my_parts = [p for p in range(scenes.SOUP_PARTS) if p % world == rank] if is_soup else None
-    scene = make_workload(args.workload, args.width, args.height, only_parts=my_parts, soup_split=args.soup_split)
+    need_all = is_soup and ("replicated" in soup_modes or (rank == 0 and want_cpu))
+    scene = make_workload(args.workload, args.width, args.height, only_parts=None if need_all else my_parts, soup_split=args.soup_split)
+    if args.bounces is not None:
+        scene.bounces = args.bounces
     W, H, bounces = scene.width, scene.height, scene.bounces
     ctx = rtcore.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    group = None
+    if world > 1 or args.pipeline:
+        gname = f"bench-{os.environ.get('MASTER_PORT', '0')}-{os.environ.get('TORCHELASTIC_RUN_ID', 'solo')}-{os.getppid() if world > 1 else os.getpid()}"
+        group = rtcore.Group(ctx, gname, rank, world, W, H)
 
     # ---- scene upload (untimed) and acceleration-structure build (timed separately: Mtri/s) ----
     def upload(geoms):
@@ -256,8 +328,14 @@ def run_gpu(args):
             dg.append(scenes.Geometry(v, i, t))
         return dg
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    phase_keys = ("total_ms", "setup_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms")
     n_tris_total = SOUP_SIZES[args.workload][0] if is_soup else scene.triangle_count
-    bcast_ms = 0.0
+    build_variants = {}
     if not is_soup:
         dev_blases = [upload(geoms) for geoms in scene.blases]
         torch.cuda.synchronize()
@@ -268,77 +346,72 @@ def run_gpu(args):
                 for b in blases:
                     b.free()
             blases = ctx.build_blas_batch(dev_blases, device=True) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True)]
-            if rep > 0:
+            if rep > 0 or args.build_reps == 0:
                 build_ms.append(ctx.build_timing())
         bt = min(build_ms, key=lambda t: t["total_ms"])
+        build_total_ms, share_ms = bt["total_ms"], 0.0
         build_note = "one batched build of all BLASes on every GPU (scene replicated)"
     else:
-        # cfg5: the soup is 8 index ranges = 8 BLASes; rank r builds parts p with p % N == r, then every BLAS
-        # blob is broadcast (NCCL over NVLink) from its builder and adopted by the other ranks.
-        own = {}
-        phase_keys = ("total_ms", "setup_ms", "morton_ms", "sort_ms", "hierarchy_ms", "refit_ms")
+        # cfg5 ("BLASes are built per GPU and broadcast"). Two ways to get the 8 BLASes onto every GPU, measured side by side:
+        #   split:      rank r builds parts p % N == r; every part is PULLED by the other ranks from its builder's memory over NVLink
+        #               (rt_group_share_blas: CUDA-IPC mapping + copy engine on a separate stream, overlapping the puller's next builds).
+        #               Wall time of the whole phase, slowest rank (host clock: the pulls run beside the builds).
+        #   replicated: every rank builds all 8 parts itself; sum of the builds' CUDA-event times, slowest rank.
+        dev_parts = {p: upload(scene.blases[p]) for p in (range(scenes.SOUP_PARTS) if "replicated" in soup_modes else my_parts)}
+        torch.cuda.synchronize()
+        blases = [None] * scenes.SOUP_PARTS
         bt = {k: 0.0 for k in phase_keys}
-        for p in my_parts:
-            dg = upload(scene.blases[p])
-            torch.cuda.synchronize()
-            best, b = None, None
-            for rep in range(args.build_reps + 1):
+        best_own = {}
+        for p in sorted(dev_parts):                      # warm the allocator / scratch, and the per-part kernel times
+            b = None
+            for rep in range(max(1, args.build_reps)):
                 if b is not None:
                     b.free()
-                b = ctx.build_blas(dg, device=True)
+                b = ctx.build_blas(dev_parts[p], device=True)
                 t = ctx.build_timing()
-                if rep > 0 or args.build_reps == 0:
-                    best = t if best is None or t["total_ms"] < best["total_ms"] else best
-            own[p] = b
-            for k in phase_keys:
-                bt[k] += best[k]
-            del dg
+                best_own[p] = t if p not in best_own or t["total_ms"] < best_own[p]["total_ms"] else best_own[p]
+            b.free()
+        if "replicated" in soup_modes:
+            rep_ms = sum(best_own[p]["total_ms"] for p in range(scenes.SOUP_PARTS))
+            build_variants["replicated"] = {"ms": rmax(rep_ms), "note": "every GPU builds all 8 parts itself (sum of the 8 builds' CUDA-event times, slowest rank)"}
+        if "split" in soup_modes and world > 1:
+            best = None
+            for rep in range(2):
+                for b in blases:
+                    if b is not None:
+                        b.free()
+                blases = [None] * scenes.SOUP_PARTS
+                barrier()
+                t0 = time.perf_counter()
+                own_ms = 0.0
+                for p in range(scenes.SOUP_PARTS):
+                    owner = p % world
+                    mine = None
+                    if owner == rank:
+                        mine = ctx.build_blas(dev_parts[p], device=True)
+                        own_ms += ctx.build_timing()["total_ms"]
+                    blases[p] = group.share_blas(p, owner, mine)
+                pull_ms = group.share_finish()           # waits for this rank's pulls, then a barrier of the group
+                wall = (time.perf_counter() - t0) * 1000.0
+                cur = {"ms": rmax(wall), "own_builds_ms": rmax(own_ms), "pull_ms": rmax(pull_ms), "rank0_host_ms": group.share_host_ms()}
+                best = cur if best is None or cur["ms"] < best["ms"] else best
+            gb = sum(int(blases[p].info().storage_bytes) for p in range(scenes.SOUP_PARTS) if p % world != rank) / 1e9
+            best["pulled_gb_per_rank"] = gb
+            best["pull_gbs"] = gb / max(best["pull_ms"], 1e-9) * 1e3
+            best["note"] = (f"{len(my_parts)} of 8 parts built per GPU, the others pulled from their builders over NVLink while the next part is built "
+                            f"(host wall clock of the phase, slowest rank)")
+            build_variants["split"] = best
+        else:
+            for p in range(scenes.SOUP_PARTS):
+                blases[p] = ctx.build_blas(dev_parts[p], device=True)
+        for k in phase_keys:
+            bt[k] = sum(best_own[p][k] for p in best_own)
         bt["primitives"] = n_tris_total
-        infos = {p: own[p].info() for p in my_parts}
-        blases = [None] * scenes.SOUP_PARTS
-        for p in my_parts:
-            blases[p] = own[p]
-        if world > 1:
-            tms = torch.tensor([bt[k] for k in phase_keys], dtype=torch.float64, device=dev)
-            dist.all_reduce(tms, op=dist.ReduceOp.MAX)          # the slowest rank's build defines the build time
-            bt.update(dict(zip(phase_keys, [float(x) for x in tms.tolist()])))
-            meta = [None] * scenes.SOUP_PARTS
-            for p in range(scenes.SOUP_PARTS):
-                obj = [None]
-                if p in infos:
-                    i = infos[p]
-                    obj = [dict(triangle_count=i.triangle_count, node_count=i.node_count, root_ref=i.root_ref, max_depth=i.max_depth,
-                                lo=list(i.bounds_lo), hi=list(i.bounds_hi), storage_bytes=i.storage_bytes)]
-                dist.broadcast_object_list(obj, src=p % world)
-                meta[p] = obj[0]
-            bufs = {}
-            for p in range(scenes.SOUP_PARTS):
-                if p in own:
-                    bufs[p] = rtcore.device_view(infos[p].device_storage, int(infos[p].storage_bytes), dev)
-                else:
-                    bufs[p] = torch.empty(int(meta[p]["storage_bytes"]), dtype=torch.uint8, device=dev)
-            dist.barrier(); torch.cuda.synchronize()
-            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            b0.record()
-            for p in range(scenes.SOUP_PARTS):
-                dist.broadcast(bufs[p], src=p % world)
-            b1.record()
-            torch.cuda.synchronize()
-            bc = torch.tensor([b0.elapsed_time(b1)], dtype=torch.float64, device=dev)
-            dist.all_reduce(bc, op=dist.ReduceOp.MAX)
-            bcast_ms = float(bc.item())
-            for p in range(scenes.SOUP_PARTS):
-                if p not in own:
-                    m = meta[p]
-                    info = rtcore.RtBlasInfo()
-                    info.triangle_count, info.node_count, info.root_ref, info.max_depth = m["triangle_count"], m["node_count"], m["root_ref"], m["max_depth"]
-                    for k in range(3):
-                        info.bounds_lo[k], info.bounds_hi[k] = m["lo"][k], m["hi"][k]
-                    info.storage_bytes = m["storage_bytes"]
-                    blases[p] = ctx.import_blas(info, bufs[p])
-            del bufs
-        build_note = (f"{scenes.SOUP_PARTS} BLASes of {n_tris_total // scenes.SOUP_PARTS} triangles, {len(my_parts)} built per GPU, "
-                      f"blobs broadcast with NCCL ({bcast_ms:.2f} ms); build time = slowest rank's builds + broadcast")
+        fastest = min(build_variants, key=lambda m: build_variants[m]["ms"])
+        build_total_ms = build_variants[fastest]["ms"]
+        share_ms = build_variants.get("split", {}).get("pull_ms", 0.0)
+        build_note = f"8 BLASes of {n_tris_total // scenes.SOUP_PARTS} triangles; reported = the faster way ({fastest}); see build.variants"
+        del dev_parts
     tlas = ctx.build_tlas(scene.instances, blases)
     tlas_t = ctx.build_timing()
     ctx.set_hit_records(scene.hit_records)
@@ -348,7 +421,9 @@ def run_gpu(args):
     # ---- buffers ----
     px_packed = ctx.rows_packed_pixels(W, H, BLOCK_ROWS, world)
     mode = args.gather if world > 1 else "single"
-    shared, shared_ptrs, token = [], [], None
+    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
+    host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
+    host_np = host_frame.numpy()
     if world > 1:
         packed = torch.zeros((px_packed, 4), dtype=torch.uint8, device=dev)
         if mode == "gather":
@@ -356,76 +431,9 @@ def run_gpu(args):
             gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
         elif mode == "allgather":
             gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev)
-        else:
-            # two framebuffers on rank 0 (double buffer: frame k may still be read while frame k + 1 is written), mapped by every rank
-            handles = [None, None]
-            ok = 1
-            try:
-                if os.environ.get("RTCORE_BENCH_NO_IPC"):
-                    raise RuntimeError("disabled by RTCORE_BENCH_NO_IPC (test hook of the fallback)")
-                if rank == 0:
-                    for k in range(2):
-                        ptr, h = ctx.frame_share_create(W * H * 4 + 256)      # + the frame's "done" and "free" counters
-                        shared_ptrs.append(ptr); handles[k] = h
-            except Exception as e:      # noqa: BLE001
-                sys.stderr.write(f"[bench] shared framebuffer unavailable on rank 0 ({e}); falling back to the NCCL gather\n")
-                ok = 0
-            dist.broadcast_object_list(handles, src=0)
-            try:
-                if rank != 0 and ok and handles[0] is not None:
-                    shared_ptrs = [ctx.frame_share_open(h) for h in handles]
-                elif rank != 0:
-                    ok = 0
-            except Exception as e:      # noqa: BLE001
-                sys.stderr.write(f"[bench] rank {rank} cannot map rank 0's framebuffer ({e}); falling back to the NCCL gather\n")
-                ok = 0
-            agree = torch.tensor([ok], dtype=torch.int32, device=dev)
-            dist.all_reduce(agree, op=dist.ReduceOp.MIN)
-            if int(agree.item()) == 0:          # CUDA IPC not usable here: every rank takes the packed-bands + NCCL path instead
-                for p_ in shared_ptrs:
-                    try:
-                        (ctx.frame_share_free if rank == 0 else ctx.frame_share_close)(p_)
-                    except Exception:   # noqa: BLE001
-                        pass
-                shared_ptrs = []
-                mode = "gather"
-                args.gather = "gather"
-                gathered = torch.zeros((world, px_packed, 4), dtype=torch.uint8, device=dev) if rank == 0 else None
-                gather_list = [gathered[r] for r in range(world)] if rank == 0 else None
-            else:
-                if rank == 0:
-                    shared = [rtcore.device_view(p, W * H * 4, dev).view(H, W, 4) for p in shared_ptrs]
-                token = torch.zeros(1, dtype=torch.int32, device=dev)
-    frame = torch.zeros((H, W, 4), dtype=torch.uint8, device=dev)
-    host_frame = torch.zeros((H, W, 4), dtype=torch.uint8).pin_memory()
-    host_np = host_frame.numpy()
-    step_no = [0]
-    frame_uses = [0, 0]
+    gflags = rtcore.GROUP_OUT_DEVICE | (rtcore.GROUP_PIPELINE if args.pipeline else rtcore.GROUP_ASYNC)
 
-    def step_multi(consume=None):
-        """One frame at N > 1; on rank 0 `consume(frame)` is enqueued once the frame is complete. Returns the frame tensor on rank 0."""
-        if mode == "p2p":
-            k, use = step_no[0] & 1, step_no[0] >> 1
-            step_no[0] += 1
-            if args.barrier == "flags":
-                fu = frame_uses[k]                              # how often THIS path (whole-frame `done` counter) has used buffer k
-                frame_uses[k] += 1
-                done_ctr, free_ctr = shared_ptrs[k] + W * H * 4, shared_ptrs[k] + W * H * 4 + 4
-                ctx.flag_wait_ge(free_ctr, use)                 # rank 0 has handed buffer k back `use` times: safe to overwrite it
-                ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
-                ctx.flag_add(done_ctr)                          # this rank's pixels of frame k have landed in rank 0's memory
-                if rank == 0:
-                    ctx.flag_wait_ge(done_ctr, world * (fu + 1))    # ... and so have everybody else's: the frame is complete
-                    if consume:
-                        consume(shared[k])
-                    ctx.flag_add(free_ctr)
-                    return shared[k]
-                return None
-            ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, shared_ptrs[k], device=True, async_=True, full_frame=True)
-            dist.all_reduce(token)          # frame-complete barrier on the stream: every rank's stores have landed
-            if rank == 0 and consume:
-                consume(shared[k])
-            return shared[k] if rank == 0 else None
+    def step_nccl(consume=None):
         ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, async_=True)
         if mode == "gather":
             dist.gather(packed, gather_list, dst=0)
@@ -435,64 +443,29 @@ def run_gpu(args):
             ctx.unpack_rows(gathered, W, H, BLOCK_ROWS, world, frame)
             if consume:
                 consume(frame)
-            return frame
-        return None
-
-    # ---- e2e at N > 1 (p2p + counters): row-chunk pipeline. Packed rows [a, b) of every rank together are image rows [a*N, b*N).
-    chunk_bounds, chunk_uses, ctx2, copy_stream = None, [0, 0], None, None
-    if mode == "p2p" and args.barrier == "flags" and args.e2e_chunks > 1:
-        local_rows = px_packed // W
-        nc, wsum, acc, chunk_bounds = args.e2e_chunks, args.e2e_chunks * (args.e2e_chunks + 1) // 2, 0, [0]
-        for c in range(nc):
-            acc += nc - c
-            end = local_rows if c == nc - 1 else min(local_rows, (local_rows * acc // wsum + 7) // 8 * 8)
-            if end > chunk_bounds[-1]:
-                chunk_bounds.append(end)
-        if rank == 0:
-            copy_stream = torch.cuda.Stream(device=dev)
-            ctx2 = rtcore.Context(local_rank)           # only enqueues flag waits / adds on the copy stream
-            ctx2.set_stream(copy_stream.cuda_stream)
-
-    def step_e2e_chunked():
-        k, use = step_no[0] & 1, step_no[0] >> 1
-        step_no[0] += 1
-        cu = chunk_uses[k]
-        chunk_uses[k] += 1
-        tail = shared_ptrs[k] + W * H * 4
-        ctx.flag_wait_ge(tail + 4, use)
-        for c in range(len(chunk_bounds) - 1):
-            a, b = chunk_bounds[c], chunk_bounds[c + 1]
-            ctx.trace_rows_range(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, a, b - a, shared_ptrs[k], full_frame=True)
-            ctx.flag_add(tail + 8 + 4 * c)
-            if rank == 0:
-                ctx2.flag_wait_ge(tail + 8 + 4 * c, world * (cu + 1))      # on the copy stream: every rank's rows of this chunk have landed
-                g0, g1 = a * world, min(b * world, H)
-                with torch.cuda.stream(copy_stream):
-                    host_frame[g0:g1].copy_(shared[k][g0:g1], non_blocking=True)
-        if rank == 0:
-            ctx2.flag_add(tail + 4)                     # buffer handed back once its last rows are on the host
-        torch.cuda.synchronize()
 
     def step_device():
-        if world == 1:
+        if group is not None and mode in ("single", "p2p"):
+            group.trace(tlas, cam, W, H, bounces, gflags)
+        elif world == 1:
             ctx.trace_device(tlas, cam, W, H, bounces, frame, async_=True)
         else:
-            step_multi()
+            step_nccl()
+
+    def finish_device():
+        if group is not None:
+            group.join()                 # stream-ordered: the context stream (torch's) waits for the group's second stream
 
     def step_e2e():
         # reference-facing call with HOST buffers: camera struct in (16 B), RGBA8 framebuffer out (pinned host memory)
         if world == 1:
             ctx.trace(tlas, cam, W, H, bounces, rgba_out=host_np)
-        elif chunk_bounds is not None:
-            step_e2e_chunked()
-        else:
-            step_multi(consume=lambda f: host_frame.copy_(f, non_blocking=True))
-            torch.cuda.synchronize()
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
+            return host_np
+        if mode == "p2p":
+            return group.trace_host(tlas, cam, W, H, bounces)        # every rank copies its bands over its own PCIe link; rank 0 gets the frame
+        step_nccl(consume=lambda f: host_frame.copy_(f, non_blocking=True))
         torch.cuda.synchronize()
+        return host_np
 
     # ---- one stats pass: ray counts + traversal counters for the byte model (untimed, slower kernel) ----
     if world == 1:
@@ -500,17 +473,17 @@ def run_gpu(args):
     else:
         ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True, stats=True)
     st = ctx.trace_stats()
-    cnt = torch.tensor([st[k] for k in ("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested", "instances_entered",
-                                        "primary_hits", "secondary_hits", "near_edge_hits")], dtype=torch.int64, device=dev)
+    stat_keys = ("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested", "instances_entered", "primary_hits", "secondary_hits", "near_edge_hits")
+    cnt = torch.tensor([st[k] for k in stat_keys], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(cnt)
-    tot = dict(zip(("rays_primary", "rays_secondary", "nodes_visited", "triangles_tested", "instances_entered",
-                    "primary_hits", "secondary_hits", "near_edge_hits"), [int(x) for x in cnt.tolist()]))
+    tot = dict(zip(stat_keys, [int(x) for x in cnt.tolist()]))
     total_rays = tot["rays_primary"] + tot["rays_secondary"]
 
     # ---- timed region: device-resident ----
     for _ in range(warmup):
         step_device()
+    finish_device()
     barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     l0 = ctx.launch_count()
@@ -518,15 +491,13 @@ def run_gpu(args):
     e0.record()
     for _ in range(steps):
         step_device()
+    finish_device()
     e1.record()
     barrier()
     l1 = ctx.launch_count()
-    ms_total = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_step = float(ms_total.item()) / steps
+    ms_step = rmax(e0.elapsed_time(e1)) / steps
 
-    # trace-kernel-only time on this rank (CUDA events on the launching stream, inside the library)
+    # trace-kernel-only time of ONE frame on every rank (CUDA events on the launching stream, inside the library)
     k_ms = []
     for _ in range(min(steps, 10)):
         if world == 1:
@@ -534,10 +505,8 @@ def run_gpu(args):
         else:
             ctx.trace_rows(tlas, cam, W, H, bounces, BLOCK_ROWS, rank, world, packed, device=True)
         k_ms.append(ctx.trace_ms())
-    kern = torch.tensor([float(np.mean(k_ms))], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(kern, op=dist.ReduceOp.MAX)
-    kernel_ms = float(kern.item())
+    per_rank_kernel_ms = rall(float(np.mean(k_ms)))
+    kernel_ms = max(per_rank_kernel_ms)
 
     # ---- timed region: end to end through the host-buffer call ----
     for _ in range(2):
@@ -546,31 +515,41 @@ def run_gpu(args):
     t0 = time.perf_counter()
     e2e_steps = max(3, steps // 2)
     for _ in range(e2e_steps):
-        step_e2e()
+        e2e_frame = step_e2e()
     barrier()
-    e2e_ms = torch.tensor([(time.perf_counter() - t0) * 1000.0 / e2e_steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = rmax((time.perf_counter() - t0) * 1000.0 / e2e_steps)
     clocks = sampler.stop() if sampler else None
+    e2e_crc = zlib.crc32(np.ascontiguousarray(e2e_frame).tobytes()) if rank == 0 else None
 
-    # checksums of the full frame and of the hit records (primary + secondary): variants of the kernels must reproduce them exactly
+    # checksums of the full frame and of the hit records (primary + secondary): variants of the kernels must reproduce them exactly.
+    # Rank 0 holds a replica of the scene, so it also renders the whole frame ALONE: the frame the N GPUs assembled must equal it.
     crc = None
-    if world == 1:
-        import zlib
+    if rank == 0:
         prim_c = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
         sec_c = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
         ctx.trace_device(tlas, cam, W, H, bounces, frame, prim_c, sec_c)
-        crc = {"rgba": zlib.crc32(frame.cpu().numpy().tobytes()), "primary_hits": zlib.crc32(prim_c.cpu().numpy().tobytes()),
-               "secondary_hits": zlib.crc32(sec_c.cpu().numpy().tobytes())}
+        solo = frame.cpu().numpy()
+        gp = prim_c.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
+        gs = sec_c.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
+        crc = {"rgba": zlib.crc32(solo.tobytes()), "primary_hits": zlib.crc32(gp.tobytes()), "secondary_hits": zlib.crc32(gs.tobytes()),
+               "e2e_frame_rgba": e2e_crc}
         del prim_c, sec_c
-    else:
-        import zlib
-        # the assembled frame of the multi-GPU path must be the single-GPU frame, bit for bit
-        step_multi(consume=lambda f: host_frame.copy_(f, non_blocking=True))
-        torch.cuda.synchronize()
-        ctx.sync()                          # also surfaces a device watchdog (flag wait timed out) as an error
+    if world > 1:
+        if mode == "p2p":
+            ptr = group.trace(tlas, cam, W, H, bounces, rtcore.GROUP_OUT_DEVICE)
+            if rank == 0:
+                crc["assembled_rgba"] = zlib.crc32(rtcore.device_view(ptr, W * H * 4, dev).cpu().numpy().tobytes())
+        else:
+            step_nccl()
+            torch.cuda.synchronize()
+            if rank == 0:
+                crc["assembled_rgba"] = zlib.crc32(frame.cpu().numpy().tobytes())
         if rank == 0:
-            crc = {"rgba": zlib.crc32(host_frame.numpy().tobytes()), "gather": mode, "barrier": args.barrier if mode == "p2p" else "nccl"}
+            crc["gather"] = mode
+            crc["assembled_equals_single_gpu_frame"] = bool(crc["assembled_rgba"] == crc["rgba"] == crc["e2e_frame_rgba"])
+    elif rank == 0:
+        crc["assembled_equals_single_gpu_frame"] = bool(crc["e2e_frame_rgba"] == crc["rgba"])
+    ctx.sync()                          # also surfaces a device watchdog (flag wait timed out) as an error
 
     if rank == 0:
         hbm, peak_src = peaks()
@@ -578,77 +557,85 @@ def run_gpu(args):
         # per launch on one GPU: this rank's share of the frame (1/world of the bytes) over its kernel time
         achieved = algo_bytes / world / (kernel_ms * 1e-3) / 1e9
         n_tris = n_tris_total
-        build_total_ms = bt["total_ms"] + bcast_ms
         build_gbs = n_tris * B_TRI_BUILD / (build_total_ms * 1e-3) / 1e9
         traffic, traffic_src = ncu_traffic("k_trace", args.workload) if world == 1 else (None, None)
         btraffic, btraffic_src = ncu_traffic("build", args.workload)
+        # ---- the bound that binds: SM issue slots. Warp-instructions of one frame (live ncu counter pass of the same library and
+        # workload; the committed capture only if ncu cannot run here) over kernel time x 4 schedulers x SMs x measured SM clock ----
+        sm_count = ctx.device_info()["sm_count"]
+        clock_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        live = count_instructions(args) if (world == 1 and not args.no_issue_counters) else None
+        committed = ncu_issue(args.workload)
+        warp_inst = live["warp_inst"] if live else (committed or {}).get("warp_instructions_per_frame")
+        issue_peak = sm_count * 4 * clock_mhz * 1e6 / 1e9                     # G warp-instructions / s
+        issue = None
+        if warp_inst:
+            issue_ach = warp_inst / world / (kernel_ms * 1e-3) / 1e9
+            issue = {"bound": "issue", "achieved": issue_ach, "peak": issue_peak, "unit": "Gwarp-inst/s", "frac": issue_ach / issue_peak,
+                     "warp_instructions_per_frame": warp_inst,
+                     "lanes_per_instruction": (live["thread_inst"] / live["warp_inst"]) if live else None,
+                     "simd_ideal_frac": (live["thread_inst"] / 32.0 / world / (kernel_ms * 1e-3) / 1e9 / issue_peak) if live else None,
+                     "counters": "live: ncu --metrics smsp__inst_executed.sum,smsp__thread_inst_executed.sum on one frame of this run's library and workload"
+                                 if live else "committed capture (profiles/ncu_traffic.json): ncu could not run in this process environment",
+                     "sm_clock_mhz": clock_mhz, "sm_count": sm_count}
+        hbm_roof = {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                    "traffic_source": traffic_src, "peak_source": peak_src,
+                    "note": "SURVEY 8(d) figure: ALGORITHMIC bytes (served mostly by L1/L2) over the HBM peak; measured DRAM traffic is `traffic`",
+                    "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass of this run",
+                    "algorithmic_bytes_per_launch": algo_bytes / world}
+        roofline = dict(issue) if issue else dict(hbm_roof)
+        roofline.update({"kernel": "k_trace (stage 0 + stage 1 of one frame)", "traffic": traffic, "traffic_source": traffic_src,
+                         "hbm_algorithmic": hbm_roof,
+                         "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
+                                     "instances": tot["instances_entered"] / total_rays, "bytes": algo_bytes / total_rays}})
         line = {
             "metric": "Mrays/s (primary+secondary rays per second)", "value": total_rays / (ms_step * 1e-3) / 1e6, "unit": "Mrays/s",
             "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(scene, args, world),
             "rays_per_step": total_rays, "rays_primary": tot["rays_primary"], "rays_secondary": tot["rays_secondary"],
-            "trace_kernel_ms": kernel_ms,
-            "e2e": {"value": total_rays / (float(e2e_ms.item()) * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": float(e2e_ms.item()),
+            "trace_kernel_ms": kernel_ms, "trace_kernel_ms_per_rank": {"min": min(per_rank_kernel_ms), "max": max(per_rank_kernel_ms), "all": per_rank_kernel_ms},
+            "e2e": {"value": total_rays / (e2e_ms * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": 16, "d2h_bytes_per_step": W * H * 4,
                     "note": "rt_trace with a pinned host framebuffer: camera struct in, RGBA8 frame out" if world == 1 else
-                            ("every rank traces its share in %d shrinking row chunks straight into rank 0's frame; rank 0 copies the finished image rows "
-                             "to pinned host memory while the next chunk is traced" % (len(chunk_bounds) - 1) if chunk_bounds is not None else
-                             "frame assembled on rank 0, then copied to pinned host memory")},
+                            ("rt_group_trace(RT_GROUP_OUT_HOST): every rank copies its bands over its own PCIe link into the group's shared pinned host frame; "
+                             "rank 0 returns when all shares have landed" if mode == "p2p" else "frame assembled on rank 0 (NCCL), then copied to pinned host memory")},
             "gpu_launches": int(l1 - l0),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
-                         "traffic_source": traffic_src, "kernel": "k_trace (stage 0 + stage 1 of one frame)", "peak_source": peak_src,
-                         "note": "achieved = ALGORITHMIC bytes (served mostly by L1/L2) over HBM peak, as SURVEY 8(d) defines it; the kernels are bound by "
-                                 "issue slots x SIMD divergence and L1/L2 latency: see `sm_issue`",
-                         "sm_issue": ncu_issue(args.workload),
-                         "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass",
-                         "algorithmic_bytes_per_launch": algo_bytes / world,
-                         "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
-                                     "instances": tot["instances_entered"] / total_rays, "bytes": algo_bytes / total_rays}},
+            "roofline": roofline,
             "build": {"metric": "LBVH build Mtri/s (first setup kernel .. last refit kernel, CUDA events)",
                       "value": n_tris / (build_total_ms * 1e-3) / 1e6, "unit": "Mtri/s", "ms": build_total_ms, "phases_ms": bt,
-                      "broadcast_ms": bcast_ms, "note": build_note, "tlas_ms": tlas_t["total_ms"],
+                      "share_ms": share_ms, "note": build_note, "tlas_ms": tlas_t["total_ms"], "variants": build_variants or None,
                       "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
                                    "bytes_per_triangle": B_TRI_BUILD, "traffic": btraffic, "traffic_source": btraffic_src}},
             "traversal": tot,
             "crc32": crc,
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline and world == 1:
+        if want_cpu:
+            # the CPU arm and the parity of the rows it traced, same run, at EVERY N (rank 0 holds the whole scene):
+            # hit ids / t / u / v bit-exact, RGBA8 within 1 LSB
             res = cpu_arm(scene, args.cpu_seconds, 1, 0)
             cb = cpu_build_baseline(scene)
             line["cpu_baseline"] = {"value": res["mrays_per_s"], "unit": "Mrays/s", "cores": res["threads"], "kind": "port",
                                     "sample": f"rows 0..{H} step {res['rows'][2]} of the frame ({res['rays_per_step']} rays), oracle LBVH traversal; "
                                               f"CPU LBVH build of {cb['triangles']} triangles: {cb['mtris_per_s']:.2f} Mtri/s",
                                     "build_mtris_per_s": cb["mtris_per_s"]}
-            # parity of the rows the CPU traced, same run (hit ids bit-exact, RGBA within 1 LSB)
             from parity import compare_hits, compare_rgba
-            prim = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
-            sec = torch.zeros((H, W, 7), dtype=torch.int32, device=dev)
-            ctx.trace_device(tlas, cam, W, H, bounces, frame, prim, sec)
             rows = slice(*res["rows"])
             rgba_o, prim_o, sec_o, _ = res["oracle"].trace(rows=res["rows"], want_hits=True)
-            gp = prim.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
-            gs = sec.cpu().numpy().view(rtcore.HIT_DTYPE).reshape(H, W)
             rp, rs = compare_hits(gp, prim_o, rows), compare_hits(gs, sec_o, rows)
-            rc = compare_rgba(frame.cpu().numpy(), rgba_o, rows)
-            line["parity"] = {"rows_checked": len(range(*res["rows"])), "primary": {k: rp[k] for k in ("rays", "hits", "id_mismatches", "near_edge_rays", "t_bit_mismatches")},
-                              "secondary": {k: rs[k] for k in ("rays", "hits", "id_mismatches", "near_edge_rays", "t_bit_mismatches")}, "rgba": rc}
+            rc = compare_rgba(solo, rgba_o, rows)
+            keys = ("rays", "hits", "id_mismatches", "near_edge_rays", "t_bit_mismatches", "u_bit_mismatches", "v_bit_mismatches")
+            line["parity"] = {"rows_checked": len(range(*res["rows"])), "primary": {k: rp[k] for k in keys}, "secondary": {k: rs[k] for k in keys}, "rgba": rc,
+                              "frame_checked": "rank 0's own full-frame render; the frame the N GPUs assembled and the e2e host frame have the same CRC-32: "
+                                               + str(crc["assembled_equals_single_gpu_frame"])}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
-        if ctx2 is not None:
-            ctx2.close()
-        if mode == "p2p":               # peers unmap first, then the owner frees
-            shared = []
-            if rank != 0:
-                for p_ in shared_ptrs:
-                    ctx.frame_share_close(p_)
-            dist.barrier()
-            if rank == 0:
-                for p_ in shared_ptrs:
-                    ctx.frame_share_free(p_)
+    if group is not None:
+        group.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -665,18 +652,17 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per oracle step (bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "allgather", "gather"],
-                    help="N > 1: how the bands reach rank 0. p2p = every rank's trace kernel stores its pixels straight into rank 0's "
-                         "framebuffer over NVLink (CUDA IPC mapping) + one tiny NCCL all-reduce as the frame-complete barrier; "
-                         "allgather / gather = packed bands + NCCL collective + unpack kernel on rank 0")
-    ap.add_argument("--barrier", default="flags", choices=["flags", "nccl"],
-                    help="--gather p2p: how a frame is declared complete. flags = stream-ordered counters in rank 0's shared frame "
-                         "(every rank adds 1 after its trace, rank 0 waits for N; a second counter hands the buffer back): no collective "
-                         "on the step; nccl = a 4-byte all-reduce per frame")
-    ap.add_argument("--e2e-chunks", type=int, default=1,
-                    help="N > 1, p2p + flags: the e2e step traces every rank's share in this many shrinking row chunks with one 'done' counter "
-                         "each, and rank 0 copies the finished image rows of ALL ranks to the host while the next chunk is traced. Measured "
-                         "with 3 chunks (profiles/README.md r02k): N = 2 e2e 4475 vs 4398 Mrays/s, N = 8 8293 vs 8979 (the per-rank chunks get "
-                         "too small) -> default 1 = one chunk, frame copied after the frame barrier")
+                    help="N > 1: how the bands reach rank 0. p2p = the render group of the C ABI (rt_group_*): every rank's trace kernel stores "
+                         "its pixels straight into rank 0's framebuffer over NVLink, stream-ordered counters as the frame handshake, no collective; "
+                         "allgather / gather = packed bands + NCCL collective + unpack kernel on rank 0 (the comparison the north_star names)")
+    ap.add_argument("--no-pipeline", dest="pipeline", action="store_false",
+                    help="device-timed steps: do NOT alternate consecutive frames over two streams (RT_GROUP_PIPELINE). Pipelined, frame k + 1's "
+                         "first rays fill the tail of frame k's persistent kernels - the fixed per-frame cost that limits scaling at 8 GPUs")
+    ap.add_argument("--bounces", type=int, default=None, help="override the workload's bounce count (0 or 1)")
+    ap.add_argument("--soup-build", default="both", choices=["both", "split", "replicated"],
+                    help="cfg5 at N > 1: split = per-GPU builds + NVLink pulls of the other parts, replicated = every GPU builds all parts; both = "
+                         "measure both, report the faster")
+    ap.add_argument("--no-issue-counters", action="store_true", help="skip the live ncu instruction-count pass (N = 1) behind roofline.frac")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")
     args = ap.parse_args()

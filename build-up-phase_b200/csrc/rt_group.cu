@@ -92,6 +92,9 @@ struct rt_group {
     // BLAS exchange
     cudaStream_t pull_stream = nullptr; cudaEvent_t pull_e0 = nullptr, pull_e1 = nullptr;
     bool pull_started = false; float last_share_ms = 0.0f;
+    double share_wait_s = 0.0, share_open_s = 0.0, share_alloc_s = 0.0;   // host time of the last finished exchange: waiting for owners, IPC opens, allocations
+    double cur_wait_s = 0.0, cur_open_s = 0.0, cur_alloc_s = 0.0;
+    uint64_t b_launches_seen = 0;
     uint32_t slot_seq[GROUP_SLOTS] = {};
     std::vector<void*> peer_maps;
     std::vector<BlasRecord*> staged_records;
@@ -163,6 +166,11 @@ extern "C" {
 int rt_group_rank(const rt_group* g) { return g ? g->rank : -1; }
 int rt_group_world(const rt_group* g) { return g ? g->world : 0; }
 float rt_group_last_share_ms(const rt_group* g) { return g ? g->last_share_ms : 0.0f; }
+int rt_group_last_share_host_ms(const rt_group* g, float out[3]) {
+    if (!g || !out) return RT_ERROR_INVALID_ARG;
+    out[0] = (float)(g->share_wait_s * 1e3); out[1] = (float)(g->share_open_s * 1e3); out[2] = (float)(g->share_alloc_s * 1e3);
+    return RT_SUCCESS;
+}
 const char* rt_group_last_error(const rt_group* g) { return g ? g->err.c_str() : "no group"; }
 
 void rt_group_destroy(rt_group* g) {
@@ -360,6 +368,7 @@ int rt_group_trace(rt_group* g, const rt_tlas* tlas, const rt_camera* cam, uint3
                        (uint32_t)g->rank, (uint32_t)g->world, (uint8_t*)g->dev_frame[k], nullptr, nullptr);
     if (rc != RT_SUCCESS) { g->err = c->err; g->ctx->err = c->err; g->shm->abort.store(1); return rc; }
     if ((rc = rt_flag_add(c, done)) != RT_SUCCESS) { g->err = c->err; return rc; }          // this rank's pixels have landed in rank 0's memory
+    if (c != g->ctx) { g->ctx->launches += c->launches - g->b_launches_seen; g->b_launches_seen = c->launches; }   // rt_kernel_launch_count(ctx) covers the group's second stream
     if (g->rank == 0) {
         if ((rc = rt_flag_wait_ge(c, done, (uint32_t)g->world * (use + 1u))) != RT_SUCCESS) { g->err = c->err; return rc; }   // ... and everybody else's
         if (frame_out) *frame_out = (const uint8_t*)g->dev_frame[k];
@@ -389,13 +398,18 @@ int rt_group_share_blas(rt_group* g, uint32_t slot, int owner_rank, const rt_bla
         *out = const_cast<rt_blas*>(mine);
         return RT_SUCCESS;
     }
+    double t0 = now_s();
     if (!wait_until(g->shm, [&] { return S.seq.load(std::memory_order_acquire) >= seq; }))
         return gfail(g, RT_ERROR_INTERNAL, "rank %d: rank %d never published BLAS slot %u", g->rank, owner_rank, slot);
+    double t1 = now_s();
+    g->cur_wait_s += t1 - t0;
     cudaIpcMemHandle_t h;
     memcpy(&h, S.handle, 64);
     void* peer = nullptr;
     G_CUDA(g, cudaIpcOpenMemHandle(&peer, h, cudaIpcMemLazyEnablePeerAccess));
     g->peer_maps.push_back(peer);
+    t0 = now_s();
+    g->cur_open_s += t0 - t1;
     const uint32_t N = S.triangle_count;
     BlasStorage* st = new BlasStorage();
     st->n_tris = N; st->n_blas = 1;
@@ -405,6 +419,7 @@ int rt_group_share_blas(rt_group* g, uint32_t slot, int owner_rank, const rt_bla
     if (cudaMalloc(&st->dev, st->bytes) != cudaSuccess) { delete st; cudaGetLastError(); return gfail(g, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for the pulled BLAS failed", (size_t)S.storage_bytes); }
     st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
     st->refs = 1;
+    g->cur_alloc_s += now_s() - t0;
     rt_blas* hnd = new rt_blas();
     hnd->st = st; hnd->index = 0;
     BlasRecord& R = hnd->rec;
@@ -437,6 +452,8 @@ int rt_group_share_finish(rt_group* g) {
     g->peer_maps.clear();
     for (BlasRecord* r : g->staged_records) cudaFreeHost(r);
     g->staged_records.clear();
+    g->share_wait_s = g->cur_wait_s; g->share_open_s = g->cur_open_s; g->share_alloc_s = g->cur_alloc_s;
+    g->cur_wait_s = g->cur_open_s = g->cur_alloc_s = 0.0;
     return host_barrier(g);                                // after it owners may free / update what they shared
 }
 

@@ -44,7 +44,7 @@ EXPORTED_SYMBOLS = [
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version", "rt_copy_to_host",
     "rt_group_create", "rt_group_destroy", "rt_group_trace", "rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world",
-    "rt_group_share_blas", "rt_group_share_finish", "rt_group_last_share_ms", "rt_group_host_frame_begin", "rt_group_host_frame_end", "rt_group_last_error",
+    "rt_group_share_blas", "rt_group_share_finish", "rt_group_last_share_ms", "rt_group_last_share_host_ms", "rt_group_host_frame_begin", "rt_group_host_frame_end", "rt_group_last_error",
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
     "rt_obj_group_count", "rt_obj_vertices", "rt_obj_indices", "rt_obj_group_name", "rt_obj_group_first_triangle",
@@ -208,6 +208,7 @@ def load(build_if_missing: bool = True):
     for name in ("rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world", "rt_group_share_finish"):
         getattr(L, name).argtypes = [vp]
     L.rt_group_share_blas.argtypes = [vp, u32, i32, vp, C.POINTER(vp)]
+    L.rt_group_last_share_host_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.rt_group_last_share_ms.argtypes = [vp]
     L.rt_group_last_share_ms.restype = C.c_float
     L.rt_group_host_frame_begin.argtypes = [vp, C.POINTER(vp)]
@@ -633,6 +634,11 @@ class Group:
     def share_finish(self) -> float:
         self._check(self.L.rt_group_share_finish(self.h))
         return float(self.L.rt_group_last_share_ms(self.h))
+
+    def share_host_ms(self) -> dict:
+        a = (C.c_float * 3)()
+        self._check(self.L.rt_group_last_share_host_ms(self.h, a))
+        return {"wait_for_owner_ms": float(a[0]), "ipc_open_ms": float(a[1]), "alloc_ms": float(a[2])}
 
     def close(self):
         if getattr(self, "h", None):

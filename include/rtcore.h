@@ -359,6 +359,8 @@ RT_API int  rt_group_world(const rt_group* group);
 RT_API int  rt_group_share_blas(rt_group* group, uint32_t slot, int owner_rank, const rt_blas* mine, rt_blas** out);
 RT_API int  rt_group_share_finish(rt_group* group);
 RT_API float rt_group_last_share_ms(const rt_group* group);   /* device time of this rank's pulls between the first share and share_finish */
+/* Host milliseconds of the last finished exchange on this rank: {waiting for owners to publish, cudaIpcOpenMemHandle, cudaMalloc of the copies}. */
+RT_API int  rt_group_last_share_host_ms(const rt_group* group, float out[3]);
 
 /* Copies device memory of this context's GPU (e.g. the frame rt_group_trace returned with RT_GROUP_OUT_DEVICE) to host memory, ordered
  * after the work enqueued on the context stream; returns when the bytes are there. For callers that do not link the CUDA runtime. */

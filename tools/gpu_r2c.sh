@@ -1,0 +1,16 @@
+#!/bin/bash
+# N GPUs: inst10m default + soup10m (split vs replicated build); usage: gpu_r2c.sh N TAG
+N=${1:-2}; TAG=${2:-r2c}
+mkdir -p gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+timeout 900 $TR bench.py --gpus $N > gpurun_out/bench_${TAG}_n$N.json 2> gpurun_out/bench_${TAG}_n$N.err; echo "rc=$?" >> gpurun_out/bench_${TAG}_n$N.err
+timeout 900 $TR bench.py --gpus $N --workload soup10m --steps 5 > gpurun_out/bench_${TAG}_soup10m_n$N.json 2> gpurun_out/bench_${TAG}_soup10m_n$N.err; echo "rc=$?" >> gpurun_out/bench_${TAG}_soup10m_n$N.err
+for f in gpurun_out/bench_${TAG}*n$N.err; do echo "== $f"; tail -n 4 $f; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/bench_*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f, 'N', d['n_gpus'], round(d['value']), 'e2e', round(d['e2e']['value']), 'kernel ms', d['trace_kernel_ms_per_rank']['min'], d['trace_kernel_ms_per_rank']['max'], 'step', d['ms_per_step'], 'build', round(d['build']['value']), d['build'].get('variants'), d.get('parity',{}).get('primary'), d['crc32'])
+    except Exception as e: print(f, 'ERR', e)
+PY
