@@ -31,6 +31,7 @@ struct rt_context {
     std::string err;
     // shader data
     float* d_hit_records = nullptr; uint32_t n_records = 0;
+    uint4* d_anyhit = nullptr; uint32_t n_anyhit = 0;            // any-hit records {kind, log2_res, flags, first mask word} followed by the mask words (one allocation)
     bool own_hit_records = true;                                  // false for the render group's internal second context (it borrows the user context's table)
     std::vector<float> miss = {0.0f, 0.0f, 0.2f};                 // miss records, 3 floats each; record 0 = main.cpp:1065
     rt_ray_params rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, RT_RAY_FLAG_OPAQUE, 0u};   // main.cpp:1047-1052
@@ -42,7 +43,7 @@ struct rt_context {
     void* queue = nullptr; size_t queue_cap = 0;       // bounce queue of the two-stage wavefront
     uint32_t* qflags = nullptr; size_t qflags_cap = 0; // per-entry publication flags of the fused launch (hold the epoch of the launch that wrote the entry)
     uint32_t trace_epoch = 0;
-    uint32_t* d_counters = nullptr;                    // ray-fetch / queue counters of the persistent trace kernels
+    void* d_counters = nullptr; size_t counters_cap = 0;   // per launch: 16 ray-fetch / queue counters + 2 x n_regions region fetch counters of the persistent trace kernels
     unsigned long long* d_stats = nullptr;
     int* d_error = nullptr;
     cudaEvent_t ev[8]{};

@@ -148,6 +148,7 @@ int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st);
 // ---- trace (csrc/trace.cu) -----------------------------------------------------------------------
 struct TraceParams {
     const BvhNode* tlas_nodes;
+    uint32_t tlas_smem_nodes;   // TLAS node slots 0..this-1 hold every node of the TLAS (launch_trace stages them in shared memory when they fit; 0 = do not)
     const InstanceRec* instances;
     int32_t tlas_root;
     float tlas_absmax[3];
@@ -163,6 +164,7 @@ struct TraceParams {
     uint32_t ray_flags;         // RT_RAY_FLAG_*; anything beyond OPAQUE/NO_OPAQUE selects the GENERAL kernel variant
     uint32_t bounces;
     const float* hit_records; uint32_t n_records;
+    const uint4* anyhit; uint32_t n_anyhit;   // any-hit records {kind, log2_res, flags, first mask word (index into this array, in 32-bit words)}, GENERAL variant only
     float miss[3];
     uint8_t* rgba;              // packed local_rows x width x 4, or (full_frame) the whole height x width x 4 image, possibly peer memory
     uint32_t bgra;              // 1: store B,G,R,A byte order (the sample's swapchain format) instead of R,G,B,A
@@ -178,7 +180,31 @@ struct TraceParams {
     // queue_flags[i] = epoch (a per-launch number, so the flags never need clearing); counters[3] counts finished primary rays
     uint32_t* queue_flags; uint32_t epoch; uint32_t queue_capacity;
     int* error_flag;            // device int: set to 2 by the fused kernel's watchdog (a claim that is never published)
+    // region-major ray numbering (RT_REGIONS >= 1): a region = RT_REGION_TW x RT_REGION_TH tiles; ray ids are padded to whole regions
+    uint32_t regions_x, n_regions;
+    uint32_t n_sm;              // RT_REGIONS == 2: SMs of the device (home region of a warp = smid * n_regions / n_sm)
+    uint32_t* region_next;      // RT_REGIONS == 2: 2 * n_regions fetch counters (stage 0 | stage 1), zeroed per launch together with `counters`
 };
+// RT_REGIONS: 0 = rays numbered tile-major along image rows; 1 = region-major numbering (the rays in flight at any time cover a compact
+// 2-D patch of the image, i.e. a handful of instances, instead of a full-width strip), one global fetch counter; 2 = region-major numbering
+// AND one fetch counter per region with every SM starting in its own home regions (all warps of an SM work on the same patch: L1 reuse).
+// Measured on B200, inst10m 4K + bounce (profiles/README.md r2_f): 0 / 1 / 2 -> 3518 / 3511 / 3355 Mrays/s (regions of 8x8, 8x16, 32x16 tiles:
+// 3169 / 3259 / 3393): the locality of the row-major tile order is already enough for L2, and SM-affine regions cost more at the
+// refill and in the kernel tail than they return in L1 hits. Default 0; the other modes stay as build options.
+#ifndef RT_REGIONS
+#define RT_REGIONS 0
+#endif
+#ifndef RT_REGION_TW
+#define RT_REGION_TW 16
+#endif
+#ifndef RT_REGION_TH
+#define RT_REGION_TH 16
+#endif
+constexpr uint32_t TRACE_REGION_TILES = RT_REGIONS ? RT_REGION_TW * RT_REGION_TH : 1u;
+// ray slots (= tile-major ray ids, whole tiles, padded to whole regions) of a launch of `rows` packed rows
+inline uint32_t trace_regions_x(uint32_t width) { return RT_REGIONS ? (((width + 7u) >> 3) + RT_REGION_TW - 1u) / RT_REGION_TW : ((width + 7u) >> 3); }
+inline uint32_t trace_regions_y(uint32_t rows) { return RT_REGIONS ? (((rows + 3u) >> 2) + RT_REGION_TH - 1u) / RT_REGION_TH : ((rows + 3u) >> 2); }
+inline uint64_t trace_tiles_padded(uint32_t width, uint32_t rows) { return (uint64_t)trace_regions_x(width) * trace_regions_y(rows) * TRACE_REGION_TILES; }
 constexpr size_t TRACE_QUEUE_ENTRY_BYTES = 48;
 // per ray slot: the ray record + its index entry + its share of the tile mask / block sums (rounded up)
 constexpr size_t TRACE_BOUNCE_AUX_BYTES_PER_SLOT = 4 + 1;

@@ -100,7 +100,6 @@ int rt_create(int device_ordinal, rt_context** out) {
     ok = ok && cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_error, 64) == cudaSuccess;
-    ok = ok && cudaMalloc(&ctx->d_counters, 8 * 64) == cudaSuccess;
     ok = ok && cudaMemset(ctx->d_error, 0, 64) == cudaSuccess;
     if (!ok) { rt_destroy(ctx); return RT_ERROR_CUDA; }          // releases whatever was created so far
     if (const char* v = getenv("RTCORE_E2E_CHUNKS")) { int k = atoi(v); if (k >= 1 && k <= 8) ctx->e2e_chunks = k; }
@@ -113,7 +112,7 @@ void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    if (ctx->own_hit_records) cudaFree(ctx->d_hit_records);
+    if (ctx->own_hit_records) { cudaFree(ctx->d_hit_records); cudaFree(ctx->d_anyhit); }
     cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->qflags); cudaFree(ctx->d_counters);
     for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -645,6 +644,33 @@ int rt_set_miss_records(rt_context* ctx, const float* rgb, uint32_t count) {
     return RT_SUCCESS;
 }
 
+int rt_set_anyhit_records(rt_context* ctx, const rt_anyhit_record* records, uint32_t count) {
+    if (!ctx || (count && !records)) return RT_ERROR_INVALID_ARG;
+    if (!ctx->own_hit_records) return fail(ctx, RT_ERROR_INVALID_ARG, "shader data of a group's internal context follows the user context");
+    // one device array: count x {kind, log2_res, flags, first mask word} (16 B each), then the masks back to back
+    std::vector<uint32_t> blob(4 * (size_t)count);
+    for (uint32_t i = 0; i < count; ++i) {
+        const rt_anyhit_record& r = records[i];
+        if (r.kind > RT_ANYHIT_ALPHA_MASK || r.log2_res > 10u || (r.kind == RT_ANYHIT_ALPHA_MASK && !r.mask))
+            return fail(ctx, RT_ERROR_INVALID_ARG, "any-hit record %u: kind <= ALPHA_MASK, log2_res <= 10, mask set", i);
+        blob[4 * i] = r.kind; blob[4 * i + 1] = r.log2_res; blob[4 * i + 2] = r.flags; blob[4 * i + 3] = 0;
+        if (r.kind == RT_ANYHIT_ALPHA_MASK) {
+            const size_t words = (((size_t)1 << (2 * r.log2_res)) + 31) / 32;
+            blob[4 * i + 3] = (uint32_t)blob.size();
+            blob.insert(blob.end(), r.mask, r.mask + words);
+        }
+    }
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_anyhit) { cudaFree(ctx->d_anyhit); ctx->d_anyhit = nullptr; }
+    ctx->n_anyhit = 0;
+    if (count) {
+        RT_CUDA(ctx, cudaMalloc((void**)&ctx->d_anyhit, blob.size() * 4));
+        RT_CUDA(ctx, cudaMemcpy(ctx->d_anyhit, blob.data(), blob.size() * 4, cudaMemcpyHostToDevice));
+        ctx->n_anyhit = count;
+    }
+    return RT_SUCCESS;
+}
+
 int rt_set_ray_params(rt_context* ctx, const rt_ray_params* params) {
     if (!ctx) return RT_ERROR_INVALID_ARG;
     if (params) ctx->rp = *params; else ctx->rp = {0.0f, 100.0f, 0xffu, 0u, 1u, 1u, RT_RAY_FLAG_OPAQUE, 0u};
@@ -656,6 +682,7 @@ int rt_set_ray_params(rt_context* ctx, const rt_ray_params* params) {
 int rt_context_mirror_shader_state(rt_context* dst, const rt_context* src) {
     if (!dst || !src || dst->own_hit_records) return RT_ERROR_INVALID_ARG;
     dst->d_hit_records = src->d_hit_records; dst->n_records = src->n_records;
+    dst->d_anyhit = src->d_anyhit; dst->n_anyhit = src->n_anyhit;
     dst->miss = src->miss; dst->rp = src->rp;
     return RT_SUCCESS;
 }
@@ -712,6 +739,7 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     P.full_frame = (full_frame && dev_out) ? 1u : 0u;
     P.bgra = (flags & RT_TRACE_OUT_BGRA) ? 1u : 0u;
     P.tlas_nodes = tlas->nodes; P.instances = tlas->inst; P.tlas_root = tlas->root;
+    P.tlas_smem_nodes = tlas->n > 1 ? tlas->n - 1 : 0;     // Karras numbering: the n - 1 internal nodes of n leaves are slots 0..n-2
     for (int k = 0; k < 3; ++k) { P.tlas_absmax[k] = tlas->n && tlas->lo[k] <= tlas->hi[k] ? fmaxf(fabsf(tlas->lo[k]), fabsf(tlas->hi[k])) : 0.0f; P.cam_pos[k] = cam->pos[k]; P.miss[k] = ctx->miss[3 * (size_t)ctx->rp.miss_index + k]; }
     // raygen constants of main.cpp:1038-1039; tan is evaluated once on the host in fp32
     P.aspect_y = tanf((cam->yfov_deg * 0.017453292519943295f) * 0.5f);
@@ -721,6 +749,7 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     P.tmin = ctx->rp.tmin; P.tmax = ctx->rp.tmax; P.cull_mask = ctx->rp.cull_mask; P.sbt_offset = ctx->rp.sbt_record_offset;
     P.sbt_stride = ctx->rp.sbt_record_stride; P.bounce_seed = ctx->rp.bounce_seed; P.bounces = bounces; P.ray_flags = ctx->rp.ray_flags;
     P.hit_records = ctx->d_hit_records; P.n_records = ctx->n_records;
+    P.anyhit = ctx->d_anyhit; P.n_anyhit = ctx->n_anyhit;
     int rc;
     if (dev_out) { P.rgba = rgba_out; P.primary_hits = primary_hits_out; P.secondary_hits = secondary_hits_out; }
     else {
@@ -774,12 +803,22 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     }
     const bool two_streams = chunks > 1;
     // per-chunk scratch: ray slots (tile-major over whole 8x4 tiles), index list, tile masks + block sums, publication flags
-    size_t ray_off[9] = {0}, idx_off[9] = {0}, mask_off[9] = {0}, slot_off[9] = {0};
+    size_t ray_off[9] = {0}, idx_off[9] = {0}, mask_off[9] = {0}, slot_off[9] = {0}, ctr_off[9] = {0};
+    {
+        size_t words = 0;                                 // per chunk: 16 counters + 2 x n_regions region fetch counters
+        for (uint32_t c = 0; c < chunks; ++c) {
+            ctr_off[c] = words;
+            words += 16 + 2 * (size_t)trace_regions_x(width) * trace_regions_y(row_begin[c + 1] - row_begin[c]);
+            words = (words + 15) & ~(size_t)15;
+        }
+        ctr_off[chunks] = words;
+        if ((rc = ensure(ctx, &ctx->d_counters, &ctx->counters_cap, words * 4)) != RT_SUCCESS) return rc;
+    }
     if (bounces > 0) {
         size_t bytes = 0, slots_total = 0;
         for (uint32_t c = 0; c < chunks; ++c) {
             const uint32_t rows = row_begin[c + 1] - row_begin[c];
-            const uint64_t tiles = (uint64_t)((width + 7u) >> 3) * ((rows + 3u) >> 2), slots = tiles * 32u;
+            const uint64_t tiles = trace_tiles_padded(width, rows), slots = tiles * 32u;
             ray_off[c] = bytes; bytes += align_up(slots * TRACE_QUEUE_ENTRY_BYTES, 256);
             idx_off[c] = bytes; bytes += align_up(slots * 4, 256);
             mask_off[c] = bytes; bytes += align_up((tiles + tiles / 1024 + 16) * 4, 256);
@@ -806,7 +845,11 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
         Pc.epoch = ctx->trace_epoch;
         Pc.row0 = row_begin[c];
         Pc.local_rows = row_begin[c + 1] - row_begin[c];
-        Pc.counters = ctx->d_counters + 16 * c;
+        Pc.counters = (uint32_t*)ctx->d_counters + ctr_off[c];
+        Pc.region_next = Pc.counters + 16;
+        Pc.regions_x = trace_regions_x(width);
+        Pc.n_regions = Pc.regions_x * trace_regions_y(Pc.local_rows);
+        Pc.n_sm = (uint32_t)ctx->prop.multiProcessorCount;
         if (bounces > 0) {
             Pc.queue = (float4*)((uint8_t*)ctx->queue + ray_off[c]);
             Pc.bounce_index = (uint32_t*)((uint8_t*)ctx->queue + idx_off[c]);

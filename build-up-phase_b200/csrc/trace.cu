@@ -41,6 +41,21 @@ namespace {
 #endif
 constexpr int TRACE_THREADS = 128;
 constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
+// BIG kernel variant: ONE 1024-thread CTA per SM (same 32 warps, same 64-register cap) whose dynamic shared memory holds a copy of the
+// TLAS nodes, staged once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier). Top-level node fetches - every ray starts there, and
+// the rays that miss everything never leave it - then are LDS.128 instead of divergent L1 tag look-ups, and the TLAS stops competing
+// with the BLAS nodes for L1 lines. Selected when the TLAS has RT_SMEM_TLAS_MIN_NODES..RT_SMEM_TLAS_MAX_NODES nodes.
+constexpr int TRACE_THREADS_BIG = 1024;
+#ifndef RT_SMEM_TLAS
+#define RT_SMEM_TLAS 1
+#endif
+#ifndef RT_SMEM_TLAS_MAX_NODES
+#define RT_SMEM_TLAS_MAX_NODES 1024      // 64 KB of the SM's 256 KB L1/shared array
+#endif
+#ifndef RT_SMEM_TLAS_MIN_NODES
+#define RT_SMEM_TLAS_MIN_NODES 15
+#endif
+constexpr uint32_t SMEM_TLAS_HEADER = 128;    // mbarrier (8 B) + padding: the node copy is 128-byte aligned
 constexpr int REFILL_THRESHOLD = RT_REFILL_THRESHOLD;     // leave the traversal loop when fewer lanes are active
 #ifndef RT_NODE_CAP
 #define RT_NODE_CAP 6
@@ -72,6 +87,19 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 #ifndef RT_LDG256
 #define RT_LDG256 0
 #endif
+// Ray numbering / fetch counters: RT_REGIONS (rt_internal.h). A region = REGION_TW x REGION_TH tiles of 8x4 pixels; ray ids are
+// region-major (regions row-major over the launch, tiles row-major inside a region, 32 pixels per tile), padded to whole regions.
+constexpr uint32_t REGION_TW = RT_REGIONS ? RT_REGION_TW : 1u, REGION_TH = RT_REGIONS ? RT_REGION_TH : 1u;
+constexpr uint32_t TPR = REGION_TW * REGION_TH, RPR = TPR * 32u;    // tiles / rays per region
+// RT_SMEM_STACK = S > 0: the first S entries of every lane's traversal stack live in shared memory ([entry][thread]: conflict-free),
+// deeper entries in local memory; 0: the whole stack in local memory (which goes through L1 like the node fetches do).
+#ifndef RT_SMEM_STACK
+#define RT_SMEM_STACK 0
+#endif
+// the node loop's "too few lanes left" test every RT_CAP_EVERY-th iteration only (it costs a vote + popc + branch per node step)
+#ifndef RT_CAP_EVERY
+#define RT_CAP_EVERY 1
+#endif
 #ifndef RT_FAST_SLAB
 #define RT_FAST_SLAB 1
 #endif
@@ -79,8 +107,11 @@ constexpr int NODE_CAP = RT_NODE_CAP;                     // leave the inner nod
 // Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
 // on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
 struct F8 { float4 a, b; };
+// GENERIC: the node may live in shared memory (the staged TLAS) or in global memory (a BLAS): generic-address loads (LD.E.128), no branch
+template <bool GENERIC>
 __device__ __forceinline__ F8 ldg256(const void* p) {
     F8 r;
+    if (GENERIC) { r.a = *reinterpret_cast<const float4*>(p); r.b = *(reinterpret_cast<const float4*>(p) + 1); return r; }
 #if RT_LDG256
     asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) : "l"(p));
@@ -238,9 +269,13 @@ struct RayId { bool in_buffer, valid; uint32_t lidx, pixel, tm, out; };   // tm:
 // traverses; the pixel identity is recomputed for the epilogue (a dozen integer instructions instead of five live registers).
 __device__ __forceinline__ RayId primary_id(const TraceParams& P, uint32_t idx, uint32_t tiles_x, uint32_t& x, uint32_t& y) {
     RayId id;
-    const uint32_t tile = idx >> 5, within = idx & 31u;
-    x = (tile % tiles_x) * 8u + (within & 7u);
-    const uint32_t lr = P.row0 + (tile / tiles_x) * 4u + (within >> 3);
+    const uint32_t within = idx & 31u;
+    const uint32_t tile_lin = idx >> 5, region = tile_lin / TPR, tin = tile_lin - region * TPR;
+    const uint32_t ry = region / P.regions_x, rx = region - ry * P.regions_x;
+    const uint32_t tile_x = rx * REGION_TW + (tin % REGION_TW), tile_y = ry * REGION_TH + (tin / REGION_TW);
+    (void)tiles_x;
+    x = tile_x * 8u + (within & 7u);
+    const uint32_t lr = P.row0 + tile_y * 4u + (within >> 3);
     const uint32_t band = lr / P.block_rows;
     y = (band * P.part_count + P.part_index) * P.block_rows + (lr - band * P.block_rows);
     id.in_buffer = x < P.width && lr < P.row0 + P.local_rows;
@@ -397,16 +432,58 @@ __device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueu
 // The shaders' epilogue runs inside this kernel for the lanes whose ray just finished. (Measured alternatives, both
 // slower on B200 - profiles/README.md r01h: a separate warp-convergent shading kernel with refill thresholds 16..28,
 // and speculative traversal with one postponed leaf.)
-template <int STAGE, bool STATS, int STACK, bool GENERAL>
-__global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
+template <int STAGE, bool STATS, int STACK, bool GENERAL, bool BIG>
+__global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ? 1 : TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
+    const BvhNode* tlas_nodes = P.tlas_nodes;
+    if (BIG) {
+        // stage the TLAS nodes: one thread arms the mbarrier with the byte count and issues ONE bulk copy; everyone waits on phase 0
+        extern __shared__ __align__(128) unsigned char s_dyn[];
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(s_dyn);
+        const uint32_t dst = bar + SMEM_TLAS_HEADER;
+        const uint32_t bytes = P.tlas_smem_nodes * (uint32_t)sizeof(BvhNode);
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst), "l"(P.tlas_nodes), "r"(bytes), "r"(bar) : "memory");
+        }
+        __syncthreads();
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                         : "=r"(done) : "r"(bar) : "memory");
+        }
+        tlas_nodes = reinterpret_cast<const BvhNode*>(s_dyn + SMEM_TLAS_HEADER);
+    }
     const uint32_t lt_mask = (1u << lane) - 1u;
     const uint32_t tiles_x = (P.width + 7u) >> 3;
     const uint32_t tiles_y = (P.local_rows + 3u) >> 2;
     constexpr bool FUSED = STAGE == 2;       // both stages in one launch: a lane holds a primary OR a secondary ray (`sec`)
-    const uint32_t total = STAGE == 1 ? P.counters[2] : tiles_x * tiles_y * 32u;
+    (void)tiles_y;
+    const uint32_t n_prim = P.n_regions * RPR;                             // ray ids are padded to whole regions; the padding is never `valid`
+    const uint32_t total = STAGE == 1 ? P.counters[2] : n_prim;
     uint32_t* fetch_counter = P.counters + (STAGE == 1 ? 1 : 0);
     constexpr int THRESHOLD = REFILL_THRESHOLD;
+    // RT_REGIONS == 2 (not in the fused launch, which keeps the one global counter): every region has its own fetch counter. Stage 0 hands
+    // out the rays of an image region, stage 1 those of a contiguous chunk of the (region-ordered) bounce list. The warps of an SM start in
+    // that SM's home region and move on to the next open one when theirs is exhausted, so they all work on the same patch of the image (the
+    // same one or two instances) and the BLAS nodes one warp pulls into L1 are hits for the others.
+    constexpr bool USE_REGIONS = RT_REGIONS == 2 && !FUSED;
+    uint32_t my_region = 0, region_len = 1;
+    uint32_t* region_next = nullptr;
+    if (USE_REGIONS) {
+        uint32_t smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        my_region = (uint32_t)(((uint64_t)(smid % P.n_sm) * P.n_regions) / P.n_sm);      // warp-uniform
+        region_len = STAGE == 1 ? (total + P.n_regions - 1u) / P.n_regions : RPR;
+        if (region_len == 0u) region_len = 1u;
+        region_next = P.region_next + (STAGE == 1 ? P.n_regions : 0u);
+    }
+#if RT_SMEM_STACK > 0
+    __shared__ int32_t s_stack[RT_SMEM_STACK][BIG ? TRACE_THREADS_BIG : TRACE_THREADS];
+#endif
 
     Counters c, c1;                          // c1: FUSED only, the secondary rays' ray/hit counts
 
@@ -422,17 +499,37 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
     int32_t cur = REF_DONE;
     int sp = 0;
     bool in_blas = false;
-    const BvhNode* nodes = P.tlas_nodes;
+    const BvhNode* nodes = tlas_nodes;
     const TriRec* tris = nullptr;
     Slab sl; Woop wp;
     sl.rdx = sl.rdy = sl.rdz = sl.cnx = sl.cny = sl.cnz = sl.cfx = sl.cfy = sl.cfz = 0.0f; sl.px = sl.py = sl.pz = false;
     wp.okx = wp.oky = wp.okz = wp.Sx = wp.Sy = wp.Sz = 0.0f; wp.z0 = wp.z1 = false;
     uint32_t cur_slot = 0;
     uint32_t cur_iflags = 0;                 // GENERAL: instance flags of the BLAS being traversed
+    uint32_t cur_sbt = 0;                    // GENERAL: instanceShaderBindingTableRecordOffset of that instance (any-hit record lookup)
     V3 cur_od = {0.0f, 0.0f, 0.0f};          // GENERAL: object-space ray direction (facing test)
     float best_t = P.tmax, best_u = 0.0f, best_v = 0.0f, best_w0 = 0.0f;
     uint32_t best_slot = NO_HIT, best_tri = 0;
-    int32_t stack[STACK];
+    int32_t stack[STACK - RT_SMEM_STACK > 0 ? STACK - RT_SMEM_STACK : 1];
+#if RT_CAP_EVERY > 1
+    uint32_t cap_ctr = 0;
+#endif
+    auto push = [&](int32_t v) {
+#if RT_SMEM_STACK > 0
+        if (sp < RT_SMEM_STACK) s_stack[sp][threadIdx.x] = v; else stack[sp - RT_SMEM_STACK] = v;
+#else
+        stack[sp] = v;
+#endif
+        ++sp;
+    };
+    auto pop = [&]() -> int32_t {
+        --sp;
+#if RT_SMEM_STACK > 0
+        return sp < RT_SMEM_STACK ? s_stack[sp][threadIdx.x] : stack[sp - RT_SMEM_STACK];
+#else
+        return stack[sp];
+#endif
+    };
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
@@ -440,13 +537,43 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         if (need && !(FUSED && prim_empty)) {
             const int leader = __ffs(need) - 1;
             uint32_t base = 0;
-            if (lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(need));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (FUSED && base + (uint32_t)__popc(need) >= total) prim_empty = true;
+            uint32_t idx = 0xFFFFFFFFu;                                     // the ray this lane gets; 0xFFFFFFFF: none this round
+            if (USE_REGIONS) {
+                const uint32_t n = (uint32_t)__popc(need);
+                bool pool_empty = false;
+                for (;;) {
+                    if (lane == leader) base = atomicAdd(region_next + my_region, n);
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (base < region_len) break;
+                    // this region is exhausted: look for an open one, 32 candidates per step (plain loads; the atomic decides)
+                    bool found = false;
+                    for (uint32_t ofs = 1; ofs < P.n_regions; ofs += 32u) {
+                        uint32_t r = my_region + ofs + (uint32_t)lane;
+                        if (r >= P.n_regions) r -= P.n_regions;
+                        const bool open = ofs + (uint32_t)lane < P.n_regions && ld_volatile_u32(region_next + r) < region_len;
+                        const unsigned m = __ballot_sync(0xffffffffu, open);
+                        if (m) { my_region = __shfl_sync(0xffffffffu, r, __ffs(m) - 1); found = true; break; }
+                    }
+                    if (!found) { pool_empty = true; break; }
+                }
+                if (!have_ray && !exhausted && !pending) {
+                    if (pool_empty) exhausted = true;
+                    else {
+                        const uint32_t k = base + __popc(need & lt_mask);
+                        if (k < region_len) { idx = my_region * region_len + k; if (idx >= total) idx = 0xFFFFFFFFu; }
+                    }
+                }
+            } else {
+                if (lane == leader) base = atomicAdd(fetch_counter, (uint32_t)__popc(need));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (FUSED && base + (uint32_t)__popc(need) >= total) prim_empty = true;
+                if (!have_ray && !exhausted && !pending) {
+                    idx = base + __popc(need & lt_mask);
+                    if (idx >= total) { idx = 0xFFFFFFFFu; if (!FUSED) exhausted = true; }
+                }
+            }
             if (!have_ray && !exhausted && !pending) {
-                const uint32_t idx = base + __popc(need & lt_mask);
-                if (idx >= total) { if (!FUSED) exhausted = true; }
-                else {
+                if (idx != 0xFFFFFFFFu) {
                     have_ray = true;
                     bool valid = true;
                     if (STAGE != 1) {
@@ -467,9 +594,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
-                    stack[sp++] = REF_DONE;
+                    push(REF_DONE);
                     in_blas = false;
-                    nodes = P.tlas_nodes;
+                    nodes = tlas_nodes;
                     cur = valid ? P.tlas_root : REF_DONE;
                     if (cur == REF_EMPTY) cur = REF_DONE;
                     slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
@@ -508,9 +635,9 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                     pending = false; have_ray = true; sec = true;
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
-                    stack[sp++] = REF_DONE;
+                    push(REF_DONE);
                     in_blas = false;
-                    nodes = P.tlas_nodes;
+                    nodes = tlas_nodes;
                     cur = P.tlas_root;
                     if (cur == REF_EMPTY) cur = REF_DONE;
                     slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
@@ -535,7 +662,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
         // ================= two-level while-while traversal =================
         while (cur != REF_DONE) {
             while ((uint32_t)cur < (uint32_t)REF_SENTINEL_MIN) {               // internal node
-                const F8 na = ldg256(&nodes[cur].c[0]), nb = ldg256(&nodes[cur].c[1]);
+                const F8 na = ldg256<BIG>(&nodes[cur].c[0]), nb = ldg256<BIG>(&nodes[cur].c[1]);
                 const float4 a0 = na.a, a1 = na.b, b0 = nb.a, b1 = nb.b;
                 if (STATS) ++c.nodes;
                 float t0, t1;
@@ -544,12 +671,16 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                 const int32_t r0 = __float_as_int(a1.z), r1 = __float_as_int(b1.z);
                 if (hit0 && hit1) {
                     const bool swap = t1 < t0;
-                    stack[sp++] = swap ? r0 : r1;
+                    push(swap ? r0 : r1);
                     cur = swap ? r1 : r0;
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
-                else cur = stack[--sp];
+                else cur = pop();
+#if RT_CAP_EVERY > 1
+                if (NODE_CAP > 0 && (++cap_ctr % RT_CAP_EVERY) == 0 && __popc(__activemask()) < NODE_CAP) break;
+#else
                 if (NODE_CAP > 0 && __popc(__activemask()) < NODE_CAP) break;   // do not idle the warp behind a few long node chains
+#endif
             }
             if (cur < 0) {                                                       // leaf
                 const uint32_t first = leaf_first(cur), count = leaf_count(cur);
@@ -567,11 +698,11 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         woop_setup(wp, oo, od);
                         nodes = R->nodes; tris = R->tris;
                         cur_slot = first;
-                        if (GENERAL) { cur_iflags = __ldg(&R->sbt_flags) >> 24; cur_od = od; }
+                        if (GENERAL) { const uint32_t sf = __ldg(&R->sbt_flags); cur_iflags = sf >> 24; cur_sbt = sf & 0xFFFFFFu; cur_od = od; }
                         in_blas = true;
-                        stack[sp++] = REF_POP_INSTANCE;
+                        push(REF_POP_INSTANCE);
                         cur = root;
-                    } else cur = stack[--sp];
+                    } else cur = pop();
                 } else {
                     bool terminated = false;
                     for (uint32_t k = 0; k < count; ++k) {
@@ -579,6 +710,7 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                         const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
                         if (STATS) ++c.tris;
                         float t, bu, bv, bw0;
+                        bool anyhit_terminates = false;
                         if (woop_test(wp, q0, q1, q2, t, bu, bv, bw0) && t > P.tmin && t < P.tmax) {
                             if (GENERAL) {
                                 // opacity: geometry flag -> instance FORCE_* -> ray flags; then the opacity culls
@@ -597,6 +729,24 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                                     const bool front = (dot3(cross3(ed1, ed2), cur_od) > 0.0f) != ((cur_iflags & RT_INSTANCE_TRIANGLE_FLIP_FACING) != 0u);
                                     if (front ? (rf & RT_RAY_FLAG_CULL_FRONT_FACING_TRIANGLES) : (rf & RT_RAY_FLAG_CULL_BACK_FACING_TRIANGLES)) continue;
                                 }
+                                // any-hit stage of the hit group (include/rtcore.h, rt_anyhit_record): non-opaque candidates inside the
+                                // current ray interval only; fixed-function alpha test on the candidate's barycentrics
+                                if (!opaque && P.n_anyhit) {
+                                    if (t > best_t) continue;
+                                    const uint32_t ar = cur_sbt + __float_as_uint(q2.y) * P.sbt_stride + P.sbt_offset;
+                                    if (ar < P.n_anyhit) {
+                                        const uint4 a = __ldg(P.anyhit + ar);
+                                        if (a.x == RT_ANYHIT_ALPHA_MASK) {
+                                            const uint32_t res = 1u << a.y;
+                                            uint32_t cu = (uint32_t)(int)(bu * (float)res), cv = (uint32_t)(int)(bv * (float)res);
+                                            cu = min(cu, res - 1u); cv = min(cv, res - 1u);
+                                            const uint32_t bit = cv * res + cu;
+                                            const uint32_t word = __ldg(reinterpret_cast<const uint32_t*>(P.anyhit) + a.w + (bit >> 5));
+                                            if (((word >> (bit & 31u)) & 1u) == 0u) continue;             // ignoreIntersectionEXT
+                                        }
+                                        if (a.z & RT_ANYHIT_TERMINATE_RAY) anyhit_terminates = true;      // terminateRayEXT after the commit below
+                                    }
+                                }
                             }
                             bool better = t < best_t;
                             if (t == best_t && best_slot != NO_HIT) {
@@ -610,19 +760,19 @@ __global__ void __launch_bounds__(TRACE_THREADS, TRACE_MIN_BLOCKS) k_trace(const
                                 better = ci != bi ? ci < bi : (geo != bg ? geo < bg : prim < bp);
                             }
                             if (better) { best_t = t; best_u = bu; best_v = bv; best_w0 = bw0; best_slot = cur_slot; best_tri = first + k; }
-                            if (GENERAL && (P.ray_flags & RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT)) { terminated = true; break; }
+                            if (GENERAL && ((P.ray_flags & RT_RAY_FLAG_TERMINATE_ON_FIRST_HIT) || anyhit_terminates)) { terminated = true; break; }
                         }
                     }
                     if (GENERAL && terminated) { cur = REF_DONE; break; }
-                    cur = stack[--sp];
+                    cur = pop();
                 }
             } else if (cur == REF_POP_INSTANCE) {                                // back to world space
                 in_blas = false;
-                nodes = P.tlas_nodes;
+                nodes = tlas_nodes;
                 slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
-                cur = stack[--sp];
+                cur = pop();
             } else if (cur == REF_EMPTY) {
-                cur = stack[--sp];
+                cur = pop();
             }
             // warp-level compaction trigger: too few lanes still traversing -> go refill the idle ones
             if (!warp_exhausted && __popc(__activemask()) < THRESHOLD) break;
@@ -767,24 +917,35 @@ __global__ void __launch_bounds__(256) k_unpack_rows(const uchar4* __restrict__ 
     out[(size_t)y * width + x] = packed_all[((size_t)part * rows_per_part + lr) * width + x];
 }
 
-template <int STAGE, bool STATS, int STACK, bool GENERAL>
-int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
+template <int STAGE, bool STATS, int STACK, bool GENERAL, bool BIG>
+int launch_stage_v(const TraceParams& p, int sm_count, cudaStream_t st) {
+    constexpr int THREADS = BIG ? TRACE_THREADS_BIG : TRACE_THREADS;
+    const size_t smem = BIG ? SMEM_TLAS_HEADER + (size_t)p.tlas_smem_nodes * sizeof(BvhNode) : 0;
     static int per_device[64] = {};     // occupancy of this instantiation, cached per device ordinal
     int dev = 0;
     cudaGetDevice(&dev);
     int blocks_per_sm = dev >= 0 && dev < 64 ? per_device[dev] : 0;
     if (blocks_per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK, GENERAL>, TRACE_THREADS, 0) != cudaSuccess || blocks_per_sm < 1)
+        if (BIG && cudaFuncSetAttribute(k_trace<STAGE, STATS, STACK, GENERAL, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(SMEM_TLAS_HEADER + (size_t)RT_SMEM_TLAS_MAX_NODES * sizeof(BvhNode))) != cudaSuccess) return -1;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK, GENERAL, BIG>, THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
         if (dev >= 0 && dev < 64) per_device[dev] = blocks_per_sm;
     }
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     uint32_t blocks = (uint32_t)(sm_count * blocks_per_sm);            // persistent: a multiple of the SM count
-    const uint32_t max_useful = (tiles + (TRACE_THREADS / 32) - 1) / (TRACE_THREADS / 32);
+    const uint32_t max_useful = (tiles + (THREADS / 32) - 1) / (THREADS / 32);
     if (STAGE != 1 && blocks > max_useful) blocks = max_useful;
     if (blocks == 0) return 0;
-    k_trace<STAGE, STATS, STACK, GENERAL><<<blocks, TRACE_THREADS, 0, st>>>(p);
+    k_trace<STAGE, STATS, STACK, GENERAL, BIG><<<blocks, THREADS, smem, st>>>(p);
     return 1;
+}
+template <int STAGE, bool STATS, int STACK, bool GENERAL>
+int launch_stage(const TraceParams& p, int sm_count, cudaStream_t st) {
+#if RT_SMEM_TLAS
+    if (p.tlas_smem_nodes) return launch_stage_v<STAGE, STATS, STACK, GENERAL, true>(p, sm_count, st);
+#endif
+    return launch_stage_v<STAGE, STATS, STACK, GENERAL, false>(p, sm_count, st);
 }
 
 template <bool STATS, int STACK, bool GENERAL>
@@ -795,7 +956,7 @@ int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
     int n = launch_stage<0, STATS, STACK, GENERAL>(p, sm_count, st);
     if (p.bounces > 0) {
 #if RT_BOUNCE_ORDERED
-        const uint32_t n_words = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
+        const uint32_t n_words = p.n_regions * TPR;            // one mask word per (padded) tile
         const uint32_t blocks = (n_words + BIDX_CHUNK - 1) / BIDX_CHUNK;
         uint32_t* block_sums = p.tile_mask + n_words;
         k_bounce_count<<<blocks, BIDX_THREADS, 0, st>>>(p.tile_mask, n_words, block_sums, p.counters);
@@ -809,21 +970,25 @@ int launch_both(const TraceParams& p, int sm_count, cudaStream_t st) {
 
 template <int STACK>
 int launch_stack(const TraceParams& p, bool stats, int sm_count, cudaStream_t st) {
-    // the sample's flags (Opaque) and NoOpaque change nothing without an any-hit stage: fast variant
-    const bool general = (p.ray_flags & ~(uint32_t)(RT_RAY_FLAG_OPAQUE | RT_RAY_FLAG_NO_OPAQUE)) != 0u;
+    // the sample's flags (Opaque) and NoOpaque change nothing without any-hit records: fast variant
+    const bool general = (p.ray_flags & ~(uint32_t)(RT_RAY_FLAG_OPAQUE | RT_RAY_FLAG_NO_OPAQUE)) != 0u ||
+                         (p.n_anyhit != 0u && !(p.ray_flags & RT_RAY_FLAG_OPAQUE));        // any-hit records can only matter for non-opaque candidates
     if (general) return stats ? launch_both<true, STACK, true>(p, sm_count, st) : launch_both<false, STACK, true>(p, sm_count, st);
     return stats ? launch_both<true, STACK, false>(p, sm_count, st) : launch_both<false, STACK, false>(p, sm_count, st);
 }
 
 }  // namespace
 
-int launch_trace(const TraceParams& p, bool stats, int stack_needed, int sm_count, cudaStream_t st) {
+int launch_trace(const TraceParams& p_in, bool stats, int stack_needed, int sm_count, cudaStream_t st) {
+    TraceParams p = p_in;
+    if (!RT_SMEM_TLAS || p.tlas_smem_nodes < RT_SMEM_TLAS_MIN_NODES || p.tlas_smem_nodes > RT_SMEM_TLAS_MAX_NODES) p.tlas_smem_nodes = 0;
     const uint32_t tiles = ((p.width + 7u) >> 3) * ((p.local_rows + 3u) >> 2);
     if (tiles == 0) return 0;
-    if (cudaMemsetAsync(p.counters, 0, 16, st) != cudaSuccess) return -1;
+    // the 16 counters and (RT_REGIONS == 2) the 2 x n_regions region fetch counters behind them: one memset
+    if (cudaMemsetAsync(p.counters, 0, 4 * (16 + (RT_REGIONS == 2 ? 2 * (size_t)p.n_regions : 0)), st) != cudaSuccess) return -1;
 #if RT_BOUNCE_ORDERED
     const bool fused = RT_FUSED_STAGES && (uint64_t)p.width * p.local_rows <= (uint64_t)RT_FUSED_MAX_PIXELS;
-    if (p.bounces > 0 && !fused && cudaMemsetAsync(p.tile_mask, 0, sizeof(uint32_t) * (size_t)tiles, st) != cudaSuccess) return -1;
+    if (p.bounces > 0 && !fused && cudaMemsetAsync(p.tile_mask, 0, sizeof(uint32_t) * (size_t)p.n_regions * TPR, st) != cudaSuccess) return -1;
 #endif
     int n;
     if (stack_needed <= 64) n = launch_stack<64>(p, stats, sm_count, st);

@@ -40,7 +40,7 @@ EXPORTED_SYMBOLS = [
     "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_last_build_scratch_bytes", "rt_tlas_storage_bytes", "rt_blas_device_reference",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
-    "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
+    "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_anyhit_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version", "rt_copy_to_host",
     "rt_group_create", "rt_group_destroy", "rt_group_trace", "rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world",
@@ -50,6 +50,13 @@ EXPORTED_SYMBOLS = [
     "rt_obj_group_count", "rt_obj_vertices", "rt_obj_indices", "rt_obj_group_name", "rt_obj_group_first_triangle",
     "rt_obj_group_triangle_count", "rt_obj_geometry", "rt_write_ppm", "rt_write_png", "rt_srgb8_table",
 ]
+
+
+ANYHIT_ACCEPT, ANYHIT_ALPHA_MASK, ANYHIT_TERMINATE_RAY = 0, 1, 1
+
+
+class RtAnyHitRecord(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("log2_res", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32), ("mask", C.c_void_p)]
 
 
 class RtGeometry(C.Structure):
@@ -182,6 +189,7 @@ def load(build_if_missing: bool = True):
     L.rt_set_miss_color.argtypes = [vp, C.POINTER(C.c_float)]
     L.rt_set_miss_records.argtypes = [vp, vp, u32]
     L.rt_set_ray_params.argtypes = [vp, C.POINTER(RtRayParams)]
+    L.rt_set_anyhit_records.argtypes = [vp, vp, u32]
     L.rt_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, vp, vp, vp]
     L.rt_trace_rows.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
     L.rt_trace_rows_range.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, u32, u32, u32, u32, u32, vp, vp, vp]
@@ -487,6 +495,15 @@ class Context:
     def set_miss_records(self, rgb: np.ndarray):
         rgb = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
         self._check(self.L.rt_set_miss_records(self.h, rgb.ctypes.data, rgb.shape[0]))
+
+    def set_anyhit_records(self, records):
+        """Any-hit records of the hit groups: list of (kind, log2_res, flags, mask words as a uint32 array or None); [] removes the table."""
+        masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint32) for _, _, _, m in records]
+        arr = (RtAnyHitRecord * max(1, len(records)))()
+        for i, (kind, log2_res, flags, _) in enumerate(records):
+            arr[i].kind, arr[i].log2_res, arr[i].flags = kind, log2_res, flags
+            arr[i].mask = None if masks[i] is None else masks[i].ctypes.data
+        self._check(self.L.rt_set_anyhit_records(self.h, C.cast(arr, C.c_void_p) if records else None, len(records)))
 
     def set_ray_params(self, tmin=0.0, tmax=100.0, cull_mask=0xFF, sbt_record_offset=0, sbt_record_stride=1, bounce_seed=1,
                        ray_flags=RAY_FLAG_OPAQUE, miss_index=0):

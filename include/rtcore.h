@@ -45,7 +45,7 @@ enum {
 
 /* ---- geometry flags (rt_geometry.flags) ------------------------------------------------ */
 #define RT_GEOMETRY_OPAQUE          0x1u  /* VK_GEOMETRY_OPAQUE_BIT_KHR, main.cpp:741 */
-#define RT_GEOMETRY_NO_DUPLICATE_ANY_HIT 0x2u /* VK_GEOMETRY_NO_DUPLICATE_ANY_HIT_INVOCATION_BIT_KHR: accepted; no any-hit stage exists in this ABI */
+#define RT_GEOMETRY_NO_DUPLICATE_ANY_HIT 0x2u /* VK_GEOMETRY_NO_DUPLICATE_ANY_HIT_INVOCATION_BIT_KHR: accepted; the any-hit records below are pure functions of the candidate */
 #define RT_GEOMETRY_DEVICE_POINTERS 0x100u /* vertices/indices/transform are CUDA device pointers */
 
 /* ---- build flags ---------------------------------------------------------------------- */
@@ -64,8 +64,8 @@ enum {
 
 /* ---- ray flags (rt_ray_params.ray_flags): the gl_RayFlags*EXT argument of traceRayEXT (main.cpp:1048 passes Opaque) ----
  * Opacity of a candidate: geometry RT_GEOMETRY_OPAQUE, overridden by the instance FORCE_* flags, overridden by the ray
- * OPAQUE / NO_OPAQUE flags. No any-hit stage exists in this ABI (the sample registers none), so a non-opaque candidate
- * is accepted like an opaque one; opacity only feeds CULL_OPAQUE / CULL_NO_OPAQUE.
+ * OPAQUE / NO_OPAQUE flags. Opacity feeds CULL_OPAQUE / CULL_NO_OPAQUE, and a surviving NON-opaque candidate runs the any-hit
+ * record of its hit group (rt_set_anyhit_records; without records - the sample registers none - it is accepted like an opaque one).
  * Facing (object space, so the baked geometry transform counts and the instance transform does not): a triangle is
  * FRONT facing when its vertices appear clockwise from the ray origin, i.e. ((v1-v0) x (v2-v0)) . dir > 0, inverted by
  * RT_INSTANCE_TRIANGLE_FLIP_FACING; facing culls are ignored for instances with TRIANGLE_FACING_CULL_DISABLE.
@@ -268,6 +268,29 @@ RT_API int  rt_set_miss_color(rt_context* ctx, const float rgb[3]);          /* 
 /* Several miss shaders (each one, like the sample's, writes a constant colour): count x {r,g,b}; rt_ray_params.miss_index selects. */
 RT_API int  rt_set_miss_records(rt_context* ctx, const float* rgb, uint32_t count);
 RT_API int  rt_set_ray_params(rt_context* ctx, const rt_ray_params* params); /* NULL restores the defaults */
+
+/* The ANY_HIT stage of the hit groups (the reference maps the stage at shader_module.h:90 and creates no any-hit shader,
+ * main.cpp:1199-1216). A C ABI cannot carry shader code, so the stage is a fixed-function alpha test described by the record of the
+ * hit group, indexed like the hit records (instanceSbtOffset + geometryIndex * sbtRecordStride + sbtRecordOffset, main.cpp:1260-1262;
+ * an index past the table = no any-hit shader = accept):
+ *   RT_ANYHIT_ACCEPT      no any-hit shader in this hit group.
+ *   RT_ANYHIT_ALPHA_MASK  the candidate's barycentrics (u -> vertex 1, v -> vertex 2) select one cell of a res x res bit mask over
+ *                         [0,1)^2, res = 1 << log2_res <= 1024: cell = (min(int(u * res), res - 1), min(int(v * res), res - 1)),
+ *                         bit index = cell_v * res + cell_u (LSB first). Bit 0 = ignoreIntersectionEXT, bit 1 = accept.
+ *   flags RT_ANYHIT_TERMINATE_RAY: an accepted candidate also ends the ray (terminateRayEXT): hit/miss stays defined, WHICH hit does not.
+ * It runs for NON-opaque candidates only, after the opacity and facing culls, and only for candidates not farther than the closest
+ * hit committed so far (the current ray interval). Masks are host memory, copied by the call. count 0 removes the table. */
+#define RT_ANYHIT_ACCEPT        0u
+#define RT_ANYHIT_ALPHA_MASK    1u
+#define RT_ANYHIT_TERMINATE_RAY 0x1u
+typedef struct rt_anyhit_record {
+    uint32_t kind;             /* RT_ANYHIT_* */
+    uint32_t log2_res;         /* 0..10 */
+    uint32_t flags;            /* RT_ANYHIT_TERMINATE_RAY */
+    uint32_t reserved;
+    const uint32_t* mask;      /* (res * res + 31) / 32 words, host memory; NULL with RT_ANYHIT_ACCEPT */
+} rt_anyhit_record;
+RT_API int  rt_set_anyhit_records(rt_context* ctx, const rt_anyhit_record* records, uint32_t count);
 
 /* ---- dispatch --------------------------------------------------------------------------- */
 /* vkCmdTraceRaysKHR(width, height, 1): raygen + traversal + closest-hit/miss + imageStore.

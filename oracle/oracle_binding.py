@@ -52,9 +52,14 @@ class OrcStats(C.Structure):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
 
 
+class OrcAnyHitRecord(C.Structure):
+    _fields_ = [("kind", C.c_uint32), ("log2_res", C.c_uint32), ("flags", C.c_uint32), ("reserved", C.c_uint32), ("mask", C.c_void_p)]
+
+
 class OrcShaderData(C.Structure):
     _fields_ = [("hit_records_rgb", C.c_void_p), ("hit_record_count", C.c_uint32), ("miss_rgb", C.c_float * 3),
-                ("miss_records_rgb", C.c_void_p), ("miss_record_count", C.c_uint32)]
+                ("miss_records_rgb", C.c_void_p), ("miss_record_count", C.c_uint32),
+                ("anyhit_records", C.c_void_p), ("anyhit_record_count", C.c_uint32)]
 
 
 class OrcBlasInfo(C.Structure):
@@ -154,11 +159,23 @@ class OracleScene:
             self.sd.miss_rgb[k] = float(scene.miss_color[k])
         self.sd.miss_records_rgb = None
         self.sd.miss_record_count = 0
+        self.sd.anyhit_records = None
+        self.sd.anyhit_record_count = 0
 
     def set_miss_records(self, rgb):
         self.miss_records = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)
         self.sd.miss_records_rgb = self.miss_records.ctypes.data
         self.sd.miss_record_count = self.miss_records.shape[0]
+
+    def set_anyhit_records(self, records):
+        """records: list of (kind, log2_res, flags, mask words as a uint32 array or None); [] removes the table."""
+        self._anyhit_masks = [None if m is None else np.ascontiguousarray(m, dtype=np.uint32) for _, _, _, m in records]
+        self._anyhit = (OrcAnyHitRecord * max(1, len(records)))()
+        for i, (kind, log2_res, flags, _) in enumerate(records):
+            self._anyhit[i].kind, self._anyhit[i].log2_res, self._anyhit[i].flags = kind, log2_res, flags
+            self._anyhit[i].mask = None if self._anyhit_masks[i] is None else self._anyhit_masks[i].ctypes.data
+        self.sd.anyhit_records = C.cast(self._anyhit, C.c_void_p) if records else None
+        self.sd.anyhit_record_count = len(records)
 
     def trace(self, width: Optional[int] = None, height: Optional[int] = None, bounces: Optional[int] = None,
               mode: int = MODE_BVH, rows=(0, None, 1), ray_params: Optional[OrcRayParams] = None,

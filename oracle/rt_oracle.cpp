@@ -368,33 +368,57 @@ static inline bool id_less(uint32_t i0, uint32_t g0, uint32_t p0, uint32_t i1, u
 // Ray flag semantics [spec: GL_EXT_ray_tracing / Vulkan "Ray Intersection Culling"], stated once for both sides:
 //  * opacity of a candidate = geometry OPAQUE bit, overridden by the instance FORCE_OPAQUE / FORCE_NO_OPAQUE flags,
 //    overridden by the ray Opaque / NoOpaque flags; CullOpaque / CullNoOpaque then drop it. There is no any-hit
-//    shader in the sample (main.cpp:1199-1216 builds raygen + miss + closest-hit only), so a surviving non-opaque
-//    candidate is accepted like an opaque one.
+//    shader in the sample (main.cpp:1199-1216 builds raygen + miss + closest-hit only), so without any-hit records a surviving
+//    non-opaque candidate is accepted like an opaque one.
 //  * facing is decided in object space: front = vertices clockwise as seen from the ray origin, i.e.
 //    ((v1-v0) x (v2-v0)) . d > 0, inverted by the instance FLIP_FACING flag; CullBack/CullFront are ignored for
 //    instances with TRIANGLE_FACING_CULL_DISABLE (what the sample sets, main.cpp:852).
-// Returns true when a candidate was ACCEPTED (TerminateOnFirstHit ends the ray there).
-static inline bool consider(Best& best, const RayPre& r, const Tri& tr, uint32_t inst_id, const OInst* I,
-                            float tmin, float tmax, uint32_t ray_flags) {
+//  * any-hit stage (rt_oracle.h, orc_anyhit_record): runs for non-opaque survivors that are not farther than the committed closest hit.
+struct RayCfg { uint32_t ray_flags; const orc_anyhit_record* anyhit; uint32_t n_anyhit, sbt_stride, sbt_offset; };
+// the alpha-test any-hit shader: true = accept, false = ignoreIntersectionEXT
+static inline bool anyhit_accepts(const orc_anyhit_record& a, float u, float v) {
+    if (a.kind != ORC_ANYHIT_ALPHA_MASK || !a.mask) return true;
+    const uint32_t res = 1u << a.log2_res;
+    uint32_t cu = (uint32_t)(int)(u * (float)res), cv = (uint32_t)(int)(v * (float)res);
+    if (cu > res - 1u) cu = res - 1u;
+    if (cv > res - 1u) cv = res - 1u;
+    const uint32_t bit = cv * res + cu;
+    return ((a.mask[bit >> 5] >> (bit & 31u)) & 1u) != 0u;
+}
+// Returns 0 when the candidate was rejected, 1 when it was ACCEPTED, 2 when it was accepted and ends the ray (TerminateOnFirstHit, or
+// terminateRayEXT of an any-hit record).
+static inline int consider(Best& best, const RayPre& r, const Tri& tr, uint32_t inst_id, const OInst* I,
+                           float tmin, float tmax, const RayCfg& rc) {
+    const uint32_t ray_flags = rc.ray_flags;
     float t, u, v, w0;
-    if (!woop(r, tr, t, u, v, w0)) return false;
-    if (!(t > tmin && t < tmax)) return false;      // tmin < t < tmax, both exclusive
+    if (!woop(r, tr, t, u, v, w0)) return 0;
+    if (!(t > tmin && t < tmax)) return 0;      // tmin < t < tmax, both exclusive
     bool opaque = (tr.flags & ORC_GEOM_OPAQUE) != 0u;
     if (I->flags & ORC_INST_FORCE_OPAQUE) opaque = true;
     else if (I->flags & ORC_INST_FORCE_NO_OPAQUE) opaque = false;
     if (ray_flags & ORC_RAY_OPAQUE) opaque = true;
     else if (ray_flags & ORC_RAY_NO_OPAQUE) opaque = false;
-    if (opaque ? (ray_flags & ORC_RAY_CULL_OPAQUE) : (ray_flags & ORC_RAY_CULL_NO_OPAQUE)) return false;
+    if (opaque ? (ray_flags & ORC_RAY_CULL_OPAQUE) : (ray_flags & ORC_RAY_CULL_NO_OPAQUE)) return 0;
     if ((ray_flags & (ORC_RAY_CULL_BACK | ORC_RAY_CULL_FRONT)) && !(I->flags & ORC_INST_FACING_CULL_DISABLE)) {
         V3 n = cross3(sub(tr.v1, tr.v0), sub(tr.v2, tr.v0));
         bool front = (dot3(n, r.d) > 0.0f) != ((I->flags & ORC_INST_FLIP_FACING) != 0u);
-        if (front ? (ray_flags & ORC_RAY_CULL_FRONT) : (ray_flags & ORC_RAY_CULL_BACK)) return false;
+        if (front ? (ray_flags & ORC_RAY_CULL_FRONT) : (ray_flags & ORC_RAY_CULL_BACK)) return 0;
+    }
+    int accepted = (ray_flags & ORC_RAY_TERMINATE_ON_FIRST_HIT) ? 2 : 1;
+    if (!opaque && rc.n_anyhit) {
+        if (t > best.t) return 0;               // outside the current ray interval: the any-hit shader is not invoked
+        const uint64_t rec = (uint64_t)I->sbt + (uint64_t)tr.geo * rc.sbt_stride + rc.sbt_offset;
+        if (rec < rc.n_anyhit) {
+            const orc_anyhit_record& a = rc.anyhit[rec];
+            if (!anyhit_accepts(a, u, v)) return 0;
+            if (a.flags & ORC_ANYHIT_TERMINATE) accepted = 2;
+        }
     }
     bool better = t < best.t || (t == best.t && id_less(inst_id, tr.geo, tr.prim, best.inst, best.geo, best.prim));
-    if (!better) return true;
+    if (!better) return accepted;
     best.t = t; best.inst = inst_id; best.geo = tr.geo; best.prim = tr.prim; best.u = u; best.v = v; best.w0 = w0;
     best.I = I; best.tri = &tr;
-    return true;
+    return accepted;
 }
 
 // conservative slab test state for one (ray, space)
@@ -435,8 +459,7 @@ struct Counters { uint64_t nodes = 0, tris = 0, insts = 0; };
 
 // returns true when the ray was terminated (TerminateOnFirstHit and a candidate accepted)
 static bool traverse_blas(const orc_blas* B, const RayPre& r, uint32_t inst_id, const OInst* I, float tmin, float tmax,
-                          uint32_t ray_flags, Best& best, Counters& cnt) {
-    const bool first_hit = (ray_flags & ORC_RAY_TERMINATE_ON_FIRST_HIT) != 0u;
+                          const RayCfg& rc, Best& best, Counters& cnt) {
     const Lbvh& bvh = B->bvh;
     if (bvh.root == REF_EMPTY) return false;
     Slab s = slab_pre(r.o, r.d, B->bounds);
@@ -447,7 +470,7 @@ static bool traverse_blas(const orc_blas* B, const RayPre& r, uint32_t inst_id, 
             uint32_t f = leaf_first(cur), c = leaf_count(cur);
             for (uint32_t i = 0; i < c; ++i) {
                 ++cnt.tris;
-                if (consider(best, r, B->sorted_tris[f + i], inst_id, I, tmin, tmax, ray_flags) && first_hit) return true;
+                if (consider(best, r, B->sorted_tris[f + i], inst_id, I, tmin, tmax, rc) == 2) return true;
             }
             if (sp == 0) break;
             cur = stack[--sp];
@@ -476,18 +499,18 @@ static inline bool enter_instance(const TraceCtx& c, uint32_t i, V3 o, V3 d, flo
     const OInst& I = c.T->inst[i];
     if (!I.active) return false;
     if ((I.mask & c.rp.cull_mask) == 0) return false;
-    const bool first_hit = (c.rp.ray_flags & ORC_RAY_TERMINATE_ON_FIRST_HIT) != 0u;
+    const RayCfg rc = {c.rp.ray_flags, c.sd->anyhit_records, c.sd->anyhit_records ? c.sd->anyhit_record_count : 0u, c.rp.sbt_record_stride, c.rp.sbt_record_offset};
     ++cnt.insts;
     V3 oo = xform_point(I.w2o, o), od = xform_vec(I.w2o, d);
     RayPre r = ray_pre(oo, od);
     if (c.mode == ORC_MODE_BRUTE || !I.blas->has_bvh) {
         for (const Tri& tr : I.blas->tris) {
             ++cnt.tris;
-            if (consider(best, r, tr, i, &I, tmin, tmax, c.rp.ray_flags) && first_hit) return true;
+            if (consider(best, r, tr, i, &I, tmin, tmax, rc) == 2) return true;
         }
         return false;
     }
-    return traverse_blas(I.blas, r, i, &I, tmin, tmax, c.rp.ray_flags, best, cnt);
+    return traverse_blas(I.blas, r, i, &I, tmin, tmax, rc, best, cnt);
 }
 
 static Best trace_ray(const TraceCtx& c, V3 o, V3 d, float tmin, float tmax, Counters& cnt) {

@@ -77,9 +77,20 @@ typedef struct orc_stats {
              instances_entered, primary_hits, secondary_hits, near_edge_hits;
 } orc_stats;
 
+/* Any-hit shader of a hit group [spec: GL_EXT_ray_tracing any-hit stage; the reference maps the stage at shader_module.h:90 but creates
+ * no any-hit shader, main.cpp:1199-1216]. A C ABI cannot carry shader code, so the stage is a fixed-function alpha test described by the
+ * record: the candidate's barycentrics (u -> vertex 1, v -> vertex 2) select one cell of a res x res bit mask over [0,1)^2,
+ * cell = (min(int(u * res), res - 1), min(int(v * res), res - 1)), bit index = cell_v * res + cell_u (LSB first); bit 0 =
+ * ignoreIntersectionEXT, bit 1 = accept; ORC_ANYHIT_TERMINATE additionally ends the ray on an accepted candidate (terminateRayEXT).
+ * Runs for NON-opaque candidates only, after the opacity and facing culls, and only for candidates that are not farther than the
+ * closest hit committed so far. Indexed like the hit records (main.cpp:1260-1262); an index past the table = no any-hit shader. */
+typedef struct orc_anyhit_record { uint32_t kind, log2_res, flags, reserved; const uint32_t* mask; } orc_anyhit_record;
+enum { ORC_ANYHIT_ACCEPT = 0, ORC_ANYHIT_ALPHA_MASK = 1, ORC_ANYHIT_TERMINATE = 0x1 };
+
 typedef struct orc_shader_data {
     const float* hit_records_rgb; uint32_t hit_record_count; float miss_rgb[3];
     const float* miss_records_rgb; uint32_t miss_record_count;   /* optional table of constant-colour miss shaders; NULL = {miss_rgb} */
+    const orc_anyhit_record* anyhit_records; uint32_t anyhit_record_count;   /* optional; NULL/0 = no any-hit shaders (the sample) */
 } orc_shader_data;
 
 enum { ORC_MODE_BRUTE = 0, ORC_MODE_BVH = 1 };

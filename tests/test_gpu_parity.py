@@ -718,3 +718,77 @@ def test_rows_range_needs_whole_bands(rt, ctx):
         assert np.array_equal(out.cpu().numpy(), full)
     finally:
         sh.free()
+
+
+def _anyhit_records(n, seed=5):
+    """One any-hit record per hit group: ACCEPT, or an alpha mask of 2^k x 2^k cells (k = 0..5) with ~55 % of the bits set."""
+    rng = np.random.default_rng(seed)
+    recs = []
+    for i in range(n):
+        if i % 4 == 3:
+            recs.append((0, 0, 0, None))                                   # RT_ANYHIT_ACCEPT: no any-hit shader in this hit group
+            continue
+        k = [3, 5, 0, 2, 4, 1][i % 6]
+        bits = rng.random((1 << k) * (1 << k)) < 0.55
+        if k == 0:
+            bits[:] = (i % 2 == 0)                                         # a 1x1 mask: everything ignored / everything accepted
+        words = np.zeros(((1 << (2 * k)) + 31) // 32, dtype=np.uint32)
+        for b in np.nonzero(bits)[0]:
+            words[b >> 5] |= np.uint32(1 << (int(b) & 31))
+        recs.append((1, k, 0, words))
+    return recs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ray_flags", [0x0, 0x2, 0x10, 0x80, 0x1], ids=lambda f: f"rayflags{f:#04x}")
+def test_anyhit_alpha_masks_vs_brute_force(rt, ctx, oracle, ray_flags):
+    """SURVEY 8(f) row 2, the any-hit stage (shader_module.h:90): alpha-mask records on the non-opaque geometries of the flag
+    scene. ids, t, u, v bit-exact and RGBA8 within +-1 LSB against the oracle's brute force, primary and bounce rays."""
+    scene = _flag_scene(seed=12)
+    recs = _anyhit_records(len(scene.hit_records))
+    sh = rt.SceneHandles(ctx, scene)
+    o = oracle.OracleScene(scene)
+    try:
+        ctx.set_ray_params(ray_flags=ray_flags)
+        base = sh.trace(want_hits=True)
+        ctx.set_anyhit_records(recs)
+        g = sh.trace(want_hits=True)
+        o.set_anyhit_records(recs)
+        r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=ray_flags))
+    finally:
+        ctx.set_anyhit_records([])
+        ctx.set_ray_params()
+        o.close()
+        sh.free()
+    rp, rs, rc = assert_parity(g, r, what=f"anyhit{ray_flags:#x}")
+    changed = int((g[1]["primitive_id"] != base[1]["primitive_id"]).sum())
+    if ray_flags & 0x1 or ray_flags & 0x80:
+        assert changed == 0, "Opaque ray flag / CullNoOpaque: no candidate reaches the any-hit stage"
+    else:
+        assert changed > 300, "the masks must actually cut holes into this scene"
+    print("anyhit", hex(ray_flags), rp, rs, rc, "changed", changed)
+
+
+@pytest.mark.gpu
+def test_anyhit_terminate_ray(rt, ctx, oracle):
+    """terminateRayEXT from an any-hit record: WHICH hit is undefined, the hit/miss mask is not."""
+    scene = _flag_scene(seed=13)
+    scene.bounces = 0
+    recs = [(k, l, 1, m) for k, l, _, m in _anyhit_records(len(scene.hit_records), seed=6)]
+    sh = rt.SceneHandles(ctx, scene)
+    o = oracle.OracleScene(scene)
+    try:
+        ctx.set_ray_params(ray_flags=0x2)                                   # NoOpaque: every candidate runs its any-hit record
+        ctx.set_anyhit_records(recs)
+        o.set_anyhit_records(recs)
+        _, prim, _ = sh.trace(want_hits=True)
+        r = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=0x2))
+        mg, mr = prim["instance_id"] != MISS, r[1]["instance_id"] != MISS
+        assert np.array_equal(mg, mr) and mg.sum() > 1000
+        with pytest.raises(rt.RtError):
+            ctx.set_anyhit_records([(1, 11, 0, np.zeros(4, dtype=np.uint32))])     # log2_res > 10
+    finally:
+        ctx.set_anyhit_records([])
+        ctx.set_ray_params()
+        o.close()
+        sh.free()

@@ -330,3 +330,127 @@ def test_bounce_definition_restated(oracle):
     ok = clear & ~spec1 & ~spec2
     expect = np.clip(0.5 * col1 + 0.5 * col2, 0, 1) * 255.0
     assert np.abs(rgba.reshape(-1, 4)[rays][ok][:, :3].astype(np.float64) - expect[ok]).max() <= 1.0
+
+
+# ---- the any-hit stage (rt_oracle.h orc_anyhit_record; SURVEY 8(f) row 2, stage mapping shader_module.h:90) ------------------------------
+def _anyhit_scene(seed=14):
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=300, n_instances=8, seed=seed, width=160, height=100, bounces=1, shared_edges=True)
+    for b, geoms in enumerate(scene.blases):
+        for g, geo in enumerate(geoms):
+            geo.flags = 1 if (b + g) % 3 == 0 else 0                      # two thirds of the geometries are NOT opaque
+    for i, I in enumerate(scene.instances):
+        I.flags = [0x1, 0x1 | 0x8, 0x1, 0x1 | 0x4, 0x1, 0x1, 0x1 | 0x8, 0x1][i % 8]    # some FORCE_NO_OPAQUE / FORCE_OPAQUE
+        I.mask = 0xFF
+    return scene
+
+
+def _mask_records(n, seed=3):
+    rng = np.random.default_rng(seed)
+    recs, bits_of = [], []
+    for i in range(n):
+        if i % 5 == 4:
+            recs.append((0, 0, 0, None)); bits_of.append(None)
+            continue
+        k = [3, 5, 2, 4, 1][i % 5]
+        bits = rng.random((1 << k, 1 << k)) < 0.5                           # [cell_v, cell_u]
+        words = np.zeros(((1 << (2 * k)) + 31) // 32, dtype=np.uint32)
+        for b in np.nonzero(bits.reshape(-1))[0]:
+            words[b >> 5] |= np.uint32(1 << (int(b) & 31))
+        recs.append((1, k, 0, words)); bits_of.append(bits)
+    return recs, bits_of
+
+
+def test_anyhit_brute_force_equals_bvh(oracle):
+    """With alpha-mask any-hit records the closest ACCEPTED hit is still independent of the traversal order."""
+    scene = _anyhit_scene()
+    recs, _ = _mask_records(len(scene.hit_records))
+    o = oracle.OracleScene(scene)
+    rp = oracle.ray_params(ray_flags=0x0)
+    base = o.trace(mode=oracle.MODE_BRUTE, ray_params=rp)
+    o.set_anyhit_records(recs)
+    a = o.trace(mode=oracle.MODE_BRUTE, ray_params=rp)
+    b = o.trace(mode=oracle.MODE_BVH, ray_params=rp)
+    opaque_ray = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=0x1))
+    o.close()
+    assert a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes() and np.array_equal(a[0], b[0])
+    assert int((a[1]["primitive_id"] != base[1]["primitive_id"]).sum()) > 300, "the masks must cut holes"
+    assert opaque_ray[1].tobytes() == base[1].tobytes(), "gl_RayFlagsOpaqueEXT: the any-hit stage never runs"
+
+
+def test_anyhit_vs_float64_world_space(oracle):
+    """INDEPENDENT statement of the any-hit semantics: all candidates of every primary ray in float64 world space (Moeller-Trumbore),
+    opacity = geometry flag overridden by the instance FORCE_* flags, non-opaque candidates looked up in the hit group's bit mask at
+    cell (int(u * res), int(v * res)) with u -> vertex 1, v -> vertex 2, closest accepted candidate wins. Rays with a candidate within
+    1e-4 of an edge or of a mask-cell boundary, or with two accepted candidates closer than 1e-4 in t, are skipped as ambiguous."""
+    scene = _anyhit_scene()
+    recs, bits_of = _mask_records(len(scene.hit_records))
+    o = oracle.OracleScene(scene)
+    o.set_anyhit_records(recs)
+    _, prim, _, _ = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=0x0), bounces=0)
+    o.close()
+    W, H = scene.width, scene.height
+    f32 = np.float32
+    ay = f32(oracle.lib().orc_aspect_y(f32(scene.yfov_deg)))
+    ax = f32(ay * f32(W) / f32(H))
+    ndcx = ((np.arange(W, dtype=np.float32) + f32(0.5)) / f32(W) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = ((np.arange(H, dtype=np.float32) + f32(0.5)) / f32(H) * f32(2.0) - f32(1.0)).astype(np.float32)
+    D = np.empty((H, W, 3))
+    D[..., 0] = (ndcx * ax).astype(np.float64)[None, :]
+    D[..., 1] = (-(ndcy * ay)).astype(np.float64)[:, None]
+    D[..., 2] = -1.0
+    D = D.reshape(-1, 3)
+    O = np.broadcast_to(np.asarray(scene.camera_pos, dtype=np.float64), D.shape)
+    tri, ids = _world_triangles(scene)
+    # per world triangle: opaque? which any-hit record?
+    geo_flags = {(b, g): geo.flags for b, geoms in enumerate(scene.blases) for g, geo in enumerate(geoms)}
+    opaque = np.zeros(tri.shape[0], dtype=bool)
+    for k in range(tri.shape[0]):
+        I = scene.instances[ids[k, 0]]
+        op = bool(geo_flags[(I.blas, int(ids[k, 1]))] & 1)
+        if I.flags & 0x4: op = True
+        elif I.flags & 0x8: op = False
+        opaque[k] = op
+    rec = ids[:, 4] + ids[:, 1]                                             # instanceSbtOffset + geometryIndex (stride 1, offset 0)
+    n = D.shape[0]
+    best_t = np.full(n, np.inf); second_t = np.full(n, np.inf); best_k = np.full(n, -1); ambiguous = np.zeros(n, dtype=bool)
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    for k in range(tri.shape[0]):
+        pvec = np.cross(D, e2[k]); det = pvec @ e1[k]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tvec = O - tri[k, 0]
+            u = np.einsum("rc,rc->r", tvec, pvec) * inv
+            qvec = np.cross(tvec, e1[k])
+            v = np.einsum("rc,rc->r", D, qvec) * inv
+            t = (qvec @ e2[k]) * inv
+        margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
+        in_t = (t > 0.0) & (t < 100.0) & (np.abs(det) > 1e-12)
+        ambiguous |= in_t & (np.abs(margin) < 1e-4)
+        cand = in_t & (margin > 0)
+        if not opaque[k] and rec[k] < len(recs) and bits_of[rec[k]] is not None:
+            bits = bits_of[rec[k]]; res = bits.shape[0]
+            fu, fv = u * res, v * res
+            near_cell = (np.abs(fu - np.rint(fu)) < 1e-4) | (np.abs(fv - np.rint(fv)) < 1e-4)
+            ambiguous |= cand & near_cell
+            cu = np.clip(np.floor(np.where(cand, fu, 0)).astype(np.int64), 0, res - 1)
+            cv = np.clip(np.floor(np.where(cand, fv, 0)).astype(np.int64), 0, res - 1)
+            cand &= bits[cv, cu]
+        tt = np.where(cand, t, np.inf)
+        better = tt < best_t
+        second_t = np.where(better, best_t, np.minimum(second_t, tt))
+        best_k = np.where(better, k, best_k)
+        best_t = np.where(better, tt, best_t)
+    hit = np.isfinite(best_t)
+    with np.errstate(invalid="ignore"):
+        clear = ~ambiguous & np.where(hit, second_t - best_t > 1e-4 * np.maximum(1.0, best_t), True)
+    p = prim.reshape(-1)
+    ohit = p["instance_id"] != MISS
+    assert clear.sum() > 0.85 * n and (clear & hit).sum() > 1200
+    assert np.array_equal(ohit[clear], hit[clear])
+    c = clear & hit
+    want = ids[best_k[c]]
+    assert np.array_equal(p["instance_id"][c], want[:, 0]) and np.array_equal(p["geometry_index"][c], want[:, 1])
+    assert np.array_equal(p["primitive_id"][c], want[:, 2])
+    assert np.abs(p["t"][c] - best_t[c]).max() < 1e-4 * best_t[c].max()
+    # the masks really decided: some clear rays pass THROUGH a masked-out candidate that lies in front of their accepted hit
+    print("anyhit f64 pin: clear rays", int(clear.sum()), "of", n, "hits", int(c.sum()))
