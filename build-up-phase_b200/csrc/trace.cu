@@ -46,8 +46,12 @@ constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 
 // the rays that miss everything never leave it - then are LDS.128 instead of divergent L1 tag look-ups, and the TLAS stops competing
 // with the BLAS nodes for L1 lines. Selected when the TLAS has RT_SMEM_TLAS_MIN_NODES..RT_SMEM_TLAS_MAX_NODES nodes.
 constexpr int TRACE_THREADS_BIG = 1024;
+// Measured on B200 (inst10m 4K + bounce, 1023 TLAS nodes = 64 KB; profiles/README.md r2_g, prof_trace_r2_g.json): 3281 Mrays/s WITH the
+// staged TLAS vs 3499 without. ncu: l1tex throughput 75 % -> 81 % (stage 0) and 71 % -> 82 % (stage 1) - shared-memory reads go through
+// the same L1TEX data pipeline, and the generic-address loads (LD.E.128 instead of LDG.E.128.CONSTANT) that let one loop walk both
+// spaces cost 3.5 % more warp-instructions and the BLAS nodes their read-only path. Default 0; the variant stays as a build option.
 #ifndef RT_SMEM_TLAS
-#define RT_SMEM_TLAS 1
+#define RT_SMEM_TLAS 0
 #endif
 #ifndef RT_SMEM_TLAS_MAX_NODES
 #define RT_SMEM_TLAS_MAX_NODES 1024      // 64 KB of the SM's 256 KB L1/shared array
