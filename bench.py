@@ -211,7 +211,7 @@ def count_instructions(args):
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
     if not os.path.exists(ncu) or os.environ.get("RTCORE_BENCH_NO_NCU"):
         return None
-    cmd = [ncu, "--metrics", "smsp__inst_executed.sum,smsp__thread_inst_executed.sum", "--clock-control", "none", "-k", "regex:k_trace",
+    cmd = [ncu, "--metrics", "smsp__inst_executed.sum,smsp__thread_inst_executed.sum,l1tex__data_pipe_lsu_wavefronts.sum", "--clock-control", "none", "-k", "regex:k_trace",
            "--csv", sys.executable, os.path.join(ROOT, "tools", "frame_once.py"), "--workload", args.workload]
     if args.width:
         cmd += ["--width", str(args.width)]
@@ -229,7 +229,7 @@ def count_instructions(args):
         rows = [r for r in csv.reader(io.StringIO(p.stdout)) if len(r) > 6]
         hdr = next(r for r in rows if "Metric Name" in r)
         ni, vi, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
-        out = {"warp_inst": 0.0, "thread_inst": 0.0, "kernels": set()}
+        out = {"warp_inst": 0.0, "thread_inst": 0.0, "lsu_wavefronts": 0.0, "kernels": set()}
         for r in rows:
             if r is hdr or len(r) <= max(ni, vi, ki):
                 continue
@@ -239,6 +239,8 @@ def count_instructions(args):
                 out["kernels"].add(r[ki][:40])
             elif r[ni] == "smsp__thread_inst_executed.sum":
                 out["thread_inst"] += v
+            elif r[ni] == "l1tex__data_pipe_lsu_wavefronts.sum":
+                out["lsu_wavefronts"] += v
         out["kernels"] = len(out["kernels"])
         return out if out["warp_inst"] > 0 else None
     except Exception:       # noqa: BLE001
@@ -345,7 +347,8 @@ def run_gpu(args):
             if blases is not None:
                 for b in blases:
                     b.free()
-            blases = ctx.build_blas_batch(dev_blases, device=True) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True)]
+            bf = rtcore.RT_BUILD_ALLOW_COMPACTION if args.compact else 0
+            blases = ctx.build_blas_batch(dev_blases, device=True, flags=bf) if len(dev_blases) > 1 else [ctx.build_blas(dev_blases[0], device=True, flags=bf)]
             if rep > 0 or args.build_reps == 0:
                 build_ms.append(ctx.build_timing())
         bt = min(build_ms, key=lambda t: t["total_ms"])
@@ -412,6 +415,14 @@ def run_gpu(args):
         share_ms = build_variants.get("split", {}).get("pull_ms", 0.0)
         build_note = f"8 BLASes of {n_tris_total // scenes.SOUP_PARTS} triangles; reported = the faster way ({fastest}); see build.variants"
         del dev_parts
+    compaction = None
+    if args.compact and not is_soup:
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        b0, b1 = ctx.compact_blas(blases[0])            # the whole batch
+        torch.cuda.synchronize()
+        compaction = {"bytes_before": b0, "bytes_after": b1, "host_ms": (time.perf_counter() - t0) * 1e3,
+                      "note": "rt_compact_blas after the timed build (VK_COPY_ACCELERATION_STRUCTURE_MODE_COMPACT_KHR); not part of build.value"}
     tlas = ctx.build_tlas(scene.instances, blases)
     tlas_t = ctx.build_timing()
     ctx.set_hit_records(scene.hit_records)
@@ -583,7 +594,26 @@ def run_gpu(args):
                     "note": "SURVEY 8(d) figure: ALGORITHMIC bytes (served mostly by L1/L2) over the HBM peak; measured DRAM traffic is `traffic`",
                     "bytes_model": "64*nodes + 56*triangles + 64*instances + 4*pixels (SURVEY 8d), counters from the RT_TRACE_STATS pass of this run",
                     "algorithmic_bytes_per_launch": algo_bytes / world}
-        roofline = dict(issue) if issue else dict(hbm_roof)
+        # ---- the other unit the node fetches load: the LSU data pipe of L1TEX, one wavefront per cycle and SM (ncu: 75-82 % of peak on
+        # inst10m, above the issue-slot utilisation). Same live counter pass; reported as the primary roofline when its fraction is the larger
+        l1tex = None
+        if live and live.get("lsu_wavefronts"):
+            wf_ach = live["lsu_wavefronts"] / world / (kernel_ms * 1e-3) / 1e9
+            wf_peak = sm_count * clock_mhz * 1e6 / 1e9                           # G wavefronts / s: one per cycle and SM
+            l1tex = {"bound": "l1tex-lsu", "achieved": wf_ach, "peak": wf_peak, "unit": "Gwavefronts/s", "frac": wf_ach / wf_peak,
+                     "wavefronts_per_frame": live["lsu_wavefronts"],
+                     "counters": "live: ncu --metrics l1tex__data_pipe_lsu_wavefronts.sum on one frame of this run's library and workload; "
+                                 "peak = 1 wavefront per cycle per SM at the SM clock sampled during the timed region",
+                     "sm_clock_mhz": clock_mhz, "sm_count": sm_count}
+        if issue and l1tex and l1tex["frac"] > issue["frac"]:
+            roofline = dict(l1tex)
+            roofline["sm_issue"] = issue
+        elif issue:
+            roofline = dict(issue)
+            if l1tex:
+                roofline["l1tex_lsu"] = l1tex
+        else:
+            roofline = dict(hbm_roof)
         roofline.update({"kernel": "k_trace (stage 0 + stage 1 of one frame)", "traffic": traffic, "traffic_source": traffic_src,
                          "hbm_algorithmic": hbm_roof,
                          "per_ray": {"nodes": tot["nodes_visited"] / total_rays, "triangles": tot["triangles_tested"] / total_rays,
@@ -608,6 +638,7 @@ def run_gpu(args):
                       "roofline": {"bound": "hbm", "achieved": build_gbs, "peak": hbm, "unit": "GB/s", "frac": build_gbs / hbm,
                                    "bytes_per_triangle": B_TRI_BUILD, "traffic": btraffic, "traffic_source": btraffic_src}},
             "traversal": tot,
+            "compaction": compaction,
             "crc32": crc,
             "clocks": clocks,
         }
@@ -662,6 +693,7 @@ def main():
     ap.add_argument("--soup-build", default="both", choices=["both", "split", "replicated"],
                     help="cfg5 at N > 1: split = per-GPU builds + NVLink pulls of the other parts, replicated = every GPU builds all parts; both = "
                          "measure both, report the faster")
+    ap.add_argument("--compact", action="store_true", help="build with RT_BUILD_ALLOW_COMPACTION and trace the compacted BLASes (rt_compact_blas)")
     ap.add_argument("--no-issue-counters", action="store_true", help="skip the live ncu instruction-count pass (N = 1) behind roofline.frac")
     ap.add_argument("--soup-split", default="slab", choices=["slab", "index"],
                     help="cfg5 soup: 8 BLASes as x-slabs of the volume (default) or as index ranges of a fully mixed soup")

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
         s_keys[t] = rec;
     }
     __syncthreads();
-    seg_sort_passes(seg_smem, vb, (int)MORTON_BITS);
+    seg_sort_passes(seg_smem, vb, (int)MORTON_BITS, n);
     for (uint32_t i = tid; i < n; i += SEG_THREADS) keys_out[first + i] = s_keys[i];
 }
 
@@ -395,6 +395,12 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
 // capacity of the border-job queue: 2 unfinished subtrees + one orphan per straddling ancestor (tree height <= 64 key
 // bits + 32 index bits) of each border leaf, and never more than one orphan per split of the tile
 __host__ __device__ constexpr uint32_t tree_jobs_per_tile() { return 2u + 2u * 96u; }
+inline uint64_t tree_job_capacity_host(uint32_t n) {
+    const uint64_t tiles = ((uint64_t)n + TREE_TILE - 1) / TREE_TILE;
+    const uint64_t per_tile = tree_jobs_per_tile() < (uint32_t)TREE_TILE + 2u ? tree_jobs_per_tile() : (uint32_t)TREE_TILE + 2u;
+    const uint64_t cap = tiles * per_tile;
+    return cap < 2ull * n + 2 ? cap : 2ull * n + 2;
+}
 
 // Phase 2: one thread per border job climbs through global memory: deposit {half, far end} at the split, fence,
 // arrival counter; the second arriver unions and writes the finished node into its Karras slot.
@@ -402,15 +408,18 @@ template <int LEAF_MAX, class Seg>
 __global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
                                                     const float4* __restrict__ jobs, const uint32_t* __restrict__ job_count,
                                                     float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg seg) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *job_count) return;
+    // grid-stride over the jobs: the queue's CAPACITY is ~130 entries per tile, its length ~3, so the grid is sized by the machine
+    // (border_grid) and not by the capacity; a thread never waits for another one (the first arrival at a split retires), so taking
+    // several jobs in turn cannot deadlock
+    const uint32_t n_jobs = *job_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_jobs; i += gridDim.x * blockDim.x) {
     const float4 q0 = __ldg(jobs + 3 * (size_t)i), q1 = __ldg(jobs + 3 * (size_t)i + 1), q2 = __ldg(jobs + 3 * (size_t)i + 2);
     TreeJob j;
     j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
     j.ref = __float_as_int(q1.z); j.height = __float_as_uint(q1.w);
     j.l = __float_as_uint(q2.x); j.r = __float_as_uint(q2.y);
     seg.seg_of(__ldg(keys + j.l) >> vb, j.seg_first, j.seg_count);
-    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); return; }
+    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); continue; }
     auto merges_right = [&](uint32_t l, uint32_t r) {
         const int dl = l > 0u ? delta_global(keys, vb, l - 1u) : -1;
         const int dr = r + 1u < n ? delta_global(keys, vb, r) : -1;
@@ -444,6 +453,15 @@ __global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict_
         }
         if (root) { seg.on_root(j); break; }
     }
+    }
+}
+// grid of the border kernel: enough threads for the jobs a build really has (a few per tile), at most 16 CTAs per SM
+inline uint32_t border_grid(uint32_t n) {
+    const uint32_t by_jobs = (uint32_t)((tree_job_capacity_host(n) + 127) / 128);
+    const uint32_t by_tiles = (uint32_t)(((uint64_t)(n + TREE_TILE - 1) / TREE_TILE * 4 + 127) / 128) + 1u;
+    uint32_t g = by_jobs < by_tiles ? by_jobs : by_tiles;
+    if (g > 148u * 16u) g = 148u * 16u;
+    return g ? g : 1u;
 }
 
 __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
@@ -558,14 +576,152 @@ __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_inst(cons
 
 inline int div_up(uint32_t a, uint32_t b) { return (int)((a + b - 1) / b); }
 
+// ---- compaction (rt_compact_blas; VK_COPY_ACCELERATION_STRUCTURE_MODE_COMPACT_KHR) ---------------------------------------------
+// Slot i of a segment is Karras' internal node i: its leaf range starts (or ends) at leaf i and extends in direction d for as long as
+// the common prefix with leaf i stays longer than delta(i, i - d). The build writes the node only when that range holds more than
+// BLAS_LEAF_MAX leaves (smaller subtrees collapse into the parent's leaf reference), which can be decided from the sorted records alone:
+// live(i) <=> delta(i, i + BLAS_LEAF_MAX * d) > delta(i, i - d), with delta = -1 outside the segment.
+constexpr int CPT_THREADS = 256, CPT_ITEMS = 8, CPT_CHUNK = CPT_THREADS * CPT_ITEMS;
+
+__device__ __forceinline__ int delta_seg(const uint64_t* __restrict__ keys, int vb, uint32_t i, int64_t j, uint32_t first, uint32_t count) {
+    if (j < (int64_t)first || j >= (int64_t)first + count) return -1;
+    const uint64_t ka = __ldg(keys + i) >> vb, kb = __ldg(keys + j) >> vb;
+    return ka == kb ? 64 + __clz((int)(i ^ (uint32_t)j)) : __clzll((long long)(ka ^ kb));
+}
+__device__ __forceinline__ bool slot_is_live(const uint64_t* __restrict__ keys, int vb, uint32_t n, const BlasRecord* __restrict__ records, uint32_t i,
+                                             uint32_t& first) {
+    first = 0;
+    if (i >= n) return false;
+    const BlasRecord& R = records[(uint32_t)((__ldg(keys + i) >> vb) >> MORTON_BITS)];
+    first = R.first;
+    const uint32_t count = R.tri_count;
+    if (count <= (uint32_t)BLAS_LEAF_MAX || i - first + 2u > count) return false;           // no internal nodes / not a node slot
+    const int dr = delta_seg(keys, vb, i, (int64_t)i + 1, first, count), dl = delta_seg(keys, vb, i, (int64_t)i - 1, first, count);
+    const int d = dr > dl ? 1 : -1;
+    const int dmin = d > 0 ? dl : dr;
+    return delta_seg(keys, vb, i, (int64_t)i + (int64_t)BLAS_LEAF_MAX * d, first, count) > dmin;
+}
+
+// pass 1a: live slots per chunk
+__global__ void __launch_bounds__(CPT_THREADS) k_compact_count(const uint64_t* __restrict__ keys, int vb, uint32_t n, const BlasRecord* __restrict__ records,
+                                                              uint32_t* __restrict__ chunk_sums) {
+    __shared__ uint32_t s_w[CPT_THREADS / 32];
+    uint32_t c = 0, first;
+#pragma unroll
+    for (int k = 0; k < CPT_ITEMS; ++k) c += slot_is_live(keys, vb, n, records, blockIdx.x * CPT_CHUNK + k * CPT_THREADS + threadIdx.x, first) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < CPT_THREADS / 32; ++w) t += s_w[w]; chunk_sums[blockIdx.x] = t; }
+}
+// pass 1b: exclusive scan of the chunk sums (one CTA, serial over 1024-wide steps: n / 2048 values)
+__global__ void __launch_bounds__(1024) k_compact_scan(uint32_t* __restrict__ chunk_sums, uint32_t n_chunks) {
+    __shared__ uint32_t s_w[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < n_chunks; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_chunks ? chunk_sums[i] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t excl = s_carry + (warp ? s_w[warp - 1] : 0u) + inc - v;
+        if (i < n_chunks) chunk_sums[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = excl + v;
+        __syncthreads();
+    }
+}
+// pass 1c: cidx[i] = number of live slots before i; cidx[n] = live total. Items are strided (slot = chunk base + k * CPT_THREADS + tid),
+// so the in-chunk rank is: live slots of earlier strides (all threads) + live slots of this stride in earlier threads.
+__global__ void __launch_bounds__(CPT_THREADS) k_compact_index(const uint64_t* __restrict__ keys, int vb, uint32_t n, const BlasRecord* __restrict__ records,
+                                                              const uint32_t* __restrict__ chunk_sums, uint32_t* __restrict__ cidx) {
+    __shared__ uint32_t s_w[CPT_THREADS / 32];
+    __shared__ uint32_t s_run;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_run = chunk_sums[blockIdx.x];
+    __syncthreads();
+    for (int k = 0; k < CPT_ITEMS; ++k) {
+        const uint32_t i = blockIdx.x * CPT_CHUNK + k * CPT_THREADS + threadIdx.x;
+        uint32_t first;
+        const bool live = slot_is_live(keys, vb, n, records, i, first);
+        const unsigned m = __ballot_sync(0xffffffffu, live);
+        if (lane == 0) s_w[warp] = __popc(m);
+        __syncthreads();
+        uint32_t before = s_run + __popc(m & ((1u << lane) - 1u));
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (i <= n) cidx[i] = before;                                   // i == n: the total (no slot n exists, so live is false there)
+        __syncthreads();
+        if (threadIdx.x == CPT_THREADS - 1) s_run = before + (live ? 1u : 0u);
+        __syncthreads();
+    }
+}
+// pass 2: live node i -> dst[cidx[i]]; internal child refs (relative to the segment's first slot) are re-based on the compact numbering
+__global__ void __launch_bounds__(256) k_compact_nodes(const BvhNode* __restrict__ src, BvhNode* __restrict__ dst, const uint32_t* __restrict__ cidx,
+                                                      const uint64_t* __restrict__ keys, int vb, uint32_t n, const BlasRecord* __restrict__ records) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t c = __ldg(cidx + i);
+    if (__ldg(cidx + i + 1) == c) return;                                // dead slot
+    const uint32_t first = records[(uint32_t)((__ldg(keys + i) >> vb) >> MORTON_BITS)].first;
+    const uint32_t cfirst = __ldg(cidx + first);
+    const float4* s4 = reinterpret_cast<const float4*>(src + i);
+    float4 q0 = __ldg(s4), q1 = __ldg(s4 + 1), q2 = __ldg(s4 + 2), q3 = __ldg(s4 + 3);
+    const int32_t r0 = __float_as_int(q1.z), r1 = __float_as_int(q3.z);
+    if (r0 >= 0 && r0 < REF_SENTINEL_MIN) q1.z = __int_as_float((int32_t)(__ldg(cidx + first + (uint32_t)r0) - cfirst));
+    if (r1 >= 0 && r1 < REF_SENTINEL_MIN) q3.z = __int_as_float((int32_t)(__ldg(cidx + first + (uint32_t)r1) - cfirst));
+    float4* d4 = reinterpret_cast<float4*>(dst + c);
+    d4[0] = q0; d4[1] = q1; d4[2] = q2; d4[3] = q3;
+}
+
+// the records of the compacted storage: node base = new nodes + compact index of the BLAS's first slot
+__global__ void __launch_bounds__(256) k_compact_records(const BlasRecord* __restrict__ src, BlasRecord* __restrict__ dst, uint32_t n_blas,
+                                                        const uint32_t* __restrict__ cidx, const BvhNode* nodes, const TriRec* tris) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blas) return;
+    BlasRecord R = src[b];
+    const uint32_t c0 = __ldg(cidx + R.first), c1 = __ldg(cidx + R.first + R.tri_count);
+    R.nodes = nodes + c0; R.tris = tris + R.first; R.node_slots = c1 - c0;
+    dst[b] = R;
+}
+
 }  // namespace
 
-uint32_t tree_job_capacity(uint32_t n) {
-    const uint64_t tiles = ((uint64_t)n + TREE_TILE - 1) / TREE_TILE;
-    const uint64_t per_tile = tree_jobs_per_tile() < (uint32_t)TREE_TILE + 2u ? tree_jobs_per_tile() : (uint32_t)TREE_TILE + 2u;
-    const uint64_t cap = tiles * per_tile;
-    return (uint32_t)(cap < 2ull * n + 2 ? cap : 2ull * n + 2);
+int launch_compact_records(const BlasRecord* src, BlasRecord* dst, uint32_t n_blas, const uint32_t* cidx, const BvhNode* nodes, const TriRec* tris, cudaStream_t st) {
+    k_compact_records<<<div_up(n_blas, 256), 256, 0, st>>>(src, dst, n_blas, cidx, nodes, tris);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
 }
+
+size_t compact_scratch_bytes(uint32_t n) { return 4ull * (div_up(n + 1u, CPT_CHUNK) + 1) + 256; }
+
+int launch_compact_index(const uint64_t* keys, int vb, uint32_t n, const BlasRecord* records, uint32_t* cidx, void* scratch, cudaStream_t st) {
+    const uint32_t chunks = (uint32_t)div_up(n + 1u, CPT_CHUNK);          // slot n included: it receives the total
+    uint32_t* chunk_sums = reinterpret_cast<uint32_t*>(scratch);
+    k_compact_count<<<chunks, CPT_THREADS, 0, st>>>(keys, vb, n, records, chunk_sums);
+    k_compact_scan<<<1, 1024, 0, st>>>(chunk_sums, chunks);
+    k_compact_index<<<chunks, CPT_THREADS, 0, st>>>(keys, vb, n, records, chunk_sums, cidx);
+    return cudaGetLastError() == cudaSuccess ? 3 : -1;
+}
+int launch_compact_nodes(const BvhNode* src, BvhNode* dst, const uint32_t* cidx, const uint64_t* keys, int vb, uint32_t n,
+                         const BlasRecord* records, cudaStream_t st) {
+    if (n == 0) return 0;
+    k_compact_nodes<<<div_up(n, 256), 256, 0, st>>>(src, dst, cidx, keys, vb, n, records);
+    return cudaGetLastError() == cudaSuccess ? 1 : -1;
+}
+
+uint32_t tree_job_capacity(uint32_t n) { return (uint32_t)tree_job_capacity_host(n); }
 
 int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b) {
     int launches = 0;
@@ -573,7 +729,12 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
     if (a.n_tris == 0) return 0;
     if (ev) cudaEventRecord(ev->e[0], st);
     const int vb = a.sort.packed_val_bits;
-    if (a.sort.seg_records && vb > 0 && a.sort.seg_fused) {
+    if (a.reuse_keys) {
+        // refit-only update (RT_BUILD_MODE_REFIT): bake the new vertices, keep the sorted records of the last full build (= the topology)
+        k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
+        ++launches;
+        if (ev) { cudaEventRecord(ev->e[1], st); cudaEventRecord(ev->e[2], st); }
+    } else if (a.sort.seg_records && vb > 0 && a.sort.seg_fused) {
         // every BLAS fits one CTA: setup + Morton + sort fused, one launch (its time is reported as sort_ms)
         // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute: set it once per device
         static bool attr_set[64] = {};
@@ -598,8 +759,8 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
         if (sl < 0) return -1;
         launches += sl;
     }
-    const uint64_t* keys = *sorted_in_b ? a.s.keys_b : a.s.keys_a;
-    const uint32_t* vals = *sorted_in_b ? a.s.vals_b : a.s.vals_a;
+    const uint64_t* keys = a.reuse_keys ? a.reuse_keys : (*sorted_in_b ? a.s.keys_b : a.s.keys_a);
+    const uint32_t* vals = a.reuse_keys ? a.reuse_vals : (*sorted_in_b ? a.s.vals_b : a.s.vals_a);
     if (ev) cudaEventRecord(ev->e[3], st);
     if (cudaMemsetAsync(a.s.arrived, 0, sizeof(uint32_t) * ((size_t)a.n_tris + 1), st) != cudaSuccess) return -1;   // counters + job count
     if (ev) cudaEventRecord(ev->e[4], st);
@@ -608,7 +769,7 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
         const uint32_t tiles = (uint32_t)div_up(a.n_tris, TREE_TILE);
         uint32_t* job_count = a.s.arrived + a.n_tris;
         k_refit_tris<<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count);
-        k_tree_border<BLAS_LEAF_MAX, TriSegments><<<div_up(tree_job_capacity(a.n_tris), 128), 128, 0, st>>>(keys, vb, a.n_tris, a.nodes, a.s.jobs, job_count,
+        k_tree_border<BLAS_LEAF_MAX, TriSegments><<<border_grid(a.n_tris), 128, 0, st>>>(keys, vb, a.n_tris, a.nodes, a.s.jobs, job_count,
                                                                                                           a.s.xchg, a.s.far_end, a.s.arrived, seg);
     }
     launches += 2;
@@ -635,7 +796,7 @@ int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st) {
         const InstSegment seg{a.n, a.root_out, a.bounds_out};
         uint32_t* job_count = a.s.arrived + a.n;
         k_refit_inst<<<div_up(a.n, TREE_TILE), TREE_TILE, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, seg, a.s.jobs, job_count);
-        k_tree_border<TLAS_LEAF_MAX, InstSegment><<<div_up(tree_job_capacity(a.n), 128), 128, 0, st>>>(keys, vb, a.n, a.nodes, a.s.jobs, job_count,
+        k_tree_border<TLAS_LEAF_MAX, InstSegment><<<border_grid(a.n), 128, 0, st>>>(keys, vb, a.n, a.nodes, a.s.jobs, job_count,
                                                                                                      a.s.xchg, a.s.far_end, a.s.arrived, seg);
     }
     launches += 2;

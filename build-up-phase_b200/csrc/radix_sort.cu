@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_sort(const uint64_t* __r
     // coalesced load; padding (~0) sorts last and stays last
     for (uint32_t i = tid; i < SEG_SORT_CAPACITY; i += SEG_THREADS) s_keys[i] = i < n ? in[first + i] : ~0ull;
     __syncthreads();
-    seg_sort_passes(seg_smem, shift0, key_bits);
+    seg_sort_passes(seg_smem, shift0, key_bits, n);
     for (uint32_t i = tid; i < n; i += SEG_THREADS) out[first + i] = s_keys[i];
 }
 

@@ -390,8 +390,8 @@ int rt_group_share_blas(rt_group* g, uint32_t slot, int owner_rank, const rt_bla
             cudaIpcMemHandle_t h;
             G_CUDA(g, cudaIpcGetMemHandle(&h, mine->st->dev));
             memcpy(S.handle, &h, 64);
-            S.triangle_count = mine->rec.tri_count; S.n_geoms = mine->rec.n_geoms; S.root_ref = mine->rec.root; S.max_depth = mine->rec.height;
-            for (int k = 0; k < 3; ++k) { S.lo[k] = mine->rec.lo[k]; S.hi[k] = mine->rec.hi[k]; }
+            S.triangle_count = mine->r().tri_count; S.n_geoms = mine->r().n_geoms; S.root_ref = mine->r().root; S.max_depth = mine->r().height;
+            for (int k = 0; k < 3; ++k) { S.lo[k] = mine->r().lo[k]; S.hi[k] = mine->r().hi[k]; }
             S.storage_bytes = mine->st->bytes;
             S.seq.store(seq, std::memory_order_release);
         }
@@ -422,9 +422,10 @@ int rt_group_share_blas(rt_group* g, uint32_t slot, int owner_rank, const rt_bla
     g->cur_alloc_s += now_s() - t0;
     rt_blas* hnd = new rt_blas();
     hnd->st = st; hnd->index = 0;
-    BlasRecord& R = hnd->rec;
+    hnd->st->host_recs.assign(1, BlasRecord{});
+    BlasRecord& R = hnd->r();
     memset(&R, 0, sizeof(R));
-    R.nodes = st->nodes; R.tris = st->tris; R.root = S.root_ref; R.height = S.max_depth; R.tri_count = N; R.n_geoms = S.n_geoms; R.first = 0;
+    R.nodes = st->nodes; R.tris = st->tris; R.root = S.root_ref; R.height = S.max_depth; R.tri_count = N; R.n_geoms = S.n_geoms; R.first = 0; R.node_slots = N;
     for (int k = 0; k < 3; ++k) { R.lo[k] = S.lo[k]; R.hi[k] = S.hi[k]; }
     BlasRecord* staged = nullptr;                      // pinned: the record copy is asynchronous like the blob's
     if (cudaMallocHost((void**)&staged, sizeof(BlasRecord)) != cudaSuccess) { rt_free_blas(g->ctx, hnd); return gfail(g, RT_ERROR_OUT_OF_MEMORY, "cudaMallocHost"); }

@@ -62,11 +62,18 @@ struct BlasStorage {
     size_t bytes = 0;
     BvhNode* nodes = nullptr; TriRec* tris = nullptr; BlasRecord* records = nullptr;
     uint32_t n_tris = 0, n_blas = 0;
+    uint32_t n_node_slots = 0;      // node slots in `nodes` (n_tris after a build; the live-node count after rt_compact_blas)
+    // retained by builds with RT_BUILD_ALLOW_UPDATE / RT_BUILD_ALLOW_COMPACTION: the sorted Morton records of the last full build
+    // (packed `key << key_vb | id`, or keys + ids when key_vb == 0) - they ARE the tree topology
+    uint64_t* keys = nullptr; uint32_t* vals = nullptr; int key_vb = 0;
+    uint32_t build_flags = 0;
+    bool compacted = false;
+    std::vector<BlasRecord> host_recs;   // host copies of records[]
 };
 struct rt_blas {
     BlasStorage* st = nullptr;
     uint32_t index = 0;
-    BlasRecord rec{};               // host copy
+    BlasRecord& r() const { return st->host_recs[index]; }     // host copy of this BLAS's record (shared by all handles of a batch: compaction updates it once)
 };
 struct rt_tlas {
     void* dev = nullptr; size_t bytes = 0;

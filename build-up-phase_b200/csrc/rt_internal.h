@@ -62,7 +62,7 @@ struct __align__(16) BlasRecord {
     uint32_t tri_count;
     uint32_t n_geoms;
     uint32_t first;             // first primitive of this BLAS inside a batched build
-    uint32_t pad[1];
+    uint32_t node_slots;        // node slots of this BLAS behind `nodes` (tri_count after a build, its live-node count after compaction)
 };
 static_assert(sizeof(BlasRecord) == 64, "BlasRecord must be 64 B");
 
@@ -125,10 +125,21 @@ struct BlasBuildArgs {
     int*      bounds_ordered;         // n_blas * 6 ints (ordered-int encoded floats), pre-initialised
     BuildScratch s;
     SortPlan  sort;
+    // refit-only update: the sorted records of the last full build (device; packed when sort.packed_val_bits > 0). The setup kernel
+    // bakes the new vertices, Morton + sort are skipped and the tree pass runs over these records: same topology, new boxes.
+    const uint64_t* reuse_keys = nullptr; const uint32_t* reuse_vals = nullptr;
 };
 struct BuildEvents { cudaEvent_t e[6]; };  // setup | morton | sort | hierarchy | refit | end
 uint32_t tree_job_capacity(uint32_t n);   // upper bound of the border-job queue length for n leaves
 int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b);
+// Compaction (rt_compact_blas). Pass 1: live flags of the n Karras slots from the sorted records (a slot is dead iff its node's leaf
+// range holds <= BLAS_LEAF_MAX leaves), exclusive prefix -> cidx[n + 1] (cidx[n] = live total). Pass 2: live node i -> dst[cidx[i]] with
+// its internal child refs re-based. scratch: (n + 1) uint32 for cidx + compact_scratch_bytes(n).
+size_t compact_scratch_bytes(uint32_t n);
+int launch_compact_index(const uint64_t* keys, int vb, uint32_t n, const BlasRecord* records, uint32_t* cidx, void* scratch, cudaStream_t st);
+int launch_compact_nodes(const BvhNode* src, BvhNode* dst, const uint32_t* cidx, const uint64_t* keys, int vb, uint32_t n,
+                         const BlasRecord* records, cudaStream_t st);
+int launch_compact_records(const BlasRecord* src, BlasRecord* dst, uint32_t n_blas, const uint32_t* cidx, const BvhNode* nodes, const TriRec* tris, cudaStream_t st);
 
 struct TlasBuildArgs {
     const rt_instance* instances;     // device copy of the caller's 64-byte records (blas field = BlasRecord device address)

@@ -193,7 +193,7 @@ int rt_tlas_build_sizes(rt_context* ctx, uint32_t max_instances, rt_build_sizes*
 
 static void storage_release(BlasStorage* st) {
     if (!st) return;
-    if (--st->refs <= 0) { cudaFree(st->dev); delete st; }
+    if (--st->refs <= 0) { cudaFree(st->dev); cudaFree(st->keys); cudaFree(st->vals); delete st; }
 }
 
 // update != nullptr: rebuild that (single, unshared) BLAS inside its existing device allocation, so that its handle
@@ -257,13 +257,14 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
     if (update) {
         st = update->st;
         if (st->n_blas != 1 || n_blas != 1) return fail(ctx, RT_ERROR_INVALID_ARG, "rt_update_blas needs a BLAS that was built on its own (not part of a batch)");
-        if (st->n_tris != N || update->rec.n_geoms != geom_counts[0])
+        if (st->n_tris != N || update->r().n_geoms != geom_counts[0])
             return fail(ctx, RT_ERROR_INVALID_ARG, "rt_update_blas: geometry/triangle counts differ from the original build (%u/%u vs %u/%u)",
-                        geom_counts[0], N, update->rec.n_geoms, st->n_tris);
+                        geom_counts[0], N, update->r().n_geoms, st->n_tris);
+        if (st->compacted) return fail(ctx, RT_ERROR_INVALID_ARG, "rt_update_blas: a compacted BLAS cannot be updated (Vulkan: compaction copies drop ALLOW_UPDATE)");
         ++st->refs;    // the guard below drops it again
     } else {
         st = new BlasStorage();
-        st->n_tris = N; st->n_blas = n_blas;
+        st->n_tris = N; st->n_blas = n_blas; st->n_node_slots = N;
         const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
         st->bytes = blas_storage_bytes(N, n_blas);
         cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
@@ -271,7 +272,11 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
         st->nodes = (BvhNode*)st->dev; st->tris = (TriRec*)((uint8_t*)st->dev + nodes_b); st->records = (BlasRecord*)((uint8_t*)st->dev + nodes_b + tris_b);
         st->refs = 1;   // held by this function until handles exist
     }
-    for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->nodes + recs[b].first; recs[b].tris = st->tris + recs[b].first; }
+    for (uint32_t b = 0; b < n_blas; ++b) { recs[b].nodes = st->nodes + recs[b].first; recs[b].tris = st->tris + recs[b].first; recs[b].node_slots = recs[b].tri_count; }
+    // refit-only update: needs the sorted records of the last full build, in the record format this build would choose again
+    const bool refit = update && (build_flags & RT_BUILD_MODE_REFIT) != 0;
+    if (refit && (!st->keys || st->key_vb != sp.packed_val_bits || (st->key_vb == 0 && !st->vals)))
+        return fail(ctx, RT_ERROR_INVALID_ARG, "RT_BUILD_MODE_REFIT needs a BLAS whose last full build had RT_BUILD_ALLOW_UPDATE");
     struct Guard { BlasStorage* s; ~Guard() { if (s) storage_release(s); } } guard{st};
 
     // ---- scratch ----
@@ -358,6 +363,7 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
     // ---- device build ----
     a.geoms = d_descs; a.n_geoms = n_geoms; a.geom_tri_first = d_prefix; a.n_tris = N; a.n_blas = n_blas; a.seg_bits = seg_bits;
     a.tris_sorted = st->tris; a.nodes = st->nodes; a.records = st->records; a.bounds_ordered = d_bounds; a.sort = sp;
+    if (refit) { a.reuse_keys = st->keys; a.reuse_vals = st->vals; }
     BuildEvents be; for (int k = 0; k < 6; ++k) be.e[k] = ctx->ev[k];
     bool in_b = false;
     int launches = 0;
@@ -382,12 +388,29 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
         cudaEventElapsedTime(&ctx->timing.refit_ms, be.e[4], be.e[5]);
         cudaEventElapsedTime(&ctx->timing.total_ms, be.e[0], be.e[5]);
     }
-    ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N; ctx->dbg_vb = sp.packed_val_bits;
+    if (!refit) { ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N; ctx->dbg_vb = sp.packed_val_bits; }
+    // ALLOW_UPDATE / ALLOW_COMPACTION: the BLAS keeps the sorted records of this (full) build: they are its topology
+    if (!refit) {
+        const uint32_t keep = build_flags & (RT_BUILD_ALLOW_UPDATE | RT_BUILD_ALLOW_COMPACTION);
+        if (!keep || N == 0) { cudaFree(st->keys); cudaFree(st->vals); st->keys = nullptr; st->vals = nullptr; }
+        else {
+            if (!st->keys) { cudaError_t ce = cudaMalloc((void**)&st->keys, 8ull * N); if (ce != cudaSuccess) return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc for the retained sort records failed"); }
+            RT_CUDA(ctx, cudaMemcpyAsync(st->keys, ctx->dbg_keys, 8ull * N, cudaMemcpyDeviceToDevice, ctx->stream));
+            if (sp.packed_val_bits == 0) {
+                if (!st->vals) { cudaError_t ce = cudaMalloc((void**)&st->vals, 4ull * N); if (ce != cudaSuccess) return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc for the retained sort records failed"); }
+                RT_CUDA(ctx, cudaMemcpyAsync(st->vals, ctx->dbg_vals, 4ull * N, cudaMemcpyDeviceToDevice, ctx->stream));
+            } else { cudaFree(st->vals); st->vals = nullptr; }
+            RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            st->key_vb = sp.packed_val_bits;
+        }
+        st->build_flags = build_flags;
+    }
+    st->host_recs = recs;
 
-    if (update) { update->rec = recs[0]; return RT_SUCCESS; }
+    if (update) return RT_SUCCESS;
     for (uint32_t b = 0; b < n_blas; ++b) {
         rt_blas* h = new rt_blas();
-        h->st = st; h->index = b; h->rec = recs[b];
+        h->st = st; h->index = b;
         ++st->refs;
         out_array[b] = h;
     }
@@ -410,6 +433,54 @@ int rt_build_blas(rt_context* ctx, const rt_geometry* geoms, uint32_t n_geoms, u
     if (!out) return RT_ERROR_INVALID_ARG;
     uint32_t counts[1] = {n_geoms};
     return rt_build_blas_batch(ctx, geoms, counts, 1, build_flags, out);
+}
+
+int rt_compact_blas(rt_context* ctx, rt_blas* blas, uint64_t* bytes_before, uint64_t* bytes_after) {
+    if (!ctx || !blas || !blas->st) return RT_ERROR_INVALID_ARG;
+    BlasStorage* st = blas->st;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (bytes_before) *bytes_before = st->bytes;
+    if (bytes_after) *bytes_after = st->bytes;
+    if (st->compacted) return RT_SUCCESS;
+    const uint32_t N = st->n_tris, n_blas = st->n_blas;
+    if (N == 0) { st->compacted = true; return RT_SUCCESS; }
+    if (!st->keys || !(st->build_flags & RT_BUILD_ALLOW_COMPACTION) || (st->key_vb == 0 && !st->vals))
+        return fail(ctx, RT_ERROR_INVALID_ARG, "rt_compact_blas needs a BLAS built with RT_BUILD_ALLOW_COMPACTION");
+    // pass 1: compact index of every Karras slot (scratch: cidx[N + 1] + chunk sums)
+    const size_t need = align_up(4ull * ((size_t)N + 1), 256) + compact_scratch_bytes(N);
+    int rc = ensure(ctx, &ctx->scratch, &ctx->scratch_cap, need);
+    if (rc != RT_SUCCESS) return rc;
+    ctx->dbg_n = 0;                                                  // the scratch no longer holds the last build's sorted keys
+    uint32_t* cidx = (uint32_t*)ctx->scratch;
+    void* aux = (uint8_t*)ctx->scratch + align_up(4ull * ((size_t)N + 1), 256);
+    int l = launch_compact_index(st->keys, st->key_vb, N, st->records, cidx, aux, ctx->stream);
+    if (l < 0) return fail(ctx, RT_ERROR_CUDA, "compaction launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    ctx->launches += (uint64_t)l;
+    uint32_t live = 0;
+    RT_CUDA(ctx, cudaMemcpyAsync(&live, cidx + N, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // new right-sized storage: nodes[live] | tris[N] | records[n_blas]
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)(live ? live : 1), 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    const size_t bytes = nodes_b + tris_b + sizeof(BlasRecord) * (size_t)n_blas + 256;
+    void* dev = nullptr;
+    cudaError_t ce = cudaMalloc(&dev, bytes);
+    if (ce != cudaSuccess) return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc(%zu) for the compacted BLAS failed: %s", bytes, cudaGetErrorString(ce));
+    BvhNode* nnodes = (BvhNode*)dev; TriRec* ntris = (TriRec*)((uint8_t*)dev + nodes_b); BlasRecord* nrecs = (BlasRecord*)((uint8_t*)dev + nodes_b + tris_b);
+    l = launch_compact_nodes(st->nodes, nnodes, cidx, st->keys, st->key_vb, N, st->records, ctx->stream);
+    if (l < 0) { cudaFree(dev); return fail(ctx, RT_ERROR_CUDA, "compaction launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    ctx->launches += (uint64_t)l;
+    cudaError_t e1 = cudaMemcpyAsync(ntris, st->tris, sizeof(TriRec) * (size_t)N, cudaMemcpyDeviceToDevice, ctx->stream);
+    const int l2 = launch_compact_records(st->records, nrecs, n_blas, cidx, nnodes, ntris, ctx->stream);
+    if (l2 < 0) { cudaFree(dev); return fail(ctx, RT_ERROR_CUDA, "compaction launch failed: %s", cudaGetErrorString(cudaGetLastError())); }
+    ctx->launches += (uint64_t)l2;
+    cudaError_t e2 = cudaMemcpyAsync(st->host_recs.data(), nrecs, sizeof(BlasRecord) * (size_t)n_blas, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e3 = cudaStreamSynchronize(ctx->stream);
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess) { cudaFree(dev); return fail(ctx, RT_ERROR_CUDA, "compaction copy failed"); }
+    cudaFree(st->dev); cudaFree(st->keys); cudaFree(st->vals);
+    st->keys = nullptr; st->vals = nullptr;
+    st->dev = dev; st->bytes = bytes; st->nodes = nnodes; st->tris = ntris; st->records = nrecs; st->n_node_slots = live; st->compacted = true;
+    if (bytes_after) *bytes_after = bytes;
+    return RT_SUCCESS;
 }
 
 void rt_free_blas(rt_context* ctx, rt_blas* blas) {
@@ -435,11 +506,11 @@ uint64_t rt_tlas_storage_bytes(const rt_context* ctx, const rt_tlas* tlas) { ret
 
 int rt_blas_get_info(rt_context* ctx, const rt_blas* blas, rt_blas_info* out) {
     if (!ctx || !blas || !out) return RT_ERROR_INVALID_ARG;
-    out->triangle_count = blas->rec.tri_count;
-    out->node_count = blas->rec.tri_count;     // Karras slots [0, n); slot indices are BLAS-relative
-    out->root_ref = blas->rec.root;
-    out->max_depth = blas->rec.height;
-    for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = blas->rec.lo[k]; out->bounds_hi[k] = blas->rec.hi[k]; }
+    out->triangle_count = blas->r().tri_count;
+    out->node_count = blas->r().node_slots;    // Karras slots [0, n) after a build (slot indices are BLAS-relative); the live nodes after compaction
+    out->root_ref = blas->r().root;
+    out->max_depth = blas->r().height;
+    for (int k = 0; k < 3; ++k) { out->bounds_lo[k] = blas->r().lo[k]; out->bounds_hi[k] = blas->r().hi[k]; }
     out->storage_bytes = blas->st->n_blas == 1 ? (uint64_t)blas->st->bytes : 0;
     out->device_storage = blas->st->n_blas == 1 ? blas->st->dev : nullptr;
     return RT_SUCCESS;
@@ -449,9 +520,9 @@ int rt_blas_export(rt_context* ctx, const rt_blas* blas, void* nodes_out, void* 
     if (!ctx || !blas) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    const size_t n = blas->rec.tri_count;
-    if (nodes_out && n) RT_CUDA(ctx, cudaMemcpy(nodes_out, blas->rec.nodes, sizeof(BvhNode) * n, cudaMemcpyDeviceToHost));
-    if (tris_out && n) RT_CUDA(ctx, cudaMemcpy(tris_out, blas->rec.tris, sizeof(TriRec) * n, cudaMemcpyDeviceToHost));
+    const size_t n = blas->r().tri_count, nn = blas->r().node_slots;
+    if (nodes_out && nn) RT_CUDA(ctx, cudaMemcpy(nodes_out, blas->r().nodes, sizeof(BvhNode) * nn, cudaMemcpyDeviceToHost));
+    if (tris_out && n) RT_CUDA(ctx, cudaMemcpy(tris_out, blas->r().tris, sizeof(TriRec) * n, cudaMemcpyDeviceToHost));
     return RT_SUCCESS;
 }
 
@@ -478,10 +549,10 @@ int rt_debug_last_sorted_keys(rt_context* ctx, uint64_t* keys_out, uint32_t* pri
 int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device_blob, rt_blas** out) {
     if (!ctx || !info || !device_blob || !out) return RT_ERROR_INVALID_ARG;
     RT_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint32_t N = info->triangle_count;
+    const uint32_t N = info->triangle_count, NN = info->node_count;
     BlasStorage* st = new BlasStorage();
-    st->n_tris = N; st->n_blas = 1;
-    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)N, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
+    st->n_tris = N; st->n_blas = 1; st->n_node_slots = NN; st->compacted = NN != N;
+    const size_t nodes_b = align_up(sizeof(BvhNode) * (size_t)NN, 256), tris_b = align_up(sizeof(TriRec) * (size_t)N, 256);
     st->bytes = nodes_b + tris_b + sizeof(BlasRecord) + 256;
     if (info->storage_bytes != st->bytes) { delete st; return fail(ctx, RT_ERROR_INVALID_ARG, "blob size mismatch"); }
     cudaError_t ce = cudaMalloc(&st->dev, st->bytes);
@@ -490,9 +561,10 @@ int rt_blas_import(rt_context* ctx, const rt_blas_info* info, const void* device
     st->refs = 1;
     rt_blas* h = new rt_blas();
     h->st = st; h->index = 0;
-    BlasRecord& R = h->rec;
+    st->host_recs.assign(1, BlasRecord{});
+    BlasRecord& R = h->r();
     memset(&R, 0, sizeof(R));
-    R.nodes = st->nodes; R.tris = st->tris; R.root = info->root_ref; R.height = info->max_depth; R.tri_count = N; R.n_geoms = 0; R.first = 0;
+    R.nodes = st->nodes; R.tris = st->tris; R.root = info->root_ref; R.height = info->max_depth; R.tri_count = N; R.n_geoms = 0; R.first = 0; R.node_slots = NN;
     for (int k = 0; k < 3; ++k) { R.lo[k] = info->bounds_lo[k]; R.hi[k] = info->bounds_hi[k]; }
     cudaError_t e1 = cudaMemcpyAsync(st->dev, device_blob, nodes_b + tris_b, cudaMemcpyDeviceToDevice, ctx->stream);
     // n_geoms travels in the source record

@@ -24,7 +24,11 @@ RT_ERROR_INVALID_ARG, RT_ERROR_CUDA, RT_ERROR_OUT_OF_MEMORY = -1, -2, -3
 RT_ERROR_STACK_DEPTH, RT_ERROR_SBT_RANGE, RT_ERROR_INTERNAL = -4, -5, -6
 RT_GEOMETRY_OPAQUE = 0x1
 RT_GEOMETRY_DEVICE_POINTERS = 0x100
+RT_BUILD_ALLOW_UPDATE = 0x1
+RT_BUILD_ALLOW_COMPACTION = 0x2
 RT_BUILD_PREFER_FAST_TRACE = 0x4
+RT_BUILD_PREFER_FAST_BUILD = 0x8
+RT_BUILD_MODE_REFIT = 0x1000
 RT_BUILD_INSTANCES_ON_DEVICE = 0x100
 RT_BUILD_NO_PACKED_SORT = 0x200
 RT_TRACE_OUT_DEVICE = 0x1
@@ -37,7 +41,7 @@ RT_REF_EMPTY = 0x7FFFFFFD
 EXPORTED_SYMBOLS = [
     "rt_create", "rt_destroy", "rt_last_error", "rt_device_info", "rt_set_stream", "rt_sync", "rt_release_scratch",
     "rt_blas_build_sizes", "rt_tlas_build_sizes", "rt_build_blas", "rt_build_blas_batch", "rt_build_tlas",
-    "rt_update_tlas", "rt_update_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
+    "rt_update_tlas", "rt_update_blas", "rt_compact_blas", "rt_free_blas", "rt_free_tlas", "rt_last_build_timing", "rt_last_build_ms",
     "rt_last_build_scratch_bytes", "rt_tlas_storage_bytes", "rt_blas_device_reference",
     "rt_blas_get_info", "rt_blas_export", "rt_debug_last_sorted_keys", "rt_blas_import", "rt_tlas_get_info",
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_anyhit_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
@@ -167,6 +171,7 @@ def load(build_if_missing: bool = True):
     L.rt_build_tlas.argtypes = [vp, vp, u32, u32, C.POINTER(vp)]
     L.rt_update_tlas.argtypes = [vp, vp, vp, u32, u32]
     L.rt_update_blas.argtypes = [vp, vp, C.POINTER(RtGeometry), u32, u32]
+    L.rt_compact_blas.argtypes = [vp, vp, C.POINTER(u64), C.POINTER(u64)]
     L.rt_free_blas.argtypes = [vp, vp]
     L.rt_free_blas.restype = None
     L.rt_free_tlas.argtypes = [vp, vp]
@@ -423,6 +428,13 @@ class Context:
         arr = self._geom_array(geoms, keep, device)
         self._check(self.L.rt_update_blas(self.h, blas.handle, arr, len(geoms), RT_BUILD_PREFER_FAST_TRACE | flags))
 
+    def compact_blas(self, blas: Blas):
+        """rt_compact_blas: packs the live nodes of the BLAS (or of the whole batch it was built in) into a right-sized allocation.
+        Returns (bytes_before, bytes_after). TLASes referencing it must be rebuilt."""
+        b0, b1 = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.rt_compact_blas(self.h, blas.handle, C.byref(b0), C.byref(b1)))
+        return int(b0.value), int(b1.value)
+
     def build_blas_batch(self, blases, device: bool = False, flags: int = 0) -> List[Blas]:
         keep: list = []
         flat = [g for b in blases for g in b]
@@ -667,12 +679,12 @@ class SceneHandles:
     """Builds a scenes.Scene on a Context the way the sample's main() does: BLASes (batched when there is
     more than one), TLAS, hit records, miss colour."""
 
-    def __init__(self, ctx: Context, scene, batch: bool = True):
+    def __init__(self, ctx: Context, scene, batch: bool = True, build_flags: int = 0):
         self.ctx, self.scene = ctx, scene
         if len(scene.blases) > 1 and batch:
-            self.blases = ctx.build_blas_batch(scene.blases)
+            self.blases = ctx.build_blas_batch(scene.blases, flags=build_flags)
         else:
-            self.blases = [ctx.build_blas(g) for g in scene.blases]
+            self.blases = [ctx.build_blas(g, flags=build_flags) for g in scene.blases]
         self.blas_timing = ctx.build_timing()
         self.tlas = ctx.build_tlas(scene.instances, self.blases)
         self.tlas_timing = ctx.build_timing()
@@ -684,6 +696,11 @@ class SceneHandles:
         s = self.scene
         return self.ctx.trace(self.tlas, self.cam, width or s.width, height or s.height,
                               s.bounces if bounces is None else bounces, want_hits=want_hits, stats=stats)
+
+    def rebuild_tlas(self):
+        """After rt_compact_blas (device addresses changed): a new TLAS over the same instances."""
+        self.tlas.free()
+        self.tlas = self.ctx.build_tlas(self.scene.instances, self.blases)
 
     def free(self):
         self.tlas.free()

@@ -49,7 +49,15 @@ enum {
 #define RT_GEOMETRY_DEVICE_POINTERS 0x100u /* vertices/indices/transform are CUDA device pointers */
 
 /* ---- build flags ---------------------------------------------------------------------- */
-#define RT_BUILD_PREFER_FAST_TRACE  0x4u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, main.cpp:751 */
+#define RT_BUILD_ALLOW_UPDATE       0x1u  /* VK_BUILD_ACCELERATION_STRUCTURE_ALLOW_UPDATE_BIT_KHR: the BLAS keeps its sorted Morton records (8 B per triangle)
+                                            so that rt_update_blas(RT_BUILD_MODE_REFIT) can re-fit the boxes without re-sorting */
+#define RT_BUILD_ALLOW_COMPACTION   0x2u  /* VK_BUILD_ACCELERATION_STRUCTURE_ALLOW_COMPACTION_BIT_KHR: the BLAS (or batch) keeps its sorted Morton records
+                                            until rt_compact_blas() has packed its live nodes */
+#define RT_BUILD_PREFER_FAST_TRACE  0x4u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_TRACE_BIT_KHR, main.cpp:751,887: what the reference asks for and what
+                                            every build here does by default (two-triangle leaves: measured 1/2/3/4/6/8 per leaf -> 3124/3236/3198/3145/2981/2823 Mrays/s) */
+#define RT_BUILD_PREFER_FAST_BUILD  0x8u  /* VK_BUILD_ACCELERATION_STRUCTURE_PREFER_FAST_BUILD_BIT_KHR: accepted; the LBVH build is the fast build already */
+#define RT_BUILD_MODE_REFIT         0x1000u /* rt_update_blas only: VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR proper - keep the tree TOPOLOGY of the
+                                              last full build (needs RT_BUILD_ALLOW_UPDATE at that build) and only re-fit the boxes to the new vertices */
 #define RT_BUILD_INSTANCES_ON_DEVICE 0x100u /* rt_build_tlas: the rt_instance array is DEVICE memory (what the reference's instance buffer is, main.cpp:860-868);
                                               its `blas` fields must then hold rt_blas_device_reference() values, not host handles */
 #define RT_BUILD_NO_PACKED_SORT     0x200u /* keep (key, id) pairs in separate arrays during the sort (the general path; test hook) */
@@ -212,9 +220,13 @@ RT_API int  rt_build_blas_batch(rt_context* ctx, const rt_geometry* geoms, const
                                 uint32_t n_blas, uint32_t build_flags, rt_blas** out_array);
 
 /* VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR for a BLAS built by rt_build_blas: same geometry and triangle counts,
- * new vertex data / transforms (the per-frame loop of an animated mesh, main.cpp:1444-1448). The BLAS is re-built inside its
- * existing device allocation (a full LBVH build costs ~0.16 ns per triangle, so no refit-only shortcut with its quality
- * loss is offered); the handle stays valid. As in Vulkan, a TLAS that references it must be rebuilt or updated afterwards. */
+ * new vertex data / transforms (the per-frame loop of an animated mesh, main.cpp:1444-1448), inside the existing device
+ * allocation; the handle stays valid. As in Vulkan, a TLAS that references it must be rebuilt or updated afterwards.
+ *   default:              a full LBVH re-build (new Morton order, new topology): the tree quality of a fresh build.
+ *   RT_BUILD_MODE_REFIT:  the topology of the last full build is kept (its sorted Morton records were retained because that build
+ *                         had RT_BUILD_ALLOW_UPDATE); only the triangle records and every node box are recomputed, by the same
+ *                         bottom-up pass the build uses. Skips the Morton and sort phases; tree quality degrades as the mesh
+ *                         moves away from the pose it was sorted for (measured: profiles/README.md r2_i). */
 RT_API int  rt_update_blas(rt_context* ctx, rt_blas* blas, const rt_geometry* geoms, uint32_t n_geoms, uint32_t build_flags);
 
 RT_API int  rt_build_tlas(rt_context* ctx, const rt_instance* instances, uint32_t n_instances, uint32_t build_flags, rt_tlas** out);
@@ -226,6 +238,13 @@ RT_API int  rt_update_tlas(rt_context* ctx, rt_tlas* tlas, const rt_instance* in
  * address a DEVICE-resident rt_instance array (RT_BUILD_INSTANCES_ON_DEVICE) must carry in its `blas` field. 0 on error. */
 RT_API uint64_t rt_blas_device_reference(const rt_context* ctx, const rt_blas* blas);
 
+/* VK_COPY_ACCELERATION_STRUCTURE_MODE_COMPACT_KHR. The build leaves the node of every collapsed subtree (<= 2 triangles: about a
+ * third of the Karras slots) unused; compaction packs the live nodes (order-preserving, so siblings stay adjacent), moves the BLAS -
+ * or the whole batch it was built in: every handle of the batch stays valid - into a right-sized allocation (64 B x live nodes +
+ * 48 B x triangles) and releases the old one. Needs RT_BUILD_ALLOW_COMPACTION at the build. Device addresses change: TLASes that
+ * reference the BLAS(es) must be rebuilt afterwards, as in Vulkan. *bytes_before / *bytes_after (may be NULL) report the storage. */
+RT_API int  rt_compact_blas(rt_context* ctx, rt_blas* blas, uint64_t* bytes_before, uint64_t* bytes_after);
+
 RT_API void rt_free_blas(rt_context* ctx, rt_blas* blas);
 RT_API void rt_free_tlas(rt_context* ctx, rt_tlas* tlas);
 
@@ -235,7 +254,7 @@ RT_API float rt_last_build_ms(const rt_context* ctx);
 /* Introspection used by the parity tests (build invariants) and by multi-GPU BLAS broadcast. */
 typedef struct rt_blas_info {
     uint32_t triangle_count;
-    uint32_t node_count;        /* 64-byte internal nodes stored */
+    uint32_t node_count;        /* 64-byte node slots stored (= triangle_count after a build, = live nodes after rt_compact_blas) */
     int32_t  root_ref;          /* >=0 internal node, <0 leaf, RT_REF_EMPTY for an empty BLAS */
     uint32_t max_depth;
     float    bounds_lo[3], bounds_hi[3];

@@ -84,6 +84,8 @@ def lib():
         L.orc_build_blas.restype = C.c_void_p
         L.orc_build_blas.argtypes = [C.POINTER(OrcGeometry), C.c_uint32, C.c_int, C.c_int]
         L.orc_free_blas.argtypes = [C.c_void_p]
+        L.orc_refit_blas.restype = C.c_int
+        L.orc_refit_blas.argtypes = [C.c_void_p, C.POINTER(OrcGeometry), C.c_uint32]
         L.orc_build_tlas.restype = C.c_void_p
         L.orc_build_tlas.argtypes = [C.POINTER(OrcInstance), C.c_uint32, C.c_int]
         L.orc_free_tlas.argtypes = [C.c_void_p]
@@ -161,6 +163,13 @@ class OracleScene:
         self.sd.miss_record_count = 0
         self.sd.anyhit_records = None
         self.sd.anyhit_record_count = 0
+
+    def refit_blas(self, i: int, geoms):
+        """orc_refit_blas: new vertices for BLAS i, topology of its last full build."""
+        arr = _geom_array(geoms, self._keep)
+        rc = lib().orc_refit_blas(self.blases[i], arr, len(geoms))
+        if rc != 0:
+            raise RuntimeError(f"orc_refit_blas failed: {rc}")
 
     def set_miss_records(self, rgb):
         self.miss_records = np.ascontiguousarray(rgb, dtype=np.float32).reshape(-1, 3)

@@ -246,6 +246,7 @@ struct orc_blas {
     Box bounds = empty_box();
     bool has_bvh = false;
     Lbvh bvh;
+    std::vector<uint64_t> build_keys;   // Morton keys (build order) of the last FULL build: a refit re-uses them, i.e. keeps the topology
 };
 
 struct OInst {
@@ -306,6 +307,7 @@ static void blas_build_bvh(orc_blas* B) {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i) { pb[i] = tri_box(B->tris[i]); keys[i] = morton30(pb[i], B->bounds); }
     lbvh_build(B->bvh, pb, keys, LEAF_MAX);
+    B->build_keys = keys;
     B->sorted_tris.resize(N);
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i) B->sorted_tris[i] = B->tris[B->bvh.prims[i]];
@@ -622,6 +624,22 @@ orc_blas* orc_build_blas(const orc_geometry* geoms, uint32_t n_geoms, int build_
     return B;
 }
 void orc_free_blas(orc_blas* b) { delete b; }
+
+// VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR as the product's RT_BUILD_MODE_REFIT defines it: same geometry / triangle counts, new
+// vertices; the sorted order (hence Karras' tree) of the last full build is kept, triangle records and every node box are recomputed.
+int orc_refit_blas(orc_blas* B, const orc_geometry* geoms, uint32_t n_geoms) {
+    if (!B || !B->has_bvh || n_geoms != B->n_geoms) return -1;
+    std::vector<Tri> tris; Box bounds;
+    gather_tris(geoms, n_geoms, tris, bounds);
+    if (tris.size() != B->tris.size()) return -1;
+    B->tris.swap(tris); B->bounds = bounds;
+    const int64_t N = (int64_t)B->tris.size();
+    std::vector<Box> pb(N);
+    for (int64_t i = 0; i < N; ++i) pb[i] = tri_box(B->tris[i]);
+    lbvh_build(B->bvh, pb, B->build_keys, LEAF_MAX);             // old keys -> old order and topology; new boxes
+    for (int64_t i = 0; i < N; ++i) B->sorted_tris[i] = B->tris[B->bvh.prims[i]];
+    return 0;
+}
 
 orc_tlas* orc_build_tlas(const orc_instance* inst, uint32_t n, int build_bvh) {
     orc_tlas* T = new orc_tlas();

@@ -97,6 +97,8 @@ enum { ORC_MODE_BRUTE = 0, ORC_MODE_BVH = 1 };
 
 orc_blas* orc_build_blas(const orc_geometry* geoms, uint32_t n_geoms, int build_bvh, int key_bits);
 void      orc_free_blas(orc_blas*);
+/* refit-only update (the product's RT_BUILD_MODE_REFIT): new vertices, the topology of the last full build; 0 on success */
+int       orc_refit_blas(orc_blas*, const orc_geometry* geoms, uint32_t n_geoms);
 orc_tlas* orc_build_tlas(const orc_instance* inst, uint32_t n, int build_bvh);
 void      orc_free_tlas(orc_tlas*);
 

@@ -79,3 +79,28 @@ def walk_compare_bvh(nodes_a, root_a, nodes_b, root_b):
                 stack.append(ref)
         count += 1
     return count
+
+
+def walk_compare_bvh_renumbered(nodes_a, root_a, nodes_b, root_b):
+    """Lock-step walk of two BVHs that may number their internal nodes differently (e.g. before / after compaction): boxes and heights
+    bit-exact, leaf refs equal, internal refs followed pairwise. Returns the list of (index_a, index_b) pairs of the reachable nodes."""
+    def internal(r):
+        return 0 <= r < 0x7FFFFFF0
+    if internal(root_a) != internal(root_b) or (not internal(root_a) and root_a != root_b):
+        raise AssertionError(f"root {root_a} vs {root_b}")
+    pairs = []
+    stack = [(root_a, root_b)] if internal(root_a) else []
+    while stack:
+        ra, rb = stack.pop()
+        pairs.append((ra, rb))
+        a, b = nodes_a[ra], nodes_b[rb]
+        for half in (0, 1):
+            ha, hb = a[8 * half:8 * half + 8], b[8 * half:8 * half + 8]
+            if not (np.array_equal(ha[:6], hb[:6]) and ha[7] == hb[7]):
+                raise AssertionError(f"node {ra}/{rb} half {half}: {ha} != {hb}")
+            fa, fb = int(np.int32(ha[6])), int(np.int32(hb[6]))
+            if internal(fa) != internal(fb) or (not internal(fa) and fa != fb):
+                raise AssertionError(f"node {ra}/{rb} half {half}: refs {fa} vs {fb}")
+            if internal(fa):
+                stack.append((fa, fb))
+    return pairs

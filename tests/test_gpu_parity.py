@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from build_up_phase_b200 import scenes
-from parity import MISS, assert_parity, compare_hits, walk_compare_bvh
+from parity import MISS, assert_parity, compare_hits, walk_compare_bvh, walk_compare_bvh_renumbered
 
 pytestmark = pytest.mark.gpu
 
@@ -791,4 +791,109 @@ def test_anyhit_terminate_ray(rt, ctx, oracle):
         ctx.set_anyhit_records([])
         ctx.set_ray_params()
         o.close()
+        sh.free()
+
+
+
+def _animated(f):
+    """Frame f of a moving height field: same grid, the bumps drift (what a refit is for) - not a new random surface."""
+    S = scenes
+    g = S.heightfield(60, 40, -3.0, 3.0, -2.0, 2.0, 0.5, 40)
+    v = g.vertices.copy()
+    v[:, 2] = (v[:, 2] * np.float32(1.0 + 0.15 * f) + np.float32(0.05 * f) * np.sin(v[:, 0] * np.float32(2.0) + np.float32(f))).astype(np.float32)
+    v[:, 0] = (v[:, 0] + np.float32(0.02 * f) * np.cos(v[:, 1] * np.float32(3.0))).astype(np.float32)
+    return S.Geometry(np.ascontiguousarray(v), g.indices, None)
+
+
+def test_blas_refit_update_keeps_topology(rt, ctx, oracle):
+    """SURVEY 8(f) row 3, VK_BUILD_ACCELERATION_STRUCTURE_MODE_UPDATE_KHR proper: RT_BUILD_MODE_REFIT keeps the sorted order / tree of the
+    last full build (RT_BUILD_ALLOW_UPDATE) and re-fits every box. Bit-for-bit equal to the oracle's refit (same nodes, same sorted
+    triangles), traces like a brute force over the new geometry, and differs from a full rebuild of the same frame."""
+    S = scenes
+    inst = [S.Instance(S.rotation_3x4(np.array([0.2, 1.0, 0.0]), 0.3, np.array([0.0, 0.0, 0.0])), 3, 0xFF, 0, 1, 0)]
+    scene = S.Scene("refit", [[_animated(0)]], inst, S.SAMPLE_HIT_RECORDS[:1].copy(), width=320, height=200, bounces=1)
+    sh = rt.SceneHandles(ctx, scene, build_flags=rt.RT_BUILD_ALLOW_UPDATE)
+    o = oracle.OracleScene(scene)
+    try:
+        n0, t0 = sh.blases[0].export()
+        prim_order0 = t0[:, 10].copy()
+        for f in (1, 2):
+            geo = _animated(f)
+            ctx.update_blas(sh.blases[0], [geo], flags=rt.RT_BUILD_ALLOW_UPDATE | rt.RT_BUILD_MODE_REFIT)
+            timing = ctx.build_timing()
+            assert timing["sort_ms"] < 0.01 and timing["morton_ms"] < 0.01, "a refit runs no Morton pass and no sort"
+            ctx.update_tlas(sh.tlas, inst, sh.blases)
+            n1, t1 = sh.blases[0].export()
+            assert np.array_equal(t1[:, 10], prim_order0), "a refit keeps the sorted triangle order"
+            assert not np.array_equal(t1[:, :9], t0[:, :9])
+            o.refit_blas(0, [geo])
+            _, on, ot, _, _ = o.blas_export(0)
+            info, oinfo = sh.blases[0].info(), o.blas_info(0)
+            assert info.root_ref == oinfo.root_ref and info.max_depth == oinfo.max_depth
+            assert walk_compare_bvh(n1, info.root_ref, on, oinfo.root_ref) > 1000
+            assert np.array_equal(t1[:, :11], ot[:, :11])
+            g = sh.trace(want_hits=True)
+            sc = S.Scene("refit", [[geo]], inst, scene.hit_records, width=320, height=200, bounces=1)
+            ob = oracle.OracleScene(sc)
+            r = ob.trace(mode=oracle.MODE_BRUTE)
+            ob.close()
+            rp, rs, rc = assert_parity(g, r, what=f"refit{f}")
+            assert rp["hits"] > 5000
+        # the same frame, fully rebuilt: a different (re-sorted) tree, the same image
+        ctx.update_blas(sh.blases[0], [_animated(2)], flags=rt.RT_BUILD_ALLOW_UPDATE)
+        ctx.update_tlas(sh.tlas, inst, sh.blases)
+        n2, t2 = sh.blases[0].export()
+        assert not np.array_equal(t2[:, 10], prim_order0)
+        g2 = sh.trace(want_hits=True)
+        assert np.array_equal(g2[0], g[0]) and g2[1].tobytes() == g[1].tobytes()
+        # a BLAS built without ALLOW_UPDATE has nothing to refit from
+        plain = ctx.build_blas([_animated(0)])
+        with pytest.raises(rt.RtError):
+            ctx.update_blas(plain, [_animated(1)], flags=rt.RT_BUILD_MODE_REFIT)
+        plain.free()
+    finally:
+        o.close()
+        sh.free()
+
+
+@pytest.mark.parametrize("kind", ["single", "batch"])
+def test_blas_compaction(rt, ctx, oracle, kind):
+    """SURVEY 8(f) row 3, VK_COPY_ACCELERATION_STRUCTURE_MODE_COMPACT_KHR: rt_compact_blas packs the live nodes (order-preserving, dense)
+    into a right-sized allocation. Same tree (lock-step walk: boxes bit-exact, leaf refs equal), same frame and hit records."""
+    if kind == "single":
+        scene = scenes.tess_scene(nx=120, ny=80, width=320, height=200, bounces=1)
+    else:
+        scene = scenes.random_scene(n_blas=5, tris_per_blas=700, n_instances=12, seed=31, width=320, height=200, bounces=1, shared_edges=True)
+    sh = rt.SceneHandles(ctx, scene, build_flags=rt.RT_BUILD_ALLOW_COMPACTION)
+    try:
+        before = sh.trace(want_hits=True)
+        exported = [(b.export()[0], b.info().root_ref, b.info().node_count) for b in sh.blases]
+        b0, b1 = ctx.compact_blas(sh.blases[0])
+        assert b1 < b0
+        sh.rebuild_tlas()
+        after = sh.trace(want_hits=True)
+        assert np.array_equal(before[0], after[0]) and before[1].tobytes() == after[1].tobytes() and before[2].tobytes() == after[2].tobytes()
+        live_total = 0
+        for b, (n_old, root_old, slots_old) in zip(sh.blases, exported):
+            info = b.info()
+            n_new = b.export()[0]
+            pairs = walk_compare_bvh_renumbered(n_old, root_old, n_new, info.root_ref)
+            assert info.node_count == len(pairs) <= slots_old, "exactly the reachable nodes are kept"
+            assert sorted(p[1] for p in pairs) == list(range(len(pairs))), "dense numbering"
+            by_old = sorted(pairs)
+            assert all(by_old[i][1] < by_old[i + 1][1] for i in range(len(by_old) - 1)), "order-preserving: siblings stay adjacent"
+            live_total += len(pairs)
+            assert info.triangle_count == slots_old
+        n_tris = sum(b.info().triangle_count for b in sh.blases)
+        assert 0.3 * n_tris < live_total < 0.8 * n_tris
+        print("compaction", kind, "bytes", b0, "->", b1, "live nodes", live_total, "of", n_tris, "slots")
+        assert ctx.compact_blas(sh.blases[0]) == (b1, b1)                  # idempotent
+        if kind == "single":
+            with pytest.raises(rt.RtError):
+                ctx.update_blas(sh.blases[0], scene.blases[0])             # a compacted BLAS cannot be updated
+        plain = ctx.build_blas(scene.blases[0])
+        with pytest.raises(rt.RtError):
+            ctx.compact_blas(plain)                                         # needs RT_BUILD_ALLOW_COMPACTION
+        plain.free()
+    finally:
         sh.free()

@@ -454,3 +454,28 @@ def test_anyhit_vs_float64_world_space(oracle):
     assert np.abs(p["t"][c] - best_t[c]).max() < 1e-4 * best_t[c].max()
     # the masks really decided: some clear rays pass THROUGH a masked-out candidate that lies in front of their accepted hit
     print("anyhit f64 pin: clear rays", int(clear.sum()), "of", n, "hits", int(c.sum()))
+
+
+def test_oracle_refit_keeps_topology_and_stays_exact(oracle):
+    """orc_refit_blas (the restatement of RT_BUILD_MODE_REFIT): the sorted order of the last full build is kept, every box is re-fitted
+    to the moved triangles, and the BVH traversal still equals the brute force over the new geometry."""
+    S = scenes
+    g0 = S.heightfield(40, 30, -3.0, 3.0, -2.0, 2.0, 0.5, 40)
+    v = g0.vertices.copy()
+    v[:, 2] = (v[:, 2] * np.float32(1.4) + np.float32(0.1) * np.sin(v[:, 0] * np.float32(2.0))).astype(np.float32)
+    g1 = S.Geometry(np.ascontiguousarray(v), g0.indices, None)
+    inst = [S.Instance(S.rotation_3x4(np.array([0.2, 1.0, 0.0]), 0.3, np.array([0.0, 0.0, 0.0])), 3, 0xFF, 0, 1, 0)]
+    scene = S.Scene("refit", [[g0]], inst, S.SAMPLE_HIT_RECORDS[:1].copy(), width=200, height=120, bounces=1)
+    o = oracle.OracleScene(scene)
+    _, n0, t0, k0, p0 = o.blas_export(0)
+    o.refit_blas(0, [g1])
+    _, n1, t1, k1, p1 = o.blas_export(0)
+    assert np.array_equal(k0, k1) and np.array_equal(p0, p1), "keys and order of the last full build are kept"
+    assert not np.array_equal(n0, n1) and not np.array_equal(t0, t1)
+    a = o.trace(mode=oracle.MODE_BVH)
+    o.close()
+    fresh = oracle.OracleScene(S.Scene("refit", [[g1]], inst, scene.hit_records, width=200, height=120, bounces=1))
+    b = fresh.trace(mode=oracle.MODE_BRUTE)
+    fresh.close()
+    assert a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes() and np.array_equal(a[0], b[0])
+    assert a[3]["primary_hits"] > 2000

@@ -17,7 +17,7 @@ VARIANTS = {
     "leaf1": ["RT_BLAS_LEAF_MAX=1"], "leaf3": ["RT_BLAS_LEAF_MAX=3"], "leaf4": ["RT_BLAS_LEAF_MAX=4"], "leaf8": ["RT_BLAS_LEAF_MAX=8"],   # (r02a)
     # ray numbering / fetch counters (r2_f) and the shared-memory short stack
     "reg0": ["RT_REGIONS=0"], "reg1": ["RT_REGIONS=1"], "reg2": ["RT_REGIONS=2"],
-    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "smemtlas_reg2": ["RT_REGIONS=2"], "smemtlas_stack8": ["RT_SMEM_STACK=8"],
+    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "ldg256_blk7": ["RT_LDG256=1", "RT_TRACE_MIN_BLOCKS=7"], "smemtlas_reg2": ["RT_REGIONS=2"], "smemtlas_stack8": ["RT_SMEM_STACK=8"],
     "smemtlas_cap8": ["RT_NODE_CAP=8"], "smemtlas_thr16": ["RT_REFILL_THRESHOLD=16"],
     "reg2_8x8": ["RT_REGION_TW=8", "RT_REGION_TH=8"], "reg2_32x16": ["RT_REGION_TW=32", "RT_REGION_TH=16"], "reg2_8x16": ["RT_REGION_TW=8", "RT_REGION_TH=16"],
     "reg1_32x32": ["RT_REGIONS=1", "RT_REGION_TW=32", "RT_REGION_TH=32"],
