@@ -22,6 +22,7 @@
 // problem (multiples of 148 SMs x resident CTAs for the big ones), no tensor cores (nothing here
 // is a contraction).
 #include <float.h>
+#include <stdlib.h>
 
 #include "rt_device.cuh"
 #include "seg_sort.cuh"
@@ -455,13 +456,21 @@ __global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict_
     }
     }
 }
-// grid of the border kernel: enough threads for the jobs a build really has (a few per tile), at most 16 CTAs per SM
+// grid of the border kernel: one thread per job the build is expected to have (RT_BORDER_JOBS_PER_TILE per tile: 2 unfinished subtrees
+// + one orphan per straddling ancestor of the two border leaves), never more than the queue's capacity; the grid-stride loop covers the rest
+#ifndef RT_BORDER_JOBS_PER_TILE
+#define RT_BORDER_JOBS_PER_TILE 16
+#endif
 inline uint32_t border_grid(uint32_t n) {
-    const uint32_t by_jobs = (uint32_t)((tree_job_capacity_host(n) + 127) / 128);
-    const uint32_t by_tiles = (uint32_t)(((uint64_t)(n + TREE_TILE - 1) / TREE_TILE * 4 + 127) / 128) + 1u;
-    uint32_t g = by_jobs < by_tiles ? by_jobs : by_tiles;
-    if (g > 148u * 16u) g = 148u * 16u;
-    return g ? g : 1u;
+    static int per_tile = 0;
+    if (per_tile == 0) {
+        per_tile = RT_BORDER_JOBS_PER_TILE;
+        if (const char* v = getenv("RTCORE_BORDER_JOBS_PER_TILE")) { const int k = atoi(v); if (k >= 1 && k <= 256) per_tile = k; }
+    }
+    const uint64_t by_jobs = (tree_job_capacity_host(n) + 127) / 128;
+    const uint64_t by_tiles = (((uint64_t)n + TREE_TILE - 1) / TREE_TILE * (uint64_t)per_tile + 127) / 128 + 1u;
+    const uint64_t g = by_jobs < by_tiles ? by_jobs : by_tiles;
+    return g ? (uint32_t)g : 1u;
 }
 
 __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,

@@ -31,12 +31,14 @@ __device__ __forceinline__ uint64_t expand4(uint64_t cnt, int q) {
 // Sorts the SEG_SORT_CAPACITY records in s_keys (padding = ~0 sorts last) by bits [shift0, shift0 + key_bits). All threads of
 // the 1024-thread CTA call it after a __syncthreads(); the records are sorted and visible to all threads on return.
 //
-// n_real <= SEG_THREADS (the sample scene's 4 triangles, a TLAS of up to 1024 instances: the per-frame update path): a RANK sort instead
-// of the 8 counting passes over all 11,264 padded slots - thread i counts the records that sort before its own (key bits, then position:
-// stable, hence the very same order the passes produce) with broadcast shared-memory reads, ~6 instructions per comparison.
+// n_real <= SEG_RANK_SORT_MAX (the sample scene's 4 triangles, small TLASes): a RANK sort instead of the 8 counting passes over all 11,264
+// padded slots - thread i counts the records that sort before its own (key bits, then position: stable, hence the very same order the
+// passes produce) with broadcast shared-memory reads, ~8 instructions per comparison. Measured on B200 (rt_update_tlas, 1024 instances,
+// profiles/README.md r2_j): rank sort 0.123 ms vs 0.074 ms with the passes - n^2 comparisons on ONE SM lose beyond a few hundred records.
+constexpr uint32_t SEG_RANK_SORT_MAX = 256;
 __device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shift0, int key_bits, uint32_t n_real = SEG_SORT_CAPACITY) {
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);                         // the segment, sorted by the passes so far
-    if (n_real <= (uint32_t)SEG_THREADS) {
+    if (n_real <= SEG_RANK_SORT_MAX) {
         const uint32_t i = threadIdx.x;
         const uint64_t mask = key_bits >= 64 ? ~0ull : ((1ull << key_bits) - 1ull);
         uint64_t mine = 0, mk = 0;

@@ -479,3 +479,99 @@ def test_oracle_refit_keeps_topology_and_stays_exact(oracle):
     fresh.close()
     assert a[1].tobytes() == b[1].tobytes() and a[2].tobytes() == b[2].tobytes() and np.array_equal(a[0], b[0])
     assert a[3]["primary_hits"] > 2000
+
+
+# ---- float64 pin of the whole flag surface: opacity resolution, opacity culls, facing culls with FLIP / CULL_DISABLE -------------------------
+def _primary_rays(oracle, scene):
+    W, H = scene.width, scene.height
+    f32 = np.float32
+    ay = f32(oracle.lib().orc_aspect_y(f32(scene.yfov_deg)))
+    ax = f32(ay * f32(W) / f32(H))
+    ndcx = ((np.arange(W, dtype=np.float32) + f32(0.5)) / f32(W) * f32(2.0) - f32(1.0)).astype(np.float32)
+    ndcy = ((np.arange(H, dtype=np.float32) + f32(0.5)) / f32(H) * f32(2.0) - f32(1.0)).astype(np.float32)
+    D = np.empty((H, W, 3))
+    D[..., 0] = (ndcx * ax).astype(np.float64)[None, :]
+    D[..., 1] = (-(ndcy * ay)).astype(np.float64)[:, None]
+    D[..., 2] = -1.0
+    D = D.reshape(-1, 3)
+    return np.broadcast_to(np.asarray(scene.camera_pos, dtype=np.float64), D.shape), D
+
+
+def _flagged_closest_f64(scene, O, D, ray_flags):
+    """Closest ACCEPTED candidate per ray, float64, world space, straight from the Vulkan rules: opacity = geometry OPAQUE bit, overridden by
+    the instance FORCE_OPAQUE / FORCE_NO_OPAQUE, overridden by the ray Opaque / NoOpaque; CullOpaque / CullNoOpaque; a triangle is front
+    facing when ((v1-v0) x (v2-v0)) . d > 0 in OBJECT space (= world space times the sign of the instance matrix determinant), inverted by
+    FLIP_FACING; facing culls are off for instances with TRIANGLE_FACING_CULL_DISABLE. Returns (t, triangle index, clear, ids)."""
+    tri, ids = _world_triangles(scene)
+    geo_flags = {(b, g): geo.flags for b, geoms in enumerate(scene.blases) for g, geo in enumerate(geoms)}
+    n = D.shape[0]
+    best_t = np.full(n, np.inf); second_t = np.full(n, np.inf); best_k = np.full(n, -1); ambiguous = np.zeros(n, dtype=bool)
+    e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
+    for k in range(tri.shape[0]):
+        I = scene.instances[ids[k, 0]]
+        opaque = bool(geo_flags[(I.blas, int(ids[k, 1]))] & 1)
+        if I.flags & 0x4: opaque = True
+        elif I.flags & 0x8: opaque = False
+        if ray_flags & 0x1: opaque = True
+        elif ray_flags & 0x2: opaque = False
+        if (opaque and ray_flags & 0x40) or (not opaque and ray_flags & 0x80):
+            continue
+        pvec = np.cross(D, e2[k]); det = pvec @ e1[k]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tvec = O - tri[k, 0]
+            u = np.einsum("rc,rc->r", tvec, pvec) * inv
+            qvec = np.cross(tvec, e1[k])
+            v = np.einsum("rc,rc->r", D, qvec) * inv
+            t = (qvec @ e2[k]) * inv
+        margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
+        in_t = (t > 0.0) & (t < 100.0) & (np.abs(det) > 1e-12)
+        ambiguous |= in_t & (np.abs(margin) < 1e-4)
+        cand = in_t & (margin > 0)
+        if (ray_flags & 0x30) and not (I.flags & 0x1):
+            A = np.asarray(I.transform, dtype=np.float64).reshape(3, 4)[:, :3]
+            facing = np.sign(np.linalg.det(A)) * (D @ np.cross(e1[k], e2[k]))        # > 0: front (clockwise from the ray origin), object space
+            ambiguous |= cand & (np.abs(facing) < 1e-9)
+            front = (facing > 0) != bool(I.flags & 0x2)
+            cand &= ~np.where(front, bool(ray_flags & 0x20), bool(ray_flags & 0x10))
+        tt = np.where(cand, t, np.inf)
+        better = tt < best_t
+        second_t = np.where(better, best_t, np.minimum(second_t, tt))
+        best_k = np.where(better, k, best_k)
+        best_t = np.where(better, tt, best_t)
+    hit = np.isfinite(best_t)
+    with np.errstate(invalid="ignore"):
+        clear = ~ambiguous & np.where(hit, second_t - best_t > 1e-4 * np.maximum(1.0, best_t), True)
+    return best_t, best_k, clear, ids
+
+
+@pytest.mark.parametrize("ray_flags", [0x10, 0x20, 0x40, 0x80, 0x2 | 0x20 | 0x80, 0x2 | 0x20, 0x1 | 0x10, 0x0], ids=lambda f: f"rayflags{f:#04x}")
+def test_ray_flags_vs_float64_world_space(oracle, ray_flags):
+    """The flag semantics pinned independently of the oracle's own arithmetic (the culls had known-answer pins on the
+    8-triangle scene only): every unambiguous primary ray of a fuzz scene with non-opaque geometries and FLIP / FORCE_* / CULL_DISABLE
+    instances gets the same hit / miss and the same ids from the float64 statement above and from the oracle."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=250, n_instances=10, seed=9, width=160, height=100, bounces=0, shared_edges=True)
+    for b, geoms in enumerate(scene.blases):
+        for g, geo in enumerate(geoms):
+            geo.flags = 1 if (b + g) % 2 == 0 else 0
+    for i, I in enumerate(scene.instances):
+        I.flags = [0x0, 0x1, 0x2, 0x4, 0x8, 0x2 | 0x8, 0x0, 0x4 | 0x2, 0x1 | 0x8, 0x0][i % 10]
+        I.mask = 0xFF
+    o = oracle.OracleScene(scene)
+    _, prim, _, _ = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(ray_flags=ray_flags))
+    o.close()
+    O, D = _primary_rays(oracle, scene)
+    best_t, best_k, clear, ids = _flagged_closest_f64(scene, O, D, ray_flags)
+    hit = np.isfinite(best_t)
+    p = prim.reshape(-1)
+    ohit = p["instance_id"] != MISS
+    if (ray_flags & 0x2) and (ray_flags & 0x80):
+        assert not hit.any() and not ohit.any(), "NoOpaque makes every candidate non-opaque and CullNoOpaque drops them all"
+        return
+    assert clear.sum() > 0.85 * D.shape[0] and (clear & hit).sum() > 250
+    assert np.array_equal(ohit[clear], hit[clear])
+    c = clear & hit
+    want = ids[best_k[c]]
+    assert np.array_equal(p["instance_id"][c], want[:, 0]) and np.array_equal(p["geometry_index"][c], want[:, 1])
+    assert np.array_equal(p["primitive_id"][c], want[:, 2])
+    assert np.abs(p["t"][c] - best_t[c]).max() < 1e-4 * best_t[c].max()
