@@ -80,6 +80,8 @@ std::string shm_name_of(const char* name, const char* suffix) {
 struct rt_group {
     rt_context* ctx = nullptr;          // the caller's context (may be null: host-only group, no CUDA — barrier + shared host frame)
     rt_context* ctx_b = nullptr;        // second context on the same device: odd frames of a pipelined sequence
+    // pipelined host output: the frame that has been enqueued but not completed yet
+    bool hp_pending = false; uint32_t hp_k = 0, hp_use = 0; rt_context* hp_ctx = nullptr;
     int rank = 0, world = 1;
     uint32_t max_w = 0, max_h = 0;
     GroupShm* shm = nullptr; size_t shm_bytes = 0;
@@ -290,7 +292,9 @@ int rt_group_join(rt_group* g) {
 
 int rt_group_sync(rt_group* g) {
     if (!g || !g->ctx) return RT_ERROR_INVALID_ARG;
-    int rc = rt_group_join(g);
+    int rc = rt_group_flush_host(g, nullptr);
+    if (rc != RT_SUCCESS) return rc;
+    rc = rt_group_join(g);
     if (rc != RT_SUCCESS) return rc;
     if (g->ctx_b && (rc = rt_sync(g->ctx_b)) != RT_SUCCESS) { g->ctx->err = g->ctx_b->err; return rc; }
     return rt_sync(g->ctx);
@@ -299,6 +303,7 @@ int rt_group_sync(rt_group* g) {
 // ---- host frame handshake (also usable on its own: a caller may fill its bands of the shared host frame by other means) ------------
 int rt_group_host_frame_begin(rt_group* g, uint8_t** frame_out) {
     if (!g || g->host_open) return RT_ERROR_INVALID_ARG;
+    if (g->hp_pending) { const int rc = rt_group_flush_host(g, nullptr); if (rc != RT_SUCCESS) return rc; }
     const uint32_t k = (uint32_t)(g->host_no & 1u), use = (uint32_t)(g->host_no >> 1);
     ++g->host_no;
     // buffer k still holds the frame of `use - 1`, which rank 0's caller may read until rank 0 enters this use
@@ -323,6 +328,25 @@ int rt_group_host_frame_end(rt_group* g, const uint8_t** frame_out) {
     return RT_SUCCESS;
 }
 
+// completes the pending frame of a pipelined host-output sequence: this rank's copies have landed (event), its share is announced,
+// rank 0 waits for everybody's
+int rt_group_flush_host(rt_group* g, const uint8_t** frame_out) {
+    if (!g) return RT_ERROR_INVALID_ARG;
+    if (frame_out) *frame_out = nullptr;
+    if (!g->hp_pending) return RT_SUCCESS;
+    g->hp_pending = false;
+    int rc = rt_host_frame_wait(g->hp_ctx);
+    if (rc != RT_SUCCESS) { g->shm->abort.store(1); g->err = g->hp_ctx->err; g->ctx->err = g->hp_ctx->err; return rc; }
+    const uint32_t k = g->hp_k, use = g->hp_use;
+    g->shm->host_done[k].fetch_add(1, std::memory_order_acq_rel);
+    if (g->rank == 0) {
+        if (!wait_until(g->shm, [&] { return g->shm->host_done[k].load(std::memory_order_acquire) >= (uint32_t)g->world * (use + 1u); }))
+            return gfail(g, RT_ERROR_INTERNAL, "host frame %u incomplete after 60 s: %u of %u shares", k, g->shm->host_done[k].load(), (uint32_t)g->world * (use + 1u));
+        if (frame_out) *frame_out = g->host_frames + (size_t)k * g->host_frame_bytes;
+    }
+    return RT_SUCCESS;
+}
+
 int rt_group_trace(rt_group* g, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
                    uint32_t flags, const uint8_t** frame_out) {
     if (!g || !g->ctx || !tlas || !cam) return RT_ERROR_INVALID_ARG;
@@ -333,6 +357,28 @@ int rt_group_trace(rt_group* g, const rt_tlas* tlas, const rt_camera* cam, uint3
     if (to_host == ((flags & RT_GROUP_OUT_DEVICE) != 0)) return gfail(g, RT_ERROR_INVALID_ARG, "exactly one of RT_GROUP_OUT_DEVICE / RT_GROUP_OUT_HOST");
     G_CUDA(g, cudaSetDevice(g->ctx->device));
     int rc;
+    if (to_host && (flags & RT_GROUP_PIPELINE)) {
+        // ---- two host frames in flight: enqueue frame k, then complete frame k - 1 ----
+        if (g->host_open) return gfail(g, RT_ERROR_INVALID_ARG, "a host frame opened with rt_group_host_frame_begin is still open");
+        const uint32_t k = (uint32_t)(g->host_no & 1u), use = (uint32_t)(g->host_no >> 1);
+        ++g->host_no;
+        // buffer k holds frame `k - 2` of the sequence, which rank 0's caller may read until rank 0 enters this use
+        if (g->rank == 0) g->shm->host_enter[k].store(use + 1u, std::memory_order_release);
+        else if (!wait_until(g->shm, [&] { return g->shm->host_enter[k].load(std::memory_order_acquire) >= use + 1u; }))
+            return gfail(g, RT_ERROR_INTERNAL, "rank %d: rank 0 never entered frame %llu", g->rank, (unsigned long long)(g->host_no - 1));
+        rt_context* c = (k == 1u && g->ctx_b) ? g->ctx_b : g->ctx;
+        if (c != g->ctx && (rc = rt_context_mirror_shader_state(c, g->ctx)) != RT_SUCCESS) return rc;
+        uint8_t* frame = g->host_frames + (size_t)k * g->host_frame_bytes;
+        rc = rt_trace_rows(c, tlas, cam, width, height, bounces, RT_TRACE_OUT_FULL_FRAME | RT_TRACE_ASYNC, BAND_ROWS, (uint32_t)g->rank, (uint32_t)g->world, frame, nullptr, nullptr);
+        if (c != g->ctx) { g->ctx->launches += c->launches - g->b_launches_seen; g->b_launches_seen = c->launches; }
+        if (rc != RT_SUCCESS) { g->shm->abort.store(1); g->err = c->err; g->ctx->err = c->err; return rc; }
+        const uint8_t* done_frame = nullptr;
+        if ((rc = rt_group_flush_host(g, &done_frame)) != RT_SUCCESS) return rc;        // frame k - 1
+        if (frame_out) *frame_out = done_frame;
+        g->hp_pending = true; g->hp_k = k; g->hp_use = use; g->hp_ctx = c;
+        return RT_SUCCESS;
+    }
+    if (g->hp_pending && (rc = rt_group_flush_host(g, nullptr)) != RT_SUCCESS) return rc;
     if (to_host) {
         if ((rc = join_streams(g)) != RT_SUCCESS) return rc;
         uint8_t* frame = nullptr;

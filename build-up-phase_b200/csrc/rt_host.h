@@ -22,6 +22,9 @@ struct rt_context {
     int trace_chunks = 1;                                         // row chunks of a DEVICE-output trace (RTCORE_TRACE_CHUNKS); measured 3.56/3.55/3.67/3.67/4.02/4.07 ms for
                                                                   // 1/2/3/4/6/8 chunks: tail filling only pays back the extra launches, so the default is one launch
     cudaEvent_t chunk_ev[8]{};
+    cudaEvent_t host_ev = nullptr;                                // recorded on copy_stream behind the copies of an ASYNC host-output trace (rt_host_frame_wait)
+    bool host_pending = false;                                    // such a trace is in flight: the staging buffer and the error word are not to be reused yet
+    int* h_err_pinned = nullptr;                                  // pinned: the device watchdog word of that trace, copied behind its frame
     int e2e_chunks = 3;                                            // row chunks of a HOST-output trace (RTCORE_E2E_CHUNKS): chunk c is copied device->host
                                                                    // while chunk c + 1 is traced; the chunks alternate over two compute streams (the next
                                                                    // chunk's CTAs fill the previous chunk's kernel tails) and shrink towards the end of the

@@ -97,6 +97,8 @@ int rt_create(int device_ordinal, rt_context** out) {
     for (auto& e : ctx->ev) ok = ok && cudaEventCreate(&e) == cudaSuccess;
     for (auto& e : ctx->chunk_ev) ok = ok && cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&ctx->host_ev, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMallocHost((void**)&ctx->h_err_pinned, 64) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&ctx->join_ev, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_stats, 8 * sizeof(unsigned long long)) == cudaSuccess;
     ok = ok && cudaMalloc(&ctx->d_error, 64) == cudaSuccess;
@@ -120,6 +122,8 @@ void rt_destroy(rt_context* ctx) {
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    if (ctx->host_ev) cudaEventDestroy(ctx->host_ev);
+    if (ctx->h_err_pinned) cudaFreeHost(ctx->h_err_pinned);
     if (ctx->join_ev) cudaEventDestroy(ctx->join_ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -162,6 +166,7 @@ int rt_set_stream(rt_context* ctx, void* cuda_stream) {
 
 int rt_sync(rt_context* ctx) {
     if (!ctx) return RT_ERROR_INVALID_ARG;
+    if (ctx->host_pending) { const int rc = rt_host_frame_wait(ctx); if (rc != RT_SUCCESS) return rc; }
     int h_err = 0;
     RT_CUDA(ctx, cudaMemcpyAsync(&h_err, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->stream));
     RT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -767,6 +772,20 @@ uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_r
     return ((bands + part_count - 1) / part_count) * block_rows * (uint64_t)width;
 }
 
+int rt_host_frame_wait(rt_context* ctx) {
+    if (!ctx) return RT_ERROR_INVALID_ARG;
+    if (!ctx->host_pending) return RT_SUCCESS;
+    RT_CUDA(ctx, cudaSetDevice(ctx->device));
+    RT_CUDA(ctx, cudaEventSynchronize(ctx->host_ev));
+    ctx->host_pending = false;
+    if (*ctx->h_err_pinned) {
+        *ctx->h_err_pinned = 0;
+        cudaMemsetAsync(ctx->d_error, 0, 4, ctx->stream);
+        return fail(ctx, RT_ERROR_INTERNAL, "trace watchdog fired (bounce-queue entry never published)");
+    }
+    return RT_SUCCESS;
+}
+
 // range_rows == 0: all packed rows of this part; else only the packed rows [range_first, range_first + range_rows) (device output)
 static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera* cam, uint32_t width, uint32_t height, uint32_t bounces,
                            uint32_t flags, uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t range_first, uint32_t range_rows,
@@ -831,6 +850,13 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
         if (secondary_hits_out) { if ((rc = ensure(ctx, &ctx->hits2, &ctx->hits2_cap, pixels * sizeof(rt_hit))) != RT_SUCCESS) return rc; P.secondary_hits = (rt_hit*)ctx->hits2; }
     }
     const bool stats = (flags & RT_TRACE_STATS) != 0;
+    // RT_TRACE_ASYNC with a HOST framebuffer: trace + copies are enqueued, the call returns, rt_host_frame_wait() completes the frame.
+    // The staging buffer (and the watchdog word) still belong to the previous such frame until its copies are done.
+    const bool async_host = !dev_out && (flags & RT_TRACE_ASYNC) != 0 && !stats && !primary_hits_out && !secondary_hits_out;
+    if (!dev_out && ctx->host_pending) {
+        if (async_host) RT_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->host_ev, 0));
+        else if ((rc = rt_host_frame_wait(ctx)) != RT_SUCCESS) return rc;
+    }
     if (stats) { RT_CUDA(ctx, cudaMemsetAsync(ctx->d_stats, 0, 64, ctx->stream)); P.stats = ctx->d_stats; }
     // Row chunks (multiples of 8 rows). Host output: every finished chunk is copied device->host on the copy stream while the next
     // one is traced. Several chunks alternate over TWO compute streams: the persistent kernels of chunk c + 1 are queued behind
@@ -838,6 +864,7 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
     const uint32_t total_rows = P.local_rows;
     uint32_t chunks = 1;
     if (pixels >= (1u << 20)) chunks = (uint32_t)(dev_out ? ctx->trace_chunks : ctx->e2e_chunks);
+    if (async_host) chunks = 1;        // the copy of this frame overlaps the NEXT frame's trace: no reason to pay a kernel tail per chunk
     // chunk c covers rows [row_begin[c], row_begin[c + 1]), multiples of 8. Host output: the chunks SHRINK towards the end of the frame
     // (weights 4 : 3 : 2 : 1 for four chunks), because only the copy of the last chunk is not hidden behind a trace
     uint32_t row_begin[10] = {0};
@@ -964,6 +991,16 @@ static int trace_rows_impl(rt_context* ctx, const rt_tlas* tlas, const rt_camera
             RT_CUDA(ctx, cudaMemcpyAsync(rgba_out + 4 * p0, P.rgba + 4 * p0, np * 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (primary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(primary_hits_out + p0, P.primary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
             if (secondary_hits_out) RT_CUDA(ctx, cudaMemcpyAsync(secondary_hits_out + p0, P.secondary_hits + p0, np * sizeof(rt_hit), cudaMemcpyDeviceToHost, ctx->copy_stream));
+        }
+        if (async_host) {
+            // the watchdog word travels behind the frame; rt_host_frame_wait() looks at it
+            if (bounces > 0) {
+                RT_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev[1], 0));
+                RT_CUDA(ctx, cudaMemcpyAsync(ctx->h_err_pinned, ctx->d_error, 4, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            } else *ctx->h_err_pinned = 0;
+            RT_CUDA(ctx, cudaEventRecord(ctx->host_ev, ctx->copy_stream));
+            ctx->host_pending = true;
+            return RT_SUCCESS;
         }
         RT_CUDA(ctx, cudaStreamSynchronize(ctx->copy_stream));
     }

@@ -47,7 +47,7 @@ EXPORTED_SYMBOLS = [
     "rt_set_hit_records", "rt_set_miss_color", "rt_set_miss_records", "rt_set_anyhit_records", "rt_set_ray_params", "rt_trace", "rt_trace_rows", "rt_trace_rows_range",
     "rt_rows_packed_pixels", "rt_unpack_rows", "rt_frame_share_create", "rt_frame_share_open", "rt_frame_share_close", "rt_frame_share_free", "rt_flag_add", "rt_flag_wait_ge", "rt_last_trace_stats", "rt_last_trace_ms",
     "rt_kernel_launch_count", "rt_version", "rt_copy_to_host",
-    "rt_group_create", "rt_group_destroy", "rt_group_trace", "rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world",
+    "rt_group_create", "rt_group_destroy", "rt_group_trace", "rt_group_flush_host", "rt_host_frame_wait", "rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world",
     "rt_group_share_blas", "rt_group_share_finish", "rt_group_last_share_ms", "rt_group_last_share_host_ms", "rt_group_host_frame_begin", "rt_group_host_frame_end", "rt_group_last_error",
     # include/rtcore_io.h
     "rt_obj_load", "rt_obj_parse", "rt_obj_free", "rt_obj_last_error", "rt_obj_vertex_count", "rt_obj_triangle_count",
@@ -218,6 +218,8 @@ def load(build_if_missing: bool = True):
     L.rt_group_destroy.argtypes = [vp]
     L.rt_group_destroy.restype = None
     L.rt_group_trace.argtypes = [vp, vp, C.POINTER(RtCamera), u32, u32, u32, u32, C.POINTER(vp)]
+    L.rt_group_flush_host.argtypes = [vp, C.POINTER(vp)]
+    L.rt_host_frame_wait.argtypes = [vp]
     for name in ("rt_group_sync", "rt_group_join", "rt_group_barrier", "rt_group_rank", "rt_group_world", "rt_group_share_finish"):
         getattr(L, name).argtypes = [vp]
     L.rt_group_share_blas.argtypes = [vp, u32, i32, vp, C.POINTER(vp)]
@@ -629,12 +631,21 @@ class Group:
         self._check(self.L.rt_group_trace(self.h, tlas.handle, C.byref(cam), width, height, bounces, flags, C.byref(p)))
         return p.value
 
-    def trace_host(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int) -> Optional[np.ndarray]:
-        """RT_GROUP_OUT_HOST: every rank copies its bands over its own PCIe link; rank 0 gets a numpy VIEW of the shared pinned frame."""
-        p = self.trace(tlas, cam, width, height, bounces, GROUP_OUT_HOST)
+    def trace_host(self, tlas: Tlas, cam: RtCamera, width: int, height: int, bounces: int, pipeline: bool = False) -> Optional[np.ndarray]:
+        """RT_GROUP_OUT_HOST: every rank copies its bands over its own PCIe link; rank 0 gets a numpy VIEW of the shared pinned frame.
+        pipeline=True (RT_GROUP_PIPELINE): two frames in flight; the view is the PREVIOUS frame (None for the first call), flush_host() the last."""
+        p = self.trace(tlas, cam, width, height, bounces, GROUP_OUT_HOST | (GROUP_PIPELINE if pipeline else 0))
         if not p:
             return None
         return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint8)), shape=(height, width, 4))
+
+    def flush_host(self, width: int, height: int) -> Optional[np.ndarray]:
+        """rt_group_flush_host: completes the pending frame of a pipelined host-output sequence; rank 0 gets its view."""
+        p = C.c_void_p()
+        self._check(self.L.rt_group_flush_host(self.h, C.byref(p)))
+        if not p.value:
+            return None
+        return np.ctypeslib.as_array(C.cast(p.value, C.POINTER(C.c_uint8)), shape=(height, width, 4))
 
     def host_frame_begin(self) -> int:
         p = C.c_void_p()

@@ -90,7 +90,10 @@ enum {
 /* ---- rt_trace output flags -------------------------------------------------------------- */
 #define RT_TRACE_OUT_DEVICE 0x1u  /* rgba_out / hit buffers are device pointers */
 #define RT_TRACE_STATS      0x2u  /* also accumulate traversal counters (slower kernel variant) */
-#define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait) */
+#define RT_TRACE_ASYNC      0x4u  /* with RT_TRACE_OUT_DEVICE: enqueue on the context stream and return (rt_sync() to wait).
+                                    With a HOST framebuffer (pinned memory, no hit buffers): trace and device->host copies are enqueued and the
+                                    call returns; rt_host_frame_wait() returns when the frame is complete in the host buffer. One such frame
+                                    may be in flight per context (the next host-output trace waits for it first). */
 #define RT_TRACE_OUT_BGRA   0x10u /* store B,G,R,A byte order — the sample copies its image raw into a B8G8R8A8 swapchain (main.cpp:50,971-974,1371-1375);
                                     the default is the logical R,G,B,A of imageStore(vec4(hitValue, 0.0)) */
 #define RT_TRACE_OUT_FULL_FRAME 0x8u /* rt_trace_rows: rgba_out is the WHOLE width*height*4 frame and this part's pixels land at their final
@@ -337,6 +340,8 @@ RT_API int  rt_trace_rows_range(rt_context* ctx, const rt_tlas* tlas, const rt_c
                                 uint32_t width, uint32_t height, uint32_t bounces, uint32_t flags,
                                 uint32_t block_rows, uint32_t part_index, uint32_t part_count, uint32_t first_row, uint32_t n_rows,
                                 uint8_t* rgba_out, rt_hit* primary_hits_out, rt_hit* secondary_hits_out);
+/* Completes the host-output trace that was enqueued with RT_TRACE_ASYNC (no-op when none is in flight). */
+RT_API int  rt_host_frame_wait(rt_context* ctx);
 RT_API uint64_t rt_rows_packed_pixels(uint32_t width, uint32_t height, uint32_t block_rows, uint32_t part_count);
 /* Rank 0 after the gather: scatter part_count packed buffers (contiguous, each
  * rt_rows_packed_pixels()*4 bytes, device memory) into the final width*height*4 framebuffer (device). */
@@ -372,8 +377,14 @@ RT_API int  rt_frame_share_free(rt_context* ctx, void* device_ptr);             
  *   RT_GROUP_ASYNC (device output): enqueue and return; rt_group_sync() waits for everything enqueued so far.
  *   RT_GROUP_PIPELINE (device output, implies ASYNC): consecutive frames alternate over two internal streams, so frame k + 1's
  *     first rays fill the tail of frame k's persistent kernels (the per-frame fixed cost that limits scaling at 8 GPUs).
+ *   RT_GROUP_PIPELINE with RT_GROUP_OUT_HOST: two frames in flight. Call k enqueues frame k (trace + this rank's PCIe copies, on
+ *     alternating internal contexts) and then COMPLETES frame k - 1: on rank 0 *frame_out is the finished frame k - 1 (NULL for the
+ *     first call), valid until the next group trace. rt_group_flush_host() completes the last frame. Frame k's copies and the
+ *     ranks' handshake thus overlap frame k + 1's trace.
  * Every rank must make the same sequence of group calls. A group of world = 1 is valid (no peer traffic). */
 typedef struct rt_group rt_group;
+/* Completes the pending frame of a pipelined host-output sequence (no-op without one); on rank 0 *frame_out (may be NULL) is that frame. */
+RT_API int  rt_group_flush_host(rt_group* group, const uint8_t** frame_out);
 #define RT_GROUP_OUT_DEVICE 0x1u
 #define RT_GROUP_OUT_HOST   0x2u
 #define RT_GROUP_ASYNC      0x4u

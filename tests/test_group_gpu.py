@@ -57,6 +57,19 @@ def _worker(rank, world, name, q, n_dev):
             f = g.trace_host(tlas, cam, W, H, 1)
             if rank == 0:
                 frames.append(f.copy())
+        # pipelined host output: two frames in flight, call k returns frame k - 1; a different camera per frame shows which frame came back
+        cams = [ctx.camera((0.3 * i, -0.2 * i, 10.0 + i), scene.yfov_deg) for i in range(5)]
+        piped = []
+        for i in range(5):
+            f = g.trace_host(tlas, cams[i], W, H, 1, pipeline=True)
+            if rank == 0:
+                assert (f is None) == (i == 0)
+                if f is not None:
+                    piped.append(f.copy())
+        f = g.flush_host(W, H)
+        if rank == 0:
+            piped.append(f.copy())
+        assert g.flush_host(W, H) is None                                  # nothing pending any more
         # a smaller frame than the group's maximum
         f = g.trace_host(tlas, cam, 160, 96, 0)
         small = f.copy() if rank == 0 else None
@@ -65,8 +78,10 @@ def _worker(rank, world, name, q, n_dev):
             sh = rtcore.SceneHandles(ctx1, scene)
             ref, _, _ = sh.trace(want_hits=False)
             ref_small, _, _ = ctx1.trace(sh.tlas, sh.cam, 160, 96, 0)
-            sh.free(); ctx1.close()
             out["equal"] = [bool(np.array_equal(fr, ref)) for fr in frames]
+            out["piped_equal"] = [bool(np.array_equal(piped[i], ctx1.trace(sh.tlas, cams[i], W, H, 1)[0])) for i in range(5)]
+            out["piped_distinct"] = len({fr.tobytes() for fr in piped})
+            sh.free(); ctx1.close()
             out["small_equal"] = bool(np.array_equal(small, ref_small))
             out["nonblack"] = int((ref[..., :3].max(axis=-1) > 60).sum())
         g.barrier()
@@ -102,6 +117,7 @@ def test_group_frames_equal_single_context(world):
     assert out["nonblack"] > 5000
     assert out["equal"] == [True] * 8, out           # 3 device frames, 2 pipelined, 3 host frames
     assert out["small_equal"]
+    assert out["piped_equal"] == [True] * 5 and out["piped_distinct"] == 5, out      # frame k - 1 really is frame k - 1
     print("group", world, out, {r: res[r][0].get("share_ms") for r in res})
 
 
