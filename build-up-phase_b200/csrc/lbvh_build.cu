@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
     }
     __syncthreads();
     seg_sort_passes(seg_smem, vb, (int)MORTON_BITS, n);
-    for (uint32_t i = tid; i < n; i += SEG_THREADS) keys_out[first + i] = s_keys[i];
+    seg_store_bulk(keys_out + first, s_keys, n);          // the sorted segment leaves shared memory as one TMA bulk copy (UBLKCP)
 }
 
 // ---- hierarchy emission + refit, one bottom-up pass ---------------------------------------------------

@@ -255,11 +255,12 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_sort(const uint64_t* __r
     const int tid = threadIdx.x;
     const uint32_t first = recs ? recs[blockIdx.x].first : 0u, n = recs ? recs[blockIdx.x].tri_count : single_n;   // recs == nullptr: the whole input is one segment
     if (n == 0) return;
-    // coalesced load; padding (~0) sorts last and stays last
-    for (uint32_t i = tid; i < SEG_SORT_CAPACITY; i += SEG_THREADS) s_keys[i] = i < n ? in[first + i] : ~0ull;
+    // the segment: one TMA bulk copy (cp.async.bulk + mbarrier); padding (~0) sorts last and stays last
+    for (uint32_t i = n + tid; i < SEG_SORT_CAPACITY; i += SEG_THREADS) s_keys[i] = ~0ull;
+    seg_load_bulk(s_keys, in + first, n, reinterpret_cast<uint64_t*>(seg_smem + SEG_SMEM_MBAR_OFFSET));
     __syncthreads();
     seg_sort_passes(seg_smem, shift0, key_bits, n);
-    for (uint32_t i = tid; i < n; i += SEG_THREADS) out[first + i] = s_keys[i];
+    seg_store_bulk(out + first, s_keys, n);
 }
 
 }  // namespace

@@ -16,7 +16,8 @@ namespace rt {
 // bound by the rate of MATCH.ANY itself, ~60 cycles per warp instruction and SM; profiles/README.md r01x/r01y.)
 constexpr int SEG_THREADS = 1024, SEG_WARPS = SEG_THREADS / 32, SEG_ITEMS = 11;     // 11: odd stride -> blocked shared-memory access without bank pile-ups
 static_assert(SEG_THREADS * SEG_ITEMS == (int)SEG_SORT_CAPACITY, "segment capacity");
-constexpr size_t SEG_SMEM_BYTES = sizeof(uint64_t) * SEG_SORT_CAPACITY + sizeof(uint16_t) * 16 * SEG_THREADS + sizeof(uint64_t) * (4 * SEG_WARPS + 4) + 64;
+constexpr size_t SEG_SMEM_MBAR_OFFSET = sizeof(uint64_t) * SEG_SORT_CAPACITY + sizeof(uint16_t) * 16 * SEG_THREADS + sizeof(uint64_t) * (4 * SEG_WARPS + 4);   // 8-byte aligned
+constexpr size_t SEG_SMEM_BYTES = SEG_SMEM_MBAR_OFFSET + 64;
 
 __device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int o) {
     const uint32_t lo = __shfl_up_sync(0xffffffffu, (uint32_t)v, o), hi = __shfl_up_sync(0xffffffffu, (uint32_t)(v >> 32), o);
@@ -108,6 +109,48 @@ __device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shi
             s_keys[(uint32_t)s_off[d * SEG_THREADS + tid] + (uint32_t)((rk >> (4 * i)) & 15ull)] = key[i];
         }
         __syncthreads();
+    }
+}
+
+// ---- TMA bulk copies of a whole sorted segment (sm_100a: cp.async.bulk, SASS UBLKCP) ----------------------------------------------------
+// The sorted records of a segment are ONE contiguous run of n x 8 bytes in shared and in global memory, so one elected thread moves them
+// with a single bulk copy instead of every thread looping over 8-byte stores. Needs 16-byte alignment on both sides: the even part of an
+// evenly placed segment goes through the bulk copy, an odd head / tail record through plain stores.
+__device__ __forceinline__ void seg_store_bulk(uint64_t* __restrict__ gdst, const uint64_t* s_src, uint32_t n) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(gdst) & 15u) == 0;
+    const uint32_t n_bulk = aligned ? (n & ~1u) : 0u;
+    if (n_bulk) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");          // this thread's generic-proxy writes to the segment -> visible to the async proxy
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         ::"l"(gdst), "r"((uint32_t)__cvta_generic_to_shared(s_src)), "r"(n_bulk * 8u) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    for (uint32_t i = n_bulk + threadIdx.x; i < n; i += blockDim.x) gdst[i] = s_src[i];
+    if (n_bulk && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");     // the copy has left shared memory AND landed before the CTA retires
+}
+// global -> shared: one bulk copy completing on an mbarrier (8 bytes at `bar`, 8-byte aligned shared memory); every thread waits on phase 0
+__device__ __forceinline__ void seg_load_bulk(uint64_t* s_dst, const uint64_t* __restrict__ gsrc, uint32_t n, uint64_t* bar) {
+    const bool aligned = (reinterpret_cast<uintptr_t>(gsrc) & 15u) == 0;
+    const uint32_t n_bulk = aligned ? (n & ~1u) : 0u;
+    const uint32_t b = (uint32_t)__cvta_generic_to_shared(bar);
+    if (n_bulk) {
+        if (threadIdx.x == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(n_bulk * 8u) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"((uint32_t)__cvta_generic_to_shared(s_dst)), "l"(gsrc), "r"(n_bulk * 8u), "r"(b) : "memory");
+        }
+    }
+    for (uint32_t i = n_bulk + threadIdx.x; i < n; i += blockDim.x) s_dst[i] = gsrc[i];
+    if (n_bulk) {
+        __syncthreads();                                                         // the barrier is initialised
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(b) : "memory");
     }
 }
 

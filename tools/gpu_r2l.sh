@@ -1,6 +1,6 @@
 #!/bin/bash
 # r2_l: N GPUs of one box: inst10m (default bench line) and soup100m (cfg5) with parity + CPU arm; usage: gpu_r2l.sh N
-N=${1:-8}; TAG=r2l
+N=${1:-8}; TAG=${2:-r2l}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name --format=csv,noheader | sort | uniq -c > gpurun_out/gpus_${TAG}_n$N.txt
 if [ "$N" = 1 ]; then TR="python"; else TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29541"; fi
