@@ -9,7 +9,7 @@ import time
 import numpy as np
 import pytest
 
-from build_up_phase_b200 import partition
+import partition_model as partition
 
 W, H, BR = 96, 52, 8           # 52 rows: 7 bands, the last one short (4 rows) -> ragged shares
 FRAMES = 7

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from build_up_phase_b200 import partition
+import partition_model as partition
 
 
 @pytest.mark.parametrize("h,br,n", [(2160, 8, 8), (250, 8, 3), (17, 4, 2), (8, 8, 4), (1, 4, 2)])
