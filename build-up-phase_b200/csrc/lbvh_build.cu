@@ -310,6 +310,16 @@ struct InstSegment {
     }
 };
 
+template <int LEAF_MAX, class Seg>
+__device__ __forceinline__ void climb_global(TreeJob j, const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+                                             float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg);
+// RT_TREE_INLINE_BORDER=1: the threads that hold a tile's unfinished subtrees / orphans continue through global memory themselves, right
+// after the tile quiesces, instead of handing them to a second kernel through the job queue (no k_tree_border launch).
+#ifndef RT_TREE_INLINE_BORDER
+#define RT_TREE_INLINE_BORDER 0
+#endif
+struct BorderMem { float4* xchg; uint32_t* far_end; uint32_t* arrived; };
+
 // Phase 1 (inside the leaf kernels): everything a tile can finish on its own. Unfinished subtrees (at most 2 per tile:
 // the ones whose next split lies outside it) and orphans (a child deposited in shared memory whose sibling straddles
 // the tile border: at most one per straddling ancestor of the two border leaves) are appended to the border-job queue
@@ -317,7 +327,7 @@ struct InstSegment {
 template <int LEAF_MAX, class Seg>
 __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
                                                 float4* __restrict__ jobs, uint32_t* __restrict__ job_count,
-                                                const Box3& leaf_box, const Seg& seg) {
+                                                const Box3& leaf_box, const Seg& seg, const BorderMem bm) {
     __shared__ int s_delta[TREE_TILE + 1];          // s_delta[k] = delta(L0 - 1 + k)
     __shared__ uint32_t s_flag[TREE_TILE];          // bit side: that child of split L0 + k has been deposited
     __shared__ float4 s_a[2 * TREE_TILE], s_b[2 * TREE_TILE];
@@ -371,6 +381,23 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
     __syncthreads();
     const uint32_t f = s_flag[tid];
     const bool orphan = f == 1u || f == 2u;
+#if RT_TREE_INLINE_BORDER
+    (void)jobs; (void)job_count;
+    if (carried) climb_global<LEAF_MAX>(j, keys, vb, n, nodes, bm.xchg, bm.far_end, bm.arrived, seg);
+    if (orphan) {
+        const uint32_t side = f - 1u, g = L0 + tid;
+        const float4 m0 = s_a[2 * tid + side], m1 = s_b[2 * tid + side];
+        const uint32_t far = L0 + (__float_as_uint(m1.w) >> 8);
+        TreeJob o;
+        o.b.lo[0] = m0.x; o.b.lo[1] = m0.y; o.b.lo[2] = m0.z; o.b.hi[0] = m0.w; o.b.hi[1] = m1.x; o.b.hi[2] = m1.y;
+        o.ref = __float_as_int(m1.z); o.height = __float_as_uint(m1.w) & 255u;
+        if (side == 0u) { o.l = far; o.r = g; } else { o.l = g + 1u; o.r = far; }
+        seg.seg_of(__ldg(keys + o.l) >> vb, o.seg_first, o.seg_count);
+        climb_global<LEAF_MAX>(o, keys, vb, n, nodes, bm.xchg, bm.far_end, bm.arrived, seg);
+    }
+    return;
+#endif
+    (void)bm;
     const uint32_t ia = carried ? atomicAdd(&s_njobs, 1u) : 0u;
     const uint32_t ib = orphan ? atomicAdd(&s_njobs, 1u) : 0u;
     __syncthreads();
@@ -403,24 +430,12 @@ inline uint64_t tree_job_capacity_host(uint32_t n) {
     return cap < 2ull * n + 2 ? cap : 2ull * n + 2;
 }
 
-// Phase 2: one thread per border job climbs through global memory: deposit {half, far end} at the split, fence,
-// arrival counter; the second arriver unions and writes the finished node into its Karras slot.
+// Phase 2: a border job climbs through global memory: deposit {half, far end} at the split, fence, arrival counter; the second arriver
+// unions and writes the finished node into its Karras slot. Nobody ever waits: the first arrival at a split retires.
 template <int LEAF_MAX, class Seg>
-__global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
-                                                    const float4* __restrict__ jobs, const uint32_t* __restrict__ job_count,
-                                                    float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg seg) {
-    // grid-stride over the jobs: the queue's CAPACITY is ~130 entries per tile, its length ~3, so the grid is sized by the machine
-    // (border_grid) and not by the capacity; a thread never waits for another one (the first arrival at a split retires), so taking
-    // several jobs in turn cannot deadlock
-    const uint32_t n_jobs = *job_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_jobs; i += gridDim.x * blockDim.x) {
-    const float4 q0 = __ldg(jobs + 3 * (size_t)i), q1 = __ldg(jobs + 3 * (size_t)i + 1), q2 = __ldg(jobs + 3 * (size_t)i + 2);
-    TreeJob j;
-    j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
-    j.ref = __float_as_int(q1.z); j.height = __float_as_uint(q1.w);
-    j.l = __float_as_uint(q2.x); j.r = __float_as_uint(q2.y);
-    seg.seg_of(__ldg(keys + j.l) >> vb, j.seg_first, j.seg_count);
-    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); continue; }
+__device__ __forceinline__ void climb_global(TreeJob j, const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+                                             float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg) {
+    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); return; }
     auto merges_right = [&](uint32_t l, uint32_t r) {
         const int dl = l > 0u ? delta_global(keys, vb, l - 1u) : -1;
         const int dr = r + 1u < n ? delta_global(keys, vb, r) : -1;
@@ -454,6 +469,23 @@ __global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict_
         }
         if (root) { seg.on_root(j); break; }
     }
+}
+
+template <int LEAF_MAX, class Seg>
+__global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+                                                    const float4* __restrict__ jobs, const uint32_t* __restrict__ job_count,
+                                                    float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg seg) {
+    // grid-stride over the jobs: the queue's CAPACITY is ~130 entries per tile, its length a few per tile, so the grid is sized by the
+    // expected length (border_grid) and not by the capacity
+    const uint32_t n_jobs = *job_count;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_jobs; i += gridDim.x * blockDim.x) {
+        const float4 q0 = __ldg(jobs + 3 * (size_t)i), q1 = __ldg(jobs + 3 * (size_t)i + 1), q2 = __ldg(jobs + 3 * (size_t)i + 2);
+        TreeJob j;
+        j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
+        j.ref = __float_as_int(q1.z); j.height = __float_as_uint(q1.w);
+        j.l = __float_as_uint(q2.x); j.r = __float_as_uint(q2.y);
+        seg.seg_of(__ldg(keys + j.l) >> vb, j.seg_first, j.seg_count);
+        climb_global<LEAF_MAX>(j, keys, vb, n, nodes, xchg, far_end, arrived, seg);
     }
 }
 // grid of the border kernel: one thread per job the build is expected to have (RT_BORDER_JOBS_PER_TILE per tile: 2 unfinished subtrees
@@ -476,7 +508,7 @@ inline uint32_t border_grid(uint32_t n) {
 __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
                                                          const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
                                                          BvhNode* __restrict__ nodes, const TriSegments seg,
-                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {
+                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count, const BorderMem bm) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     Box3 b = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
     if (leaf < n) {
@@ -490,7 +522,7 @@ __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(cons
         b.lo[0] = fminf(fminf(q0.x, q0.w), q1.z); b.lo[1] = fminf(fminf(q0.y, q1.x), q1.w); b.lo[2] = fminf(fminf(q0.z, q1.y), q2.x);
         b.hi[0] = fmaxf(fmaxf(q0.x, q0.w), q1.z); b.hi[1] = fmaxf(fmaxf(q0.y, q1.x), q1.w); b.hi[2] = fmaxf(fmaxf(q0.z, q1.y), q2.x);
     }
-    build_tree_tile<BLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg);
+    build_tree_tile<BLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg, bm);
 }
 
 // ---- TLAS ---------------------------------------------------------------------------------------
@@ -568,7 +600,7 @@ __global__ void __launch_bounds__(256) k_inst_morton(const InstanceRec* __restri
 __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_inst(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n, const InstanceRec* __restrict__ unsorted,
                                                          const float* __restrict__ boxes, InstanceRec* __restrict__ sorted,
                                                          BvhNode* __restrict__ nodes, const InstSegment seg,
-                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count) {
+                                                         float4* __restrict__ jobs, uint32_t* __restrict__ job_count, const BorderMem bm) {
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     Box3 b = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
     if (leaf < n) {
@@ -580,7 +612,7 @@ __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_inst(cons
         const float* bx = boxes + 6 * (size_t)src_i;
         b.lo[0] = bx[0]; b.lo[1] = bx[1]; b.lo[2] = bx[2]; b.hi[0] = bx[3]; b.hi[1] = bx[4]; b.hi[2] = bx[5];
     }
-    build_tree_tile<TLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg);
+    build_tree_tile<TLAS_LEAF_MAX>(keys, vb, n, nodes, jobs, job_count, b, seg, bm);
 }
 
 inline int div_up(uint32_t a, uint32_t b) { return (int)((a + b - 1) / b); }
@@ -777,11 +809,15 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
         const TriSegments seg{a.records, keys, vb};
         const uint32_t tiles = (uint32_t)div_up(a.n_tris, TREE_TILE);
         uint32_t* job_count = a.s.arrived + a.n_tris;
-        k_refit_tris<<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count);
+        const BorderMem bm{a.s.xchg, a.s.far_end, a.s.arrived};
+        k_refit_tris<<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count, bm);
+#if !RT_TREE_INLINE_BORDER
         k_tree_border<BLAS_LEAF_MAX, TriSegments><<<border_grid(a.n_tris), 128, 0, st>>>(keys, vb, a.n_tris, a.nodes, a.s.jobs, job_count,
                                                                                                           a.s.xchg, a.s.far_end, a.s.arrived, seg);
+        ++launches;
+#endif
     }
-    launches += 2;
+    launches += 1;
     if (ev) cudaEventRecord(ev->e[5], st);
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
@@ -804,11 +840,15 @@ int launch_tlas_build(const TlasBuildArgs& a, cudaStream_t st) {
     {
         const InstSegment seg{a.n, a.root_out, a.bounds_out};
         uint32_t* job_count = a.s.arrived + a.n;
-        k_refit_inst<<<div_up(a.n, TREE_TILE), TREE_TILE, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, seg, a.s.jobs, job_count);
+        const BorderMem bm{a.s.xchg, a.s.far_end, a.s.arrived};
+        k_refit_inst<<<div_up(a.n, TREE_TILE), TREE_TILE, 0, st>>>(keys, vals, vb, a.n, a.inst_unsorted, a.boxes_unsorted, a.inst_sorted, a.nodes, seg, a.s.jobs, job_count, bm);
+#if !RT_TREE_INLINE_BORDER
         k_tree_border<TLAS_LEAF_MAX, InstSegment><<<border_grid(a.n), 128, 0, st>>>(keys, vb, a.n, a.nodes, a.s.jobs, job_count,
                                                                                                      a.s.xchg, a.s.far_end, a.s.arrived, seg);
+        ++launches;
+#endif
     }
-    launches += 2;
+    launches += 1;
     if (cudaGetLastError() != cudaSuccess) return -1;
     return launches;
 }

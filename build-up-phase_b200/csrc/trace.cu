@@ -104,6 +104,14 @@ constexpr uint32_t TPR = REGION_TW * REGION_TH, RPR = TPR * 32u;    // tiles / r
 #ifndef RT_CAP_EVERY
 #define RT_CAP_EVERY 1
 #endif
+// RT_STACK_TOS=1: top of the traversal stack in a register (see push/pop)
+#ifndef RT_STACK_TOS
+#define RT_STACK_TOS 0
+#endif
+// registers of the bounce stage: its own minimum CTAs per SM (it is the more latency-bound stage)
+#ifndef RT_TRACE_MIN_BLOCKS_S1
+#define RT_TRACE_MIN_BLOCKS_S1 RT_TRACE_MIN_BLOCKS
+#endif
 #ifndef RT_FAST_SLAB
 #define RT_FAST_SLAB 1
 #endif
@@ -437,7 +445,7 @@ __device__ __forceinline__ void enqueue_bounce(const TraceParams& P, bool enqueu
 // slower on B200 - profiles/README.md r01h: a separate warp-convergent shading kernel with refill thresholds 16..28,
 // and speculative traversal with one postponed leaf.)
 template <int STAGE, bool STATS, int STACK, bool GENERAL, bool BIG>
-__global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ? 1 : TRACE_MIN_BLOCKS) k_trace(const TraceParams P) {
+__global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ? 1 : (STAGE == 1 ? RT_TRACE_MIN_BLOCKS_S1 : TRACE_MIN_BLOCKS)) k_trace(const TraceParams P) {
     const int lane = threadIdx.x & 31;
     const BvhNode* tlas_nodes = P.tlas_nodes;
     if (BIG) {
@@ -518,6 +526,20 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
 #if RT_CAP_EVERY > 1
     uint32_t cap_ctr = 0;
 #endif
+#if RT_STACK_TOS
+    // the top of the stack lives in a register: a push directly followed by a pop (both children hit, the near one turns out to be a dead end)
+    // never touches local memory; a push onto an occupied top spills the old top first
+    int32_t tos = REF_DONE; bool tos_valid = false;
+    auto push = [&](int32_t v) {
+        if (tos_valid) { stack[sp] = tos; ++sp; }
+        tos = v; tos_valid = true;
+    };
+    auto pop = [&]() -> int32_t {
+        if (tos_valid) { tos_valid = false; return tos; }
+        --sp;
+        return stack[sp];
+    };
+#else
     auto push = [&](int32_t v) {
 #if RT_SMEM_STACK > 0
         if (sp < RT_SMEM_STACK) s_stack[sp][threadIdx.x] = v; else stack[sp - RT_SMEM_STACK] = v;
@@ -534,6 +556,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
         return stack[sp];
 #endif
     };
+#endif
 
     for (;;) {
         // ================= refill idle lanes: ballot + one atomic + shuffle =================
@@ -598,6 +621,9 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                     // ---- traceRayEXT(topLevelAS, Opaque, cullMask, ..., o, tmin, d, tmax) (main.cpp:1047-1052) ----
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
+#if RT_STACK_TOS
+                    tos_valid = false;
+#endif
                     push(REF_DONE);
                     in_blas = false;
                     nodes = tlas_nodes;
@@ -639,6 +665,9 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                     pending = false; have_ray = true; sec = true;
                     best_t = P.tmax; best_u = best_v = best_w0 = 0.0f; best_slot = NO_HIT; best_tri = 0;
                     sp = 0;
+#if RT_STACK_TOS
+                    tos_valid = false;
+#endif
                     push(REF_DONE);
                     in_blas = false;
                     nodes = tlas_nodes;

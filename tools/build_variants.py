@@ -17,13 +17,15 @@ VARIANTS = {
     "leaf1": ["RT_BLAS_LEAF_MAX=1"], "leaf3": ["RT_BLAS_LEAF_MAX=3"], "leaf4": ["RT_BLAS_LEAF_MAX=4"], "leaf8": ["RT_BLAS_LEAF_MAX=8"],   # (r02a)
     # ray numbering / fetch counters (r2_f) and the shared-memory short stack
     "reg0": ["RT_REGIONS=0"], "reg1": ["RT_REGIONS=1"], "reg2": ["RT_REGIONS=2"],
-    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "ldg256_blk7": ["RT_LDG256=1", "RT_TRACE_MIN_BLOCKS=7"], "smemtlas_reg2": ["RT_REGIONS=2"], "smemtlas_stack8": ["RT_SMEM_STACK=8"],
+    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "tos": ["RT_STACK_TOS=1"], "s1blk10": ["RT_TRACE_MIN_BLOCKS_S1=10"], "s1blk7": ["RT_TRACE_MIN_BLOCKS_S1=7"], "s1blk6": ["RT_TRACE_MIN_BLOCKS_S1=6"],
+    "tos_s1blk7": ["RT_STACK_TOS=1", "RT_TRACE_MIN_BLOCKS_S1=7"], "ldg256_blk7": ["RT_LDG256=1", "RT_TRACE_MIN_BLOCKS=7"], "smemtlas_reg2": ["RT_REGIONS=2"], "smemtlas_stack8": ["RT_SMEM_STACK=8"],
     "smemtlas_cap8": ["RT_NODE_CAP=8"], "smemtlas_thr16": ["RT_REFILL_THRESHOLD=16"],
     "reg2_8x8": ["RT_REGION_TW=8", "RT_REGION_TH=8"], "reg2_32x16": ["RT_REGION_TW=32", "RT_REGION_TH=16"], "reg2_8x16": ["RT_REGION_TW=8", "RT_REGION_TH=16"],
     "reg1_32x32": ["RT_REGIONS=1", "RT_REGION_TW=32", "RT_REGION_TH=32"],
     "smem8": ["RT_SMEM_STACK=8"], "smem16": ["RT_SMEM_STACK=16"], "reg0_smem8": ["RT_REGIONS=0", "RT_SMEM_STACK=8"],
     "capevery2": ["RT_CAP_EVERY=2"],
     # build
+    "inline_border": ["RT_TREE_INLINE_BORDER=1"], "inline_border_t256": ["RT_TREE_INLINE_BORDER=1", "RT_TREE_TILE=256"],
     "tile64": ["RT_TREE_TILE=64"], "tile256": ["RT_TREE_TILE=256"], "tile512": ["RT_TREE_TILE=512"],
     "sort8_6": ["RT_SORT_ITEMS=8", "RT_SORT_MIN_CTAS=6"], "sort12_6": ["RT_SORT_ITEMS=12", "RT_SORT_MIN_CTAS=6"],
     "ballot": ["RT_SORT_USE_BALLOT=1"],
