@@ -78,7 +78,13 @@ def _bytes(v):
 def traffic(tag):
     """profiles/ncu_traffic.json: measured DRAM bytes (read + write) per launch of the dominant kernels, taken from the full
     captures of this tag; bench.py copies the matching entry into roofline.traffic."""
-    out = {"tag": tag, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one `ncu --set full` capture each (inst10m, N = 1)"}
+    out = {}
+    try:                                     # keep the entries of earlier captures that this tag does not replace
+        out = json.load(open(os.path.join(PR, "ncu_traffic.json")))
+    except Exception:
+        pass
+    out.update({"tag": tag, "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, one `ncu --set full` capture each (inst10m, N = 1); "
+                                    "each entry names the capture it comes from (`source`)"})
     tp = os.path.join(PR, f"prof_trace_{tag}.json")
     if os.path.exists(tp):
         ks = json.load(open(tp))
