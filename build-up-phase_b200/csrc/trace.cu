@@ -34,13 +34,13 @@ namespace rt {
 namespace {
 
 #ifndef RT_TRACE_MIN_BLOCKS
-#define RT_TRACE_MIN_BLOCKS 8
+#define RT_TRACE_MIN_BLOCKS 9
 #endif
 #ifndef RT_REFILL_THRESHOLD
 #define RT_REFILL_THRESHOLD 12
 #endif
 constexpr int TRACE_THREADS = 128;
-constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 8) = 64
+constexpr int TRACE_MIN_BLOCKS = RT_TRACE_MIN_BLOCKS;     // register cap 65536 / (128 * 9) = 56 (with the min/max slab test; 8 CTAs = 64 registers before it)
 // BIG kernel variant: ONE 1024-thread CTA per SM (same 32 warps, same 64-register cap) whose dynamic shared memory holds a copy of the
 // TLAS nodes, staged once per CTA with a TMA bulk copy (cp.async.bulk + mbarrier). Top-level node fetches - every ray starts there, and
 // the rays that miss everything never leave it - then are LDS.128 instead of divergent L1 tag look-ups, and the TLAS stops competing
@@ -103,6 +103,19 @@ constexpr uint32_t TPR = REGION_TW * REGION_TH, RPR = TPR * 32u;    // tiles / r
 // the node loop's "too few lanes left" test every RT_CAP_EVERY-th iteration only (it costs a vote + popc + branch per node step)
 #ifndef RT_CAP_EVERY
 #define RT_CAP_EVERY 1
+#endif
+#ifndef RT_BRANCHLESS_NODE
+#define RT_BRANCHLESS_NODE 0
+#endif
+#ifndef RT_PRIMARY_ORIGIN_CONST
+#define RT_PRIMARY_ORIGIN_CONST 1
+#endif
+// RT_SLAB_MINMAX=1: the slab test picks near / far with min / max instead of per-axis selects on the direction sign (bit-identical values):
+// 3 instructions less per node step (no predicates to rebuild from the packed sign bytes) and three registers less in the loop, which is
+// what makes a ninth CTA per SM pay. Measured on B200 (inst10m, profiles/README.md r2_u / r2_v): select form at 8 / 9 CTAs per SM 3518 / 3479
+// Mrays/s, min/max form at 8 / 9 / 10 CTAs 3522 / 3603 / 3594.
+#ifndef RT_SLAB_MINMAX
+#define RT_SLAB_MINMAX 1
 #endif
 // RT_STACK_TOS=1: top of the traversal stack in a register (see push/pop)
 #ifndef RT_STACK_TOS
@@ -173,10 +186,26 @@ __device__ __forceinline__ void slab_setup(Slab& s, V3 o, V3 d, float ax, float 
     s.cnx = -((s.px ? o.x + e : o.x - e) * s.rdx); s.cfx = -((s.px ? o.x - e : o.x + e) * s.rdx);
     s.cny = -((s.py ? o.y + e : o.y - e) * s.rdy); s.cfy = -((s.py ? o.y - e : o.y + e) * s.rdy);
     s.cnz = -((s.pz ? o.z + e : o.z - e) * s.rdz); s.cfz = -((s.pz ? o.z - e : o.z + e) * s.rdz);
+#if RT_SLAB_MINMAX
+    // min/max form: cn* becomes the constant that goes with the box's LO plane, cf* the one that goes with its HI plane (swapped for a
+    // negative direction), so that slab_test needs no per-axis select: near = min(t_lo, t_hi), far = max(t_lo, t_hi). The padded near value
+    // can never exceed the padded far value ((hi - o + e) >= (lo - o - e)), so min/max pick exactly the values the select form picks.
+    if (!s.px) { const float t = s.cnx; s.cnx = s.cfx; s.cfx = t; }
+    if (!s.py) { const float t = s.cny; s.cny = s.cfy; s.cfy = t; }
+    if (!s.pz) { const float t = s.cnz; s.cnz = s.cfz; s.cfz = t; }
+#endif
 }
 
 // half = {lo.x lo.y lo.z hi.x} {hi.y hi.z ref height}
 __device__ __forceinline__ bool slab_test(const Slab& s, const float4 h0, const float4 h1, float tmin, float tbest, float& tn) {
+#if RT_SLAB_MINMAX
+    const float lx = __fmaf_rn(h0.x, s.rdx, s.cnx), hx = __fmaf_rn(h0.w, s.rdx, s.cfx);
+    const float ly = __fmaf_rn(h0.y, s.rdy, s.cny), hy = __fmaf_rn(h1.x, s.rdy, s.cfy);
+    const float lz = __fmaf_rn(h0.z, s.rdz, s.cnz), hz = __fmaf_rn(h1.y, s.rdz, s.cfz);
+    tn = fmaxf(fmaxf(fminf(lx, hx), fminf(ly, hy)), fmaxf(fminf(lz, hz), tmin));
+    const float tf_ = fminf(fminf(fmaxf(lx, hx), fmaxf(ly, hy)), fminf(fmaxf(lz, hz), tbest));
+    return tn <= tf_;
+#endif
     const float nx = s.px ? h0.x : h0.w, fx = s.px ? h0.w : h0.x;
     const float ny = s.py ? h0.y : h1.x, fy = s.py ? h1.x : h0.y;
     const float nz = s.pz ? h0.z : h1.y, fz = s.pz ? h1.y : h0.z;
@@ -508,6 +537,12 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
     uint32_t fin_local = 0;                  // FUSED, warp-uniform: primary rays this warp finished but has not reported yet
     uint32_t rid = 0;                        // tile-major index of the primary ray / slot of the bounce ray this lane traces
     V3 o = {0.0f, 0.0f, 0.0f}, d = {0.0f, 0.0f, 1.0f};
+    // primary-only launches: every ray starts at the camera, so the origin is read from the parameter block instead of living in three registers
+#if RT_PRIMARY_ORIGIN_CONST
+#define RAY_O (STAGE == 0 ? V3{P.cam_pos[0], P.cam_pos[1], P.cam_pos[2]} : o)
+#else
+#define RAY_O o
+#endif
     int32_t cur = REF_DONE;
     int sp = 0;
     bool in_blas = false;
@@ -702,6 +737,16 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                 const bool hit0 = slab_test(sl, a0, a1, P.tmin, best_t, t0);
                 const bool hit1 = slab_test(sl, b0, b1, P.tmin, best_t, t1);
                 const int32_t r0 = __float_as_int(a1.z), r1 = __float_as_int(b1.z);
+#if RT_BRANCHLESS_NODE
+                {   // selects + one predicated store / load instead of a four-way branch (no BSSY/BSYNC pair around it)
+                    const bool both = hit0 && hit1, any = hit0 || hit1, swap = t1 < t0;
+                    const int32_t nearr = both ? (swap ? r1 : r0) : (hit0 ? r0 : r1);
+                    if (both) push(swap ? r0 : r1);
+                    int32_t nxt = nearr;
+                    if (!any) nxt = pop();
+                    cur = nxt;
+                }
+#else
                 if (hit0 && hit1) {
                     const bool swap = t1 < t0;
                     push(swap ? r0 : r1);
@@ -709,6 +754,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
                 else cur = pop();
+#endif
 #if RT_CAP_EVERY > 1
                 if (NODE_CAP > 0 && (++cap_ctr % RT_CAP_EVERY) == 0 && __popc(__activemask()) < NODE_CAP) break;
 #else
@@ -726,7 +772,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                         if (STATS) ++c.insts;
                         float w2o[12];
                         load_w2o(R, w2o);
-                        const V3 oo = xform_point(w2o, o), od = xform_vec(w2o, d);
+                        const V3 oo = xform_point(w2o, RAY_O), od = xform_vec(w2o, d);
                         slab_setup(sl, oo, od, __ldg(&R->absmax[0]), __ldg(&R->absmax[1]), __ldg(&R->absmax[2]));
                         woop_setup(wp, oo, od);
                         nodes = R->nodes; tris = R->tris;
@@ -802,7 +848,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
             } else if (cur == REF_POP_INSTANCE) {                                // back to world space
                 in_blas = false;
                 nodes = tlas_nodes;
-                slab_setup(sl, o, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
+                slab_setup(sl, RAY_O, d, P.tlas_absmax[0], P.tlas_absmax[1], P.tlas_absmax[2]);
                 cur = pop();
             } else if (cur == REF_EMPTY) {
                 cur = pop();
@@ -821,7 +867,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                 if (sec) shade<1, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c1);
                 else shade<0, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
             } else {
-                shade<STAGE == 2 ? 0 : STAGE, STATS, GENERAL>(P, rid, tiles_x, o, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
+                shade<STAGE == 2 ? 0 : STAGE, STATS, GENERAL>(P, rid, tiles_x, RAY_O, d, best_t, best_u, best_v, best_w0, best_slot, best_tri, enqueue, e0, e1, e2, c);
             }
         }
         if (FUSED) {

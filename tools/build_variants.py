@@ -17,7 +17,10 @@ VARIANTS = {
     "leaf1": ["RT_BLAS_LEAF_MAX=1"], "leaf3": ["RT_BLAS_LEAF_MAX=3"], "leaf4": ["RT_BLAS_LEAF_MAX=4"], "leaf8": ["RT_BLAS_LEAF_MAX=8"],   # (r02a)
     # ray numbering / fetch counters (r2_f) and the shared-memory short stack
     "reg0": ["RT_REGIONS=0"], "reg1": ["RT_REGIONS=1"], "reg2": ["RT_REGIONS=2"],
-    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "tos": ["RT_STACK_TOS=1"], "s1blk10": ["RT_TRACE_MIN_BLOCKS_S1=10"], "s1blk7": ["RT_TRACE_MIN_BLOCKS_S1=7"], "s1blk6": ["RT_TRACE_MIN_BLOCKS_S1=6"],
+    "nosmemtlas": ["RT_SMEM_TLAS=0"], "smemtlas": ["RT_SMEM_TLAS=1"], "ldg256": ["RT_LDG256=1"], "tos": ["RT_STACK_TOS=1"], "branchless": ["RT_BRANCHLESS_NODE=1"], "minmax": ["RT_SLAB_MINMAX=1"], "no_oconst": ["RT_PRIMARY_ORIGIN_CONST=0"], "oconst_blk10": ["RT_TRACE_MIN_BLOCKS=10"], "blk9": ["RT_TRACE_MIN_BLOCKS=9"], "minmax_blk10": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=10"],
+    "minmax_blk9_thr10": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=9", "RT_REFILL_THRESHOLD=10"], "minmax_blk9_thr14": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=9", "RT_REFILL_THRESHOLD=14"],
+    "minmax_blk9_cap8": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=9", "RT_NODE_CAP=8"], "minmax_blk9_s1blk8": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=9", "RT_TRACE_MIN_BLOCKS_S1=8"],
+    "minmax_blk8_s1blk9": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=8", "RT_TRACE_MIN_BLOCKS_S1=9"], "minmax_blk9": ["RT_SLAB_MINMAX=1", "RT_TRACE_MIN_BLOCKS=9"], "minmax_cap8": ["RT_SLAB_MINMAX=1", "RT_NODE_CAP=8"], "branchless_cap8": ["RT_BRANCHLESS_NODE=1", "RT_NODE_CAP=8"], "branchless_thr10": ["RT_BRANCHLESS_NODE=1", "RT_REFILL_THRESHOLD=10"], "s1blk10": ["RT_TRACE_MIN_BLOCKS_S1=10"], "s1blk7": ["RT_TRACE_MIN_BLOCKS_S1=7"], "s1blk6": ["RT_TRACE_MIN_BLOCKS_S1=6"],
     "tos_s1blk7": ["RT_STACK_TOS=1", "RT_TRACE_MIN_BLOCKS_S1=7"], "ldg256_blk7": ["RT_LDG256=1", "RT_TRACE_MIN_BLOCKS=7"], "smemtlas_reg2": ["RT_REGIONS=2"], "smemtlas_stack8": ["RT_SMEM_STACK=8"],
     "smemtlas_cap8": ["RT_NODE_CAP=8"], "smemtlas_thr16": ["RT_REFILL_THRESHOLD=16"],
     "reg2_8x8": ["RT_REGION_TW=8", "RT_REGION_TH=8"], "reg2_32x16": ["RT_REGION_TW=32", "RT_REGION_TH=16"], "reg2_8x16": ["RT_REGION_TW=8", "RT_REGION_TH=16"],
