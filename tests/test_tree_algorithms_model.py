@@ -206,3 +206,47 @@ def test_oracle_lbvh_is_karras_tree(oracle):
                     stack.append(int(np.int32(r)))
             live += 1
         assert np.all(covered == 1) and live >= n // 4
+
+
+def live_rule(keys, i, leaf_max=2):
+    """The product's compaction rule (lbvh_build.cu slot_is_live), from the sorted keys alone: slot i is written by the build iff Karras' node i
+    covers more than leaf_max leaves, i.e. iff delta(i, i + leaf_max * d) > delta(i, i - d) with d the node's direction."""
+    n, delta = len(keys), _delta_fn(keys)
+    if n <= leaf_max or i > n - 2:
+        return False
+    dr, dl = delta(i, i + 1), delta(i, i - 1)
+    d = 1 if dr > dl else -1
+    dmin = dl if d > 0 else dr
+    return delta(i, i + leaf_max * d) > dmin
+
+
+@pytest.mark.parametrize("kind", ["random", "dups", "alleq", "segments"])
+@pytest.mark.parametrize("leaf_max", [1, 2, 4])
+def test_compaction_live_rule_equals_karras_range_sizes(kind, leaf_max):
+    """rt_compact_blas decides which Karras slots hold a node WITHOUT reading the (uninitialised) dead slots: from the sorted records.
+    Against the paper's own ranges: node i is written iff its range holds more than leaf_max leaves."""
+    rng = np.random.default_rng(leaf_max * 13 + len(kind))
+    for n in (2, 3, 4, 9, 64, 333):
+        keys = _keys(kind, n, rng) if kind != "segments" else np.sort(rng.integers(0, 1 << 30, size=n, dtype=np.uint64))   # the rule works per segment
+        ref = karras_top_down(keys)
+        for i in range(n - 1):
+            first, last, _ = ref[i]
+            assert live_rule(keys, i, leaf_max) == (last - first + 1 > leaf_max), (kind, leaf_max, n, i)
+
+
+def test_compaction_live_rule_equals_reachable_nodes_of_the_oracle_tree(oracle):
+    """... and against the oracle's finished LBVH: the slots the rule calls live are exactly the nodes reachable from the root."""
+    from build_up_phase_b200 import scenes
+    for scene in (scenes.tess_scene(nx=23, ny=17, width=32, height=32, bounces=0), scenes.duplicate_key_scene(700)):
+        o = oracle.OracleScene(scene)
+        info, nodes, tris, keys, prims = o.blas_export(0)
+        o.close()
+        reach, stack = set(), [int(info.root_ref)]
+        while stack:
+            s = stack.pop()
+            reach.add(s)
+            for ref_ in (int(np.int32(nodes[s][6])), int(np.int32(nodes[s][14]))):
+                if 0 <= ref_ < 0x7FFFFFF0:
+                    stack.append(ref_)
+        rule = {i for i in range(info.triangle_count - 1) if live_rule(keys, i, 2)}
+        assert rule == reach and 0.3 * info.triangle_count < len(rule) < 0.8 * info.triangle_count
