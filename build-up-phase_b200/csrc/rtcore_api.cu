@@ -114,6 +114,8 @@ void rt_destroy(rt_context* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);      // a host frame enqueued with RT_TRACE_ASYNC may still be copying
+    if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
     if (ctx->own_hit_records) { cudaFree(ctx->d_hit_records); cudaFree(ctx->d_anyhit); }
     cudaFree(ctx->scratch); cudaFree(ctx->fb); cudaFree(ctx->hits1); cudaFree(ctx->hits2);
     cudaFree(ctx->d_stats); cudaFree(ctx->d_error); cudaFree(ctx->queue); cudaFree(ctx->qflags); cudaFree(ctx->d_counters);
@@ -396,7 +398,8 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
     if (!refit) { ctx->dbg_keys = in_b ? a.s.keys_b : a.s.keys_a; ctx->dbg_vals = in_b ? a.s.vals_b : a.s.vals_a; ctx->dbg_n = N; ctx->dbg_vb = sp.packed_val_bits; }
     // ALLOW_UPDATE / ALLOW_COMPACTION: the BLAS keeps the sorted records of this (full) build: they are its topology
     if (!refit) {
-        const uint32_t keep = build_flags & (RT_BUILD_ALLOW_UPDATE | RT_BUILD_ALLOW_COMPACTION);
+        // (a refit needs a BLAS that was built on its own; a compaction also works on a whole batch)
+        const uint32_t keep = (build_flags & RT_BUILD_ALLOW_COMPACTION) | (n_blas == 1 ? (build_flags & RT_BUILD_ALLOW_UPDATE) : 0u);
         if (!keep || N == 0) { cudaFree(st->keys); cudaFree(st->vals); st->keys = nullptr; st->vals = nullptr; }
         else {
             if (!st->keys) { cudaError_t ce = cudaMalloc((void**)&st->keys, 8ull * N); if (ce != cudaSuccess) return fail(ctx, RT_ERROR_OUT_OF_MEMORY, "cudaMalloc for the retained sort records failed"); }
