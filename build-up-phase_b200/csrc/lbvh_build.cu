@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
 struct Box3 { float lo[3], hi[3]; };
 
 #ifndef RT_TREE_TILE
-#define RT_TREE_TILE 128
+#define RT_TREE_TILE 256
 #endif
 #ifndef RT_TREE_MIN_CTAS
 #define RT_TREE_MIN_CTAS (1536 / RT_TREE_TILE)
@@ -273,9 +273,6 @@ __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;" 
 __device__ __forceinline__ int delta_adjacent(uint64_t ka, uint64_t kb, uint32_t i) {
     return ka == kb ? 64 + __clz((int)(i ^ (i + 1u))) : __clzll((long long)(ka ^ kb));
 }
-__device__ __forceinline__ int delta_global(const uint64_t* __restrict__ keys, int vb, uint32_t i) {
-    return delta_adjacent(__ldg(keys + i) >> vb, __ldg(keys + i + 1) >> vb, i);
-}
 
 struct TreeJob {
     uint32_t l, r;              // sorted-leaf range of the finished subtree
@@ -283,6 +280,7 @@ struct TreeJob {
     int32_t ref;                // how the parent refers to this subtree (relative to the segment)
     uint32_t height;
     uint32_t seg_first, seg_count;
+    int dl, dr;                 // delta(l - 1), delta(r): only maintained on the border path (in a tile they are read from shared memory)
 };
 
 // Segment policies: seg_of(key) gives first/count of the segment (one BLAS of a batch, or the whole TLAS) a key belongs
@@ -311,7 +309,7 @@ struct InstSegment {
 };
 
 template <int LEAF_MAX, class Seg>
-__device__ __forceinline__ void climb_global(TreeJob j, const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+__device__ __forceinline__ void climb_global(TreeJob j, BvhNode* __restrict__ nodes,
                                              float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg);
 // RT_TREE_INLINE_BORDER=1: the threads that hold a tile's unfinished subtrees / orphans continue through global memory themselves, right
 // after the tile quiesces, instead of handing them to a second kernel through the job queue (no k_tree_border launch).
@@ -323,7 +321,30 @@ struct BorderMem { float4* xchg; uint32_t* far_end; uint32_t* arrived; };
 // Phase 1 (inside the leaf kernels): everything a tile can finish on its own. Unfinished subtrees (at most 2 per tile:
 // the ones whose next split lies outside it) and orphans (a child deposited in shared memory whose sibling straddles
 // the tile border: at most one per straddling ancestor of the two border leaves) are appended to the border-job queue
-// as 48-B records {lo.xyz hi.x | hi.yz ref height | l r - -}; one global atomic per CTA.
+// as 48-B records {lo.xyz hi.x | hi.yz ref height+deltas | l r seg_first seg_count}; one global atomic per CTA. A job carries its
+// segment and the deltas at both ends of its range, so the border kernel never loads a key or a segment record.
+//
+// RT_TREE_REGROUP = R > 0: a thread climbs for at most R merges, then the CTA meets once and the subtrees that are still
+// climbing are handed to the first threads of the CTA, which finish the tile. Every merge adds at least one leaf, so a survivor
+// holds > R leaves and at most TILE / (R + 1) of them exist (three warps of eight for R = 2 and 256-leaf tiles): the long tail of the
+// climb, where 1-3 lanes of EVERY warp keep their warp issuing, runs in the first warps only. Same deposits, same flags, same
+// node records - only who carries a subtree changes.
+#ifndef RT_TREE_REGROUP
+#define RT_TREE_REGROUP 2
+#endif
+constexpr uint32_t TREE_REGROUP_CAP = RT_TREE_REGROUP > 0 ? (uint32_t)TREE_TILE / (RT_TREE_REGROUP + 1) : 1u;
+// height (8 bits) | delta(l - 1) + 1 (8 bits) | delta(r) + 1 (8 bits): the fourth word of a border job's / a global deposit's second half
+__device__ __forceinline__ uint32_t pack_hd(uint32_t height, int dl, int dr) { return height | ((uint32_t)(dl + 1) << 8) | ((uint32_t)(dr + 1) << 16); }
+__device__ __forceinline__ void unpack_hd(uint32_t w, uint32_t& height, int& dl, int& dr) { height = w & 255u; dl = (int)((w >> 8) & 255u) - 1; dr = (int)((w >> 16) & 255u) - 1; }
+__device__ __forceinline__ TreeJob unpack_job(const float4 q0, const float4 q1, const float4 q2) {
+    TreeJob j;
+    j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
+    j.ref = __float_as_int(q1.z);
+    unpack_hd(__float_as_uint(q1.w), j.height, j.dl, j.dr);
+    j.l = __float_as_uint(q2.x); j.r = __float_as_uint(q2.y); j.seg_first = __float_as_uint(q2.z); j.seg_count = __float_as_uint(q2.w);
+    return j;
+}
+
 template <int LEAF_MAX, class Seg>
 __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
                                                 float4* __restrict__ jobs, uint32_t* __restrict__ job_count,
@@ -331,35 +352,40 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
     __shared__ int s_delta[TREE_TILE + 1];          // s_delta[k] = delta(L0 - 1 + k)
     __shared__ uint32_t s_flag[TREE_TILE];          // bit side: that child of split L0 + k has been deposited
     __shared__ float4 s_a[2 * TREE_TILE], s_b[2 * TREE_TILE];
-    __shared__ uint32_t s_njobs, s_base;
+    __shared__ float4 s_carry[2 * 3];               // the (at most two) subtrees whose next split lies outside the tile, as job records
+    __shared__ float4 s_re[TREE_REGROUP_CAP * 3];   // subtrees handed over at the regroup point
+    __shared__ uint32_t s_ncarry, s_norph, s_nre, s_base;
     const uint32_t tid = threadIdx.x, L0 = blockIdx.x * (uint32_t)TREE_TILE, leaf = L0 + tid;
     const uint64_t k0 = leaf < n ? __ldg(keys + leaf) >> vb : 0ull;
     s_delta[tid + 1] = leaf + 1u < n ? delta_adjacent(k0, __ldg(keys + leaf + 1) >> vb, leaf) : -1;
-    if (tid == 0) { s_delta[0] = L0 > 0u ? delta_adjacent(__ldg(keys + L0 - 1) >> vb, k0, L0 - 1u) : -1; s_njobs = 0u; }
+    if (tid == 0) { s_delta[0] = L0 > 0u ? delta_adjacent(__ldg(keys + L0 - 1) >> vb, k0, L0 - 1u) : -1; s_ncarry = 0u; s_norph = 0u; s_nre = 0u; }
     s_flag[tid] = 0u;
     __syncthreads();
 
     // In the tile the subtree is {lt, rt} (tile-local ends), box, ref, height; a deposit is two float4:
     // {lo.xyz hi.x} {hi.y hi.z ref height | far_end_local << 8}.
-    TreeJob j;
-    bool carried = false;
-    if (leaf < n) {
-        j.b = leaf_box; j.height = 0;
-        seg.seg_of(k0, j.seg_first, j.seg_count);
-        j.ref = leaf_ref(leaf - j.seg_first, 1);
+    TreeJob j = {};
+    uint32_t lt = tid, rt = tid;
+    // climbs until the subtree is a root, leaves the tile, is the first to arrive at its split (all: false) or has merged max_merges times (true)
+    auto climb = [&](int max_merges) -> bool {
         const uint32_t rel = L0 - j.seg_first;                               // tile-local -> segment-relative (mod 2^32)
-        uint32_t lt = tid, rt = tid;
-        for (;;) {
-            if (rt - lt + 1u == j.seg_count) { j.l = L0 + lt; j.r = L0 + rt; seg.on_root(j); break; }
+        for (int merges = 0;;) {
+            if (rt - lt + 1u == j.seg_count) { j.l = L0 + lt; j.r = L0 + rt; seg.on_root(j); return false; }
             const bool right = s_delta[rt + 1u] > s_delta[lt];
             const uint32_t slot = right ? rt : lt - 1u;                      // split g = L0 + slot; lt - 1 wraps to 2^32-1 at the tile's left end
-            if (slot >= (uint32_t)TREE_TILE - 1u) { carried = true; j.l = L0 + lt; j.r = L0 + rt; break; }
+            if (slot >= (uint32_t)TREE_TILE - 1u) {                          // next split outside the tile -> border job
+                float4* q = s_carry + 3 * atomicAdd(&s_ncarry, 1u);
+                q[0] = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
+                q[1] = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(pack_hd(j.height, s_delta[lt], s_delta[rt + 1u])));
+                q[2] = make_float4(__uint_as_float(L0 + lt), __uint_as_float(L0 + rt), __uint_as_float(j.seg_first), __uint_as_float(j.seg_count));
+                return false;
+            }
             const uint32_t side = right ? 0u : 1u;
             const float4 m0 = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
             const float4 m1 = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height | ((right ? lt : rt) << 8)));
             s_a[2 * slot + side] = m0; s_b[2 * slot + side] = m1;
             fence_cta();
-            if (atomicOr(&s_flag[slot], 1u << side) == 0u) break;          // first arrival: the sibling finishes this node
+            if (atomicOr(&s_flag[slot], 1u << side) == 0u) return false;     // first arrival: the sibling finishes this node
             fence_cta();
             const float4 s0 = s_a[2 * slot + (side ^ 1u)], s1 = s_b[2 * slot + (side ^ 1u)];
             const uint32_t sw = __float_as_uint(s1.w);
@@ -376,48 +402,79 @@ __device__ __forceinline__ void build_tree_tile(const uint64_t* __restrict__ key
                 dst[2 * side] = m0; dst[2 * side + 1] = make_float4(m1.x, m1.y, m1.z, __uint_as_float(__float_as_uint(m1.w) & 255u));
                 dst[2 * (side ^ 1u)] = s0; dst[2 * (side ^ 1u) + 1] = make_float4(s1.x, s1.y, s1.z, __uint_as_float(sw & 255u));
             }
+            if (max_merges > 0 && ++merges == max_merges) return true;
         }
+    };
+    bool climbing = false;
+    if (leaf < n) {
+        j.b = leaf_box; j.height = 0;
+        seg.seg_of(k0, j.seg_first, j.seg_count);
+        j.ref = leaf_ref(leaf - j.seg_first, 1);
+        climbing = climb(RT_TREE_REGROUP);
     }
+#if RT_TREE_REGROUP > 0
+    if (climbing) {                                                           // hand the subtree over
+        float4* q = s_re + 3 * atomicAdd(&s_nre, 1u);
+        q[0] = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
+        q[1] = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height | (lt << 8) | (rt << 17)));
+        q[2] = make_float4(__uint_as_float(j.seg_first), __uint_as_float(j.seg_count), 0.0f, 0.0f);
+    }
+    __syncthreads();
+    if (tid < s_nre) {
+        const float4 q0 = s_re[3 * tid], q1 = s_re[3 * tid + 1], q2 = s_re[3 * tid + 2];
+        j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
+        j.ref = __float_as_int(q1.z);
+        const uint32_t w = __float_as_uint(q1.w);
+        j.height = w & 255u; lt = (w >> 8) & 511u; rt = w >> 17;
+        j.seg_first = __float_as_uint(q2.x); j.seg_count = __float_as_uint(q2.y);
+        climb(0);
+    }
+#else
+    (void)climbing;
+#endif
     __syncthreads();
     const uint32_t f = s_flag[tid];
     const bool orphan = f == 1u || f == 2u;
 #if RT_TREE_INLINE_BORDER
     (void)jobs; (void)job_count;
-    if (carried) climb_global<LEAF_MAX>(j, keys, vb, n, nodes, bm.xchg, bm.far_end, bm.arrived, seg);
+    if (tid < s_ncarry) climb_global<LEAF_MAX>(unpack_job(s_carry[3 * tid], s_carry[3 * tid + 1], s_carry[3 * tid + 2]), nodes, bm.xchg, bm.far_end, bm.arrived, seg);
     if (orphan) {
         const uint32_t side = f - 1u, g = L0 + tid;
         const float4 m0 = s_a[2 * tid + side], m1 = s_b[2 * tid + side];
-        const uint32_t far = L0 + (__float_as_uint(m1.w) >> 8);
+        const uint32_t farl = __float_as_uint(m1.w) >> 8;
         TreeJob o;
         o.b.lo[0] = m0.x; o.b.lo[1] = m0.y; o.b.lo[2] = m0.z; o.b.hi[0] = m0.w; o.b.hi[1] = m1.x; o.b.hi[2] = m1.y;
         o.ref = __float_as_int(m1.z); o.height = __float_as_uint(m1.w) & 255u;
-        if (side == 0u) { o.l = far; o.r = g; } else { o.l = g + 1u; o.r = far; }
-        seg.seg_of(__ldg(keys + o.l) >> vb, o.seg_first, o.seg_count);
-        climb_global<LEAF_MAX>(o, keys, vb, n, nodes, bm.xchg, bm.far_end, bm.arrived, seg);
+        if (side == 0u) { o.l = L0 + farl; o.r = g; o.dl = s_delta[farl]; o.dr = s_delta[tid + 1u]; }
+        else { o.l = g + 1u; o.r = L0 + farl; o.dl = s_delta[tid + 1u]; o.dr = s_delta[farl + 1u]; }
+        seg.seg_of(k0, o.seg_first, o.seg_count);
+        climb_global<LEAF_MAX>(o, nodes, bm.xchg, bm.far_end, bm.arrived, seg);
     }
     return;
 #endif
     (void)bm;
-    const uint32_t ia = carried ? atomicAdd(&s_njobs, 1u) : 0u;
-    const uint32_t ib = orphan ? atomicAdd(&s_njobs, 1u) : 0u;
+    const uint32_t ib = orphan ? atomicAdd(&s_norph, 1u) : 0u;
     __syncthreads();
-    if (tid == 0 && s_njobs) s_base = atomicAdd(job_count, s_njobs);
+    const uint32_t ncarry = s_ncarry;
+    if (tid == 0 && ncarry + s_norph) s_base = atomicAdd(job_count, ncarry + s_norph);
     __syncthreads();
-    if (carried) {
-        float4* q = jobs + 3 * (size_t)(s_base + ia);
-        q[0] = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
-        q[1] = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
-        q[2] = make_float4(__uint_as_float(j.l), __uint_as_float(j.r), 0.0f, 0.0f);
+    if (tid < ncarry) {
+        float4* q = jobs + 3 * (size_t)(s_base + tid);
+        q[0] = s_carry[3 * tid]; q[1] = s_carry[3 * tid + 1]; q[2] = s_carry[3 * tid + 2];
     }
     if (orphan) {
+        // an orphan deposited at split g = L0 + tid covers [far, g] (left child, merges to the right) or [g + 1, far] (right child); both lie
+        // in the segment of leaf g: a right child that reaches back to a segment's first leaf would be that segment's root, not an orphan
         const uint32_t side = f - 1u, g = L0 + tid;
-        float4* q = jobs + 3 * (size_t)(s_base + ib);
+        float4* q = jobs + 3 * (size_t)(s_base + ncarry + ib);
         float4 m1 = s_b[2 * tid + side];
-        const uint32_t far = L0 + (__float_as_uint(m1.w) >> 8);
-        m1.w = __uint_as_float(__float_as_uint(m1.w) & 255u);
+        const uint32_t farl = __float_as_uint(m1.w) >> 8, far = L0 + farl, h = __float_as_uint(m1.w) & 255u;
+        m1.w = __uint_as_float(side == 0u ? pack_hd(h, s_delta[farl], s_delta[tid + 1u]) : pack_hd(h, s_delta[tid + 1u], s_delta[farl + 1u]));
+        uint32_t sf, sc;
+        seg.seg_of(k0, sf, sc);
         q[0] = s_a[2 * tid + side]; q[1] = m1;
-        q[2] = side == 0u ? make_float4(__uint_as_float(far), __uint_as_float(g), 0.0f, 0.0f)
-                          : make_float4(__uint_as_float(g + 1u), __uint_as_float(far), 0.0f, 0.0f);
+        q[2] = side == 0u ? make_float4(__uint_as_float(far), __uint_as_float(g), __uint_as_float(sf), __uint_as_float(sc))
+                          : make_float4(__uint_as_float(g + 1u), __uint_as_float(far), __uint_as_float(sf), __uint_as_float(sc));
     }
 }
 // capacity of the border-job queue: 2 unfinished subtrees + one orphan per straddling ancestor (tree height <= 64 key
@@ -430,78 +487,127 @@ inline uint64_t tree_job_capacity_host(uint32_t n) {
     return cap < 2ull * n + 2 ? cap : 2ull * n + 2;
 }
 
-// Phase 2: a border job climbs through global memory: deposit {half, far end} at the split, fence, arrival counter; the second arriver
-// unions and writes the finished node into its Karras slot. Nobody ever waits: the first arrival at a split retires.
-template <int LEAF_MAX, class Seg>
-__device__ __forceinline__ void climb_global(TreeJob j, const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
-                                             float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg) {
-    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); return; }
-    auto merges_right = [&](uint32_t l, uint32_t r) {
-        const int dl = l > 0u ? delta_global(keys, vb, l - 1u) : -1;
-        const int dr = r + 1u < n ? delta_global(keys, vb, r) : -1;
-        return dr > dl;
-    };
-    bool right = merges_right(j.l, j.r);
-    for (;;) {
-        const uint32_t g = right ? j.r : j.l - 1u, side = right ? 0u : 1u;
-        const float4 m0 = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
-        const float4 m1 = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
-        float4* dep = xchg + 4 * (size_t)g;
-        dep[2 * side] = m0; dep[2 * side + 1] = m1;
-        far_end[2 * (size_t)g + side] = right ? j.l : j.r;
-        fence_gpu();
-        if (atomicAdd(arrived + g, 1u) == 0u) break;
-        fence_gpu();
-        const float4 s0 = __ldcg(dep + 2 * (side ^ 1u)), s1 = __ldcg(dep + 2 * (side ^ 1u) + 1);
-        const uint32_t sfar = __ldcg(far_end + 2 * (size_t)g + (side ^ 1u));
-        if (right) j.r = sfar; else j.l = sfar;
-        j.b.lo[0] = fminf(j.b.lo[0], s0.x); j.b.lo[1] = fminf(j.b.lo[1], s0.y); j.b.lo[2] = fminf(j.b.lo[2], s0.z);
-        j.b.hi[0] = fmaxf(j.b.hi[0], s0.w); j.b.hi[1] = fmaxf(j.b.hi[1], s1.x); j.b.hi[2] = fmaxf(j.b.hi[2], s1.y);
-        const uint32_t count = j.r - j.l + 1u;
-        const bool root = count == j.seg_count;
-        if (!root) right = merges_right(j.l, j.r);
-        if (count <= (uint32_t)LEAF_MAX) { j.ref = leaf_ref(j.l - j.seg_first, count); j.height = 0; }
-        else {
-            const uint32_t ns = (!root && right) ? j.r : j.l;
-            j.ref = (int32_t)(ns - j.seg_first); j.height = max(j.height, __float_as_uint(s1.w)) + 1u;
-            float4* dst = reinterpret_cast<float4*>(nodes + ns);
-            dst[2 * side] = m0; dst[2 * side + 1] = m1; dst[2 * (side ^ 1u)] = s0; dst[2 * (side ^ 1u) + 1] = s1;
-        }
-        if (root) { seg.on_root(j); break; }
-    }
+// Phase 2: a border job climbs through global memory. Arrival at a split is ONE acquire-add on the split's counter:
+//   0 -> this is the first child: it deposits {half, far end}, release-adds 1 more (counter 2 = "deposit complete") and retires;
+//   2 -> the sibling's deposit is complete (and visible: the acquire-add read the value of its release-add): union, write the finished node
+//        into its Karras slot, go on one level;
+//   1 -> the sibling has announced itself but its deposit is still in flight: the job keeps its place and looks again (acquire load) on the
+//        next turn of its lane's loop. The sibling never waits for anybody, so this resolves after one store latency.
+// The second child - the one that carries the chain on - pays one atomic and one load round trip per level and no fence; the release fence
+// is paid by the child that retires. (The deposit-first protocol, stores -> fence -> add -> fence -> loads on every arrival, spent 54 % of
+// this kernel's stall samples in its two fences: profiles/README.md r2_y.)
+// A subtree carries delta(l - 1) and delta(r) (8 bits each, +1 so that -1 fits, next to the height in the deposit): the union of two
+// siblings inherits the outer delta of each, so the direction of the next merge needs no key loads (14 % of the stall samples and another
+// dependent L2 round trip per level).
+__device__ __forceinline__ uint32_t atom_add_acquire(uint32_t* p, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.acquire.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_add_release(uint32_t* p, uint32_t v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
 }
 
+// one turn of a job: an arrival (waiting == false) or another look at a sibling whose deposit was in flight (waiting == true);
+// false when the job retires (first arrival at its split, or it completed its segment's root)
 template <int LEAF_MAX, class Seg>
-__global__ void __launch_bounds__(128) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
+__device__ __forceinline__ bool climb_level(TreeJob& j, bool& waiting, BvhNode* __restrict__ nodes,
+                                            float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg) {
+    const bool right = j.dr > j.dl;
+    const uint32_t g = right ? j.r : j.l - 1u, side = right ? 0u : 1u;
+    const float4 m0 = make_float4(j.b.lo[0], j.b.lo[1], j.b.lo[2], j.b.hi[0]);
+    float4* dep = xchg + 4 * (size_t)g;
+    if (!waiting) {
+        const uint32_t seen = atom_add_acquire(arrived + g, 1u);
+        if (seen == 0u) {
+            dep[2 * side] = m0;
+            dep[2 * side + 1] = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(pack_hd(j.height, j.dl, j.dr)));
+            far_end[2 * (size_t)g + side] = right ? j.l : j.r;
+            red_add_release(arrived + g, 1u);
+            return false;
+        }
+        if (seen == 1u) { waiting = true; return true; }
+    } else {
+        if (ld_acquire(arrived + g) != 3u) return true;
+        waiting = false;
+    }
+    const float4 s0 = __ldcg(dep + 2 * (side ^ 1u));
+    float4 s1 = __ldcg(dep + 2 * (side ^ 1u) + 1);
+    const uint32_t sfar = __ldcg(far_end + 2 * (size_t)g + (side ^ 1u));
+    uint32_t sh; int sdl, sdr;
+    unpack_hd(__float_as_uint(s1.w), sh, sdl, sdr);
+    s1.w = __uint_as_float(sh);
+    const float4 m1n = make_float4(j.b.hi[1], j.b.hi[2], __int_as_float(j.ref), __uint_as_float(j.height));
+    if (right) { j.r = sfar; j.dr = sdr; } else { j.l = sfar; j.dl = sdl; }
+    j.b.lo[0] = fminf(j.b.lo[0], s0.x); j.b.lo[1] = fminf(j.b.lo[1], s0.y); j.b.lo[2] = fminf(j.b.lo[2], s0.z);
+    j.b.hi[0] = fmaxf(j.b.hi[0], s0.w); j.b.hi[1] = fmaxf(j.b.hi[1], s1.x); j.b.hi[2] = fmaxf(j.b.hi[2], s1.y);
+    const uint32_t count = j.r - j.l + 1u;
+    const bool root = count == j.seg_count;
+    if (count <= (uint32_t)LEAF_MAX) { j.ref = leaf_ref(j.l - j.seg_first, count); j.height = 0; }
+    else {
+        const uint32_t ns = (!root && j.dr > j.dl) ? j.r : j.l;
+        j.ref = (int32_t)(ns - j.seg_first); j.height = max(j.height, sh) + 1u;
+        float4* dst = reinterpret_cast<float4*>(nodes + ns);
+        dst[2 * side] = m0; dst[2 * side + 1] = m1n; dst[2 * (side ^ 1u)] = s0; dst[2 * (side ^ 1u) + 1] = s1;
+    }
+    if (root) { seg.on_root(j); return false; }
+    return true;
+}
+template <int LEAF_MAX, class Seg>
+__device__ __forceinline__ void climb_global(TreeJob j, BvhNode* __restrict__ nodes,
+                                             float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg& seg) {
+    if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); return; }
+    bool waiting = false;
+    while (climb_level<LEAF_MAX>(j, waiting, nodes, xchg, far_end, arrived, seg)) {}
+}
+
+// Every lane walks its own strided share of the job queue and fetches its next job the moment the current one retires: most jobs retire at
+// their first deposit and a few climb many levels, so one job per thread left a warp running with 4.8 of 32 lanes for as long as its longest climb
+// (profiles/README.md r2_y). The grid is what the device holds at once (RT_BORDER_CTAS_PER_SM), not the length of the queue.
+#ifndef RT_BORDER_CTAS_PER_SM
+#define RT_BORDER_CTAS_PER_SM 12
+#endif
+template <int LEAF_MAX, class Seg>
+__global__ void __launch_bounds__(128, RT_BORDER_CTAS_PER_SM) k_tree_border(const uint64_t* __restrict__ keys, int vb, uint32_t n, BvhNode* __restrict__ nodes,
                                                     const float4* __restrict__ jobs, const uint32_t* __restrict__ job_count,
                                                     float4* __restrict__ xchg, uint32_t* __restrict__ far_end, uint32_t* __restrict__ arrived, const Seg seg) {
-    // grid-stride over the jobs: the queue's CAPACITY is ~130 entries per tile, its length a few per tile, so the grid is sized by the
-    // expected length (border_grid) and not by the capacity
-    const uint32_t n_jobs = *job_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_jobs; i += gridDim.x * blockDim.x) {
-        const float4 q0 = __ldg(jobs + 3 * (size_t)i), q1 = __ldg(jobs + 3 * (size_t)i + 1), q2 = __ldg(jobs + 3 * (size_t)i + 2);
-        TreeJob j;
-        j.b.lo[0] = q0.x; j.b.lo[1] = q0.y; j.b.lo[2] = q0.z; j.b.hi[0] = q0.w; j.b.hi[1] = q1.x; j.b.hi[2] = q1.y;
-        j.ref = __float_as_int(q1.z); j.height = __float_as_uint(q1.w);
-        j.l = __float_as_uint(q2.x); j.r = __float_as_uint(q2.y);
-        seg.seg_of(__ldg(keys + j.l) >> vb, j.seg_first, j.seg_count);
-        climb_global<LEAF_MAX>(j, keys, vb, n, nodes, xchg, far_end, arrived, seg);
+    (void)keys; (void)vb; (void)n;
+    const uint32_t n_jobs = *job_count, stride = gridDim.x * blockDim.x;
+    uint32_t next = blockIdx.x * blockDim.x + threadIdx.x;
+    TreeJob j = {};
+    bool have = false, waiting = false;
+    for (;;) {
+        if (!have) {
+            if (next >= n_jobs) break;
+            j = unpack_job(__ldg(jobs + 3 * (size_t)next), __ldg(jobs + 3 * (size_t)next + 1), __ldg(jobs + 3 * (size_t)next + 2));
+            next += stride;
+            if (j.r - j.l + 1u == j.seg_count) { seg.on_root(j); continue; }
+        }
+        have = climb_level<LEAF_MAX>(j, waiting, nodes, xchg, far_end, arrived, seg);
     }
 }
-// grid of the border kernel: one thread per job the build is expected to have (RT_BORDER_JOBS_PER_TILE per tile: 2 unfinished subtrees
-// + one orphan per straddling ancestor of the two border leaves), never more than the queue's capacity; the grid-stride loop covers the rest
-#ifndef RT_BORDER_JOBS_PER_TILE
-#define RT_BORDER_JOBS_PER_TILE 16
-#endif
+// grid of the border kernel: the CTAs the device holds at once (the lanes loop over the queue), never more than one thread per possible job
 inline uint32_t border_grid(uint32_t n) {
-    static int per_tile = 0;
-    if (per_tile == 0) {
-        per_tile = RT_BORDER_JOBS_PER_TILE;
-        if (const char* v = getenv("RTCORE_BORDER_JOBS_PER_TILE")) { const int k = atoi(v); if (k >= 1 && k <= 256) per_tile = k; }
+    static int per_sm = 0, sms[64] = {};
+    if (per_sm == 0) {
+        per_sm = RT_BORDER_CTAS_PER_SM;
+        if (const char* v = getenv("RTCORE_BORDER_CTAS_PER_SM")) { const int k = atoi(v); if (k >= 1 && k <= 64) per_sm = k; }
+    }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int sm = 148;
+    if (dev >= 0 && dev < 64) {
+        if (sms[dev] == 0 && cudaDeviceGetAttribute(&sms[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms[dev] = 148;
+        sm = sms[dev];
     }
     const uint64_t by_jobs = (tree_job_capacity_host(n) + 127) / 128;
-    const uint64_t by_tiles = (((uint64_t)n + TREE_TILE - 1) / TREE_TILE * (uint64_t)per_tile + 127) / 128 + 1u;
-    const uint64_t g = by_jobs < by_tiles ? by_jobs : by_tiles;
+    const uint64_t resident = (uint64_t)sm * (uint64_t)per_sm;
+    const uint64_t g = by_jobs < resident ? by_jobs : resident;
     return g ? (uint32_t)g : 1u;
 }
 

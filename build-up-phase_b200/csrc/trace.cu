@@ -132,6 +132,27 @@ constexpr uint32_t TPR = REGION_TW * REGION_TH, RPR = TPR * 32u;    // tiles / r
 // Node-half fetch. RT_LDG256=1 uses the sm_100a 256-bit load (LDG.E.ENL2.256): measured SLOWER than two LDG.128
 // on this kernel (2652 vs 2978 Mrays/s, profiles/README.md r01g), so the default is 2 x LDG.128.
 struct F8 { float4 a, b; };
+// experiments (profiles/README.md r2_x): RT_TRI_NOALLOC = 1 fetches triangle records with L1::no_allocate (a 48-byte record is used once per ray;
+// keeping it out of L1 leaves the lines to the nodes), = 2 with L1::evict_first; RT_L1_CARVEOUT >= 0 pins the shared-memory carve-out
+#ifndef RT_TRI_NOALLOC
+#define RT_TRI_NOALLOC 0
+#endif
+#ifndef RT_L1_CARVEOUT
+#define RT_L1_CARVEOUT -1
+#endif
+__device__ __forceinline__ float4 ldg_tri(const float4* p) {
+#if RT_TRI_NOALLOC == 1
+    float4 r;
+    asm("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#elif RT_TRI_NOALLOC == 2
+    float4 r;
+    asm("ld.global.nc.L1::evict_first.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+#else
+    return __ldg(p);
+#endif
+}
 // GENERIC: the node may live in shared memory (the staged TLAS) or in global memory (a BLAS): generic-address loads (LD.E.128), no branch
 template <bool GENERIC>
 __device__ __forceinline__ F8 ldg256(const void* p) {
@@ -786,7 +807,7 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                     bool terminated = false;
                     for (uint32_t k = 0; k < count; ++k) {
                         const float4* t4 = reinterpret_cast<const float4*>(tris + first + k);
-                        const float4 q0 = __ldg(t4), q1 = __ldg(t4 + 1), q2 = __ldg(t4 + 2);
+                        const float4 q0 = ldg_tri(t4), q1 = ldg_tri(t4 + 1), q2 = ldg_tri(t4 + 2);
                         if (STATS) ++c.tris;
                         float t, bu, bv, bw0;
                         bool anyhit_terminates = false;
@@ -1007,6 +1028,10 @@ int launch_stage_v(const TraceParams& p, int sm_count, cudaStream_t st) {
     if (blocks_per_sm == 0) {
         if (BIG && cudaFuncSetAttribute(k_trace<STAGE, STATS, STACK, GENERAL, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(SMEM_TLAS_HEADER + (size_t)RT_SMEM_TLAS_MAX_NODES * sizeof(BvhNode))) != cudaSuccess) return -1;
+#if RT_L1_CARVEOUT >= 0
+        // experiment: ask for a fixed shared-memory carve-out (per cent of the L1/shared array); the kernel itself uses no shared memory
+        if (!BIG) cudaFuncSetAttribute(k_trace<STAGE, STATS, STACK, GENERAL, BIG>, cudaFuncAttributePreferredSharedMemoryCarveout, RT_L1_CARVEOUT);
+#endif
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_trace<STAGE, STATS, STACK, GENERAL, BIG>, THREADS, smem) != cudaSuccess || blocks_per_sm < 1)
             blocks_per_sm = 1;
         if (dev >= 0 && dev < 64) per_device[dev] = blocks_per_sm;

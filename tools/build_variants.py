@@ -34,6 +34,11 @@ VARIANTS = {
     "ballot": ["RT_SORT_USE_BALLOT=1"],
     "lb1": ["RT_LOOKBACK_WINDOW=1"], "lb16": ["RT_LOOKBACK_WINDOW=16"],
     "setup2": ["RT_SETUP_BATCH=2"], "setup4": ["RT_SETUP_BATCH=4"],
+    # r2_x: regrouped tile climb (RT_TREE_REGROUP merges per thread, then the survivors finish in the first warp(s)); trace cache hints
+    "rg0": ["RT_TREE_REGROUP=0"], "rg1": ["RT_TREE_REGROUP=1"], "rg2": ["RT_TREE_REGROUP=2"], "rg4": ["RT_TREE_REGROUP=4"], "rg6": ["RT_TREE_REGROUP=6"],
+    "tile256_rg3": ["RT_TREE_TILE=256"], "tile256_rg5": ["RT_TREE_TILE=256", "RT_TREE_REGROUP=5"], "tile512_rg3": ["RT_TREE_TILE=512"],
+    "tile64_rg3": ["RT_TREE_TILE=64"],
+    "tri_noalloc": ["RT_TRI_NOALLOC=1"], "tri_evict_first": ["RT_TRI_NOALLOC=2"], "carve0": ["RT_L1_CARVEOUT=0"], "carve0_tri_noalloc": ["RT_L1_CARVEOUT=0", "RT_TRI_NOALLOC=1"],
 }
 if __name__ == "__main__":
     names = sys.argv[1:] or ["base"]
