@@ -51,12 +51,16 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t* p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// Peer mask of the lanes holding the same 8-bit digit: MATCH.ANY, or (RT_SORT_USE_BALLOT) 8 ballots. Measured on B200
-// (profiles/README.md, r01l): the ballot form is not faster, MATCH.ANY is not what bounds the pass.
-__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid) {
-#if !defined(RT_SORT_USE_BALLOT)
-    return __match_any_sync(0xffffffffu, valid ? (d & 255u) : 0xFFFFFFFFu);
-#else
+// Peer mask of the lanes holding the same 8-bit digit: MATCH.ANY, or 8 ballots. MATCH.ANY costs more the more DISTINCT digits the 32 lanes
+// hold (measured on B200, profiles/README.md r01l / r2_zd: on a surface mesh in grid order, few distinct digits per warp, it beats the ballots,
+// 0.57 vs 0.63 ms for the five passes of inst10m; on the uniformly random keys of the triangle soup, ~30 distinct digits per warp, it loses,
+// 0.85 vs 0.74 ms), the ballots cost the same whatever the data. Every warp therefore ranks its FIRST item with ballots, counts the distinct
+// digits it saw and picks the form for its other items (warp-uniform branch). RT_SORT_USE_BALLOT forces the ballots, RT_SORT_BALLOT_DISTINCT=33
+// forces MATCH.ANY.
+#ifndef RT_SORT_BALLOT_DISTINCT
+#define RT_SORT_BALLOT_DISTINCT 24
+#endif
+__device__ __forceinline__ uint32_t match_digit_ballot(uint32_t d, bool valid) {
     uint32_t m = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
     for (int b = 0; b < 8; ++b) {
@@ -65,6 +69,14 @@ __device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid) {
         m &= bit ? v : ~v;
     }
     return m;
+}
+__device__ __forceinline__ uint32_t match_digit(uint32_t d, bool valid, bool use_ballot) {
+#if defined(RT_SORT_USE_BALLOT)
+    (void)use_ballot;
+    return match_digit_ballot(d, valid);
+#else
+    if (use_ballot) return match_digit_ballot(d, valid);
+    return __match_any_sync(0xffffffffu, valid ? (d & 255u) : 0xFFFFFFFFu);
 #endif
 }
 
@@ -136,6 +148,7 @@ __global__ void __launch_bounds__(SORT_THREADS, RT_SORT_MIN_CTAS) k_onesweep_pas
     // item i + 1 and the ranking is stable —, (3) broadcast of the old counter value to the peers.
     constexpr int RANK_BATCH = SORT_ITEMS % 6 == 0 ? 6 : 4;     // items in flight per sweep (bounds the live registers)
     static_assert(SORT_ITEMS % RANK_BATCH == 0, "SORT_ITEMS");
+    bool use_ballot = true;                                     // item 0: ballots; they also tell how many distinct digits the warp holds
 #pragma unroll
     for (int i0 = 0; i0 < SORT_ITEMS; i0 += RANK_BATCH) {
         uint32_t prev[RANK_BATCH];
@@ -143,7 +156,11 @@ __global__ void __launch_bounds__(SORT_THREADS, RT_SORT_MIN_CTAS) k_onesweep_pas
         for (int k = 0; k < RANK_BATCH; ++k) {
             const int i = i0 + k;
             const bool valid = (wbase + i * 32) < tile_n;
-            rank[i] = match_digit((uint32_t)(key[i] >> shift), valid);
+            rank[i] = match_digit((uint32_t)(key[i] >> shift), valid, use_ballot);
+            if (i == 0) {
+                const uint32_t m0 = rank[0];
+                use_ballot = __popc(__ballot_sync(0xffffffffu, valid && lane == __ffs(m0) - 1)) >= RT_SORT_BALLOT_DISTINCT;
+            }
         }
 #pragma unroll
         for (int k = 0; k < RANK_BATCH; ++k) {

@@ -140,6 +140,9 @@ struct F8 { float4 a, b; };
 #ifndef RT_L1_CARVEOUT
 #define RT_L1_CARVEOUT -1
 #endif
+#ifndef RT_PREFETCH_LEAF
+#define RT_PREFETCH_LEAF 0      // 1: prefetch.global.L1 of the leaf's first record when a lane reaches a leaf; 2: also its last byte; 3: BLAS leaves only
+#endif
 __device__ __forceinline__ float4 ldg_tri(const float4* p) {
 #if RT_TRI_NOALLOC == 1
     float4 r;
@@ -775,6 +778,15 @@ __global__ void __launch_bounds__(BIG ? TRACE_THREADS_BIG : TRACE_THREADS, BIG ?
                 } else if (hit0) cur = r0;
                 else if (hit1) cur = r1;
                 else cur = pop();
+#endif
+#if RT_PREFETCH_LEAF
+                // experiment: a lane that reaches a leaf waits for the lanes still in the node loop; start the fetch of what it will read
+                // (first triangle record / instance record) now, without holding registers for it
+                if (cur < 0) {
+                    const char* pa = in_blas ? reinterpret_cast<const char*>(tris + leaf_first(cur)) : reinterpret_cast<const char*>(P.instances + leaf_first(cur));
+                    if (RT_PREFETCH_LEAF != 3 || in_blas) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa));
+                    if (RT_PREFETCH_LEAF == 2) asm volatile("prefetch.global.L1 [%0];" ::"l"(pa + 47));
+                }
 #endif
 #if RT_CAP_EVERY > 1
                 if (NODE_CAP > 0 && (++cap_ctr % RT_CAP_EVERY) == 0 && __popc(__activemask()) < NODE_CAP) break;
