@@ -151,6 +151,13 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
     else { keys[t] = key; vals[t] = t; }
 }
 
+#ifndef RT_SEG_EMIT_SORTED
+#define RT_SEG_EMIT_SORTED 0     // 1: the fused per-BLAS kernel also writes the SORTED triangle records and k_refit_tris<true> only streams them. Measured
+                                 // (r2_zg): the tile kernel gets 95 us faster (534 -> 439), the one-CTA-per-SM segment kernel 160 us slower (456 -> 615): off
+#endif
+#ifndef RT_SEG_EMIT_BATCH
+#define RT_SEG_EMIT_BATCH 3
+#endif
 // ---- batches of small BLASes: setup + Morton + sort of one whole BLAS in ONE CTA ---------------------------------------
 // When every BLAS of the batch fits one CTA's shared memory (SEG_SORT_CAPACITY triangles), CTA b does for BLAS b what
 // k_tri_setup, k_tri_morton and the sort do for the general case: fetch + bake its triangles (48-B records out), reduce
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(256) k_tri_morton(const TriRec* __restrict__ t
 // written once, the keys written once, already sorted.
 __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ prefix, uint32_t n_geoms,
                                                                   const BlasRecord* __restrict__ recs, TriRec* __restrict__ out,
-                                                                  uint64_t* __restrict__ keys_out, int vb) {
+                                                                  uint64_t* __restrict__ keys_out, int vb, TriRec* __restrict__ sorted_out) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);
     __shared__ float s_red[6][SEG_WARPS];
@@ -233,6 +240,35 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
     }
     __syncthreads();
     seg_sort_passes(seg_smem, vb, (int)MORTON_BITS, n);
+#if RT_SEG_EMIT_SORTED
+    // The sorted triangle records too (sorted_out != nullptr): this CTA wrote the unsorted ones a moment ago, so the gather by sorted id is
+    // served by L2 here, and the tree pass reads its leaves as one coalesced stream instead of a dependent key -> record gather
+    // (34 % of k_refit_tris' stall samples, profiles/README.md r2_y). Three records in flight per thread.
+    if (sorted_out) {
+        const uint64_t idmask = (1ull << vb) - 1ull;
+        constexpr int EB = RT_SEG_EMIT_BATCH;
+        for (uint32_t p0 = (uint32_t)tid; p0 < n; p0 += EB * SEG_THREADS) {
+            float4 q[EB][3];
+#pragma unroll
+            for (int k = 0; k < EB; ++k) {
+                const uint32_t p = p0 + (uint32_t)k * SEG_THREADS;
+                if (p < n) {
+                    const float4* src = reinterpret_cast<const float4*>(out + (uint32_t)(s_keys[p] & idmask));
+                    q[k][0] = src[0]; q[k][1] = src[1]; q[k][2] = src[2];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EB; ++k) {
+                const uint32_t p = p0 + (uint32_t)k * SEG_THREADS;
+                if (p < n) {
+                    float4* dst = reinterpret_cast<float4*>(sorted_out + first + p);
+                    q[k][2].w = __uint_as_float(__float_as_uint(q[k][2].w) >> 24);   // geometry flags (the low 24 bits carried the BLAS id)
+                    dst[0] = q[k][0]; dst[1] = q[k][1]; dst[2] = q[k][2];
+                }
+            }
+        }
+    }
+#endif
     seg_store_bulk(keys_out + first, s_keys, n);          // the sorted segment leaves shared memory as one TMA bulk copy (UBLKCP)
 }
 
@@ -611,6 +647,8 @@ inline uint32_t border_grid(uint32_t n) {
     return g ? (uint32_t)g : 1u;
 }
 
+// PRESORTED: the sorted triangle records are already in place (written by k_seg_setup_sort): stream them, nothing to gather or to write
+template <bool PRESORTED>
 __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int vb, uint32_t n,
                                                          const TriRec* __restrict__ unsorted, TriRec* __restrict__ sorted,
                                                          BvhNode* __restrict__ nodes, const TriSegments seg,
@@ -618,13 +656,18 @@ __global__ void __launch_bounds__(TREE_TILE, RT_TREE_MIN_CTAS) k_refit_tris(cons
     const uint32_t leaf = blockIdx.x * blockDim.x + threadIdx.x;
     Box3 b = {{0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 0.0f}};
     if (leaf < n) {
-        const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
-        const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
-        const float4 q0 = __ldg(src), q1 = __ldg(src + 1);
-        float4 q2 = __ldg(src + 2);
-        q2.w = __uint_as_float(__float_as_uint(q2.w) >> 24);  // geometry flags (the low 24 bits carried the BLAS id through the sort)
-        float4* dst = reinterpret_cast<float4*>(sorted + leaf);
-        dst[0] = q0; dst[1] = q1; dst[2] = q2;
+        float4 q0, q1, q2;
+        if (PRESORTED) {
+            const float4* src = reinterpret_cast<const float4*>(sorted + leaf);
+            q0 = __ldcs(src); q1 = __ldcs(src + 1); q2 = __ldcs(src + 2);
+        } else {
+            const uint32_t src_i = vb ? (uint32_t)(__ldg(keys + leaf) & ((1ull << vb) - 1ull)) : __ldg(vals + leaf);
+            const float4* src = reinterpret_cast<const float4*>(unsorted + src_i);
+            q0 = __ldg(src); q1 = __ldg(src + 1); q2 = __ldg(src + 2);
+            q2.w = __uint_as_float(__float_as_uint(q2.w) >> 24);  // geometry flags (the low 24 bits carried the BLAS id through the sort)
+            float4* dst = reinterpret_cast<float4*>(sorted + leaf);
+            dst[0] = q0; dst[1] = q1; dst[2] = q2;
+        }
         b.lo[0] = fminf(fminf(q0.x, q0.w), q1.z); b.lo[1] = fminf(fminf(q0.y, q1.x), q1.w); b.lo[2] = fminf(fminf(q0.z, q1.y), q2.x);
         b.hi[0] = fmaxf(fmaxf(q0.x, q0.w), q1.z); b.hi[1] = fmaxf(fmaxf(q0.y, q1.x), q1.w); b.hi[2] = fmaxf(fmaxf(q0.z, q1.y), q2.x);
     }
@@ -872,6 +915,7 @@ uint32_t tree_job_capacity(uint32_t n) { return (uint32_t)tree_job_capacity_host
 
 int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents* ev, bool* sorted_in_b) {
     int launches = 0;
+    bool presorted = false;
     *sorted_in_b = false;
     if (a.n_tris == 0) return 0;
     if (ev) cudaEventRecord(ev->e[0], st);
@@ -892,9 +936,11 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         if (ev) { cudaEventRecord(ev->e[1], st); cudaEventRecord(ev->e[2], st); }
-        k_seg_setup_sort<<<a.sort.n_segments, SEG_THREADS, SEG_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb);
+        k_seg_setup_sort<<<a.sort.n_segments, SEG_THREADS, SEG_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb,
+                                                                                 RT_SEG_EMIT_SORTED ? a.tris_sorted : nullptr);
         ++launches;
         *sorted_in_b = true;
+        presorted = RT_SEG_EMIT_SORTED != 0;
     } else {
         k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
         ++launches;
@@ -916,7 +962,8 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
         const uint32_t tiles = (uint32_t)div_up(a.n_tris, TREE_TILE);
         uint32_t* job_count = a.s.arrived + a.n_tris;
         const BorderMem bm{a.s.xchg, a.s.far_end, a.s.arrived};
-        k_refit_tris<<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count, bm);
+        if (presorted) k_refit_tris<true><<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count, bm);
+        else k_refit_tris<false><<<tiles, TREE_TILE, 0, st>>>(keys, vals, vb, a.n_tris, a.tris_unsorted, a.tris_sorted, a.nodes, seg, a.s.jobs, job_count, bm);
 #if !RT_TREE_INLINE_BORDER
         k_tree_border<BLAS_LEAF_MAX, TriSegments><<<border_grid(a.n_tris), 128, 0, st>>>(keys, vb, a.n_tris, a.nodes, a.s.jobs, job_count,
                                                                                                           a.s.xchg, a.s.far_end, a.s.arrived, seg);
