@@ -272,6 +272,127 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
     seg_store_bulk(keys_out + first, s_keys, n);          // the sorted segment leaves shared memory as one TMA bulk copy (UBLKCP)
 }
 
+// The same with the LIGHT segment sort (seg_sort.cuh): 512 threads x 22 triangles, {u32 Morton, u16 position} records, two CTAs per SM.
+// Bit-identical output (same stable order); RT_SEG_LIGHT=0 selects the 1024-thread kernel above.
+#ifndef RT_SEG_LIGHT
+#define RT_SEG_LIGHT 1
+#endif
+#ifndef RT_SEG_STAGE_VERTS
+#define RT_SEG_STAGE_VERTS 1
+#endif
+__global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ prefix, uint32_t n_geoms,
+                                                                    const BlasRecord* __restrict__ recs, TriRec* __restrict__ out,
+                                                                    uint64_t* __restrict__ keys_out, int vb) {
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    uint32_t* s_m = reinterpret_cast<uint32_t*>(seg_smem + SEG2_OFF_M);
+    uint16_t* s_id = reinterpret_cast<uint16_t*>(seg_smem + SEG2_OFF_ID);
+    __shared__ float s_red[6][SEG2_WARPS];
+    __shared__ float s_bounds[6];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t blas = blockIdx.x, first = recs[blas].first, n = recs[blas].tri_count;
+    if (n == 0) return;
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    uint32_t g = 0, gbeg = 1, gend = 0;                  // empty range: the first triangle looks its geometry up
+#if RT_SEG_STAGE_VERTS
+    // A BLAS that is ONE indexed geometry whose vertex array fits the (not yet used) sort arrays: copy the vertices into shared memory with
+    // coalesced loads and gather from there. The gather of nine 4-byte values per triangle is what bounds the setup phase (L1TEX wavefronts:
+    // every lane its own line), and neighbouring triangles share their vertices.
+    const float* s_verts = reinterpret_cast<const float*>(seg_smem);
+    bool staged = false;
+    {
+        const uint32_t g0 = find_geom(prefix, n_geoms, first);
+        const GeomDesc& G0 = geoms[g0];
+        const uint64_t words = (uint64_t)G0.vert_count * G0.stride_f;
+        if (G0.idx && __ldg(prefix + g0) == first && __ldg(prefix + g0 + 1) >= first + n && words != 0 && words * 4ull <= (uint64_t)SEG2_SMEM_BYTES) {
+            staged = true;                               // uniform for the CTA
+            float* dstv = reinterpret_cast<float*>(seg_smem);
+            for (uint32_t w = (uint32_t)tid; w < (uint32_t)words; w += SEG2_THREADS) dstv[w] = __ldg(G0.verts + w);
+            g = g0; gbeg = first; gend = __ldg(prefix + g0 + 1);
+        }
+    }
+    __syncthreads();
+#else
+    const float* s_verts = nullptr;
+    const bool staged = false;
+#endif
+#pragma unroll 1
+    for (int i = 0; i < SEG2_ITEMS; ++i) {
+        const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG2_THREADS;
+        if (t >= n) continue;
+        const uint32_t T = first + t;
+        if (T < gbeg || T >= gend) { g = find_geom(prefix, n_geoms, T); gbeg = __ldg(prefix + g); gend = __ldg(prefix + g + 1); }
+        const GeomDesc& G = geoms[g];
+        const uint32_t p = T - gbeg;
+        uint32_t i0, i1, i2;
+        if (G.idx) { i0 = __ldg(G.idx + 3 * (size_t)p); i1 = __ldg(G.idx + 3 * (size_t)p + 1); i2 = __ldg(G.idx + 3 * (size_t)p + 2); }
+        else { i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2; }
+        V3 v0, v1, v2;
+        if (staged) {
+            const float* a = s_verts + i0 * G.stride_f;
+            const float* b = s_verts + i1 * G.stride_f;
+            const float* c = s_verts + i2 * G.stride_f;
+            v0 = {a[0], a[1], a[2]}; v1 = {b[0], b[1], b[2]}; v2 = {c[0], c[1], c[2]};
+        } else {
+            const float* a = G.verts + (size_t)i0 * G.stride_f;
+            const float* b = G.verts + (size_t)i1 * G.stride_f;
+            const float* c = G.verts + (size_t)i2 * G.stride_f;
+            v0 = {__ldg(a), __ldg(a + 1), __ldg(a + 2)};
+            v1 = {__ldg(b), __ldg(b + 1), __ldg(b + 2)};
+            v2 = {__ldg(c), __ldg(c + 1), __ldg(c + 2)};
+        }
+        if (G.has_xform) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
+        float4* dst = reinterpret_cast<float4*>(out + T);
+        dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+        dst[1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+        dst[2] = make_float4(v2.z, __uint_as_float(G.geo_index), __uint_as_float(p), __uint_as_float(G.blas | (G.flags << 24)));
+        const float tlo[3] = {fminf(fminf(v0.x, v1.x), v2.x), fminf(fminf(v0.y, v1.y), v2.y), fminf(fminf(v0.z, v1.z), v2.z)};
+        const float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], tlo[k]); hi[k] = fmaxf(hi[k], thi[k]); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+        if (lane == 0) { s_red[k][warp] = lo[k]; s_red[3 + k][warp] = hi[k]; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+            float v = lane < SEG2_WARPS ? s_red[k][lane] : (k < 3 ? FLT_MAX : -FLT_MAX);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { const float w = __shfl_xor_sync(0xffffffffu, v, o); v = k < 3 ? fminf(v, w) : fmaxf(v, w); }
+            if (lane == 0) s_bounds[k] = v;
+        }
+    }
+    __syncthreads();
+    const float slo[3] = {s_bounds[0], s_bounds[1], s_bounds[2]}, shi[3] = {s_bounds[3], s_bounds[4], s_bounds[5]};
+#pragma unroll 2
+    for (int i = 0; i < SEG2_ITEMS; ++i) {
+        const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG2_THREADS;
+        uint32_t mk = 0xFFFFFFFFu;                         // padding sorts last and stays last
+        if (t < n) {
+            // this thread's own record, written a moment ago (L1/L2 hit)
+            const float4* src = reinterpret_cast<const float4*>(out + first + t);
+            const float4 q0 = src[0], q1 = src[1], q2 = src[2];
+            const float plo[3] = {fminf(fminf(q0.x, q0.w), q1.z), fminf(fminf(q0.y, q1.x), q1.w), fminf(fminf(q0.z, q1.y), q2.x)};
+            const float phi[3] = {fmaxf(fmaxf(q0.x, q0.w), q1.z), fmaxf(fmaxf(q0.y, q1.x), q1.w), fmaxf(fmaxf(q0.z, q1.y), q2.x)};
+            mk = morton30(plo, phi, slo, shi);
+        }
+        s_m[seg2_m_at(t)] = mk;
+        s_id[t] = (uint16_t)t;
+    }
+    __syncthreads();
+    seg2_sort_passes(seg_smem, n);
+    const uint64_t hi_bits = (uint64_t)blas << MORTON_BITS;
+    for (uint32_t p = (uint32_t)tid; p < n; p += SEG2_THREADS)
+        keys_out[first + p] = ((hi_bits | (uint64_t)s_m[seg2_m_at(p)]) << vb) | (uint64_t)(first + (uint32_t)s_id[p]);
+}
+
 // ---- hierarchy emission + refit, one bottom-up pass ---------------------------------------------------
 // The tree is Karras' binary radix tree over the (key, index) strings, but it is found BOTTOM-UP (Apetrei 2014):
 // a finished subtree over sorted leaves [l, r] merges with its right neighbour when it shares the longer prefix
@@ -936,11 +1057,22 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         if (ev) { cudaEventRecord(ev->e[1], st); cudaEventRecord(ev->e[2], st); }
+#if RT_SEG_LIGHT && !RT_SEG_EMIT_SORTED
+        {
+            static bool attr2_set[64] = {};
+            if (dev < 0 || dev >= 64 || !attr2_set[dev]) {
+                if (cudaFuncSetAttribute(k_seg2_setup_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SEG2_SMEM_BYTES) != cudaSuccess) return -1;
+                if (dev >= 0 && dev < 64) attr2_set[dev] = true;
+            }
+        }
+        k_seg2_setup_sort<<<a.sort.n_segments, SEG2_THREADS, SEG2_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb);
+#else
         k_seg_setup_sort<<<a.sort.n_segments, SEG_THREADS, SEG_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb,
                                                                                  RT_SEG_EMIT_SORTED ? a.tris_sorted : nullptr);
+        presorted = RT_SEG_EMIT_SORTED != 0;
+#endif
         ++launches;
         *sorted_in_b = true;
-        presorted = RT_SEG_EMIT_SORTED != 0;
     } else {
         k_tri_setup<<<div_up(a.n_tris, SETUP_CHUNK), SETUP_THREADS, 0, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.n_tris, a.tris_unsorted, a.bounds_ordered);
         ++launches;

@@ -78,7 +78,9 @@ struct GeomDesc {
     uint32_t has_xform;
     uint32_t flags;             // RT_GEOMETRY_* (low 8 bits are kept with every triangle)
     float    xform[12];
+    uint32_t vert_count;        // rt_geometry.vertex_count (how much of `verts` the indices may address)
 };
+static_assert(sizeof(GeomDesc) == 96, "GeomDesc layout");
 
 // ---- radix sort (csrc/radix_sort.cu) ---------------------------------------------------------
 struct BlasRecord;

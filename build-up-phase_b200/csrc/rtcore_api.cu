@@ -239,7 +239,7 @@ static int build_blas_batch_impl(rt_context* ctx, const rt_geometry* geoms, cons
                 GeomDesc& D = descs[g];
                 memset(&D, 0, sizeof(D));
                 D.stride_f = G.vertex_stride_bytes / 4; D.tri_first = (uint32_t)total; D.tri_count = G.triangle_count;
-                D.blas = b; D.geo_index = k; D.flags = G.flags & 0xFFu;
+                D.blas = b; D.geo_index = k; D.flags = G.flags & 0xFFu; D.vert_count = G.vertex_count;
                 total += G.triangle_count; bt += G.triangle_count;
                 if (!(G.flags & RT_GEOMETRY_DEVICE_POINTERS)) {
                     stage_bytes = align_up(stage_bytes, 16) + (size_t)G.vertex_count * G.vertex_stride_bytes;
