@@ -280,6 +280,9 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
 #ifndef RT_SEG_STAGE_VERTS
 #define RT_SEG_STAGE_VERTS 1
 #endif
+#ifndef RT_SEG_MORTON_BATCH
+#define RT_SEG_MORTON_BATCH 4
+#endif
 __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ prefix, uint32_t n_geoms,
                                                                     const BlasRecord* __restrict__ recs, TriRec* __restrict__ out,
                                                                     uint64_t* __restrict__ keys_out, int vb) {
@@ -315,6 +318,43 @@ __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomD
     const float* s_verts = nullptr;
     const bool staged = false;
 #endif
+    if (staged) {
+        // one indexed geometry, vertices in shared memory: the only global loads left are the three indices of a triangle, fetched TWO
+        // iterations ahead (a thread's 22 triangles were 22 dependent index round trips: 10 % of the kernel's stall samples, r2_zj)
+        const GeomDesc& G = geoms[g];
+        const uint32_t* __restrict__ idx = G.idx;
+        const uint32_t stride_f = G.stride_f, tagw = G.blas | (G.flags << 24), geo = G.geo_index;
+        const bool xf = G.has_xform != 0;
+        constexpr int AHEAD = 2;
+        uint32_t pi[AHEAD][3];
+#pragma unroll
+        for (int k = 0; k < AHEAD; ++k) {
+            const uint32_t t = (uint32_t)tid + (uint32_t)k * SEG2_THREADS;
+            if (t < n) { pi[k][0] = __ldg(idx + 3 * (size_t)t); pi[k][1] = __ldg(idx + 3 * (size_t)t + 1); pi[k][2] = __ldg(idx + 3 * (size_t)t + 2); }
+        }
+#pragma unroll
+        for (int i = 0; i < SEG2_ITEMS; ++i) {
+            const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG2_THREADS;
+            const uint32_t i0 = pi[i % AHEAD][0], i1 = pi[i % AHEAD][1], i2 = pi[i % AHEAD][2];
+            if (i + AHEAD < SEG2_ITEMS) {
+                const uint32_t tn = t + (uint32_t)AHEAD * SEG2_THREADS;
+                if (tn < n) { pi[i % AHEAD][0] = __ldg(idx + 3 * (size_t)tn); pi[i % AHEAD][1] = __ldg(idx + 3 * (size_t)tn + 1); pi[i % AHEAD][2] = __ldg(idx + 3 * (size_t)tn + 2); }
+            }
+            if (t < n) {
+                const float* a = s_verts + i0 * stride_f;
+                const float* b = s_verts + i1 * stride_f;
+                const float* c = s_verts + i2 * stride_f;
+                V3 v0 = {a[0], a[1], a[2]}, v1 = {b[0], b[1], b[2]}, v2 = {c[0], c[1], c[2]};
+                if (xf) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
+                float4* dst = reinterpret_cast<float4*>(out + first + t);
+                dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
+                dst[1] = make_float4(v1.y, v1.z, v2.x, v2.y);
+                dst[2] = make_float4(v2.z, __uint_as_float(geo), __uint_as_float(t), __uint_as_float(tagw));
+                lo[0] = fminf(lo[0], fminf(fminf(v0.x, v1.x), v2.x)); lo[1] = fminf(lo[1], fminf(fminf(v0.y, v1.y), v2.y)); lo[2] = fminf(lo[2], fminf(fminf(v0.z, v1.z), v2.z));
+                hi[0] = fmaxf(hi[0], fmaxf(fmaxf(v0.x, v1.x), v2.x)); hi[1] = fmaxf(hi[1], fmaxf(fmaxf(v0.y, v1.y), v2.y)); hi[2] = fmaxf(hi[2], fmaxf(fmaxf(v0.z, v1.z), v2.z));
+            }
+        }
+    } else {
 #pragma unroll 1
     for (int i = 0; i < SEG2_ITEMS; ++i) {
         const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG2_THREADS;
@@ -326,20 +366,12 @@ __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomD
         uint32_t i0, i1, i2;
         if (G.idx) { i0 = __ldg(G.idx + 3 * (size_t)p); i1 = __ldg(G.idx + 3 * (size_t)p + 1); i2 = __ldg(G.idx + 3 * (size_t)p + 2); }
         else { i0 = 3 * p; i1 = 3 * p + 1; i2 = 3 * p + 2; }
-        V3 v0, v1, v2;
-        if (staged) {
-            const float* a = s_verts + i0 * G.stride_f;
-            const float* b = s_verts + i1 * G.stride_f;
-            const float* c = s_verts + i2 * G.stride_f;
-            v0 = {a[0], a[1], a[2]}; v1 = {b[0], b[1], b[2]}; v2 = {c[0], c[1], c[2]};
-        } else {
-            const float* a = G.verts + (size_t)i0 * G.stride_f;
-            const float* b = G.verts + (size_t)i1 * G.stride_f;
-            const float* c = G.verts + (size_t)i2 * G.stride_f;
-            v0 = {__ldg(a), __ldg(a + 1), __ldg(a + 2)};
-            v1 = {__ldg(b), __ldg(b + 1), __ldg(b + 2)};
-            v2 = {__ldg(c), __ldg(c + 1), __ldg(c + 2)};
-        }
+        const float* a = G.verts + (size_t)i0 * G.stride_f;
+        const float* b = G.verts + (size_t)i1 * G.stride_f;
+        const float* c = G.verts + (size_t)i2 * G.stride_f;
+        V3 v0 = {__ldg(a), __ldg(a + 1), __ldg(a + 2)};
+        V3 v1 = {__ldg(b), __ldg(b + 1), __ldg(b + 2)};
+        V3 v2 = {__ldg(c), __ldg(c + 1), __ldg(c + 2)};
         if (G.has_xform) { v0 = xform_point(G.xform, v0); v1 = xform_point(G.xform, v1); v2 = xform_point(G.xform, v2); }
         float4* dst = reinterpret_cast<float4*>(out + T);
         dst[0] = make_float4(v0.x, v0.y, v0.z, v1.x);
@@ -349,6 +381,7 @@ __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomD
         const float thi[3] = {fmaxf(fmaxf(v0.x, v1.x), v2.x), fmaxf(fmaxf(v0.y, v1.y), v2.y), fmaxf(fmaxf(v0.z, v1.z), v2.z)};
 #pragma unroll
         for (int k = 0; k < 3; ++k) { lo[k] = fminf(lo[k], tlo[k]); hi[k] = fmaxf(hi[k], thi[k]); }
+    }
     }
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -371,20 +404,34 @@ __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomD
     }
     __syncthreads();
     const float slo[3] = {s_bounds[0], s_bounds[1], s_bounds[2]}, shi[3] = {s_bounds[3], s_bounds[4], s_bounds[5]};
-#pragma unroll 2
-    for (int i = 0; i < SEG2_ITEMS; ++i) {
-        const uint32_t t = (uint32_t)tid + (uint32_t)i * SEG2_THREADS;
-        uint32_t mk = 0xFFFFFFFFu;                         // padding sorts last and stays last
-        if (t < n) {
-            // this thread's own record, written a moment ago (L1/L2 hit)
-            const float4* src = reinterpret_cast<const float4*>(out + first + t);
-            const float4 q0 = src[0], q1 = src[1], q2 = src[2];
-            const float plo[3] = {fminf(fminf(q0.x, q0.w), q1.z), fminf(fminf(q0.y, q1.x), q1.w), fminf(fminf(q0.z, q1.y), q2.x)};
-            const float phi[3] = {fmaxf(fmaxf(q0.x, q0.w), q1.z), fmaxf(fmaxf(q0.y, q1.x), q1.w), fmaxf(fmaxf(q0.z, q1.y), q2.x)};
-            mk = morton30(plo, phi, slo, shi);
+    // Morton keys from this thread's own records, written a moment ago (L2 hits, ~1300 cycles under load): RT_SEG_MORTON_BATCH records' loads are
+    // in flight together (two at a time were 11 dependent round trips: 14 % of the kernel's stall samples, r2_zj)
+    constexpr int MB = RT_SEG_MORTON_BATCH;
+#pragma unroll 1
+    for (int i0 = 0; i0 < SEG2_ITEMS; i0 += MB) {
+        float4 q[MB][3];
+#pragma unroll
+        for (int k = 0; k < MB; ++k) {
+            const uint32_t t = (uint32_t)tid + (uint32_t)(i0 + k) * SEG2_THREADS;
+            if (i0 + k < SEG2_ITEMS && t < n) {
+                const float4* src = reinterpret_cast<const float4*>(out + first + t);
+                q[k][0] = src[0]; q[k][1] = src[1]; q[k][2] = src[2];
+            }
         }
-        s_m[seg2_m_at(t)] = mk;
-        s_id[t] = (uint16_t)t;
+#pragma unroll
+        for (int k = 0; k < MB; ++k) {
+            const uint32_t t = (uint32_t)tid + (uint32_t)(i0 + k) * SEG2_THREADS;
+            if (i0 + k >= SEG2_ITEMS) continue;
+            uint32_t mk = 0xFFFFFFFFu;                         // padding sorts last and stays last
+            if (t < n) {
+                const float4 q0 = q[k][0], q1 = q[k][1], q2 = q[k][2];
+                const float plo[3] = {fminf(fminf(q0.x, q0.w), q1.z), fminf(fminf(q0.y, q1.x), q1.w), fminf(fminf(q0.z, q1.y), q2.x)};
+                const float phi[3] = {fmaxf(fmaxf(q0.x, q0.w), q1.z), fmaxf(fmaxf(q0.y, q1.x), q1.w), fmaxf(fmaxf(q0.z, q1.y), q2.x)};
+                mk = morton30(plo, phi, slo, shi);
+            }
+            s_m[seg2_m_at(t)] = mk;
+            s_id[t] = (uint16_t)t;
+        }
     }
     __syncthreads();
     seg2_sort_passes(seg_smem, n);
