@@ -273,10 +273,14 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_sort(const uint64_t* __r
     const uint32_t first = recs ? recs[blockIdx.x].first : 0u, n = recs ? recs[blockIdx.x].tri_count : single_n;   // recs == nullptr: the whole input is one segment
     if (n == 0) return;
     // the segment: one TMA bulk copy (cp.async.bulk + mbarrier); padding (~0) sorts last and stays last
-    for (uint32_t i = n + tid; i < SEG_SORT_CAPACITY; i += SEG_THREADS) s_keys[i] = ~0ull;
+    const int items = n <= 1u * SEG_THREADS ? 1 : n <= 3u * SEG_THREADS ? 3 : n <= 5u * SEG_THREADS ? 5 : SEG_ITEMS;   // records per thread (block-uniform)
+    for (uint32_t i = n + tid; i < (uint32_t)items * SEG_THREADS; i += SEG_THREADS) s_keys[i] = ~0ull;
     seg_load_bulk(s_keys, in + first, n, reinterpret_cast<uint64_t*>(seg_smem + SEG_SMEM_MBAR_OFFSET));
     __syncthreads();
-    seg_sort_passes(seg_smem, shift0, key_bits, n);
+    if (items == 1) seg_sort_passes<1>(seg_smem, shift0, key_bits, n);
+    else if (items == 3) seg_sort_passes<3>(seg_smem, shift0, key_bits, n);
+    else if (items == 5) seg_sort_passes<5>(seg_smem, shift0, key_bits, n);
+    else seg_sort_passes<SEG_ITEMS>(seg_smem, shift0, key_bits, n);
     seg_store_bulk(out + first, s_keys, n);
 }
 

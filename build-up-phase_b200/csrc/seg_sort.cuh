@@ -37,6 +37,9 @@ __device__ __forceinline__ uint64_t expand4(uint64_t cnt, int q) {
 // passes produce) with broadcast shared-memory reads, ~8 instructions per comparison. Measured on B200 (rt_update_tlas, 1024 instances,
 // profiles/README.md r2_j): rank sort 0.123 ms vs 0.074 ms with the passes - n^2 comparisons on ONE SM lose beyond a few hundred records.
 constexpr uint32_t SEG_RANK_SORT_MAX = 256;
+// ITEMS: records per thread (odd: conflict-free blocked access); the passes cover the first SEG_THREADS * ITEMS slots, which must hold every
+// real record and be padded. The stand-alone kernel picks the smallest that fits (a 1024-instance TLAS sorts 1 record per thread, not 11).
+template <int ITEMS = SEG_ITEMS>
 __device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shift0, int key_bits, uint32_t n_real = SEG_SORT_CAPACITY) {
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(seg_smem);                         // the segment, sorted by the passes so far
     if (n_real <= SEG_RANK_SORT_MAX) {
@@ -60,13 +63,13 @@ __device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shi
     uint64_t* s_tot = s_wsum + 4 * SEG_WARPS;                                          // [4] packed digit totals
     uint16_t* s_off = reinterpret_cast<uint16_t*>(s_tot + 4);                          // [16][SEG_THREADS] start of (digit, thread)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint64_t key[SEG_ITEMS];
+    uint64_t key[ITEMS];
     for (int shift = shift0; shift < shift0 + key_bits; shift += 4) {
 #pragma unroll
-        for (int i = 0; i < SEG_ITEMS; ++i) key[i] = s_keys[tid * SEG_ITEMS + i];
+        for (int i = 0; i < ITEMS; ++i) key[i] = s_keys[tid * ITEMS + i];
         uint64_t cnt = 0, rk = 0;                                                      // 16 x 4-bit digit counts; 4-bit rank of record i among this thread's records of its digit
 #pragma unroll
-        for (int i = 0; i < SEG_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const int d4 = 4 * ((int)(key[i] >> shift) & 15);
             rk |= ((cnt >> d4) & 15ull) << (4 * i);
             cnt += 1ull << d4;
@@ -104,7 +107,7 @@ __device__ __forceinline__ void seg_sort_passes(unsigned char* seg_smem, int shi
             }
         }
 #pragma unroll
-        for (int i = 0; i < SEG_ITEMS; ++i) {
+        for (int i = 0; i < ITEMS; ++i) {
             const int d = (int)(key[i] >> shift) & 15;
             s_keys[(uint32_t)s_off[d * SEG_THREADS + tid] + (uint32_t)((rk >> (4 * i)) & 15ull)] = key[i];
         }
