@@ -8,19 +8,23 @@
 //   k_tri_morton  30-bit Morton code of the triangle-box centre inside its BLAS bounds;
 //                 key = (blas << 30) | morton, value = triangle id
 //   sort_pairs    onesweep radix sort (radix_sort.cu), only the significant key bytes
+//   k_seg2_setup_sort  batches of small BLASes (each <= 11,264 triangles): the three steps above for ONE BLAS in one CTA
+//                 (light shared-memory sort, two CTAs per SM, the vertices of a one-geometry BLAS staged in shared memory)
 //   k_refit_tris  hierarchy emission AND refit in one bottom-up pass over Karras' radix tree (clz on
 //                 key XOR, index-augmented for duplicate keys; found bottom-up as in Apetrei 2014, see
 //                 build_tree_tile): one thread per sorted leaf emits the sorted triangle, then climbs;
 //                 the second child to arrive at a split unions the boxes and continues. Splits inside
-//                 a CTA's 128-leaf tile meet in shared memory, only the tile-border subtrees use global
-//                 arrival counters. Because the BLAS id is the key prefix, every BLAS of a batch is
-//                 exactly one subtree of the global radix tree; subtrees of <= 2 triangles collapse
+//                 a CTA's 256-leaf tile meet in shared memory (after two merges the subtrees still climbing
+//                 are regrouped into the first warps). Because the BLAS id is the key prefix, every BLAS of
+//                 a batch is exactly one subtree of the global radix tree; subtrees of <= 2 triangles collapse
 //                 into a leaf; the thread that completes a BLAS publishes its root/bounds/height.
+//   k_tree_border the subtrees that touch a tile border finish through global memory: a job queue walked by
+//                 strided lanes, one acquire-add per arrival, deposits that carry the deltas of their range.
 // TLAS: same machinery over instance world boxes (k_inst_setup computes world->object in fp64).
 //
-// All kernels are HBM-bound streaming passes: coalesced 128-bit accesses, grids sized from the
-// problem (multiples of 148 SMs x resident CTAs for the big ones), no tensor cores (nothing here
-// is a contraction).
+// The setup / sort kernels stream their data with coalesced 128-bit accesses; the tree kernels are latency-chain
+// bound (profiles/README.md r2_x - r2_zk). Grids are sized from the problem or from the resident CTAs of the
+// device; no tensor cores (nothing here is a contraction).
 #include <float.h>
 #include <stdlib.h>
 
