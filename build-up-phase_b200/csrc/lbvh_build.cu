@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(SEG_THREADS, 1) k_seg_setup_sort(const GeomDes
 #endif
 __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomDesc* __restrict__ geoms, const uint32_t* __restrict__ prefix, uint32_t n_geoms,
                                                                     const BlasRecord* __restrict__ recs, TriRec* __restrict__ out,
-                                                                    uint64_t* __restrict__ keys_out, int vb) {
+                                                                    uint64_t* __restrict__ keys_out, int vb, TriRec* __restrict__ sorted_out) {
     extern __shared__ __align__(16) unsigned char seg_smem[];
     uint32_t* s_m = reinterpret_cast<uint32_t*>(seg_smem + SEG2_OFF_M);
     uint16_t* s_id = reinterpret_cast<uint16_t*>(seg_smem + SEG2_OFF_ID);
@@ -442,6 +442,34 @@ __global__ void __launch_bounds__(SEG2_THREADS, 2) k_seg2_setup_sort(const GeomD
     const uint64_t hi_bits = (uint64_t)blas << MORTON_BITS;
     for (uint32_t p = (uint32_t)tid; p < n; p += SEG2_THREADS)
         keys_out[first + p] = ((hi_bits | (uint64_t)s_m[seg2_m_at(p)]) << vb) | (uint64_t)(first + (uint32_t)s_id[p]);
+#if RT_SEG_EMIT_SORTED
+    // the sorted triangle records too (see k_seg_setup_sort): gathered from L2 by the CTA that wrote them; k_refit_tris<true> then streams its leaves
+    if (sorted_out) {
+        constexpr int EB = RT_SEG_EMIT_BATCH;
+        for (uint32_t p0 = (uint32_t)tid; p0 < n; p0 += EB * SEG2_THREADS) {
+            float4 q[EB][3];
+#pragma unroll
+            for (int k = 0; k < EB; ++k) {
+                const uint32_t p = p0 + (uint32_t)k * SEG2_THREADS;
+                if (p < n) {
+                    const float4* src = reinterpret_cast<const float4*>(out + first + (uint32_t)s_id[p]);
+                    q[k][0] = src[0]; q[k][1] = src[1]; q[k][2] = src[2];
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < EB; ++k) {
+                const uint32_t p = p0 + (uint32_t)k * SEG2_THREADS;
+                if (p < n) {
+                    float4* dst = reinterpret_cast<float4*>(sorted_out + first + p);
+                    q[k][2].w = __uint_as_float(__float_as_uint(q[k][2].w) >> 24);   // geometry flags (the low 24 bits carried the BLAS id)
+                    dst[0] = q[k][0]; dst[1] = q[k][1]; dst[2] = q[k][2];
+                }
+            }
+        }
+    }
+#else
+    (void)sorted_out;
+#endif
 }
 
 // ---- hierarchy emission + refit, one bottom-up pass ---------------------------------------------------
@@ -1108,7 +1136,7 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
             if (dev >= 0 && dev < 64) attr_set[dev] = true;
         }
         if (ev) { cudaEventRecord(ev->e[1], st); cudaEventRecord(ev->e[2], st); }
-#if RT_SEG_LIGHT && !RT_SEG_EMIT_SORTED
+#if RT_SEG_LIGHT
         {
             static bool attr2_set[64] = {};
             if (dev < 0 || dev >= 64 || !attr2_set[dev]) {
@@ -1116,12 +1144,13 @@ int launch_blas_build(const BlasBuildArgs& a, cudaStream_t st, const BuildEvents
                 if (dev >= 0 && dev < 64) attr2_set[dev] = true;
             }
         }
-        k_seg2_setup_sort<<<a.sort.n_segments, SEG2_THREADS, SEG2_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb);
+        k_seg2_setup_sort<<<a.sort.n_segments, SEG2_THREADS, SEG2_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb,
+                                                                                    RT_SEG_EMIT_SORTED ? a.tris_sorted : nullptr);
 #else
         k_seg_setup_sort<<<a.sort.n_segments, SEG_THREADS, SEG_SMEM_BYTES, st>>>(a.geoms, a.geom_tri_first, a.n_geoms, a.sort.seg_records, a.tris_unsorted, a.s.keys_b, vb,
                                                                                  RT_SEG_EMIT_SORTED ? a.tris_sorted : nullptr);
-        presorted = RT_SEG_EMIT_SORTED != 0;
 #endif
+        presorted = RT_SEG_EMIT_SORTED != 0;
         ++launches;
         *sorted_in_b = true;
     } else {
