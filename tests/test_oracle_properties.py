@@ -142,11 +142,12 @@ def test_ray_flag_semantics_known_answers(oracle):
     o.close()
 
 
-def _world_triangles(scene):
-    """All instanced triangles in WORLD space, float64: geometry transform (baked at BLAS build) then instance transform; plus ids."""
+def _world_triangles(scene, cull_mask=0xFF):
+    """All instanced triangles in WORLD space, float64: geometry transform (baked at BLAS build) then instance transform; plus ids.
+    Instances whose mask has no bit in common with the ray's cullMask do not exist for the ray [spec: instance culling]."""
     P, ids = [], []
     for ii, I in enumerate(scene.instances):
-        if I.mask == 0:
+        if (I.mask & cull_mask) == 0:
             continue
         M = np.asarray(I.transform, dtype=np.float64).reshape(3, 4)
         for gi, g in enumerate(scene.blases[I.blas]):
@@ -163,9 +164,10 @@ def _world_triangles(scene):
     return np.concatenate(P), np.concatenate(ids)
 
 
-def _closest_hits_f64(O, D, tri, tmin=0.0, tmax=100.0):
+def _closest_hits_f64(O, D, tri, tmin=0.0, tmax=100.0, t_eps=0.0):
     """Moeller-Trumbore of rays (O, D) against all triangles in float64. Returns (t, triangle index, clear) where clear marks the
-    rays whose answer is unambiguous: the closest hit is separated from the runner-up and no candidate lies within 1e-4 of an edge."""
+    rays whose answer is unambiguous: the closest hit is separated from the runner-up and no candidate lies within 1e-4 of an edge
+    (t_eps > 0: nor within t_eps of an end of the ray interval)."""
     e1, e2 = tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]
     n = D.shape[0]
     best_t = np.full(n, np.inf); second_t = np.full(n, np.inf)
@@ -185,6 +187,8 @@ def _closest_hits_f64(O, D, tri, tmin=0.0, tmax=100.0):
             margin = np.minimum(np.minimum(u, v), 1.0 - u - v)
             ok = (np.abs(det) > 1e-12) & (margin > 0) & (t > tmin) & (t < tmax)
             near = (np.abs(margin) < 1e-4) & (np.abs(det) > 1e-12) & (t > tmin - 1e-3) & (t < tmax + 1e-3)
+            if t_eps > 0.0:
+                near |= (margin > -1e-4) & (np.abs(det) > 1e-12) & ((np.abs(t - tmin) < t_eps) | (np.abs(t - tmax) < t_eps))
         t = np.where(ok, t, np.inf)
         kk = np.argmin(t, axis=1)
         tt = t[rows, kk]
@@ -242,6 +246,54 @@ def test_oracle_vs_float64_world_space_intersection(oracle):
     col = np.clip(np.asarray(scene.hit_records, dtype=np.float32)[rec], 0, 1) * np.float32(255)
     got = rgba.reshape(-1, 4)[c][:, :3].astype(np.float64)
     assert np.abs(got - np.rint(col))[~special].max() <= 1.0
+
+
+def test_interval_cullmask_and_sbt_rule_vs_float64_world_space(oracle):
+    """Three more rules the GLSL leaves to the driver, pinned by the same independent float64 world-space statement: the ray interval is OPEN
+    (tmin < t < tmax; the sample passes 0.0 / 100.0, main.cpp:1050-1052), an instance exists for a ray iff (mask & cullMask) != 0
+    (main.cpp:851 / 1048 pass 0xFF / 0xFF), and the hit record is instanceSbtOffset + geometryIndex * sbtRecordStride + sbtRecordOffset
+    (main.cpp:1260-1262 with stride 1 / offset 0 in the sample). The interval is chosen to cut through the scene's own hit distances, the masks
+    so that the cullMask removes some instances and keeps others."""
+    scene = scenes.random_scene(n_blas=3, tris_per_blas=300, n_instances=10, seed=21, width=160, height=100, bounces=0, shared_edges=True)
+    masks = [0x01, 0x02, 0x04, 0x08, 0x10, 0xFF, 0x03, 0x80, 0x0C, 0x00]
+    for i, I in enumerate(scene.instances):
+        I.mask = masks[i % len(masks)]
+    rng = np.random.default_rng(3)
+    scene.hit_records = rng.uniform(0.05, 0.95, size=(12, 3)).astype(np.float32)
+    cull_mask, stride, offset = 0x0B, 3, 2
+    o = oracle.OracleScene(scene)
+    _, p_all, _, _ = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(cull_mask=cull_mask))
+    t_all = p_all["t"][p_all["instance_id"] != MISS]
+    tmin, tmax = float(np.float32(np.percentile(t_all, 30))), float(np.float32(np.percentile(t_all, 80)))
+    rgba, prim, _, _ = o.trace(mode=oracle.MODE_BRUTE, ray_params=oracle.ray_params(tmin=tmin, tmax=tmax, cull_mask=cull_mask,
+                                                                                   sbt_record_offset=offset, sbt_record_stride=stride))
+    o.close()
+    O, D = _primary_rays(oracle, scene)
+    tri, ids = _world_triangles(scene, cull_mask)
+    assert set(np.unique(ids[:, 0])) == {i for i, I in enumerate(scene.instances) if I.mask & cull_mask} != set(range(len(scene.instances)))
+    best_t, best_k, clear = _closest_hits_f64(O, D, tri, tmin, tmax, t_eps=1e-3)
+    hit64 = np.isfinite(best_t)
+    p = prim.reshape(-1)
+    ohit = p["instance_id"] != MISS
+    assert clear.sum() > 0.85 * D.shape[0] and (clear & hit64).sum() > 500
+    # the interval really cuts: some rays lose their nearest surface to tmin and hit something behind it, others lose everything to tmax
+    t0, _, _ = _closest_hits_f64(O, D, tri, 0.0, 100.0)
+    assert (np.isfinite(t0) & (t0 <= tmin) & hit64).sum() > 50 and (np.isfinite(t0) & ~hit64).sum() > 50
+    assert np.array_equal(ohit[clear], hit64[clear])
+    c = clear & hit64
+    want = ids[best_k[c]]
+    assert np.array_equal(p["instance_id"][c], want[:, 0]) and np.array_equal(p["geometry_index"][c], want[:, 1])
+    assert np.array_equal(p["primitive_id"][c], want[:, 2]) and np.array_equal(p["custom_index"][c], want[:, 3])
+    assert np.all(p["t"][c] > np.float32(tmin)) and np.all(p["t"][c] < np.float32(tmax))
+    assert np.abs(p["t"][c] - best_t[c]).max() < 1e-4 * best_t[c].max()
+    rec = want[:, 4] + want[:, 1] * stride + offset
+    assert rec.max() < len(scene.hit_records) and len(np.unique(rec)) >= 4
+    special = (want[:, 2] == 1) & (want[:, 0] == 1) & (want[:, 3] == 100) & (want[:, 1] == 1)
+    col = np.clip(np.asarray(scene.hit_records, dtype=np.float32)[rec], 0, 1) * np.float32(255)
+    got = rgba.reshape(-1, 4)[c][:, :3].astype(np.float64)
+    assert np.abs(got - np.rint(col))[~special].max() <= 1.0
+    miss = clear & ~hit64
+    assert np.all(rgba.reshape(-1, 4)[miss] == np.array((0, 0, 51, 0), dtype=np.uint8))
 
 
 def _pcg(v):
