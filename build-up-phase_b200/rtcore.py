@@ -403,7 +403,8 @@ class Context:
                     keep.append(t)
                     arr[i].transform3x4 = t.ctypes.data
                 arr[i].flags = getattr(g, "flags", RT_GEOMETRY_OPAQUE) & 0xFF
-            arr[i].vertex_stride_bytes = 12
+            vv = g.vertices
+            arr[i].vertex_stride_bytes = 4 * int(vv.shape[1]) if getattr(vv, "ndim", 0) == 2 else 12   # [nv, k >= 3]: x y z first, k - 3 floats of padding
         return arr
 
     def blas_build_sizes(self, max_triangle_counts: Sequence[int]) -> RtBuildSizes:

@@ -116,7 +116,7 @@ def _geom_array(geoms, keep: list):
         keep.append(v)
         arr[i].vertices = v.ctypes.data
         arr[i].vertex_count = v.shape[0]
-        arr[i].vertex_stride_bytes = 12
+        arr[i].vertex_stride_bytes = 4 * int(v.shape[1]) if v.ndim == 2 else 12      # [nv, k >= 3]: x y z first, k - 3 floats of padding
         if g.indices is not None:
             idx = np.ascontiguousarray(g.indices, dtype=np.uint32)
             keep.append(idx)

@@ -897,3 +897,41 @@ def test_blas_compaction(rt, ctx, oracle, kind):
         plain.free()
     finally:
         sh.free()
+
+
+def _padded_copy(scene, cols, extra_rows):
+    """The same scene with every vertex array stored as [nv + extra_rows, cols]: x y z first, NaN in the padding columns (vertexStride =
+    4 * cols, main.cpp:733), and unreferenced rows of 1e30 behind the real vertices (maxVertex counts them, no index refers to them)."""
+    import copy
+    s = copy.deepcopy(scene)
+    for geoms in s.blases:
+        for g in geoms:
+            v = np.asarray(g.vertices, dtype=np.float32)
+            pv = np.full((v.shape[0] + extra_rows, cols), np.nan, dtype=np.float32)
+            pv[:v.shape[0], :3] = v
+            pv[v.shape[0]:, :3] = 1e30
+            if g.indices is None and extra_rows:                      # a non-indexed list uses every vertex: no spare rows there
+                pv = pv[:v.shape[0]]
+            g.vertices = pv
+    return s
+
+
+@pytest.mark.parametrize("n_geoms", [1, 2], ids=["one-geometry-blas", "two-geometry-blas"])
+def test_vertex_stride_and_unreferenced_vertices(rt, ctx, oracle, n_geoms):
+    """a1 (main.cpp:726-746): vertexStride and maxVertex. A BLAS that is ONE indexed geometry has its vertex array staged in shared memory by
+    the fused per-BLAS kernel (stride and all), a BLAS of several geometries gathers from global memory: both must read x y z at the stride and
+    nothing else, whatever lies in the padding or behind the last referenced vertex. Third case: a one-geometry BLAS whose vertex array is too
+    large for the staging area falls back to the global gather."""
+    base = scenes.random_scene(n_blas=4, tris_per_blas=400, n_instances=6, seed=13, width=320, height=200, bounces=1, n_geoms=n_geoms)
+    g0, r0, _ = _run(rt, ctx, oracle, base, oracle.MODE_BRUTE)
+    assert_parity(g0, r0, what=f"stride base {n_geoms}")
+    for cols, extra in ((4, 0), (5, 7), (8, 3)):
+        padded = _padded_copy(base, cols, extra)
+        g1, r1, _ = _run(rt, ctx, oracle, padded, oracle.MODE_BRUTE)
+        assert g1[1].tobytes() == g0[1].tobytes() and g1[2].tobytes() == g0[2].tobytes() and np.array_equal(g1[0], g0[0]), (cols, extra)
+        assert r1[1].tobytes() == r0[1].tobytes() and np.array_equal(r1[0], r0[0])            # the oracle reads the stride the same way
+    if n_geoms == 1:
+        big = _padded_copy(base, 3, 9000)                              # (nv + 9000) * 12 B > the 85 KB staging area: global gather
+        assert all((g.vertices.shape[0] * 12) > 87000 for geoms in big.blases for g in geoms)
+        g2, _, _ = _run(rt, ctx, oracle, big, oracle.MODE_BRUTE)
+        assert g2[1].tobytes() == g0[1].tobytes() and np.array_equal(g2[0], g0[0])
